@@ -1,0 +1,284 @@
+// bf_capi.cu -- engine state and the C-ABI declared in include/b200fold.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200fold.h"
+#include "bf_device.cuh"
+#include "bf_kernels.h"
+#include "bf_params.h"
+
+namespace {
+
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Engine {
+  bool inited = false, have_params = false;
+  int device = 0, sm_count = 0;
+  cudaStream_t stream = nullptr;
+  BfParams *hP = nullptr;  // host image
+  BfParams *dP = nullptr;  // device image
+  int *d_counters = nullptr;  // work counters (one per kernel kind)
+  DevBuf ws_mfe, ws_pf, d_mfe_scratch;
+  // staging for the host-buffer entry point
+  DevBuf d_seq, d_len, d_cut, d_nopair, d_targets, d_mfe, d_ss, d_pf, d_eval;
+  int64_t launches = 0;
+  std::string err;
+};
+
+Engine g;
+
+int fail(int code, const std::string &msg) { g.err = msg; return code; }
+int cuda_fail(cudaError_t e, const char *what) { return fail(BF_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); }
+
+#define CU(call, what)                                  \
+  do {                                                  \
+    cudaError_t e_ = (call);                            \
+    if (e_ != cudaSuccess) return cuda_fail(e_, what);  \
+  } while (0)
+
+int upload_params() {
+  if (!g.dP) CU(cudaMalloc(&g.dP, sizeof(BfParams)), "cudaMalloc(params)");
+  CU(cudaMemcpy(g.dP, g.hP, sizeof(BfParams), cudaMemcpyHostToDevice), "upload parameter image");
+  g.have_params = true;
+  return BF_OK;
+}
+
+int validate(const bf_batch_t *b, const bf_result_t *r) {
+  if (!b || !r) return fail(BF_ERR_ARG, "null batch/result");
+  if (b->B < 0 || b->stride <= 0) return fail(BF_ERR_ARG, "bad batch shape");
+  if (b->B && (!b->seq || !b->len)) return fail(BF_ERR_ARG, "seq/len missing");
+  if (b->stride > 4000) return fail(BF_ERR_ARG, "stride > 4000 not supported");
+  if ((b->want & BF_WANT_SS) && !r->mfe_ss) return fail(BF_ERR_ARG, "BF_WANT_SS without mfe_ss buffer");
+  if ((b->want & BF_WANT_MFE) && !r->mfe_dcal) return fail(BF_ERR_ARG, "BF_WANT_MFE without mfe_dcal buffer");
+  if ((b->want & BF_WANT_PF) && !r->pf) return fail(BF_ERR_ARG, "BF_WANT_PF without pf buffer");
+  if ((b->want & BF_WANT_EVAL) && (!r->eval_dcal || !b->targets || b->n_targets <= 0)) return fail(BF_ERR_ARG, "BF_WANT_EVAL without targets/eval_dcal");
+  if (b->want & (BF_WANT_BPP | BF_WANT_DEFECT)) return fail(BF_ERR_UNAVAILABLE, "bpp / ensemble defect kernels are not built yet");
+  return BF_OK;
+}
+
+// all pointers are device pointers
+int run_device(const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t st) {
+  if (b->B == 0) return BF_OK;
+  BfBatchDev db;
+  db.B = b->B; db.stride = b->stride; db.seq = b->seq; db.len = b->len; db.cut = b->cut; db.nopair = b->nopair;
+  const int wstride = b->stride + 2;
+  const int *mfe_for_scale = nullptr;
+  if (b->want & (BF_WANT_MFE | BF_WANT_SS)) {
+    int occ = bf_occupancy_mfe(two, wstride);
+    int grid = std::min(b->B, g.sm_count * occ);
+    size_t slot = bf_mfe_slot_ints(wstride) * sizeof(int);
+    // keep the workspace within a sane share of HBM
+    while (grid > g.sm_count && (size_t)grid * slot > ((size_t)48 << 30)) grid -= g.sm_count;
+    CU(g.ws_mfe.reserve((size_t)grid * slot), "cudaMalloc(mfe workspace)");
+    int *out_mfe = r->mfe_dcal;
+    if (!out_mfe) { CU(g.d_mfe_scratch.reserve((size_t)b->B * sizeof(int)), "cudaMalloc(mfe scratch)"); out_mfe = (int *)g.d_mfe_scratch.p; }
+    CU(bf_launch_mfe(g.dP, db, two, (int *)g.ws_mfe.p, wstride, grid, g.d_counters + 0, out_mfe,
+                     (b->want & BF_WANT_SS) ? r->mfe_ss : nullptr, b->stride + 1, st), "launch bf_k_mfe");
+    g.launches++;
+    mfe_for_scale = out_mfe;
+  }
+  if (b->want & BF_WANT_PF) {
+    BfBatchDev dbp = db;
+    dbp.nopair = nullptr;  // hard constraints are added after fc.pf() in the reference (sequence_utils.py:1181)
+    int occ = bf_occupancy_pf(two, wstride);
+    int grid = std::min(b->B, g.sm_count * occ);
+    size_t slot = bf_pf_slot_doubles(wstride) * sizeof(double);
+    while (grid > g.sm_count && (size_t)grid * slot > ((size_t)64 << 30)) grid -= g.sm_count;
+    CU(g.ws_pf.reserve((size_t)grid * slot), "cudaMalloc(pf workspace)");
+    // a constrained MFE is not a bound on the unconstrained ensemble: only use it for scaling when unconstrained
+    CU(bf_launch_pf(g.dP, dbp, two, (double *)g.ws_pf.p, wstride, grid, g.d_counters + 1, b->nopair ? nullptr : mfe_for_scale, r->pf, st),
+       "launch bf_k_pf");
+    g.launches++;
+  }
+  if (b->want & BF_WANT_EVAL) {
+    CU(bf_launch_eval(g.dP, db, b->targets, b->n_targets, b->stride, r->eval_dcal, st), "launch bf_k_eval");
+    g.launches++;
+  }
+  return BF_OK;
+}
+
+bool any_cut(const bf_batch_t *b, const int32_t *host_cut) {
+  if (!host_cut) return false;
+  for (int i = 0; i < b->B; i++) if (host_cut[i] > 0) return true;
+  return false;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *bf_last_error(void) { return g.err.c_str(); }
+
+int bf_init(int device) {
+  if (g.inited) return BF_OK;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return fail(BF_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(BF_ERR_ARG, "device index out of range");
+  CU(cudaSetDevice(device), "cudaSetDevice");
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+  if (prop.major < 10) return fail(BF_ERR_CUDA, std::string("built for sm_100a, found ") + prop.name);
+  g.device = device;
+  g.sm_count = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+  CU(cudaMalloc(&g.d_counters, 8 * sizeof(int)), "cudaMalloc(counters)");
+  CU(bf_upload_constants(), "upload candidate table");
+  if (!g.hP) g.hP = new BfParams;
+  g.inited = true;
+  if (g.have_params) return upload_params();
+  return BF_OK;
+}
+
+int bf_shutdown(void) {
+  if (!g.inited) return BF_OK;
+  cudaStreamSynchronize(g.stream);
+  for (DevBuf *b : {&g.ws_mfe, &g.ws_pf, &g.d_mfe_scratch, &g.d_seq, &g.d_len, &g.d_cut, &g.d_nopair, &g.d_targets, &g.d_mfe, &g.d_ss, &g.d_pf, &g.d_eval}) b->release();
+  if (g.dP) cudaFree(g.dP);
+  if (g.d_counters) cudaFree(g.d_counters);
+  cudaStreamDestroy(g.stream);
+  g.dP = nullptr; g.d_counters = nullptr; g.stream = nullptr;
+  g.inited = false;
+  return BF_OK;
+}
+
+int bf_params_load(const char *par_path) {
+  if (!par_path) return fail(BF_ERR_ARG, "null path");
+  if (!g.hP) g.hP = new BfParams;
+  std::string err;
+  if (bf_params_parse_file(par_path, g.hP, &err)) { g.have_params = false; return fail(BF_ERR_PARAMS, err); }
+  g.hP->year = 0;
+  g.have_params = true;
+  if (g.inited) return upload_params();
+  return BF_OK;
+}
+
+int bf_params_builtin(int year, const char *builtin_dir) {
+  if (year == 2004)
+    return fail(BF_ERR_UNAVAILABLE, "Turner 2004 tables are compiled into ViennaRNA, not shipped with DesiRNA; load rna_turner2004.par with bf_params_load");
+  if (year != 1999) return fail(BF_ERR_ARG, "year must be 1999 or 2004");
+  if (!builtin_dir) return fail(BF_ERR_ARG, "null builtin_dir");
+  std::string p = std::string(builtin_dir) + "/turner1999_37C.par";
+  int rc = bf_params_load(p.c_str());
+  if (rc == BF_OK) g.hP->year = 1999;
+  return rc;
+}
+
+int bf_params_get(const char *name, int i0, int i1, int i2, int i3, int i4, int i5, int32_t *out) {
+  if (!g.have_params || !g.hP) return fail(BF_ERR_NOT_INIT, "no parameters loaded");
+  if (!name || !out) return fail(BF_ERR_ARG, "null argument");
+  const BfParams &P = *g.hP;
+  auto in = [](int v, int hi) { return v >= 0 && v < hi; };
+  std::string n(name);
+#define T3(tab) if (n == #tab) { if (!in(i0, 8) || !in(i1, 5) || !in(i2, 5)) return fail(BF_ERR_ARG, "index"); *out = P.si.tab[i0][i1][i2]; return BF_OK; }
+  T3(mmH) T3(mmI) T3(mm1nI) T3(mm23I) T3(mmM) T3(mmE)
+#undef T3
+  if (n == "stack") { if (!in(i0, 8) || !in(i1, 8)) return fail(BF_ERR_ARG, "index"); *out = P.si.stack[i0][i1]; return BF_OK; }
+  if (n == "dangle5") { if (!in(i0, 8) || !in(i1, 5)) return fail(BF_ERR_ARG, "index"); *out = P.si.dangle5[i0][i1]; return BF_OK; }
+  if (n == "dangle3") { if (!in(i0, 8) || !in(i1, 5)) return fail(BF_ERR_ARG, "index"); *out = P.si.dangle3[i0][i1]; return BF_OK; }
+  if (n == "int11") { if (!in(i0, 8) || !in(i1, 8) || !in(i2, 5) || !in(i3, 5)) return fail(BF_ERR_ARG, "index"); *out = P.int11[i0][i1][i2][i3]; return BF_OK; }
+  if (n == "int21") { if (!in(i0, 8) || !in(i1, 8) || !in(i2, 5) || !in(i3, 5) || !in(i4, 5)) return fail(BF_ERR_ARG, "index"); *out = P.int21[i0][i1][i2][i3][i4]; return BF_OK; }
+  if (n == "int22") { if (!in(i0, 8) || !in(i1, 8) || !in(i2, 5) || !in(i3, 5) || !in(i4, 5) || !in(i5, 5)) return fail(BF_ERR_ARG, "index"); *out = P.int22[i0][i1][i2][i3][i4][i5]; return BF_OK; }
+  if (n == "hairpin" || n == "bulge" || n == "interior") {
+    if (!in(i0, 31)) return fail(BF_ERR_ARG, "index");
+    *out = n == "hairpin" ? P.si.hairpin[i0] : n == "bulge" ? P.si.bulge[i0] : P.si.interior[i0];
+    return BF_OK;
+  }
+  if (n == "ninio_m") { *out = P.si.ninio_m; return BF_OK; }
+  if (n == "ninio_max") { *out = P.si.ninio_max; return BF_OK; }
+  if (n == "MLbase") { *out = P.si.MLbase; return BF_OK; }
+  if (n == "MLclosing") { *out = P.si.MLclosing; return BF_OK; }
+  if (n == "MLintern") { *out = P.si.MLintern; return BF_OK; }
+  if (n == "DuplexInit") { *out = P.si.DuplexInit; return BF_OK; }
+  if (n == "TerminalAU") { *out = P.si.TerminalAU; return BF_OK; }
+  if (n == "lxc1000") { *out = (int32_t)(P.lxc * 1000.0 + 0.5); return BF_OK; }
+  if (n == "n_tetra") { *out = P.n_tetra; return BF_OK; }
+  if (n == "n_tri") { *out = P.n_tri; return BF_OK; }
+  if (n == "n_hexa") { *out = P.n_hexa; return BF_OK; }
+  if (n == "tetra_e") { if (!in(i0, 4096)) return fail(BF_ERR_ARG, "index"); *out = P.tetra_e[i0]; return BF_OK; }
+  return fail(BF_ERR_ARG, "unknown parameter name: " + n);
+}
+
+int bf_score_batch_device(const bf_batch_t *b, bf_result_t *r, void *cuda_stream) {
+  if (!g.inited) return fail(BF_ERR_NOT_INIT, "bf_init has not been called");
+  if (!g.have_params) return fail(BF_ERR_NOT_INIT, "no energy parameters loaded");
+  int rc = validate(b, r);
+  if (rc) return rc;
+  // the cut array lives on the device: the two-strand kernels handle cut == 0 rows as single strands
+  return run_device(b, r, b->cut != nullptr, cuda_stream ? (cudaStream_t)cuda_stream : g.stream);
+}
+
+int bf_score_batch(const bf_batch_t *b, bf_result_t *r) {
+  if (!g.inited) return fail(BF_ERR_NOT_INIT, "bf_init has not been called");
+  if (!g.have_params) return fail(BF_ERR_NOT_INIT, "no energy parameters loaded");
+  int rc = validate(b, r);
+  if (rc) return rc;
+  if (b->B == 0) return BF_OK;
+  for (int i = 0; i < b->B; i++) {
+    if (b->len[i] < 0 || b->len[i] > b->stride) return fail(BF_ERR_ARG, "sequence length exceeds stride");
+    if (b->cut && (b->cut[i] < 0 || b->cut[i] > b->len[i])) return fail(BF_ERR_ARG, "cut point outside sequence");
+  }
+  cudaStream_t st = g.stream;
+  const size_t B = b->B, S = b->stride;
+  const bool two = any_cut(b, b->cut);
+  bf_batch_t db = *b;
+  bf_result_t dr;
+  std::memset(&dr, 0, sizeof dr);
+  CU(g.d_seq.reserve(B * S), "cudaMalloc(seq)");
+  CU(g.d_len.reserve(B * sizeof(int)), "cudaMalloc(len)");
+  CU(cudaMemcpyAsync(g.d_seq.p, b->seq, B * S, cudaMemcpyHostToDevice, st), "H2D seq");
+  CU(cudaMemcpyAsync(g.d_len.p, b->len, B * sizeof(int), cudaMemcpyHostToDevice, st), "H2D len");
+  db.seq = (const char *)g.d_seq.p; db.len = (const int32_t *)g.d_len.p; db.cut = nullptr; db.nopair = nullptr; db.targets = nullptr;
+  if (two) {
+    CU(g.d_cut.reserve(B * sizeof(int)), "cudaMalloc(cut)");
+    CU(cudaMemcpyAsync(g.d_cut.p, b->cut, B * sizeof(int), cudaMemcpyHostToDevice, st), "H2D cut");
+    db.cut = (const int32_t *)g.d_cut.p;
+  }
+  if (b->nopair) {
+    CU(g.d_nopair.reserve(B * S), "cudaMalloc(nopair)");
+    CU(cudaMemcpyAsync(g.d_nopair.p, b->nopair, B * S, cudaMemcpyHostToDevice, st), "H2D nopair");
+    db.nopair = (const uint8_t *)g.d_nopair.p;
+  }
+  if (b->want & BF_WANT_EVAL) {
+    size_t tb = B * (size_t)b->n_targets * S;
+    CU(g.d_targets.reserve(tb), "cudaMalloc(targets)");
+    CU(cudaMemcpyAsync(g.d_targets.p, b->targets, tb, cudaMemcpyHostToDevice, st), "H2D targets");
+    db.targets = (const char *)g.d_targets.p;
+    CU(g.d_eval.reserve(B * b->n_targets * sizeof(int)), "cudaMalloc(eval)");
+    dr.eval_dcal = (int32_t *)g.d_eval.p;
+  }
+  if (b->want & (BF_WANT_MFE | BF_WANT_SS)) { CU(g.d_mfe.reserve(B * sizeof(int)), "cudaMalloc(mfe)"); dr.mfe_dcal = (int32_t *)g.d_mfe.p; }
+  if (b->want & BF_WANT_SS) { CU(g.d_ss.reserve(B * (S + 1)), "cudaMalloc(ss)"); dr.mfe_ss = (char *)g.d_ss.p; }
+  if (b->want & BF_WANT_PF) { CU(g.d_pf.reserve(B * 5 * sizeof(double)), "cudaMalloc(pf)"); dr.pf = (double *)g.d_pf.p; }
+  rc = run_device(&db, &dr, two, st);
+  if (rc) return rc;
+  if ((b->want & BF_WANT_MFE) && r->mfe_dcal) CU(cudaMemcpyAsync(r->mfe_dcal, dr.mfe_dcal, B * sizeof(int), cudaMemcpyDeviceToHost, st), "D2H mfe");
+  if (b->want & BF_WANT_SS) CU(cudaMemcpyAsync(r->mfe_ss, dr.mfe_ss, B * (S + 1), cudaMemcpyDeviceToHost, st), "D2H ss");
+  if (b->want & BF_WANT_PF) CU(cudaMemcpyAsync(r->pf, dr.pf, B * 5 * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H pf");
+  if (b->want & BF_WANT_EVAL) CU(cudaMemcpyAsync(r->eval_dcal, dr.eval_dcal, B * b->n_targets * sizeof(int), cudaMemcpyDeviceToHost, st), "D2H eval");
+  CU(cudaStreamSynchronize(st), "bf_score_batch");
+  return BF_OK;
+}
+
+int64_t bf_kernel_launches(void) { return g.launches; }
+int bf_sm_count(void) { return g.sm_count; }
+
+}  // extern "C"

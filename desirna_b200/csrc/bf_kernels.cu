@@ -1,0 +1,769 @@
+// bf_kernels.cu -- batched RNA folding kernels for sm_100a (B200).
+//
+// One persistent CTA folds one sequence at a time (sequences are pulled from an atomic
+// work counter).  The O(N^2) tables are filled as an anti-diagonal wavefront: on
+// diagonal d every cell (i, i+d) is independent, one warp owns a cell, the 32 lanes
+// split the cell's candidates (interior loops, multiloop / fML split points) and the
+// partial results meet in a warp reduction (redux.sync min for the MFE, shuffle tree
+// for the partition function).  One __syncthreads() separates diagonals.
+//
+// What replaces what (reference = DesiRNA through ViennaRNA's SWIG API):
+//   bf_k_mfe   <- fc.mfe() / fc.mfe_dimer() / RNA.fold()   energy_scores.py:151,156,354; sequence_utils.py:1183
+//   bf_k_pf    <- fc.pf() / fc.pf_dimer()                  energy_scores.py:150,157; dimer_multichain_energy.py:47
+//   bf_k_eval  <- fc.eval_structure()                      energy_scores.py:75,99
+// Recurrences: SURVEY.md A.4 (fill), A.5 (backtrack order), A.6 (inside), A.7 (two strands), A.8 (eval).
+#include "bf_kernels.h"
+
+#include "bf_device.cuh"
+
+namespace {
+
+// (u1,u2) enumeration of interior-loop candidates, u1 major: consecutive lanes walk q downwards in one row of c
+__constant__ uint8_t c_cand_u1[BF_NCAND];
+__constant__ uint8_t c_cand_u2[BF_NCAND];
+
+struct __align__(8) BfSector { short i, j; int kind; };  // kind: 0 exterior(f5 up to j) 1 multiloop part 2 pair 3 fcA from i 4 fcB up to j
+
+__device__ __forceinline__ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------- common per-sequence setup
+template <bool TWO>
+__device__ __forceinline__ void load_sequence(const BfBatchDev &b, int s, uint8_t *S, uint8_t *SP, BfCtx *X, int W) {
+  const int n = b.len[s];
+  const char *src = b.seq + (size_t)s * b.stride;
+  const uint8_t *np = b.nopair ? b.nopair + (size_t)s * b.stride : nullptr;
+  for (int k = threadIdx.x; k <= n + 1; k += blockDim.x) {
+    int code = (k >= 1 && k <= n) ? bf_base_code(src[k - 1]) : 0;
+    S[k] = (uint8_t)code;
+    SP[k] = (uint8_t)((np && k >= 1 && k <= n && np[k - 1]) ? 0 : code);
+  }
+  X->n = n;
+  int cut = (TWO && b.cut) ? b.cut[s] : 0;
+  X->cp = (cut > 1 && cut <= n) ? cut : n + 1;
+  X->W = W;
+  X->S = S;
+  X->SP = SP;
+}
+
+// =====================================================================================================
+//                                               MFE
+// =====================================================================================================
+template <bool TWO>
+__global__ void __launch_bounds__(BF_THREADS) bf_k_mfe(const BfParams *__restrict__ P, BfBatchDev b, int *ws, size_t ws_slot_ints,
+                                                       int wstride, int *work_counter, int *out_mfe, char *out_ss, int ss_stride) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ BfSmallI T;
+  __shared__ uint8_t cu1[BF_NCAND], cu2[BF_NCAND];
+  __shared__ int s_seq;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W = wstride;  // row stride of the tables, >= n+2
+
+  bf_stage(&T, &P->si);
+  for (int k = tid; k < BF_NCAND; k += blockDim.x) { cu1[k] = c_cand_u1[k]; cu2[k] = c_cand_u2[k]; }
+
+  // dynamic smem carve-up
+  const int nmax = W - 2;
+  uint8_t *S = dyn;
+  uint8_t *SP = S + align_up(nmax + 2, 16);
+  int *f5 = reinterpret_cast<int *>(SP + align_up(nmax + 2, 16));
+  int *fcA = f5 + (nmax + 4);
+  int *fcB = fcA + (nmax + 4);
+  BfSector *stk = reinterpret_cast<BfSector *>(fcB + (nmax + 4));
+
+  int *c = ws + (size_t)blockIdx.x * ws_slot_ints;
+  int *fml = c + (size_t)W * W;
+  int *fmlT = fml + (size_t)W * W;
+#define C_(i, j) c[(i) * W + (j)]
+#define M_(i, j) fml[(i) * W + (j)]
+#define MT_(j, i) fmlT[(j) * W + (i)]
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_seq = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int s = s_seq;
+    if (s >= b.B) break;
+    BfCtx X;
+    load_sequence<TWO>(b, s, S, SP, &X, W);
+    const int n = X.n, cp = X.cp;
+    // spans that are never computed must read as INF
+    const int d0 = TWO ? 1 : BF_TURN + 1;
+    for (int k = tid; k < d0 * (n + 1); k += blockDim.x) {
+      int d = k / (n + 1), i = k % (n + 1) + 1, j = i + d;
+      if (j <= n + 1 && i <= n) { M_(i, j) = BF_INF; MT_(j, i) = BF_INF; C_(i, j) = BF_INF; }
+    }
+    for (int k = tid; k <= n + 2; k += blockDim.x) { fcA[k] = 0; fcB[k] = 0; }
+    __syncthreads();
+
+    for (int d = d0; d <= n - 1; d++) {
+      if (TWO && cp <= n) {
+        // exterior-style decompositions next to the nick: fcA[k] for segment k..cp-1, fcB[k] for cp..k.
+        // Segment span is d-1, so every c it needs is final.
+        if (warp == 0) {
+          int k = cp - d;
+          if (k >= 1) {
+            int e = BF_INF;
+            for (int q = k + 1 + lane; q <= cp - 1; q += 32) {
+              int t = bf_ptype<TWO>(X, k, q);
+              if (t) {
+                int cc = C_(k, q);
+                if (cc < BF_INF) { int a, bb; bf_ext_nb<TWO>(X, k, q, &a, &bb); e = min(e, cc + bf_e_ext(T, t, a, bb) + fcA[q + 1]); }
+              }
+            }
+            e = bf_warp_min(e);
+            if (lane == 0) fcA[k] = min(e, fcA[k + 1]);
+          }
+        } else if (warp == 1) {
+          int k = cp + d - 1;
+          if (k <= n) {
+            int e = BF_INF;
+            for (int p = cp + lane; p < k; p += 32) {
+              int t = bf_ptype<TWO>(X, p, k);
+              if (t) {
+                int cc = C_(p, k);
+                if (cc < BF_INF) { int a, bb; bf_ext_nb<TWO>(X, p, k, &a, &bb); e = min(e, fcB[p - 1] + cc + bf_e_ext(T, t, a, bb)); }
+              }
+            }
+            e = bf_warp_min(e);
+            if (lane == 0) fcB[k] = min(e, fcB[k - 1]);
+          }
+        }
+        __syncthreads();
+      }
+      for (int i = 1 + warp; i + d <= n; i += BF_WARPS) {
+        const int j = i + d;
+        const int t = bf_ptype<TWO>(X, i, j);
+        int e = BF_INF;
+        if (t) {
+          const int si1 = S[i + 1], sj1 = S[j - 1];
+          if (lane == 0) {
+            if (TWO && i < cp && j >= cp) {
+              int a, bb; bf_nick_nb(X, i, j, &a, &bb);
+              e = bf_e_ext(T, bf_rtype(t), a, bb) + fcA[i + 1] + fcB[j - 1];
+            } else {
+              e = bf_e_hairpin(P, T, S, i, j, t);
+            }
+          }
+          // interior loops: lanes split the (u1,u2) candidates
+          for (int k = lane; k < BF_NCAND; k += 32) {
+            const int u1 = cu1[k], u2 = cu2[k];
+            const int p = i + 1 + u1, q = j - 1 - u2;
+            if (q <= p) continue;
+            if (TWO && (!bf_same<TWO>(X, i, p) || !bf_same<TWO>(X, q, j))) continue;
+            const int t2 = bf_ptype<TWO>(X, p, q);
+            if (!t2) continue;
+            const int cc = C_(p, q);
+            if (cc >= BF_INF) continue;
+            e = min(e, cc + bf_e_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]));
+          }
+          // multiloop closed by (i,j)
+          if (!TWO || (bf_same<TWO>(X, i, i + 1) && bf_same<TWO>(X, j - 1, j))) {
+            int dec = BF_INF;
+            const int *rowL = &M_(i + 1, 0);
+            const int *rowR = &MT_(j - 1, 0);
+            const int ulo = TWO ? i + 2 : i + 2 + BF_TURN + 1, uhi = TWO ? j - 1 : j - 2 - BF_TURN;
+            for (int u = ulo + lane; u <= uhi; u += 32) {
+              if (TWO && !bf_same<TWO>(X, u - 1, u)) continue;
+              dec = min(dec, rowL[u - 1] + rowR[u]);
+            }
+            if (dec < BF_INF) e = min(e, dec + T.MLclosing + bf_e_mlstem(T, bf_rtype(t), sj1, si1));
+          }
+          e = min(bf_warp_min(e), BF_INF);
+        }
+        // fML(i,j)
+        int m = BF_INF;
+        {
+          const int *rowL = &M_(i, 0);
+          const int *rowR = &MT_(j, 0);
+          const int ulo = TWO ? i + 1 : i + 1 + BF_TURN + 1, uhi = TWO ? j : j - 1 - BF_TURN;
+          for (int u = ulo + lane; u <= uhi; u += 32) {
+            if (TWO && !bf_same<TWO>(X, u - 1, u)) continue;
+            m = min(m, rowL[u - 1] + rowR[u]);
+          }
+          if (lane == 0) {
+            if (e < BF_INF && i > 1 && j < n && bf_same<TWO>(X, i - 1, i) && bf_same<TWO>(X, j, j + 1))
+              m = min(m, e + bf_e_mlstem(T, t, S[i - 1], S[j + 1]));
+            if (bf_same<TWO>(X, i, i + 1)) m = min(m, M_(i + 1, j) + T.MLbase);
+            if (bf_same<TWO>(X, j - 1, j)) m = min(m, M_(i, j - 1) + T.MLbase);
+          }
+          m = min(bf_warp_min(m), BF_INF);
+        }
+        if (lane == 0) { C_(i, j) = e; M_(i, j) = m; MT_(j, i) = m; }
+      }
+      __syncthreads();
+    }
+
+    // ---- exterior loop f5 (warp 0), then backtrack (warp 0)
+    if (warp == 0) {
+      if (lane == 0) f5[0] = 0;
+      __syncwarp();
+      for (int j = 1; j <= n; j++) {
+        int e = BF_INF;
+        for (int i = 1 + lane; i < j; i += 32) {
+          int t = bf_ptype<TWO>(X, i, j);
+          if (!t) continue;
+          int cc = C_(i, j);
+          if (cc >= BF_INF) continue;
+          int a, bb; bf_ext_nb<TWO>(X, i, j, &a, &bb);
+          e = min(e, f5[i - 1] + cc + bf_e_ext(T, t, a, bb) + (bf_same<TWO>(X, i, j) ? 0 : T.DuplexInit));
+        }
+        e = bf_warp_min(e);
+        if (lane == 0) f5[j] = min(e, f5[j - 1]);
+        __syncwarp();
+      }
+      if (lane == 0 && out_mfe) out_mfe[s] = f5[n];
+    }
+    if (out_ss) {
+      char *ss = out_ss + (size_t)s * ss_stride;
+      for (int k = tid; k < ss_stride; k += blockDim.x) ss[k] = (k < n) ? '.' : 0;
+    }
+    __syncthreads();
+    if (warp == 0 && out_ss) {
+      char *ss = out_ss + (size_t)s * ss_stride;
+      int sp = 0;
+      if (lane == 0) { stk[0].i = 1; stk[0].j = (short)n; stk[0].kind = 0; }
+      sp = 1;
+      __syncwarp();
+      int guard = 0;
+      while (sp > 0 && guard++ < 8 * n + 64) {
+        BfSector sec = stk[--sp];
+        __syncwarp();
+        int i = sec.i, j = sec.j;
+        bool to_pair = false;
+        if (sec.kind == 0) {
+          while (j > 0 && f5[j] == f5[j - 1]) j--;
+          if (j <= 1) continue;
+          int fu = 0;
+          for (int base = j - 1; base >= 1 && !fu; base -= 32) {
+            int u = base - lane;
+            bool ok = false;
+            if (u >= 1) {
+              int t = bf_ptype<TWO>(X, u, j);
+              if (t) {
+                int cc = C_(u, j);
+                if (cc < BF_INF) {
+                  int a, bb; bf_ext_nb<TWO>(X, u, j, &a, &bb);
+                  ok = f5[j] == f5[u - 1] + cc + bf_e_ext(T, t, a, bb) + (bf_same<TWO>(X, u, j) ? 0 : T.DuplexInit);
+                }
+              }
+            }
+            unsigned mk = __ballot_sync(BF_FULL, ok);
+            if (mk) fu = base - (__ffs(mk) - 1);
+          }
+          if (!fu) break;  // cannot happen for a consistent fill
+          if (lane == 0) { stk[sp].i = 1; stk[sp].j = (short)(fu - 1); stk[sp].kind = 0; }
+          sp++;
+          __syncwarp();
+          i = fu; to_pair = true;
+        } else if (TWO && sec.kind == 3) {
+          while (i < cp && fcA[i] == fcA[i + 1]) i++;
+          if (i >= cp) continue;
+          int fq = 0;
+          for (int base = i + 1; base <= cp - 1 && !fq; base += 32) {
+            int q = base + lane;
+            bool ok = false;
+            if (q <= cp - 1) {
+              int t = bf_ptype<TWO>(X, i, q);
+              if (t) {
+                int cc = C_(i, q);
+                if (cc < BF_INF) { int a, bb; bf_ext_nb<TWO>(X, i, q, &a, &bb); ok = fcA[i] == cc + bf_e_ext(T, t, a, bb) + fcA[q + 1]; }
+              }
+            }
+            unsigned mk = __ballot_sync(BF_FULL, ok);
+            if (mk) fq = base + (__ffs(mk) - 1);
+          }
+          if (!fq) break;
+          if (lane == 0) { stk[sp].i = (short)(fq + 1); stk[sp].j = 0; stk[sp].kind = 3; }
+          sp++;
+          __syncwarp();
+          j = fq; to_pair = true;
+        } else if (TWO && sec.kind == 4) {
+          while (j >= cp && fcB[j] == fcB[j - 1]) j--;
+          if (j < cp) continue;
+          int fp = 0;
+          for (int base = j - 1; base >= cp && !fp; base -= 32) {
+            int p = base - lane;
+            bool ok = false;
+            if (p >= cp) {
+              int t = bf_ptype<TWO>(X, p, j);
+              if (t) {
+                int cc = C_(p, j);
+                if (cc < BF_INF) { int a, bb; bf_ext_nb<TWO>(X, p, j, &a, &bb); ok = fcB[j] == fcB[p - 1] + cc + bf_e_ext(T, t, a, bb); }
+              }
+            }
+            unsigned mk = __ballot_sync(BF_FULL, ok);
+            if (mk) fp = base - (__ffs(mk) - 1);
+          }
+          if (!fp) break;
+          if (lane == 0) { stk[sp].i = 0; stk[sp].j = (short)(fp - 1); stk[sp].kind = 4; }
+          sp++;
+          __syncwarp();
+          i = fp; to_pair = true;
+        } else if (sec.kind == 1) {
+          while (j > i && bf_same<TWO>(X, j - 1, j) && M_(i, j) == M_(i, j - 1) + T.MLbase) j--;
+          while (i < j && bf_same<TWO>(X, i, i + 1) && M_(i, j) == M_(i + 1, j) + T.MLbase) i++;
+          const int mij = M_(i, j);
+          const int t = bf_ptype<TWO>(X, i, j);
+          if (t && C_(i, j) < BF_INF && i > 1 && j < n && bf_same<TWO>(X, i - 1, i) && bf_same<TWO>(X, j, j + 1) &&
+              mij == C_(i, j) + bf_e_mlstem(T, t, S[i - 1], S[j + 1])) {
+            to_pair = true;
+          } else {
+            int fu = 0;
+            for (int base = i + 1; base <= j && !fu; base += 32) {
+              int u = base + lane;
+              bool ok = false;
+              if (u <= j && bf_same<TWO>(X, u - 1, u)) {
+                int l = M_(i, u - 1), r = MT_(j, u);
+                ok = l < BF_INF && r < BF_INF && mij == l + r;
+              }
+              unsigned mk = __ballot_sync(BF_FULL, ok);
+              if (mk) fu = base + (__ffs(mk) - 1);
+            }
+            if (!fu) break;
+            if (lane == 0) {
+              stk[sp].i = (short)i; stk[sp].j = (short)(fu - 1); stk[sp].kind = 1;
+              stk[sp + 1].i = (short)fu; stk[sp + 1].j = (short)j; stk[sp + 1].kind = 1;
+            }
+            sp += 2;
+            __syncwarp();
+          }
+        } else {
+          to_pair = true;  // kind 2
+        }
+        if (!to_pair) continue;
+        // ---- pair (i,j): follow interior loops downwards
+        for (;;) {
+          if (lane == 0) { ss[i - 1] = '('; ss[j - 1] = ')'; }
+          const int t = bf_ptype<TWO>(X, i, j), cij = C_(i, j);
+          const int si1 = S[i + 1], sj1 = S[j - 1];
+          if (TWO && i < cp && j >= cp) {
+            int a, bb; bf_nick_nb(X, i, j, &a, &bb);
+            if (cij == bf_e_ext(T, bf_rtype(t), a, bb)) break;  // hairpin-like loop around the nick
+          } else if (cij == bf_e_hairpin(P, T, S, i, j, t)) break;
+          int fp = 0, fq = 0;
+          const int pmax = min(j - 2, i + BF_MAXLOOP + 1);
+          for (int p = i + 1; p <= pmax && !fp; p++) {
+            if (TWO && !bf_same<TWO>(X, i, p)) break;
+            const int minq = max(p + 1, j - i + p - BF_MAXLOOP - 2);
+            const int q = j - 1 - lane;
+            bool ok = false;
+            if (q >= minq && bf_same<TWO>(X, q, j)) {
+              int t2 = bf_ptype<TWO>(X, p, q);
+              if (t2) {
+                int cc = C_(p, q);
+                ok = cc < BF_INF && cij == cc + bf_e_intloop(P, T, p - i - 1, j - q - 1, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]);
+              }
+            }
+            unsigned mk = __ballot_sync(BF_FULL, ok);
+            if (mk) { fp = p; fq = j - 1 - (__ffs(mk) - 1); }
+          }
+          if (fp) { i = fp; j = fq; continue; }
+          // multiloop
+          int fu = 0;
+          if (!TWO || (bf_same<TWO>(X, i, i + 1) && bf_same<TWO>(X, j - 1, j))) {
+            const int en = cij - T.MLclosing - bf_e_mlstem(T, bf_rtype(t), sj1, si1);
+            for (int base = i + 2; base <= j - 1 && !fu; base += 32) {
+              int u = base + lane;
+              bool ok = false;
+              if (u <= j - 1 && bf_same<TWO>(X, u - 1, u)) {
+                int l = M_(i + 1, u - 1), r = MT_(j - 1, u);
+                ok = l < BF_INF && r < BF_INF && en == l + r;
+              }
+              unsigned mk = __ballot_sync(BF_FULL, ok);
+              if (mk) fu = base + (__ffs(mk) - 1);
+            }
+          }
+          if (fu) {
+            if (lane == 0) {
+              stk[sp].i = (short)(i + 1); stk[sp].j = (short)(fu - 1); stk[sp].kind = 1;
+              stk[sp + 1].i = (short)fu; stk[sp + 1].j = (short)(j - 1); stk[sp + 1].kind = 1;
+            }
+            sp += 2;
+            __syncwarp();
+          } else if (TWO && i < cp && j >= cp) {
+            // loop around the nick with stems inside: tried last (tie order pinned by the G5 goldens)
+            if (lane == 0) {
+              stk[sp].i = (short)(i + 1); stk[sp].j = 0; stk[sp].kind = 3;
+              stk[sp + 1].i = 0; stk[sp + 1].j = (short)(j - 1); stk[sp + 1].kind = 4;
+            }
+            sp += 2;
+            __syncwarp();
+          }
+          break;
+        }
+      }
+    }
+  }
+#undef C_
+#undef M_
+#undef MT_
+}
+
+// =====================================================================================================
+//                                     partition function (inside)
+// =====================================================================================================
+template <bool TWO>
+__global__ void __launch_bounds__(BF_THREADS) bf_k_pf(const BfParams *__restrict__ P, BfBatchDev b, double *ws, size_t ws_slot_dbl,
+                                                      int wstride, int *work_counter, const int *mfe_for_scale, double *out5) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ BfSmallD T;
+  __shared__ uint8_t cu1[BF_NCAND], cu2[BF_NCAND];
+  __shared__ int s_seq;
+  __shared__ double s_lnscale;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int W = wstride;
+  bf_stage(&T, &P->sd);
+  for (int k = tid; k < BF_NCAND; k += blockDim.x) { cu1[k] = c_cand_u1[k]; cu2[k] = c_cand_u2[k]; }
+
+  const int nmax = W - 2;
+  double *scl = reinterpret_cast<double *>(dyn);  // scale^-k
+  double *bu = scl + (nmax + 4);                   // (B(MLbase)/scale)^k
+  double *q5 = bu + (nmax + 4);
+  double *qA = q5 + (nmax + 4);
+  double *qB = qA + (nmax + 4);
+  uint8_t *S = reinterpret_cast<uint8_t *>(qB + (nmax + 4));
+  uint8_t *SP = S + align_up(nmax + 2, 16);
+
+  double *qb = ws + (size_t)blockIdx.x * ws_slot_dbl;
+  double *qm = qb + (size_t)W * W;
+  double *qm1T = qm + (size_t)W * W;  // qm1T[j][i] = qm1[i][j]
+#define QB_(i, j) qb[(i) * W + (j)]
+#define QM_(i, j) qm[(i) * W + (j)]
+#define QM1T_(j, i) qm1T[(j) * W + (i)]
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_seq = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int s = s_seq;
+    if (s >= b.B) break;
+    BfCtx X;
+    load_sequence<TWO>(b, s, S, SP, &X, W);
+    const int n = X.n, cp = X.cp;
+    if (tid == 0) {
+      // per-nucleotide scale: from the MFE when available (ViennaRNA exp_params_rescale, sfact 1.07),
+      // else ViennaRNA's default estimate of -185 cal/mol per nucleotide
+      double lns = 185.0 / T.kT;
+      if (mfe_for_scale && n > 0) {
+        double m = (double)mfe_for_scale[s] * 10.0;  // cal/mol
+        if (m < 0.0) lns = -1.07 * m / T.kT / (double)n;
+        if (lns < 185.0 / T.kT * 0.25) lns = 185.0 / T.kT * 0.25;
+      }
+      s_lnscale = lns;
+      const double sc = exp(-lns), bs = T.x_MLbase * sc;
+      scl[0] = 1.0; bu[0] = 1.0;
+      for (int k = 1; k <= n + 2; k++) { scl[k] = scl[k - 1] * sc; bu[k] = bu[k - 1] * bs; }
+    }
+    const int d0 = TWO ? 1 : BF_TURN + 1;
+    for (int k = tid; k < d0 * (n + 1); k += blockDim.x) {
+      int d = k / (n + 1), i = k % (n + 1) + 1, j = i + d;
+      if (j <= n + 1 && i <= n) { QB_(i, j) = 0.0; QM_(i, j) = 0.0; QM1T_(j, i) = 0.0; }
+    }
+    for (int k = tid; k <= n + 2; k += blockDim.x) { qA[k] = 0.0; qB[k] = 0.0; }
+    __syncthreads();
+    if (TWO && cp <= n && tid == 0) { qA[cp] = 1.0; qB[cp - 1] = 1.0; }
+    __syncthreads();
+
+    for (int d = d0; d <= n - 1; d++) {
+      if (TWO && cp <= n) {
+        if (warp == 0) {
+          int k = cp - d;
+          if (k >= 1) {
+            double sum = 0.0;
+            for (int q = k + 1 + lane; q <= cp - 1; q += 32) {
+              int t = bf_ptype<TWO>(X, k, q);
+              if (t) { int a, bb; bf_ext_nb<TWO>(X, k, q, &a, &bb); sum += QB_(k, q) * bf_x_ext(T, t, a, bb) * qA[q + 1]; }
+            }
+            sum = bf_warp_sum(sum);
+            if (lane == 0) qA[k] = sum + qA[k + 1] * scl[1];
+          }
+        } else if (warp == 1) {
+          int k = cp + d - 1;
+          if (k <= n) {
+            double sum = 0.0;
+            for (int p = cp + lane; p < k; p += 32) {
+              int t = bf_ptype<TWO>(X, p, k);
+              if (t) { int a, bb; bf_ext_nb<TWO>(X, p, k, &a, &bb); sum += qB[p - 1] * QB_(p, k) * bf_x_ext(T, t, a, bb); }
+            }
+            sum = bf_warp_sum(sum);
+            if (lane == 0) qB[k] = sum + qB[k - 1] * scl[1];
+          }
+        }
+        __syncthreads();
+      }
+      for (int i = 1 + warp; i + d <= n; i += BF_WARPS) {
+        const int j = i + d;
+        const int t = bf_ptype<TWO>(X, i, j);
+        double qbij = 0.0;
+        if (t) {
+          const int si1 = S[i + 1], sj1 = S[j - 1];
+          double acc = 0.0;
+          if (lane == 0) {
+            if (TWO && i < cp && j >= cp) {
+              int a, bb; bf_nick_nb(X, i, j, &a, &bb);
+              acc = bf_x_ext(T, bf_rtype(t), a, bb) * qA[i + 1] * qB[j - 1] * scl[2];
+            } else {
+              acc = bf_x_hairpin(P, T, S, i, j, t) * scl[d + 1];
+            }
+          }
+          for (int k = lane; k < BF_NCAND; k += 32) {
+            const int u1 = cu1[k], u2 = cu2[k];
+            const int p = i + 1 + u1, q = j - 1 - u2;
+            if (q <= p) continue;
+            if (TWO && (!bf_same<TWO>(X, i, p) || !bf_same<TWO>(X, q, j))) continue;
+            const int t2 = bf_ptype<TWO>(X, p, q);
+            if (!t2) continue;
+            acc += QB_(p, q) * bf_x_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]) * scl[u1 + u2 + 2];
+          }
+          if (!TWO || (bf_same<TWO>(X, i, i + 1) && bf_same<TWO>(X, j - 1, j))) {
+            double dec = 0.0;
+            const double *rowL = &QM_(i + 1, 0);
+            const double *rowR = &QM1T_(j - 1, 0);
+            const int ulo = TWO ? i + 2 : i + 2 + BF_TURN + 1, uhi = TWO ? j - 1 : j - 2 - BF_TURN;
+            for (int u = ulo + lane; u <= uhi; u += 32) {
+              if (TWO && !bf_same<TWO>(X, u - 1, u)) continue;
+              dec += rowL[u - 1] * rowR[u];
+            }
+            acc += dec * (T.x_MLclosing * bf_x_mlstem(T, bf_rtype(t), sj1, si1) * scl[2]);
+          }
+          qbij = bf_warp_sum(acc);
+        }
+        // qm1[i][j]: exactly one stem, starting at i, unpaired tail up to j
+        double qm1ij = 0.0;
+        if (lane == 0) {
+          if (bf_same<TWO>(X, j - 1, j)) qm1ij = QM1T_(j - 1, i) * bu[1];
+          if (t && i > 1 && j < n && bf_same<TWO>(X, i - 1, i) && bf_same<TWO>(X, j, j + 1)) qm1ij += qbij * bf_x_mlstem(T, t, S[i - 1], S[j + 1]);
+        }
+        qm1ij = __shfl_sync(BF_FULL, qm1ij, 0);
+        // qm[i][j] = sum_u (bu[u-i] + qm[i][u-1]) * qm1[u][j]   (u = i contributes qm1[i][j] itself)
+        double qmij = 0.0;
+        {
+          const double *rowL = &QM_(i, 0);
+          const double *rowR = &QM1T_(j, 0);
+          const int uhi = TWO ? j : j - BF_TURN - 1;
+          for (int u = i + 1 + lane; u <= uhi; u += 32) {
+            double left = 0.0;
+            if (!TWO || bf_same<TWO>(X, i, u)) left = bu[u - i];
+            if (!TWO || bf_same<TWO>(X, u - 1, u)) left += rowL[u - 1];
+            qmij += left * rowR[u];
+          }
+          qmij = bf_warp_sum(qmij) + qm1ij;
+        }
+        if (lane == 0) { QB_(i, j) = qbij; QM_(i, j) = qmij; QM1T_(j, i) = qm1ij; }
+      }
+      __syncthreads();
+    }
+
+    if (warp == 0) {
+      if (lane == 0) q5[0] = 1.0;
+      __syncwarp();
+      for (int j = 1; j <= n; j++) {
+        double sum = 0.0;
+        for (int i = 1 + lane; i < j; i += 32) {
+          int t = bf_ptype<TWO>(X, i, j);
+          if (!t) continue;
+          int a, bb; bf_ext_nb<TWO>(X, i, j, &a, &bb);
+          sum += q5[i - 1] * QB_(i, j) * bf_x_ext(T, t, a, bb);
+        }
+        sum = bf_warp_sum(sum);
+        if (lane == 0) q5[j] = sum + q5[j - 1] * scl[1];
+        __syncwarp();
+      }
+      if (lane == 0 && out5) {
+        const double kT = T.kT, lns = s_lnscale;
+        double *o = out5 + (size_t)s * 5;
+        o[0] = o[1] = o[2] = o[3] = 0.0;
+        o[4] = -kT * (log(q5[n]) + n * lns) / 1000.0;
+        if (TWO && cp <= n) {
+          const int nA = cp - 1, nB = n - cp + 1;
+          const double QA = qA[1], QBv = qB[n];
+          double QAB = (q5[n] - QA * QBv) * T.x_DuplexInit;
+          bool sym = (nA == nB);
+          for (int k = 1; sym && k <= nA; k++) sym = (S[k] == S[nA + k]);
+          if (sym) QAB *= 0.5;
+          const double QT = QA * QBv + QAB;
+          o[0] = -kT * (log(QA) + nA * lns) / 1000.0;
+          o[1] = -kT * (log(QBv) + nB * lns) / 1000.0;
+          o[2] = (QAB > 1e-17) ? -kT * (log(QAB) + n * lns) / 1000.0 : 999.0;
+          o[3] = -kT * (log(QT) + n * lns) / 1000.0;
+        }
+      }
+    }
+  }
+#undef QB_
+#undef QM_
+#undef QM1T_
+}
+
+// =====================================================================================================
+//                                        eval_structure
+// =====================================================================================================
+// One CTA per (sequence, target).  Thread 0 matches brackets, then every thread scores the loops
+// closed by the pairs it owns; a block reduction adds them up.
+__global__ void __launch_bounds__(128) bf_k_eval(const BfParams *__restrict__ P, BfBatchDev b, const char *targets, int n_targets,
+                                                 int tstride, int *out_e) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ BfSmallI T;
+  __shared__ int s_bad, s_sum;
+  const int s = blockIdx.x / n_targets, k = blockIdx.x % n_targets;
+  if (s >= b.B) return;
+  const int tid = threadIdx.x;
+  const int nmax = b.stride;
+  short *pt = reinterpret_cast<short *>(dyn);
+  short *stk = pt + (nmax + 4);
+  uint8_t *S = reinterpret_cast<uint8_t *>(stk + (nmax + 4));
+  uint8_t *SP = S + align_up(nmax + 2, 16);
+  bf_stage(&T, &P->si);
+  BfCtx X;
+  load_sequence<true>(b, s, S, SP, &X, nmax + 2);
+  const int n = X.n, cp = X.cp;
+  const char *db = targets + ((size_t)s * n_targets + k) * tstride;
+  for (int i = tid; i <= n + 1; i += blockDim.x) pt[i] = 0;
+  if (tid == 0) { s_bad = 0; s_sum = 0; }
+  __syncthreads();
+  if (tid == 0) {
+    int sp = 0;
+    for (int i = 1; i <= n; i++) {
+      char ch = db[i - 1];
+      if (ch == '(') stk[sp++] = (short)i;
+      else if (ch == ')') {
+        if (!sp) { s_bad = 1; break; }
+        int o = stk[--sp];
+        pt[o] = (short)i; pt[i] = (short)o;
+      }
+    }
+    if (sp) s_bad = 1;
+  }
+  __syncthreads();
+  if (s_bad) { if (tid == 0) out_e[(size_t)s * n_targets + k] = BF_INF; return; }
+  int e = 0;
+  if (tid == 0) {
+    // exterior loop
+    bool connected = false;
+    for (int i = 1; i <= n; i++) {
+      int j = pt[i];
+      if (j > i) {
+        int t = bf_ptype_bases(S[i], S[j]); if (!t) t = 7;
+        int a, bb; bf_ext_nb<true>(X, i, j, &a, &bb);
+        e += bf_e_ext(T, t, a, bb);
+        i = j;
+      }
+    }
+    for (int i = 1; i < cp && !connected; i++) if (pt[i] >= cp) connected = true;
+    if (connected && cp <= n) e += T.DuplexInit;
+  }
+  for (int i = 1 + tid; i <= n; i += blockDim.x) {
+    const int j = pt[i];
+    if (j <= i) continue;
+    int t = bf_ptype_bases(S[i], S[j]); if (!t) t = 7;
+    int nstem = 0, p1 = 0, q1 = 0, mlsum = 0, extsum = 0, unp = 0, prev = i;
+    bool nick = false;
+    for (int x = i + 1; x < j;) {
+      if (pt[x] > x) {
+        const int p = x, q = pt[x];
+        int t2 = bf_ptype_bases(S[p], S[q]); if (!t2) t2 = 7;
+        if (prev < cp && p >= cp) nick = true;
+        if (!nstem) { p1 = p; q1 = q; }
+        nstem++;
+        mlsum += bf_e_mlstem(T, t2, S[p - 1], S[q + 1]);
+        int a, bb; bf_ext_nb<true>(X, p, q, &a, &bb);
+        extsum += bf_e_ext(T, t2, a, bb);
+        prev = q; x = q + 1;
+      } else { unp++; x++; }
+    }
+    if (prev < cp && j >= cp) nick = true;
+    if (nick) {
+      int a, bb; bf_nick_nb(X, i, j, &a, &bb);
+      e += bf_e_ext(T, bf_rtype(t), a, bb) + extsum;
+    } else if (nstem == 0) {
+      e += bf_e_hairpin(P, T, S, i, j, t);
+    } else if (nstem == 1) {
+      int t2 = bf_ptype_bases(S[q1], S[p1]); if (!t2) t2 = 7;
+      e += bf_e_intloop(P, T, p1 - i - 1, j - q1 - 1, t, t2, S[i + 1], S[j - 1], S[p1 - 1], S[q1 + 1]);
+    } else {
+      e += T.MLclosing + bf_e_mlstem(T, bf_rtype(t), S[j - 1], S[i + 1]) + mlsum + unp * T.MLbase;
+    }
+  }
+  // INF-safe block sum: clamp each partial so that a forbidden loop (hairpin < 3) stays recognisable
+  e = __reduce_add_sync(BF_FULL, e);
+  if ((tid & 31) == 0) atomicAdd(&s_sum, e);
+  __syncthreads();
+  if (tid == 0) out_e[(size_t)s * n_targets + k] = s_sum;
+}
+
+}  // namespace
+
+// =====================================================================================================
+//                                        host-side launchers
+// =====================================================================================================
+static bool g_cand_uploaded = false;
+
+cudaError_t bf_upload_constants() {
+  if (g_cand_uploaded) return cudaSuccess;
+  uint8_t u1[BF_NCAND], u2[BF_NCAND];
+  int k = 0;
+  for (int a = 0; a <= BF_MAXLOOP; a++)
+    for (int c = 0; a + c <= BF_MAXLOOP; c++) { u1[k] = (uint8_t)a; u2[k] = (uint8_t)c; k++; }
+  cudaError_t e = cudaMemcpyToSymbol(c_cand_u1, u1, sizeof u1);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyToSymbol(c_cand_u2, u2, sizeof u2);
+  if (e == cudaSuccess) g_cand_uploaded = true;
+  return e;
+}
+
+size_t bf_mfe_slot_ints(int wstride) { return (size_t)3 * wstride * wstride; }
+size_t bf_pf_slot_doubles(int wstride) { return (size_t)3 * wstride * wstride; }
+
+static size_t mfe_smem(int wstride) {
+  size_t nmax = wstride - 2;
+  return 2 * ((nmax + 2 + 15) / 16 * 16) + 3 * (nmax + 4) * sizeof(int) + (2 * nmax + 16) * sizeof(BfSector);
+}
+static size_t pf_smem(int wstride) {
+  size_t nmax = wstride - 2;
+  return 5 * (nmax + 4) * sizeof(double) + 2 * ((nmax + 2 + 15) / 16 * 16);
+}
+static size_t eval_smem(int stride) { return 2 * (stride + 4) * sizeof(short) + 2 * ((stride + 2 + 15) / 16 * 16); }
+
+cudaError_t bf_launch_mfe(const BfParams *dP, const BfBatchDev &b, bool two, int *ws, int wstride, int grid, int *work_counter,
+                          int *out_mfe, char *out_ss, int ss_stride, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  size_t sm = mfe_smem(wstride);
+  auto kern = two ? bf_k_mfe<true> : bf_k_mfe<false>;
+  if (sm > 48 * 1024) { e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; }
+  kern<<<grid, BF_THREADS, sm, st>>>(dP, b, ws, bf_mfe_slot_ints(wstride), wstride, work_counter, out_mfe, out_ss, ss_stride);
+  return cudaGetLastError();
+}
+
+cudaError_t bf_launch_pf(const BfParams *dP, const BfBatchDev &b, bool two, double *ws, int wstride, int grid, int *work_counter,
+                         const int *mfe_for_scale, double *out5, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  size_t sm = pf_smem(wstride);
+  auto kern = two ? bf_k_pf<true> : bf_k_pf<false>;
+  if (sm > 48 * 1024) { e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; }
+  kern<<<grid, BF_THREADS, sm, st>>>(dP, b, ws, bf_pf_slot_doubles(wstride), wstride, work_counter, mfe_for_scale, out5);
+  return cudaGetLastError();
+}
+
+cudaError_t bf_launch_eval(const BfParams *dP, const BfBatchDev &b, const char *targets, int n_targets, int tstride, int *out_e,
+                           cudaStream_t st) {
+  if (b.B * n_targets == 0) return cudaSuccess;
+  size_t sm = eval_smem(b.stride);
+  if (sm > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(bf_k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; }
+  bf_k_eval<<<b.B * n_targets, 128, sm, st>>>(dP, b, targets, n_targets, tstride, out_e);
+  return cudaGetLastError();
+}
+
+int bf_occupancy_mfe(bool two, int wstride) {
+  int nb = 0;
+  auto kern = two ? bf_k_mfe<true> : bf_k_mfe<false>;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, BF_THREADS, mfe_smem(wstride)) != cudaSuccess) return 1;
+  return nb < 1 ? 1 : nb;
+}
+int bf_occupancy_pf(bool two, int wstride) {
+  int nb = 0;
+  auto kern = two ? bf_k_pf<true> : bf_k_pf<false>;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, BF_THREADS, pf_smem(wstride)) != cudaSuccess) return 1;
+  return nb < 1 ? 1 : nb;
+}

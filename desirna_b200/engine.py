@@ -1,0 +1,190 @@
+"""ctypes binding of libb200fold.so (C-ABI: include/b200fold.h).
+
+The library is the product: there is no CPU fallback.  Importing this module without the
+built shared object raises; calling into it without a B200 returns BF_ERR_CUDA, surfaced
+as EngineError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libb200fold.so")
+PARAMS_DIR = os.path.join(_PKG, "params")
+
+WANT_MFE, WANT_SS, WANT_PF, WANT_EVAL, WANT_BPP, WANT_DEFECT = 1, 2, 4, 8, 16, 32
+INF_DCAL = 10000000
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200fold error {code}: {msg}")
+        self.code = code
+
+
+class bf_batch_t(C.Structure):
+    _fields_ = [("B", C.c_int32), ("stride", C.c_int32), ("seq", C.c_void_p), ("len", C.c_void_p),
+                ("cut", C.c_void_p), ("nopair", C.c_void_p), ("targets", C.c_void_p),
+                ("n_targets", C.c_int32), ("want", C.c_uint32)]
+
+
+class bf_result_t(C.Structure):
+    _fields_ = [("mfe_dcal", C.c_void_p), ("mfe_ss", C.c_void_p), ("pf", C.c_void_p),
+                ("eval_dcal", C.c_void_p), ("defect", C.c_void_p), ("bpp", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(the engine has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.bf_last_error.restype = C.c_char_p
+        L.bf_init.argtypes = [C.c_int]
+        L.bf_params_load.argtypes = [C.c_char_p]
+        L.bf_params_builtin.argtypes = [C.c_int, C.c_char_p]
+        L.bf_params_get.argtypes = [C.c_char_p] + [C.c_int] * 6 + [C.POINTER(C.c_int32)]
+        L.bf_score_batch.argtypes = [C.POINTER(bf_batch_t), C.POINTER(bf_result_t)]
+        L.bf_score_batch_device.argtypes = [C.POINTER(bf_batch_t), C.POINTER(bf_result_t), C.c_void_p]
+        L.bf_kernel_launches.restype = C.c_int64
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise EngineError(rc, lib().bf_last_error().decode())
+
+
+_state = {"inited": False, "params": None}
+
+
+def init(device=None):
+    """Select the GPU (default: LOCAL_RANK or 0) and create the engine."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    _check(lib().bf_init(int(device)))
+    _state["inited"] = True
+
+
+def shutdown():
+    lib().bf_shutdown()
+    _state["inited"] = False
+
+
+def params_load(path):
+    """RNA.params_load(path) (DesiRNA.py:456)."""
+    _check(lib().bf_params_load(os.fsencode(path)))
+    _state["params"] = path
+
+
+def params_builtin(year=1999):
+    """`-p 1999|2004` selection of DesiRNA.py:455; 2004 raises EngineError(BF_ERR_UNAVAILABLE)."""
+    _check(lib().bf_params_builtin(int(year), os.fsencode(PARAMS_DIR)))
+    _state["params"] = f"builtin:{year}"
+
+
+def params_get(name, *idx):
+    idx = list(idx) + [0] * (6 - len(idx))
+    out = C.c_int32()
+    _check(lib().bf_params_get(name.encode(), *idx, C.byref(out)))
+    return out.value
+
+
+def ensure_ready(device=None):
+    if not _state["inited"]:
+        init(device)
+    if _state["params"] is None:
+        params_builtin(1999)
+
+
+def kernel_launches():
+    return int(lib().bf_kernel_launches())
+
+
+def sm_count():
+    return int(lib().bf_sm_count())
+
+
+def pack(seqs, stride=None):
+    """list of str (optionally 'A&B') -> (chars[B,stride] uint8, len[B] int32, cut[B] int32)."""
+    B = len(seqs)
+    clean, cuts = [], np.zeros(B, np.int32)
+    for k, s in enumerate(seqs):
+        if "&" in s:
+            a, b = s.split("&")[:2]
+            cuts[k] = len(a) + 1
+            s = a + b
+        clean.append(s)
+    lens = np.array([len(s) for s in clean], np.int32)
+    if stride is None:
+        stride = max(1, int(lens.max()) if B else 1)
+    buf = np.zeros((B, stride), np.uint8)
+    for k, s in enumerate(clean):
+        buf[k, :len(s)] = np.frombuffer(s.encode("ascii"), np.uint8)
+    return buf, lens, cuts
+
+
+def pack_targets(targets, stride):
+    """targets: list (per sequence) of list of dot-bracket strings ('&' dropped) -> uint8[B,T,stride]"""
+    B = len(targets)
+    T = len(targets[0]) if B else 0
+    buf = np.full((B, T, stride), ord("."), np.uint8)
+    for k, row in enumerate(targets):
+        assert len(row) == T, "every sequence needs the same number of targets"
+        for t, db in enumerate(row):
+            db = db.replace("&", "")
+            buf[k, t, :len(db)] = np.frombuffer(db.encode("ascii"), np.uint8)
+    return buf
+
+
+def score_batch(seqs, targets=None, nopair=None, want=WANT_MFE | WANT_SS | WANT_PF):
+    """Host-buffer entry point (bf_score_batch).  seqs: list of str; targets: list of lists of
+    dot-bracket strings; nopair: optional uint8[B, stride] mask.  Returns a dict of numpy arrays."""
+    ensure_ready()
+    B = len(seqs)
+    if B == 0:
+        return {"len": np.zeros(0, np.int32), "cut": np.zeros(0, np.int32), "mfe_dcal": np.zeros(0, np.int32),
+                "mfe_ss": [], "pf": np.zeros((0, 5)), "eval_dcal": np.zeros((0, 0), np.int32)}
+    buf, lens, cuts = pack(seqs)
+    stride = buf.shape[1]
+    b, r = bf_batch_t(), bf_result_t()
+    b.B, b.stride = B, stride
+    b.seq, b.len = buf.ctypes.data, lens.ctypes.data
+    b.cut = cuts.ctypes.data if cuts.any() else None
+    keep = [buf, lens, cuts]
+    if nopair is not None:
+        nopair = np.ascontiguousarray(nopair, np.uint8)
+        assert nopair.shape == (B, stride)
+        b.nopair = nopair.ctypes.data
+        keep.append(nopair)
+    out = {}
+    if targets is not None and (want & WANT_EVAL):
+        tb = pack_targets(targets, stride)
+        b.targets, b.n_targets = tb.ctypes.data, tb.shape[1]
+        out["eval_dcal"] = np.zeros((B, tb.shape[1]), np.int32)
+        r.eval_dcal = out["eval_dcal"].ctypes.data
+        keep.append(tb)
+    else:
+        want &= ~WANT_EVAL
+    if want & (WANT_MFE | WANT_SS):
+        want |= WANT_MFE
+        out["mfe_dcal"] = np.zeros(B, np.int32)
+        r.mfe_dcal = out["mfe_dcal"].ctypes.data
+    if want & WANT_SS:
+        ss = np.zeros((B, stride + 1), np.uint8)
+        r.mfe_ss = ss.ctypes.data
+    if want & WANT_PF:
+        out["pf"] = np.zeros((B, 5), np.float64)
+        r.pf = out["pf"].ctypes.data
+    b.want = want
+    _check(lib().bf_score_batch(C.byref(b), C.byref(r)))
+    if want & WANT_SS:
+        out["mfe_ss"] = [bytes(ss[k, :lens[k]]).decode("ascii") for k in range(B)]
+    out["len"], out["cut"] = lens, cuts
+    return out

@@ -1,0 +1,93 @@
+/*
+ * b200fold.h -- C-ABI of the B200-native batched RNA folding engine.
+ *
+ * DesiRNA has no FFI of its own: its hot path enters native code through ViennaRNA's
+ * SWIG module `RNA`.  Each entry point below names the reference call site it replaces
+ * (paths relative to the DesiRNA tree).  All functions return 0 on success, a BF_ERR_*
+ * code otherwise; bf_last_error() gives the message.  No allocation crosses the boundary:
+ * every buffer is caller-owned, strings are fixed-stride char arrays.
+ *
+ * Threading: one engine per process (one process per GPU, as in the reference's one
+ * worker per replica: utils/replica_exchange_monte_carlo.py:248).  Calls are serialised
+ * by the caller.
+ */
+#ifndef B200FOLD_H
+#define B200FOLD_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  BF_OK = 0,
+  BF_ERR_CUDA = 1,         /* CUDA runtime failure (no GPU, launch error, out of memory) */
+  BF_ERR_NOT_INIT = 2,     /* bf_init not called / no parameters loaded */
+  BF_ERR_PARAMS = 3,       /* parameter file missing or malformed */
+  BF_ERR_UNAVAILABLE = 4,  /* e.g. Turner 2004 tables are not packaged */
+  BF_ERR_ARG = 5           /* bad argument (null buffer, length > stride, ...) */
+};
+
+/* what to compute for every sequence of a batch */
+enum {
+  BF_WANT_MFE = 1u,    /* Zuker MFE energy                        fc.mfe()[1], RNA.fold()[1]   energy_scores.py:354 */
+  BF_WANT_SS = 2u,     /* + backtracked MFE structure             fc.mfe()[0], fc.mfe_dimer()[0] energy_scores.py:151,156 */
+  BF_WANT_PF = 4u,     /* McCaskill inside: ensemble free energy  fc.pf()[1], fc.pf_dimer()     energy_scores.py:150,157 */
+  BF_WANT_EVAL = 8u,   /* energy of the given target structures   fc.eval_structure()          energy_scores.py:75,99 */
+  BF_WANT_BPP = 16u,   /* base-pair probabilities (outside pass)  md.compute_bpp=1 + fc.pf()    energy_scores.py:369-373 */
+  BF_WANT_DEFECT = 32u /* ensemble defect of target 0             fc.ensemble_defect()          energy_scores.py:374 */
+};
+
+typedef struct {
+  int32_t B;             /* sequences in the batch */
+  int32_t stride;        /* bytes between consecutive rows of seq / nopair / each target; >= max length */
+  const char *seq;       /* B x stride, ASCII ACGU (T accepted), '&' removed by the caller */
+  const int32_t *len;    /* B lengths */
+  const int32_t *cut;    /* B or NULL: 1-based index of the first nucleotide of strand B, 0 = one strand
+                            (RNA.fold_compound("A&B"): energy_scores.py:147, dimer_multichain_energy.py:89,104) */
+  const uint8_t *nopair; /* B x stride or NULL: 1 = position may not pair -- fc.hc_add_from_db with 'x'
+                            (sequence_utils.py:1181,1198,1214).  Applies to the MFE only. */
+  const char *targets;   /* B x n_targets x stride dot-bracket strings or NULL; only '(' ')' pair */
+  int32_t n_targets;
+  uint32_t want;         /* OR of BF_WANT_* */
+} bf_batch_t;
+
+typedef struct {
+  int32_t *mfe_dcal;  /* B: MFE in dcal/mol (ViennaRNA returns kcal/mol as C float = value/100) */
+  char *mfe_ss;       /* B x (stride+1): NUL-terminated dot-bracket, no '&' (as fc.mfe_dimer) */
+  double *pf;         /* B x 5: FA, FB, FcAB, FAB, F0AB in kcal/mol; one strand: [4] = ensemble free energy */
+  int32_t *eval_dcal; /* B x n_targets: energy of each target in dcal/mol (>= 10000000: malformed / forbidden loop) */
+  double *defect;     /* B: ensemble defect of target 0 */
+  double *bpp;        /* B x stride x stride (row i-1, col j-1, i<j) or NULL */
+} bf_result_t;
+
+/* engine life cycle */
+int bf_init(int device);
+int bf_shutdown(void);
+const char *bf_last_error(void);
+
+/* RNA.params_load(path)                                                    DesiRNA.py:455-456 */
+int bf_params_load(const char *par_path);
+/* `-p 2004` keeps ViennaRNA's compiled-in defaults; `-p 1999` loads the vendored file (DesiRNA.py:455).
+ * year 1999 -> table set at `builtin_dir`/turner1999_37C.par; 2004 -> BF_ERR_UNAVAILABLE (not packaged). */
+int bf_params_builtin(int year, const char *builtin_dir);
+/* read back one integer parameter (loader cross-checks): name as in bf_params.h, up to 6 indices */
+int bf_params_get(const char *name, int i0, int i1, int i2, int i3, int i4, int i5, int32_t *out);
+
+/* Score a batch whose buffers live in HOST memory: copies in, runs the kernels, copies out, synchronises.
+ * This is the call behind score_sequence()/get_mfe_e_ss() (energy_scores.py:31-159). */
+int bf_score_batch(const bf_batch_t *batch, bf_result_t *result);
+
+/* Same, but every pointer in batch/result is a DEVICE pointer; work is enqueued on `cuda_stream`
+ * (a cudaStream_t; NULL = the engine's own stream) and NOT synchronised. */
+int bf_score_batch_device(const bf_batch_t *batch, bf_result_t *result, void *cuda_stream);
+
+/* number of kernels launched by this process since bf_init (bench.py "gpu_launches") */
+int64_t bf_kernel_launches(void);
+/* SM count of the device in use */
+int bf_sm_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
