@@ -1,0 +1,367 @@
+#!/usr/bin/env python3
+"""bench.py -- MFE+PF folds/sec on the synthetic batched fold sweep (BASELINE.json configs[1]).
+
+One "step" = one pass of the hot path (MFE fill + backtrack, partition function, eval of the
+target) over a batch of B=4096 random sequences of length L (default L=100; the other lengths
+of the sweep are timed in the same run and reported under "by_length").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--L 100] [--B 4096]
+  python bench.py --impl reference ...      # CPU arm: the oracle port on all host threads
+
+Our arm prints ONE JSON line with the driver's contract keys plus `roofline`, `cpu_baseline`,
+`e2e`, `by_length`, `clocks`, `gpu_launches`.  Timing: CUDA events on the launch stream, >= 3
+warm-up steps, L2 flushed between timed steps, max over ranks.  ViennaRNA itself is not
+installable here (no wheel, no network), so the CPU arm is the repo's C oracle
+(cpu_baseline.kind = "port"), threaded over the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SWEEP = (50, 100, 200, 400)
+P_PAIR = 6.0 / 16.0
+
+
+# ---------------------------------------------------------------- algorithmic work (SURVEY.md 8d / DESIGN.md)
+def relaxations(N):
+    """Closed-form DP relaxation counts per fold of a uniform random sequence of length N
+    (TURN=3, MAXLOOP=30, pair probability 6/16).  Returns (R_MFE, R_PFin)."""
+    T = lambda m: (m + 1) * (m + 2) // 2 if m >= 0 else 0
+    r_int = P_PAIR * sum((N - d) * T(min(30, d - 6)) for d in range(4, N))
+    r_mlc = P_PAIR * sum((N - d) * max(0, d - 9) for d in range(4, N))
+    r_fml = sum((N - d) * max(0, d - 7) for d in range(4, N))
+    r_f5 = sum(max(0, j - 4) for j in range(1, N + 1))
+    r_mfe = r_int + r_mlc + r_fml + r_f5
+    r_pf = r_int + P_PAIR * sum((N - d) * (d - 1) for d in range(4, N)) + sum((N - d) * (d + 1) for d in range(4, N)) + r_f5
+    return r_mfe, r_pf
+
+
+def synth(L, B, rank=0):
+    rng = np.random.default_rng(20240000 + L + 1000003 * rank)
+    return rng.integers(0, 4, (B, L))
+
+
+def to_strings(codes):
+    lut = np.frombuffer(b"ACGU", np.uint8)
+    return [bytes(lut[row]).decode() for row in codes]
+
+
+# ---------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------- reference arm (CPU oracle port)
+def cpu_sample(L, budget_s, threads):
+    """Time the oracle (MFE+backtrack, PF inside, eval) on a bounded sample of the L-workload."""
+    from oracle.pyoracle import Oracle, build
+    build()
+    O = Oracle(os.path.join(ROOT, "desirna_b200", "params", "turner1999_37C.par"))
+    per_fold = 2.6e-8 * L ** 3 + 1.3e-6 * L ** 2  # rough single-thread seconds, only used to size the sample
+    n = int(max(threads, min(4096, budget_s * threads / per_fold)))
+    n = max(threads, (n // threads) * threads)
+    seqs = to_strings(synth(L, n, rank=7))
+    t0 = time.perf_counter()
+    O.fold_batch(seqs, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    L = args.L
+    # warm-up + K timed steps, each a bounded sample
+    vals = []
+    budget = max(1.0, min(20.0, 60.0 / max(1, args.steps)))
+    for _ in range(min(args.warmup, 1)):
+        cpu_sample(L, 0.5, threads)
+    n_used = 0
+    t_total = 0.0
+    for _ in range(args.steps):
+        v, n, dt = cpu_sample(L, budget, threads)
+        vals.append(v); n_used = n; t_total += dt
+    value = statistics.mean(vals)
+    by = {}
+    if not args.no_sweep:
+        for l in SWEEP:
+            by[str(l)] = value if l == L else cpu_sample(l, 8.0, threads)[0]
+    line = {
+        "impl": "reference", "metric": "MFE+PF folds/sec", "value": value, "unit": "folds/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+        "config": {"workload": f"synthetic batched fold sweep: random sequences x L={L}, MFE+backtrack+PF+eval, Turner 1999", "L": L,
+                   "sample_per_step": n_used, "params": "turner1999"},
+        "cpu_baseline": {"value": value, "unit": "folds/s", "cores": threads, "kind": "port",
+                         "sample": f"{n_used} random sequences of L={L} per step, oracle/orc_fold.c on {threads} threads (ViennaRNA 2.6.4 not installable offline)"},
+        "e2e": {"value": value, "unit": "folds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "by_length": by,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------- our arm
+def load_peaks():
+    peaks = {"hbm_gbs": 6650.0, "hbm_src": "fallback", "int32_tops": 18.6, "fp64_tflops": 37.0, "smem_tbs": 37.2, "chip_src": "nominal"}
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            peaks["hbm_gbs"] = float(json.load(open(p))["hbm_gbs"]); peaks["hbm_src"] = "measured"
+        except Exception:
+            pass
+    return peaks
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from desirna_b200 import engine as eng
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng.init(local)
+    eng.params_builtin(1999)
+    dev = torch.device("cuda", local)
+    tstream = torch.cuda.Stream(device=dev)  # timed work and its CUDA events share this stream
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    WANT = eng.WANT_MFE | eng.WANT_SS | eng.WANT_PF | eng.WANT_EVAL
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    lut = torch.tensor(list(b"ACGU"), dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def make(L, B):
+        codes = synth(L, B, rank)
+        seq = lut[torch.from_numpy(codes).to(dev)].contiguous()
+        lens = torch.full((B,), L, dtype=torch.int32, device=dev)
+        bufs = dict(seq=seq, lens=lens, mfe=torch.zeros(B, dtype=torch.int32, device=dev), ss=torch.zeros((B, L + 1), dtype=torch.uint8, device=dev),
+                    pf=torch.zeros((B, 5), dtype=torch.float64, device=dev), ev=torch.zeros((B, 1), dtype=torch.int32, device=dev),
+                    targets=torch.full((B, 1, L), ord("."), dtype=torch.uint8, device=dev))
+        return codes, bufs
+
+    def step(b):
+        eng.score_batch_device(b["seq"], b["lens"], WANT, targets=b["targets"], mfe=b["mfe"], ss=b["ss"], pf=b["pf"], ev=b["ev"], stream=stream)
+
+    def measure(L, B, steps, warmup):
+        codes, b = make(L, B)
+        # pass 0: the MFE structure of every sequence becomes its target (free invariant Ed == MFE)
+        step(b)
+        torch.cuda.synchronize()
+        b["targets"][:, 0, :] = b["ss"][:, :L]
+        for _ in range(warmup):
+            step(b)
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        kms = []
+        for k in range(steps):
+            flush.fill_(k & 0xff)  # L2 flush between timed steps
+            ev[k][0].record()
+            step(b)
+            ev[k][1].record()
+            ev[k][1].synchronize()
+            kms.append(eng.last_kernel_ms())
+        barrier()
+        ms = [a.elapsed_time(c) for a, c in ev]
+        total = torch.tensor([sum(ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(total, op=dist.ReduceOp.MAX)
+        ok = bool((b["ev"][:, 0] == b["mfe"]).all().item()) and bool((b["pf"][:, 4] <= b["mfe"].double() / 100.0 + 1e-9).all().item())
+        kavg = [statistics.mean(x[i] for x in kms) for i in range(3)]
+        return dict(total_ms=float(total.item()), ms=ms, kernel_ms=kavg, ok=ok, codes=codes, bufs=b)
+
+    L, B = args.L, args.B
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.kernel_launches()
+    main = measure(L, B, args.steps, args.warmup)
+    launches = eng.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (main["total_ms"] * 1e-3)
+
+    # ---- e2e: the host-buffer C-ABI call, H2D/D2H inside the timed region (pinned host memory)
+    codes = main["codes"]
+    seq_h = torch.from_numpy(np.frombuffer(b"ACGU", np.uint8)[codes].copy()).pin_memory()
+    len_h = torch.full((B,), L, dtype=torch.int32).pin_memory()
+    tg_h = main["bufs"]["targets"].cpu().pin_memory()
+    mfe_h = torch.zeros(B, dtype=torch.int32).pin_memory(); ss_h = torch.zeros((B, L + 1), dtype=torch.uint8).pin_memory()
+    pf_h = torch.zeros((B, 5), dtype=torch.float64).pin_memory(); ev_h = torch.zeros((B, 1), dtype=torch.int32).pin_memory()
+    import ctypes as C
+    bb, rr = eng.bf_batch_t(), eng.bf_result_t()
+    bb.B, bb.stride, bb.seq, bb.len, bb.targets, bb.n_targets, bb.want = B, L, seq_h.data_ptr(), len_h.data_ptr(), tg_h.data_ptr(), 1, WANT
+    rr.mfe_dcal, rr.mfe_ss, rr.pf, rr.eval_dcal = mfe_h.data_ptr(), ss_h.data_ptr(), pf_h.data_ptr(), ev_h.data_ptr()
+    e2e_steps = max(1, args.steps)
+    for _ in range(2):
+        eng._check(eng.lib().bf_score_batch(C.byref(bb), C.byref(rr)))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng._check(eng.lib().bf_score_batch(C.byref(bb), C.byref(rr)))
+    torch.cuda.synchronize()
+    e2e_dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * e2e_steps / float(e2e_dt.item())
+    e2e_ok = bool((ev_h[:, 0] == mfe_h).all().item()) and bool((mfe_h == main["bufs"]["mfe"].cpu()).all().item())
+    h2d = seq_h.numel() + 4 * B + tg_h.numel()
+    d2h = 4 * B + ss_h.numel() + 8 * 5 * B + 4 * B
+
+    # ---- the other lengths of the sweep (fewer steps; same timing discipline)
+    by = {str(L): world * B * args.steps / (main["total_ms"] * 1e-3)}
+    kern = {str(L): main["kernel_ms"]}
+    checks = {str(L): main["ok"]}
+    if not args.no_sweep:
+        for l in SWEEP:
+            if l == L:
+                continue
+            m = measure(l, B, max(2, min(args.steps, 3)), 3)
+            by[str(l)] = world * B * len(m["ms"]) / (m["total_ms"] * 1e-3)
+            kern[str(l)] = m["kernel_ms"]; checks[str(l)] = m["ok"]
+            del m
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel (live CUDA-event kernel times of the L-workload)
+    peaks = load_peaks()
+    pk_path = os.path.join(ROOT, "profiles", "chip_peaks.json")
+    if os.path.exists(pk_path):
+        try:
+            cp = json.load(open(pk_path))
+            peaks.update(int32_tops=cp["int32_ops_per_s"] / 1e12, fp64_tflops=cp["fp64_flops_per_s"] / 1e12, smem_tbs=cp["smem_bytes_per_s"] / 1e12, chip_src="measured (profiles/chip_peaks.json)")
+        except Exception:
+            pass
+    r_mfe, r_pf = relaxations(L)
+    mfe_ms, pf_ms, ev_ms = main["kernel_ms"]
+    names = ["bf_k_mfe", "bf_k_pf", "bf_k_eval"]
+    dom = int(np.argmax(main["kernel_ms"]))
+    if dom == 1:
+        ach = 2.0 * r_pf * B / (pf_ms * 1e-3) / 1e12
+        roof = {"kernel": names[1], "bound": "fp64", "achieved": ach, "peak": peaks["fp64_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["fp64_tflops"],
+                "traffic": None, "algorithmic": f"2 flops x {r_pf:.4g} relaxations/fold x {B} folds per launch", "peak_src": peaks["chip_src"]}
+    else:
+        ach = 2.0 * r_mfe * B / (mfe_ms * 1e-3) / 1e12
+        roof = {"kernel": names[0], "bound": "int32", "achieved": ach, "peak": peaks["int32_tops"], "unit": "TOP/s", "frac": ach / peaks["int32_tops"],
+                "traffic": None, "algorithmic": f"2 int32 ops x {r_mfe:.4g} relaxations/fold x {B} folds per launch", "peak_src": peaks["chip_src"]}
+    roof["kernel_ms"] = dict(zip(names, main["kernel_ms"]))
+    roof["share_of_step"] = main["kernel_ms"][dom] / max(1e-9, sum(main["kernel_ms"]))
+    # on-chip operand traffic view (4 B per interior candidate, 8 B per split candidate; fp64 doubles it)
+    T = lambda m: (m + 1) * (m + 2) // 2 if m >= 0 else 0
+    r_int = P_PAIR * sum((L - d) * T(min(30, d - 6)) for d in range(4, L))
+    smem_mfe = (4 * r_int + 8 * (r_mfe - r_int)) * B / (mfe_ms * 1e-3) / 1e12
+    smem_pf = (8 * r_int + 16 * (r_pf - r_int)) * B / (pf_ms * 1e-3) / 1e12
+    roof["operand_tbs"] = {"bf_k_mfe": smem_mfe, "bf_k_pf": smem_pf, "peak_smem_tbs": peaks["smem_tbs"], "frac_mfe": smem_mfe / peaks["smem_tbs"], "frac_pf": smem_pf / peaks["smem_tbs"]}
+    # HBM view: the path moves ~2L+60 bytes per fold over HBM by design
+    hbm_bytes = (2 * L + 1 + 4 + 4 + 40 + 4 + L) * B
+    roof["hbm"] = {"achieved_gbs": hbm_bytes / (sum(main["kernel_ms"]) * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"], "peak_src": peaks["hbm_src"], "algorithmic_bytes_per_launch": hbm_bytes}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        v, n, dt = cpu_sample(L, 12.0, threads)
+        cpu = {"value": v, "unit": "folds/s", "cores": threads, "kind": "port",
+               "sample": f"{n} random sequences of L={L} ({dt:.1f} s), oracle/orc_fold.c on {threads} threads; ViennaRNA 2.6.4 is not installable offline"}
+    line = {
+        "metric": "MFE+PF folds/sec", "value": value, "unit": "folds/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": main["total_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32+f64", "data": "synthetic",
+        "config": {"workload": f"synthetic batched fold sweep: {B} random sequences x L={L} per GPU, MFE+backtrack+PF+eval, Turner 1999",
+                   "L": L, "B_per_gpu": B, "params": "turner1999", "parallelism": f"dp{world} (sequences sharded, no data-path collective)",
+                   "l2": "256 MiB write between timed steps"},
+        "e2e": {"value": e2e_val, "unit": "folds/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "timer": "host clock around the synchronous C-ABI call"},
+        "gpu_launches": int(launches),
+        "roofline": roof, "cpu_baseline": cpu, "by_length": by, "kernel_ms_by_length": kern,
+        "checks": {"ed_equals_mfe_and_epf_le_mfe": checks, "e2e_matches_device_path": e2e_ok},
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--L", type=int, default=100)
+    ap.add_argument("--B", type=int, default=4096)
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--peaks", action="store_true", help="measure INT32/FP64/smem chip peaks and write profiles/chip_peaks.json")
+    args = ap.parse_args()
+    args.warmup = max(3, args.warmup) if args.impl == "b200" else args.warmup
+    if args.peaks:
+        from desirna_b200 import engine as eng
+        eng.init(0)
+        pk = eng.microbench()
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(pk, open(os.path.join(ROOT, "gpurun_out", "chip_peaks.json"), "w"), indent=1)
+        print(json.dumps(pk))
+        return
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -40,6 +40,8 @@ struct Engine {
   // staging for the host-buffer entry point
   DevBuf d_seq, d_len, d_cut, d_nopair, d_targets, d_mfe, d_ss, d_pf, d_eval;
   int64_t launches = 0;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // begin/end of mfe, pf, eval in the last call
+  bool ran[3] = {false, false, false};
   std::string err;
 };
 
@@ -81,6 +83,7 @@ int run_device(const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t
   db.B = b->B; db.stride = b->stride; db.seq = b->seq; db.len = b->len; db.cut = b->cut; db.nopair = b->nopair;
   const int wstride = b->stride + 2;
   const int *mfe_for_scale = nullptr;
+  g.ran[0] = g.ran[1] = g.ran[2] = false;
   if (b->want & (BF_WANT_MFE | BF_WANT_SS)) {
     int occ = bf_occupancy_mfe(two, wstride);
     int grid = std::min(b->B, g.sm_count * occ);
@@ -90,8 +93,11 @@ int run_device(const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t
     CU(g.ws_mfe.reserve((size_t)grid * slot), "cudaMalloc(mfe workspace)");
     int *out_mfe = r->mfe_dcal;
     if (!out_mfe) { CU(g.d_mfe_scratch.reserve((size_t)b->B * sizeof(int)), "cudaMalloc(mfe scratch)"); out_mfe = (int *)g.d_mfe_scratch.p; }
+    cudaEventRecord(g.ev[0], st);
     CU(bf_launch_mfe(g.dP, db, two, (int *)g.ws_mfe.p, wstride, grid, g.d_counters + 0, out_mfe,
                      (b->want & BF_WANT_SS) ? r->mfe_ss : nullptr, b->stride + 1, st), "launch bf_k_mfe");
+    cudaEventRecord(g.ev[1], st);
+    g.ran[0] = true;
     g.launches++;
     mfe_for_scale = out_mfe;
   }
@@ -104,12 +110,18 @@ int run_device(const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t
     while (grid > g.sm_count && (size_t)grid * slot > ((size_t)64 << 30)) grid -= g.sm_count;
     CU(g.ws_pf.reserve((size_t)grid * slot), "cudaMalloc(pf workspace)");
     // a constrained MFE is not a bound on the unconstrained ensemble: only use it for scaling when unconstrained
+    cudaEventRecord(g.ev[2], st);
     CU(bf_launch_pf(g.dP, dbp, two, (double *)g.ws_pf.p, wstride, grid, g.d_counters + 1, b->nopair ? nullptr : mfe_for_scale, r->pf, st),
        "launch bf_k_pf");
+    cudaEventRecord(g.ev[3], st);
+    g.ran[1] = true;
     g.launches++;
   }
   if (b->want & BF_WANT_EVAL) {
+    cudaEventRecord(g.ev[4], st);
     CU(bf_launch_eval(g.dP, db, b->targets, b->n_targets, b->stride, r->eval_dcal, st), "launch bf_k_eval");
+    cudaEventRecord(g.ev[5], st);
+    g.ran[2] = true;
     g.launches++;
   }
   return BF_OK;
@@ -142,6 +154,7 @@ int bf_init(int device) {
   CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking), "cudaStreamCreate");
   CU(cudaMalloc(&g.d_counters, 8 * sizeof(int)), "cudaMalloc(counters)");
   CU(bf_upload_constants(), "upload candidate table");
+  for (int k = 0; k < 6; k++) CU(cudaEventCreate(&g.ev[k]), "cudaEventCreate");
   if (!g.hP) g.hP = new BfParams;
   g.inited = true;
   if (g.have_params) return upload_params();
@@ -223,7 +236,7 @@ int bf_score_batch_device(const bf_batch_t *b, bf_result_t *r, void *cuda_stream
   int rc = validate(b, r);
   if (rc) return rc;
   // the cut array lives on the device: the two-strand kernels handle cut == 0 rows as single strands
-  return run_device(b, r, b->cut != nullptr, cuda_stream ? (cudaStream_t)cuda_stream : g.stream);
+  return run_device(b, r, b->cut != nullptr, (cudaStream_t)cuda_stream);
 }
 
 int bf_score_batch(const bf_batch_t *b, bf_result_t *r) {
@@ -275,6 +288,19 @@ int bf_score_batch(const bf_batch_t *b, bf_result_t *r) {
   if (b->want & BF_WANT_PF) CU(cudaMemcpyAsync(r->pf, dr.pf, B * 5 * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H pf");
   if (b->want & BF_WANT_EVAL) CU(cudaMemcpyAsync(r->eval_dcal, dr.eval_dcal, B * b->n_targets * sizeof(int), cudaMemcpyDeviceToHost, st), "D2H eval");
   CU(cudaStreamSynchronize(st), "bf_score_batch");
+  return BF_OK;
+}
+
+int bf_last_kernel_ms(double out[3]) {
+  if (!g.inited) return fail(BF_ERR_NOT_INIT, "bf_init has not been called");
+  for (int k = 0; k < 3; k++) {
+    out[k] = -1.0;
+    if (!g.ran[k]) continue;
+    CU(cudaEventSynchronize(g.ev[2 * k + 1]), "cudaEventSynchronize");
+    float ms = 0.f;
+    CU(cudaEventElapsedTime(&ms, g.ev[2 * k], g.ev[2 * k + 1]), "cudaEventElapsedTime");
+    out[k] = ms;
+  }
   return BF_OK;
 }
 

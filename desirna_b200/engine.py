@@ -52,6 +52,8 @@ def lib():
         L.bf_score_batch.argtypes = [C.POINTER(bf_batch_t), C.POINTER(bf_result_t)]
         L.bf_score_batch_device.argtypes = [C.POINTER(bf_batch_t), C.POINTER(bf_result_t), C.c_void_p]
         L.bf_kernel_launches.restype = C.c_int64
+        L.bf_last_kernel_ms.argtypes = [C.POINTER(C.c_double)]
+        L.bf_microbench.argtypes = [C.POINTER(C.c_double)]
         _lib = L
     return _lib
 
@@ -105,6 +107,42 @@ def ensure_ready(device=None):
 
 def kernel_launches():
     return int(lib().bf_kernel_launches())
+
+
+def last_kernel_ms():
+    """(mfe_ms, pf_ms, eval_ms) of the most recent call, CUDA-event timed on the launch stream."""
+    out = (C.c_double * 3)()
+    _check(lib().bf_last_kernel_ms(out))
+    return list(out)
+
+
+def microbench():
+    """{'int32_ops', 'fp64_flops', 'smem_bytes'} per second, measured on the current GPU."""
+    ensure_ready()
+    out = (C.c_double * 3)()
+    _check(lib().bf_microbench(out))
+    return {"int32_ops_per_s": out[0], "fp64_flops_per_s": out[1], "smem_bytes_per_s": out[2]}
+
+
+def score_batch_device(seq, lens, want, cut=None, nopair=None, targets=None, mfe=None, ss=None, pf=None, ev=None, stream=0):
+    """Device-resident entry point (bf_score_batch_device).  Arguments are torch CUDA tensors:
+    seq uint8[B,stride], lens int32[B], cut int32[B], nopair uint8[B,stride], targets uint8[B,T,stride];
+    outputs mfe int32[B], ss uint8[B,stride+1], pf float64[B,5], ev int32[B,T].  Enqueues on `stream`
+    (a raw cudaStream_t handle, e.g. torch.cuda.current_stream().cuda_stream) without synchronising."""
+    ensure_ready()
+    b, r = bf_batch_t(), bf_result_t()
+    b.B, b.stride = int(seq.shape[0]), int(seq.shape[1])
+    b.seq, b.len = seq.data_ptr(), lens.data_ptr()
+    b.cut = cut.data_ptr() if cut is not None else None
+    b.nopair = nopair.data_ptr() if nopair is not None else None
+    if targets is not None:
+        b.targets, b.n_targets = targets.data_ptr(), int(targets.shape[1])
+    b.want = want
+    r.mfe_dcal = mfe.data_ptr() if mfe is not None else None
+    r.mfe_ss = ss.data_ptr() if ss is not None else None
+    r.pf = pf.data_ptr() if pf is not None else None
+    r.eval_dcal = ev.data_ptr() if ev is not None else None
+    _check(lib().bf_score_batch_device(C.byref(b), C.byref(r), C.c_void_p(stream)))
 
 
 def sm_count():

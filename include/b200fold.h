@@ -79,8 +79,15 @@ int bf_params_get(const char *name, int i0, int i1, int i2, int i3, int i4, int 
 int bf_score_batch(const bf_batch_t *batch, bf_result_t *result);
 
 /* Same, but every pointer in batch/result is a DEVICE pointer; work is enqueued on `cuda_stream`
- * (a cudaStream_t; NULL = the engine's own stream) and NOT synchronised. */
+ * (a cudaStream_t handle; NULL = the legacy default stream, as in the CUDA runtime) and NOT synchronised. */
 int bf_score_batch_device(const bf_batch_t *batch, bf_result_t *result, void *cuda_stream);
+
+/* device time (ms, CUDA events on the launch stream) of the mfe, pf and eval kernels of the most recent
+ * bf_score_batch[_device] call; -1 for a kernel that did not run.  Blocks until those kernels finished. */
+int bf_last_kernel_ms(double out[3]);
+/* micro-benchmarks for the roofline denominators: out[0] INT32 add+min op/s, out[1] FP64 flop/s (DFMA),
+ * out[2] shared-memory load bytes/s, whole chip */
+int bf_microbench(double out[3]);
 
 /* number of kernels launched by this process since bf_init (bench.py "gpu_launches") */
 int64_t bf_kernel_launches(void);

@@ -46,6 +46,10 @@ struct orc_params {
   double kT; /* cal/mol */
   /* Boltzmann weights */
   double x_mmM[8][5][5], x_mmE[8][5][5], x_d5[8][5], x_d3[8][5];
+  /* plain exp(-E*10/kT) twins of the integer tables (as ViennaRNA's vrna_exp_param_t) */
+  double x_stack[8][8], x_mmI[8][5][5], x_mm1nI[8][5][5], x_mm23I[8][5][5];
+  double x_int11[8][8][5][5], x_int21[8][8][5][5][5], x_int22[8][8][5][5][5][5];
+  double x_bulge[31], x_interior[31], x_ninio[31], x_TerminalAU;
 };
 
 static const int RTYPE[8] = {0, 2, 1, 4, 3, 6, 5, 7};
@@ -193,6 +197,29 @@ orc_params *orc_params_load(const char *path) {
     }
     P->int22[7][7][c][d][e][g] = mall;
   }
+  {
+    const double kT = P->kT;
+#define BZ(e) exp(-(double)(e) * 10.0 / kT)
+    for (int a = 0; a < 8; a++) for (int b = 0; b < 8; b++) {
+      P->x_stack[a][b] = BZ(P->stack[a][b]);
+      for (int c = 0; c < 5; c++) for (int d = 0; d < 5; d++) {
+        P->x_int11[a][b][c][d] = BZ(P->int11[a][b][c][d]);
+        for (int e = 0; e < 5; e++) {
+          P->x_int21[a][b][c][d][e] = BZ(P->int21[a][b][c][d][e]);
+          for (int g = 0; g < 5; g++) P->x_int22[a][b][c][d][e][g] = BZ(P->int22[a][b][c][d][e][g]);
+        }
+      }
+    }
+    for (int a = 0; a < 8; a++) for (int b = 0; b < 5; b++) for (int c = 0; c < 5; c++) {
+      P->x_mmI[a][b][c] = BZ(P->mmI[a][b][c]); P->x_mm1nI[a][b][c] = BZ(P->mm1nI[a][b][c]); P->x_mm23I[a][b][c] = BZ(P->mm23I[a][b][c]);
+    }
+    for (int u = 0; u <= 30; u++) {
+      P->x_bulge[u] = BZ(P->bulge[u]); P->x_interior[u] = BZ(P->interior[u]);
+      P->x_ninio[u] = BZ(MIN2(P->ninio_max, u * P->ninio_m));
+    }
+    P->x_TerminalAU = BZ(P->TerminalAU);
+#undef BZ
+  }
   return P;
 }
 void orc_params_free(orc_params *P) { free(P); }
@@ -332,24 +359,33 @@ typedef struct {
   int *S;        /* 0..n+1 */
   char *seqU;    /* 0-based upper-case with T->U */
   const unsigned char *nopair;
+  unsigned char *ptm; /* (n+2)^2 pair-type matrix honoured by the recursions */
 } ctx_t;
 
+static void ctx_make_ptm(ctx_t *X);
 static void ctx_init(ctx_t *X, const orc_params *P, const char *seq, int n, int cut, const unsigned char *nopair) {
   X->P = P; X->n = n; X->cp = (cut > 1 && cut <= n) ? cut : n + 1; X->nopair = nopair;
   X->S = (int *)calloc(n + 2, sizeof(int));
   X->seqU = (char *)calloc(n + 16, 1);
   for (int i = 1; i <= n; i++) { X->S[i] = enc(seq[i - 1]); X->seqU[i - 1] = "NACGU"[X->S[i]]; }
+  ctx_make_ptm(X);
 }
-static void ctx_free(ctx_t *X) { free(X->S); free(X->seqU); }
+static void ctx_free(ctx_t *X) { free(X->S); free(X->seqU); free(X->ptm); }
 static inline int same(const ctx_t *X, int a, int b) { return (a >= X->cp) == (b >= X->cp); }
 /* pair type honoured by the folding recursions (0 = may not pair) */
-static inline int ptype(const ctx_t *X, int i, int j) {
+static inline int ptype_slow(const ctx_t *X, int i, int j) {
   int t = PTYPE[X->S[i]][X->S[j]];
   if (!t) return 0;
   if (same(X, i, j) && j - i <= TURN) return 0;
   if (X->nopair && (X->nopair[i - 1] || X->nopair[j - 1])) return 0;
   return t;
 }
+static void ctx_make_ptm(ctx_t *X) {
+  int W = X->n + 2;
+  X->ptm = (unsigned char *)calloc((size_t)W * W, 1);
+  for (int i = 1; i <= X->n; i++) for (int j = i + 1; j <= X->n; j++) X->ptm[(size_t)i * W + j] = (unsigned char)ptype_slow(X, i, j);
+}
+static inline int ptype(const ctx_t *X, int i, int j) { return X->ptm[(size_t)i * (X->n + 2) + j]; }
 /* exterior-stem energy with strand-aware neighbours */
 static inline int ext_stem(const ctx_t *X, int i, int j, int t) {
   int a = (i > 1 && same(X, i - 1, i)) ? X->S[i - 1] : -1;
@@ -664,7 +700,26 @@ int orc_mfe(const orc_params *P, const char *seq, int n, int cut, const unsigned
 
 /* ------------------------------------------------------------------ partition function (A.6, A.7, A.10) */
 static double X_intloop(const orc_params *P, int n1, int n2, int t, int t2, int si1, int sj1, int sp1, int sq1) {
-  return boltz(P, E_intloop(P, n1, n2, t, t2, si1, sj1, sp1, sq1));
+  /* product of tabulated weights, as ViennaRNA's exp_E_IntLoop; u1+u2 <= MAXLOOP guaranteed by the callers */
+  int nl = MAX2(n1, n2), ns = MIN2(n1, n2);
+  if (nl == 0) return P->x_stack[t][t2];
+  if (ns == 0) {
+    double w = P->x_bulge[nl];
+    if (nl == 1) return w * P->x_stack[t][t2];
+    if (t > 2) w *= P->x_TerminalAU;
+    if (t2 > 2) w *= P->x_TerminalAU;
+    return w;
+  }
+  if (ns == 1) {
+    if (nl == 1) return P->x_int11[t][t2][si1][sj1];
+    if (nl == 2) return (n1 == 1) ? P->x_int21[t][t2][si1][sq1][sj1] : P->x_int21[t2][t][sq1][si1][sp1];
+    return P->x_interior[nl + 1] * P->x_ninio[nl - ns] * P->x_mm1nI[t][si1][sj1] * P->x_mm1nI[t2][sq1][sp1];
+  }
+  if (ns == 2) {
+    if (nl == 2) return P->x_int22[t][t2][si1][sp1][sq1][sj1];
+    if (nl == 3) return P->x_interior[5] * P->x_ninio[1] * P->x_mm23I[t][si1][sj1] * P->x_mm23I[t2][sq1][sp1];
+  }
+  return P->x_interior[nl + ns] * P->x_ninio[nl - ns] * P->x_mmI[t][si1][sj1] * P->x_mmI[t2][sq1][sp1];
 }
 
 double orc_pf(const orc_params *P, const char *seq, int n, int cut, double *out5, double *bpp) {
