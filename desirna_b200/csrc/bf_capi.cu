@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -37,6 +38,8 @@ struct Engine {
   BfParams *dP = nullptr;  // device image
   int *d_counters = nullptr;  // work counters (one per kernel kind)
   DevBuf ws_mfe, ws_pf, d_mfe_scratch;
+  DevBuf tri_c, tri_f, tri_qb, ws_qm, d_lnscale;  // diagonal-major fill path (bf_fill.cu)
+  bool force_generic = false;                     // BF_FORCE_GENERIC=1: route single strands through the generic kernels too
   // staging for the host-buffer entry point
   DevBuf d_seq, d_len, d_cut, d_nopair, d_targets, d_mfe, d_ss, d_pf, d_eval;
   int64_t launches = 0;
@@ -84,38 +87,64 @@ int run_device(const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t
   const int wstride = b->stride + 2;
   const int *mfe_for_scale = nullptr;
   g.ran[0] = g.ran[1] = g.ran[2] = false;
+  const bool fill_mfe = !two && !g.force_generic && bf_fill_mfe_mode(b->stride) != 0;
+  const bool fill_pf = !two && !g.force_generic && bf_fill_pf_mode(b->stride) != 0;
   if (b->want & (BF_WANT_MFE | BF_WANT_SS)) {
-    int occ = bf_occupancy_mfe(two, wstride);
-    int grid = std::min(b->B, g.sm_count * occ);
-    size_t slot = bf_mfe_slot_ints(wstride) * sizeof(int);
-    // keep the workspace within a sane share of HBM
-    while (grid > g.sm_count && (size_t)grid * slot > ((size_t)48 << 30)) grid -= g.sm_count;
-    CU(g.ws_mfe.reserve((size_t)grid * slot), "cudaMalloc(mfe workspace)");
     int *out_mfe = r->mfe_dcal;
     if (!out_mfe) { CU(g.d_mfe_scratch.reserve((size_t)b->B * sizeof(int)), "cudaMalloc(mfe scratch)"); out_mfe = (int *)g.d_mfe_scratch.p; }
     cudaEventRecord(g.ev[0], st);
-    CU(bf_launch_mfe(g.dP, db, two, (int *)g.ws_mfe.p, wstride, grid, g.d_counters + 0, out_mfe,
-                     (b->want & BF_WANT_SS) ? r->mfe_ss : nullptr, b->stride + 1, st), "launch bf_k_mfe");
+    if (fill_mfe) {
+      const size_t slot = bf_tri_slot(b->stride) * sizeof(int);
+      CU(g.tri_c.reserve((size_t)b->B * slot), "cudaMalloc(c table)");
+      CU(g.tri_f.reserve((size_t)b->B * slot), "cudaMalloc(fML table)");
+      CU(bf_launch_mfe_fill(g.dP, db, (int *)g.tri_c.p, (int *)g.tri_f.p, g.sm_count, g.d_counters + 0, st), "launch bf_k_mfe_fill");
+      CU(bf_launch_trace(g.dP, db, (const int *)g.tri_c.p, (const int *)g.tri_f.p, out_mfe, (b->want & BF_WANT_SS) ? r->mfe_ss : nullptr,
+                         b->stride + 1, st), "launch bf_k_trace");
+      g.launches += 2;
+    } else {
+      int occ = bf_occupancy_mfe(two, wstride);
+      int grid = std::min(b->B, g.sm_count * occ);
+      size_t slot = bf_mfe_slot_ints(wstride) * sizeof(int);
+      // keep the workspace within a sane share of HBM
+      while (grid > g.sm_count && (size_t)grid * slot > ((size_t)48 << 30)) grid -= g.sm_count;
+      CU(g.ws_mfe.reserve((size_t)grid * slot), "cudaMalloc(mfe workspace)");
+      CU(bf_launch_mfe(g.dP, db, two, (int *)g.ws_mfe.p, wstride, grid, g.d_counters + 0, out_mfe,
+                       (b->want & BF_WANT_SS) ? r->mfe_ss : nullptr, b->stride + 1, st), "launch bf_k_mfe");
+      g.launches++;
+    }
     cudaEventRecord(g.ev[1], st);
     g.ran[0] = true;
-    g.launches++;
     mfe_for_scale = out_mfe;
   }
   if (b->want & BF_WANT_PF) {
     BfBatchDev dbp = db;
     dbp.nopair = nullptr;  // hard constraints are added after fc.pf() in the reference (sequence_utils.py:1181)
-    int occ = bf_occupancy_pf(two, wstride);
-    int grid = std::min(b->B, g.sm_count * occ);
-    size_t slot = bf_pf_slot_doubles(wstride) * sizeof(double);
-    while (grid > g.sm_count && (size_t)grid * slot > ((size_t)64 << 30)) grid -= g.sm_count;
-    CU(g.ws_pf.reserve((size_t)grid * slot), "cudaMalloc(pf workspace)");
     // a constrained MFE is not a bound on the unconstrained ensemble: only use it for scaling when unconstrained
+    const int *scale_src = b->nopair ? nullptr : mfe_for_scale;
     cudaEventRecord(g.ev[2], st);
-    CU(bf_launch_pf(g.dP, dbp, two, (double *)g.ws_pf.p, wstride, grid, g.d_counters + 1, b->nopair ? nullptr : mfe_for_scale, r->pf, st),
-       "launch bf_k_pf");
+    if (fill_pf) {
+      const size_t slot = bf_tri_slot(b->stride) * sizeof(double);
+      CU(g.tri_qb.reserve((size_t)b->B * slot), "cudaMalloc(qb table)");
+      CU(g.d_lnscale.reserve((size_t)b->B * sizeof(double)), "cudaMalloc(lnscale)");
+      int grid = 0;
+      CU(bf_pf_fill_grid(dbp, g.sm_count, &grid), "size bf_k_pf_fill");
+      const size_t ws = bf_pf_ws_slot(b->stride) * sizeof(double);
+      if (ws) CU(g.ws_qm.reserve((size_t)grid * ws), "cudaMalloc(qm workspace)");
+      CU(bf_launch_pf_fill(g.dP, dbp, (double *)g.tri_qb.p, (double *)g.ws_qm.p, scale_src, (double *)g.d_lnscale.p, g.sm_count,
+                           g.d_counters + 1, st), "launch bf_k_pf_fill");
+      CU(bf_launch_pf_ext(g.dP, dbp, (const double *)g.tri_qb.p, (const double *)g.d_lnscale.p, r->pf, st), "launch bf_k_pf_ext");
+      g.launches += 2;
+    } else {
+      int occ = bf_occupancy_pf(two, wstride);
+      int grid = std::min(b->B, g.sm_count * occ);
+      size_t slot = bf_pf_slot_doubles(wstride) * sizeof(double);
+      while (grid > g.sm_count && (size_t)grid * slot > ((size_t)64 << 30)) grid -= g.sm_count;
+      CU(g.ws_pf.reserve((size_t)grid * slot), "cudaMalloc(pf workspace)");
+      CU(bf_launch_pf(g.dP, dbp, two, (double *)g.ws_pf.p, wstride, grid, g.d_counters + 1, scale_src, r->pf, st), "launch bf_k_pf");
+      g.launches++;
+    }
     cudaEventRecord(g.ev[3], st);
     g.ran[1] = true;
-    g.launches++;
   }
   if (b->want & BF_WANT_EVAL) {
     cudaEventRecord(g.ev[4], st);
@@ -150,6 +179,7 @@ int bf_init(int device) {
   CU(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
   if (prop.major < 10) return fail(BF_ERR_CUDA, std::string("built for sm_100a, found ") + prop.name);
   g.device = device;
+  { const char *fg = getenv("BF_FORCE_GENERIC"); g.force_generic = fg && fg[0] == '1'; }
   g.sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking), "cudaStreamCreate");
   CU(cudaMalloc(&g.d_counters, 8 * sizeof(int)), "cudaMalloc(counters)");
@@ -164,7 +194,7 @@ int bf_init(int device) {
 int bf_shutdown(void) {
   if (!g.inited) return BF_OK;
   cudaStreamSynchronize(g.stream);
-  for (DevBuf *b : {&g.ws_mfe, &g.ws_pf, &g.d_mfe_scratch, &g.d_seq, &g.d_len, &g.d_cut, &g.d_nopair, &g.d_targets, &g.d_mfe, &g.d_ss, &g.d_pf, &g.d_eval}) b->release();
+  for (DevBuf *b : {&g.tri_c, &g.tri_f, &g.tri_qb, &g.ws_qm, &g.d_lnscale, &g.ws_mfe, &g.ws_pf, &g.d_mfe_scratch, &g.d_seq, &g.d_len, &g.d_cut, &g.d_nopair, &g.d_targets, &g.d_mfe, &g.d_ss, &g.d_pf, &g.d_eval}) b->release();
   if (g.dP) cudaFree(g.dP);
   if (g.d_counters) cudaFree(g.d_counters);
   cudaStreamDestroy(g.stream);

@@ -1,0 +1,800 @@
+// bf_fill.cu -- diagonal-major wavefront kernels for single-strand folds (sm_100a).
+//
+// This is the throughput path behind score_sequence()'s fc.mfe() / fc.pf() calls
+// (utils/energy_scores.py:150-151 in the reference; recurrences: SURVEY.md A.4-A.6).
+//
+// Layout.  Every O(N^2) table is stored by anti-diagonal: entry (i,j), d = j-i >= 4, lives at
+// off(d) + i-1 with off(d) = sum_{x=4}^{d-1} (n-x).  With the 32 lanes of a warp running along
+// a diagonal, every operand of every recurrence is a stride-1 access:
+//   interior loops   c[p][q],  p = i+1+u1, q = j-1-u2  ->  diagonal d-2-(u1+u2), index i+1+u1
+//   fML / qm splits  fml[i][u-1] + fml[u][j]            ->  diagonal k-1 index i, diagonal d-k index i+k
+// so shared-memory reads are conflict-free and HBM reads/writes are coalesced.
+//
+// Interior loops look back at most 32 diagonals (u1+u2 <= 30), so only a 32-deep RING of the pair
+// table is kept on chip.  The ring is stored three times with the inner pair's sequence-dependent
+// term already folded in (generic: + mismatchI, 1xn: + mismatch1nI, bulge: + terminalAU), which
+// turns every decomposable candidate into load + add-min (MFE) or load + fma (PF) against a
+// warp-uniform length penalty.  The nine non-decomposable candidates (stack, bulge-1, 1x1, 1x2,
+// 2x1, 2x2, 2x3, 3x2) are evaluated once per cell.
+//
+// The multiloop closing term of c(i,j) is the split part of fML(i+1,j-1), produced two diagonals
+// earlier: it is kept in a 4-deep ring instead of being recomputed.
+//
+// One persistent CTA folds one sequence at a time.  Per diagonal: all warps accumulate partial
+// minima / sums for (32-cell chunk, loop-size) work units, one barrier, one thread per cell
+// combines them and writes the new diagonal, one barrier.  The exterior loop (f5 / q5) and the
+// backtrack run afterwards in one-warp-per-sequence kernels on the tables written to HBM.
+#include "bf_kernels.h"
+
+#include "bf_device.cuh"
+
+namespace {
+
+constexpr int kRing = 32;
+constexpr int kInfThr = BF_INF / 2;
+
+__host__ __device__ __forceinline__ int tri_off(int n, int d) {
+  // first entry of diagonal d (d >= 4)
+  return (d - 4) * n - (d * (d - 1) / 2 - 6);
+}
+__host__ __device__ __forceinline__ size_t tri_size(int n) { return n >= 5 ? (size_t)tri_off(n, n) : 0; }
+
+__device__ __forceinline__ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__device__ __forceinline__ int ptype_sp(const uint8_t *SP, int i, int j) { return bf_ptype_bases(SP[i], SP[j]); }
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory plan (identical arithmetic on host and device)
+// ---------------------------------------------------------------------------------------------
+struct MfePlan {
+  int rs;  // ring row stride (ints)
+  size_t o_S, o_SP, o_pg, o_pb, o_p1, o_fm, o_ring, o_dml, o_pi, o_ps, o_hs, total;
+};
+__host__ __device__ inline MfePlan mfe_plan(int nmax, int nw, bool fm_in_smem) {
+  MfePlan p;
+  p.rs = (nmax + 8 + 3) / 4 * 4;
+  size_t o = 0;
+  p.o_S = o; o += (nmax + 2 + 15) / 16 * 16;
+  p.o_SP = o; o += (nmax + 2 + 15) / 16 * 16;
+  p.o_pg = o; o += 31 * 32 * sizeof(int);
+  p.o_pb = o; o += 32 * sizeof(int);
+  p.o_p1 = o; o += 32 * sizeof(int);
+  p.o_fm = o; o += fm_in_smem ? (tri_size(nmax) + 4) * sizeof(int) : 0;
+  p.o_ring = o; o += (size_t)3 * kRing * p.rs * sizeof(int);
+  p.o_dml = o; o += (size_t)4 * p.rs * sizeof(int);
+  p.o_pi = o; o += (size_t)nw * p.rs * sizeof(int);
+  p.o_ps = o; o += (size_t)nw * p.rs * sizeof(int);
+  p.o_hs = o; o += (size_t)p.rs * sizeof(int);
+  p.total = o;
+  return p;
+}
+
+// =====================================================================================================
+//                                           MFE fill
+// =====================================================================================================
+// ctri / ftri: per-sequence tables in HBM (slot s at s * tri_slot), read later by bf_k_trace.
+template <int NW, bool FM_SMEM>
+__global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restrict__ P, BfBatchDev b, int *ctri,
+                                                         int *ftri, size_t tri_slot, int *work_counter) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ BfSmallI T;
+  __shared__ int s_seq;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nmax = b.stride;
+  const MfePlan pl = mfe_plan(nmax, NW, FM_SMEM);
+  const int RS = pl.rs;
+  uint8_t *S = dyn + pl.o_S;
+  uint8_t *SP = dyn + pl.o_SP;
+  int *pg = reinterpret_cast<int *>(dyn + pl.o_pg);   // [s][k], k = u1-2: interior[s] + ninio(|s-2u1|), INF padded
+  int *pb = reinterpret_cast<int *>(dyn + pl.o_pb);   // bulge[s]
+  int *p1 = reinterpret_cast<int *>(dyn + pl.o_p1);   // 1xn: interior[s] + ninio(s-2)
+  int *fms = reinterpret_cast<int *>(dyn + pl.o_fm);
+  int *ring = reinterpret_cast<int *>(dyn + pl.o_ring);
+  int *CG = ring, *C1 = ring + kRing * RS, *CB = ring + 2 * kRing * RS;
+  int *DML = reinterpret_cast<int *>(dyn + pl.o_dml);
+  int *PI = reinterpret_cast<int *>(dyn + pl.o_pi);
+  int *PS = reinterpret_cast<int *>(dyn + pl.o_ps);
+  int *HS = reinterpret_cast<int *>(dyn + pl.o_hs);
+
+  bf_stage(&T, &P->si);
+  __syncthreads();
+  for (int k = tid; k < 31 * 32; k += blockDim.x) {
+    const int s = k >> 5, u1 = (k & 31) + 2;
+    int v = BF_INF;
+    if (s >= 6 && u1 <= s - 2) v = T.interior[s] + min(T.ninio_max, abs(s - 2 * u1) * T.ninio_m);
+    pg[k] = v;
+  }
+  if (tid < 32) {
+    pb[tid] = (tid >= 2 && tid <= 30) ? T.bulge[tid] : BF_INF;
+    p1[tid] = (tid >= 4 && tid <= 30) ? T.interior[tid] + min(T.ninio_max, (tid - 2) * T.ninio_m) : BF_INF;
+  }
+  for (int k = tid; k < 3 * kRing * RS; k += blockDim.x) ring[k] = BF_INF;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_seq = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int sq = s_seq;
+    if (sq >= b.B) break;
+    const int n = b.len[sq];
+    {
+      const char *src = b.seq + (size_t)sq * b.stride;
+      const uint8_t *np = b.nopair ? b.nopair + (size_t)sq * b.stride : nullptr;
+      for (int k = tid; k <= n + 1; k += blockDim.x) {
+        int code = (k >= 1 && k <= n) ? bf_base_code(src[k - 1]) : 0;
+        S[k] = (uint8_t)code;
+        SP[k] = (uint8_t)((np && k >= 1 && k <= n && np[k - 1]) ? 0 : code);
+      }
+    }
+    for (int k = tid; k < 4 * RS; k += blockDim.x) DML[k] = BF_INF;
+    int *cg_out = ctri + (size_t)sq * tri_slot;
+    int *fg_out = ftri + (size_t)sq * tri_slot;
+    int *FM = FM_SMEM ? fms : fg_out;
+    __syncthreads();
+
+    for (int d = BF_TURN + 1; d <= n - 1; d++) {
+      const int ncell = n - d;
+      const int nch = (ncell + 31) >> 5;
+      const int smax = min(BF_MAXLOOP, d - 6);  // inner diagonal d-2-s >= 4
+      for (int c = 0; c < nch; c++) {
+        const int cell = c * 32 + lane;           // 0-based cell on the diagonal
+        const int i = min(cell, ncell - 1) + 1;   // clamped: idle lanes repeat the last cell and are dropped at the store
+        const int j = i + d;
+        const int t = ptype_sp(SP, i, j);
+        // ---- interior loops, decomposable classes: this warp's share of the loop sizes
+        int accg = BF_INF, acc1 = BF_INF, accb = BF_INF;
+        if (__any_sync(BF_FULL, t != 0)) {
+          for (int s = 2 + warp; s <= smax; s += NW) {
+            const int row = ((d - 2 - s) & (kRing - 1)) * RS + i;
+            accb = min(accb, min(CB[row + 1], CB[row + 1 + s]) + pb[s]);
+            if (s >= 4) acc1 = min(acc1, min(C1[row + 2], C1[row + s]) + p1[s]);
+            if (s >= 6) {
+              const int *cgp = CG + row + 3;
+              const int *pen = pg + (s << 5);
+              const int kn = s - 3;
+#pragma unroll 4
+              for (int k = 0; k < kn; k++) accg = min(accg, cgp[k] + pen[k]);
+            }
+          }
+        }
+        int tot = BF_INF;
+        if (t) {
+          const int si1 = S[i + 1], sj1 = S[j - 1];
+          tot = min(accg + T.mmI[t][si1][sj1], min(acc1 + T.mm1nI[t][si1][sj1], accb + (t > 2 ? T.TerminalAU : 0)));
+        }
+        // ---- fML split: k = u - i in [5, d-4]
+        int accs = BF_INF;
+        {
+          const int *left = FM + (i - 1);
+          for (int k = 5 + warp; k <= d - 4; k += NW)
+            accs = min(accs, left[tri_off(n, k - 1)] + FM[tri_off(n, d - k) + i + k - 1]);
+        }
+        // ---- hairpin + the non-decomposable interior candidates: one warp per chunk
+        if (warp == (c % NW)) {
+          int e = BF_INF;
+          if (t) {
+            const int si1 = S[i + 1], sj1 = S[j - 1];
+            e = bf_e_hairpin(P, T, S, i, j, t);
+            const int cu1[9] = {0, 0, 1, 1, 1, 2, 2, 2, 3}, cu2[9] = {0, 1, 0, 1, 2, 1, 2, 3, 2};
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+              const int u1 = cu1[k], u2 = cu2[k];
+              const int p = i + 1 + u1, q = j - 1 - u2;
+              if (q - p <= BF_TURN) continue;
+              int cc = CB[((q - p) & (kRing - 1)) * RS + p];  // c + terminalAU(inner pair)
+              if (cc >= kInfThr) continue;
+              const int t2 = ptype_sp(SP, p, q);
+              if (t2 > 2) cc -= T.TerminalAU;
+              e = min(e, cc + bf_e_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]));
+            }
+          }
+          if (cell < ncell) HS[cell] = e;
+        }
+        if (cell < ncell) { PI[warp * RS + cell] = tot; PS[warp * RS + cell] = accs; }
+      }
+      __syncthreads();
+      // ---- combine: one thread per cell
+      for (int cell = tid; cell < ncell; cell += blockDim.x) {
+        const int i = cell + 1, j = i + d;
+        const int t = ptype_sp(SP, i, j);
+        int e = BF_INF, sp = BF_INF;
+#pragma unroll
+        for (int w = 0; w < NW; w++) sp = min(sp, PS[w * RS + cell]);
+        if (t) {
+          e = HS[cell];
+#pragma unroll
+          for (int w = 0; w < NW; w++) e = min(e, PI[w * RS + cell]);
+          const int dm = DML[((d - 2) & 3) * RS + i + 1];
+          if (dm < kInfThr) e = min(e, dm + T.MLclosing + bf_e_mlstem(T, bf_rtype(t), S[j - 1], S[i + 1]));
+          if (e >= kInfThr) e = BF_INF;
+        }
+        if (sp >= kInfThr) sp = BF_INF;
+        int m = sp;
+        if (e < BF_INF && i > 1 && j < n) m = min(m, e + bf_e_mlstem(T, t, S[i - 1], S[j + 1]));
+        if (d > BF_TURN + 1) {
+          const int o = tri_off(n, d - 1) + i - 1;
+          m = min(m, min(FM[o + 1], FM[o]) + T.MLbase);
+        }
+        if (m >= kInfThr) m = BF_INF;
+        const int o = tri_off(n, d) + i - 1;
+        cg_out[o] = e;
+        fg_out[o] = m;
+        if (FM_SMEM) fms[o] = m;
+        DML[(d & 3) * RS + i] = sp;
+        const int row = (d & (kRing - 1)) * RS + i;
+        int eg = BF_INF, e1 = BF_INF, eb = BF_INF;
+        if (e < BF_INF) {
+          const int t2 = bf_rtype(t), a = S[j + 1], bb = S[i - 1];  // as an inner pair: sq1 = S[q+1], sp1 = S[p-1]
+          eg = e + T.mmI[t2][a][bb];
+          e1 = e + T.mm1nI[t2][a][bb];
+          eb = e + (t > 2 ? T.TerminalAU : 0);
+        }
+        CG[row] = eg; C1[row] = e1; CB[row] = eb;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// =====================================================================================================
+//                    exterior loop + backtrack: one warp per sequence, tables in HBM
+// =====================================================================================================
+struct __align__(8) Sector { short i, j; int kind; };  // 0 exterior (f5 up to j), 1 multiloop part, 2 pair
+
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32) bf_k_trace(const BfParams *__restrict__ P, BfBatchDev b, const int *__restrict__ ctri,
+                                                       const int *__restrict__ ftri, size_t tri_slot, int *out_mfe, char *out_ss,
+                                                       int ss_stride) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ BfSmallI T;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nmax = b.stride;
+  bf_stage(&T, &P->si);
+  __syncthreads();
+  const int sq = blockIdx.x * WPB + warp;
+  if (sq >= b.B) return;
+  // per-warp carve-up
+  const size_t per_warp = align_up(2 * align_up(nmax + 2, 16) + (nmax + 4) * sizeof(int) + (2 * nmax + 16) * sizeof(Sector), 16);
+  unsigned char *base = dyn + per_warp * warp;
+  uint8_t *S = base;
+  uint8_t *SP = S + align_up(nmax + 2, 16);
+  int *f5 = reinterpret_cast<int *>(SP + align_up(nmax + 2, 16));
+  Sector *stk = reinterpret_cast<Sector *>(f5 + (nmax + 4));
+  const int n = b.len[sq];
+  {
+    const char *src = b.seq + (size_t)sq * b.stride;
+    const uint8_t *np = b.nopair ? b.nopair + (size_t)sq * b.stride : nullptr;
+    for (int k = lane; k <= n + 1; k += 32) {
+      int code = (k >= 1 && k <= n) ? bf_base_code(src[k - 1]) : 0;
+      S[k] = (uint8_t)code;
+      SP[k] = (uint8_t)((np && k >= 1 && k <= n && np[k - 1]) ? 0 : code);
+    }
+  }
+  __syncwarp();
+  const int *c = ctri + (size_t)sq * tri_slot;
+  const int *fm = ftri + (size_t)sq * tri_slot;
+  auto C_ = [&](int i, int j) -> int { return (j - i > BF_TURN) ? __ldg(c + tri_off(n, j - i) + i - 1) : BF_INF; };
+  auto M_ = [&](int i, int j) -> int { return (j - i > BF_TURN) ? __ldg(fm + tri_off(n, j - i) + i - 1) : BF_INF; };
+  auto ext_e = [&](int i, int j, int t) -> int {
+    const int a = (i > 1) ? S[i - 1] : -1, bb = (j < n) ? S[j + 1] : -1;
+    return bf_e_ext(T, t, a, bb);
+  };
+
+  if (lane == 0) f5[0] = 0;
+  __syncwarp();
+  for (int j = 1; j <= n; j++) {
+    int e = BF_INF;
+    for (int i = 1 + lane; i < j - BF_TURN; i += 32) {
+      const int t = ptype_sp(SP, i, j);
+      if (!t) continue;
+      const int cc = C_(i, j);
+      if (cc >= BF_INF) continue;
+      e = min(e, f5[i - 1] + cc + ext_e(i, j, t));
+    }
+    e = bf_warp_min(e);
+    if (lane == 0) f5[j] = min(e, f5[j - 1]);
+    __syncwarp();
+  }
+  if (lane == 0 && out_mfe) out_mfe[sq] = f5[n];
+  if (!out_ss) return;
+  char *ss = out_ss + (size_t)sq * ss_stride;
+  for (int k = lane; k < ss_stride; k += 32) ss[k] = (k < n) ? '.' : 0;
+  __syncwarp();
+
+  // backtrack: same order of choices as the fill-independent rule of SURVEY.md A.5
+  int sp = 0;
+  if (lane == 0) { stk[0].i = 1; stk[0].j = (short)n; stk[0].kind = 0; }
+  sp = 1;
+  __syncwarp();
+  int guard = 0;
+  while (sp > 0 && guard++ < 8 * n + 64) {
+    Sector sec = stk[--sp];
+    __syncwarp();
+    int i = sec.i, j = sec.j;
+    bool to_pair = false;
+    if (sec.kind == 0) {
+      while (j > 0 && f5[j] == f5[j - 1]) j--;
+      if (j <= 1) continue;
+      int fu = 0;
+      for (int bs = j - 1; bs >= 1 && !fu; bs -= 32) {
+        const int u = bs - lane;
+        bool ok = false;
+        if (u >= 1) {
+          const int t = ptype_sp(SP, u, j);
+          if (t) {
+            const int cc = C_(u, j);
+            if (cc < BF_INF) ok = f5[j] == f5[u - 1] + cc + ext_e(u, j, t);
+          }
+        }
+        const unsigned mk = __ballot_sync(BF_FULL, ok);
+        if (mk) fu = bs - (__ffs(mk) - 1);
+      }
+      if (!fu) break;
+      if (lane == 0) { stk[sp].i = 1; stk[sp].j = (short)(fu - 1); stk[sp].kind = 0; }
+      sp++;
+      __syncwarp();
+      i = fu; to_pair = true;
+    } else if (sec.kind == 1) {
+      while (j > i && M_(i, j) == M_(i, j - 1) + T.MLbase) j--;
+      while (i < j && M_(i, j) == M_(i + 1, j) + T.MLbase) i++;
+      const int mij = M_(i, j);
+      const int t = ptype_sp(SP, i, j);
+      const int cij = C_(i, j);
+      if (t && cij < BF_INF && i > 1 && j < n && mij == cij + bf_e_mlstem(T, t, S[i - 1], S[j + 1])) {
+        to_pair = true;
+      } else {
+        int fu = 0;
+        for (int bs = i + 1; bs <= j && !fu; bs += 32) {
+          const int u = bs + lane;
+          bool ok = false;
+          if (u <= j) {
+            const int l = M_(i, u - 1), r = M_(u, j);
+            ok = l < BF_INF && r < BF_INF && mij == l + r;
+          }
+          const unsigned mk = __ballot_sync(BF_FULL, ok);
+          if (mk) fu = bs + (__ffs(mk) - 1);
+        }
+        if (!fu) break;
+        if (lane == 0) {
+          stk[sp].i = (short)i; stk[sp].j = (short)(fu - 1); stk[sp].kind = 1;
+          stk[sp + 1].i = (short)fu; stk[sp + 1].j = (short)j; stk[sp + 1].kind = 1;
+        }
+        sp += 2;
+        __syncwarp();
+      }
+    } else {
+      to_pair = true;
+    }
+    if (!to_pair) continue;
+    for (;;) {
+      if (lane == 0) { ss[i - 1] = '('; ss[j - 1] = ')'; }
+      const int t = ptype_sp(SP, i, j), cij = C_(i, j);
+      const int si1 = S[i + 1], sj1 = S[j - 1];
+      if (cij == bf_e_hairpin(P, T, S, i, j, t)) break;
+      int fp = 0, fq = 0;
+      const int pmax = min(j - 2, i + BF_MAXLOOP + 1);
+      for (int p = i + 1; p <= pmax && !fp; p++) {
+        const int minq = max(p + 1, j - i + p - BF_MAXLOOP - 2);
+        const int q = j - 1 - lane;
+        bool ok = false;
+        if (q >= minq) {
+          const int t2 = ptype_sp(SP, p, q);
+          if (t2) {
+            const int cc = C_(p, q);
+            ok = cc < BF_INF && cij == cc + bf_e_intloop(P, T, p - i - 1, j - q - 1, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]);
+          }
+        }
+        const unsigned mk = __ballot_sync(BF_FULL, ok);
+        if (mk) { fp = p; fq = j - 1 - (__ffs(mk) - 1); }
+      }
+      if (fp) { i = fp; j = fq; continue; }
+      int fu = 0;
+      const int en = cij - T.MLclosing - bf_e_mlstem(T, bf_rtype(t), sj1, si1);
+      for (int bs = i + 2; bs <= j - 1 && !fu; bs += 32) {
+        const int u = bs + lane;
+        bool ok = false;
+        if (u <= j - 1) {
+          const int l = M_(i + 1, u - 1), r = M_(u, j - 1);
+          ok = l < BF_INF && r < BF_INF && en == l + r;
+        }
+        const unsigned mk = __ballot_sync(BF_FULL, ok);
+        if (mk) fu = bs + (__ffs(mk) - 1);
+      }
+      if (fu) {
+        if (lane == 0) {
+          stk[sp].i = (short)(i + 1); stk[sp].j = (short)(fu - 1); stk[sp].kind = 1;
+          stk[sp + 1].i = (short)fu; stk[sp + 1].j = (short)(j - 1); stk[sp + 1].kind = 1;
+        }
+        sp += 2;
+        __syncwarp();
+      }
+      break;
+    }
+  }
+}
+
+// =====================================================================================================
+//                                   partition function (inside) fill
+// =====================================================================================================
+struct PfPlan {
+  int rs;
+  size_t o_S, o_wg, o_wb, o_w1, o_scl, o_bu, o_qm, o_qm1, o_ring, o_qms, o_pi, o_ps, o_pb, o_hs, total;
+};
+// mode 1: everything on chip; 2: qm/qm1 in HBM; 3: qm/qm1 and the two small rings (1xn, bulge) in HBM
+__host__ __device__ inline PfPlan pf_plan(int nmax, int nw, bool qm_in_smem, bool rings_in_smem) {
+  PfPlan p;
+  p.rs = (nmax + 8 + 3) / 4 * 4;
+  size_t o = 0;
+  p.o_wg = o; o += 31 * 32 * sizeof(double);
+  p.o_wb = o; o += 32 * sizeof(double);
+  p.o_w1 = o; o += 32 * sizeof(double);
+  p.o_scl = o; o += (size_t)(nmax + 8) * sizeof(double);
+  p.o_bu = o; o += (size_t)(nmax + 8) * sizeof(double);
+  p.o_qm = o; o += qm_in_smem ? (tri_size(nmax) + 4) * sizeof(double) : 0;
+  p.o_qm1 = o; o += qm_in_smem ? (tri_size(nmax) + 4) * sizeof(double) : 0;
+  p.o_ring = o; o += (size_t)(rings_in_smem ? 3 : 1) * kRing * p.rs * sizeof(double);
+  p.o_qms = o; o += (size_t)4 * p.rs * sizeof(double);
+  p.o_pi = o; o += (size_t)nw * p.rs * sizeof(double);
+  p.o_ps = o; o += (size_t)nw * p.rs * sizeof(double);
+  p.o_pb = o; o += (size_t)nw * p.rs * sizeof(double);
+  p.o_hs = o; o += (size_t)p.rs * sizeof(double);
+  p.o_S = o; o += (nmax + 2 + 15) / 16 * 16;
+  p.total = o;
+  return p;
+}
+
+// qbtri: per-sequence qb table in HBM (for the exterior pass); qmws: per-CTA qm/qm1 workspace when they do not fit on chip
+template <int NW, bool QM_SMEM, bool RG_SMEM>
+__global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restrict__ P, BfBatchDev b, double *qbtri,
+                                                        size_t tri_slot, double *qmws, size_t ws_slot, const int *mfe_for_scale,
+                                                        double *lnscale_out, int *work_counter) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ BfSmallD T;
+  __shared__ int s_seq;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nmax = b.stride;
+  const PfPlan pl = pf_plan(nmax, NW, QM_SMEM, RG_SMEM);
+  const int RS = pl.rs;
+  uint8_t *S = dyn + pl.o_S;
+  double *wg = reinterpret_cast<double *>(dyn + pl.o_wg);
+  double *wb = reinterpret_cast<double *>(dyn + pl.o_wb);
+  double *w1 = reinterpret_cast<double *>(dyn + pl.o_w1);
+  double *scl = reinterpret_cast<double *>(dyn + pl.o_scl);
+  double *bu = reinterpret_cast<double *>(dyn + pl.o_bu);
+  double *ring = reinterpret_cast<double *>(dyn + pl.o_ring);
+  double *QG = ring, *Q1, *QBB;
+  double *QMS = reinterpret_cast<double *>(dyn + pl.o_qms);
+  double *PI = reinterpret_cast<double *>(dyn + pl.o_pi);
+  double *PS = reinterpret_cast<double *>(dyn + pl.o_ps);
+  double *PB = reinterpret_cast<double *>(dyn + pl.o_pb);
+  double *HS = reinterpret_cast<double *>(dyn + pl.o_hs);
+  double *QM, *QM1;
+  if (QM_SMEM) {
+    QM = reinterpret_cast<double *>(dyn + pl.o_qm);
+    QM1 = reinterpret_cast<double *>(dyn + pl.o_qm1);
+  } else {
+    QM = qmws + (size_t)blockIdx.x * ws_slot;
+    QM1 = QM + tri_slot;
+  }
+  if (RG_SMEM) {
+    Q1 = ring + kRing * RS;
+    QBB = ring + 2 * kRing * RS;
+  } else {
+    Q1 = qmws + (size_t)blockIdx.x * ws_slot + 2 * tri_slot;
+    QBB = Q1 + kRing * RS;
+  }
+  bf_stage(&T, &P->sd);
+  for (int k = tid; k < kRing * RS; k += blockDim.x) { QG[k] = 0.0; Q1[k] = 0.0; QBB[k] = 0.0; }
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_seq = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int sq = s_seq;
+    if (sq >= b.B) break;
+    const int n = b.len[sq];
+    {
+      const char *src = b.seq + (size_t)sq * b.stride;
+      for (int k = tid; k <= n + 1; k += blockDim.x) S[k] = (uint8_t)((k >= 1 && k <= n) ? bf_base_code(src[k - 1]) : 0);
+    }
+    // per-nucleotide scale (ViennaRNA exp_params_rescale, sfact 1.07; default estimate -185 cal/mol/nt)
+    double lns = 185.0 / T.kT;
+    if (mfe_for_scale && n > 0) {
+      const double m = (double)mfe_for_scale[sq] * 10.0;
+      if (m < 0.0) lns = -1.07 * m / T.kT / (double)n;
+      if (lns < 185.0 / T.kT * 0.25) lns = 185.0 / T.kT * 0.25;
+    }
+    {
+      const double bl = log(T.x_MLbase) - lns;
+      for (int k = tid; k <= n + 2; k += blockDim.x) { scl[k] = exp(-lns * k); bu[k] = exp(bl * k); }
+    }
+    if (tid == 0 && lnscale_out) lnscale_out[sq] = lns;
+    for (int k = tid; k < 4 * RS; k += blockDim.x) QMS[k] = 0.0;
+    __syncthreads();
+    for (int k = tid; k < 31 * 32; k += blockDim.x) {
+      const int s = k >> 5, u1 = (k & 31) + 2;
+      wg[k] = (s >= 6 && u1 <= s - 2) ? T.x_interior[s] * T.x_ninio[abs(s - 2 * u1)] * scl[s + 2] : 0.0;
+    }
+    if (tid < 32) {
+      wb[tid] = (tid >= 2 && tid <= 30) ? T.x_bulge[tid] * scl[tid + 2] : 0.0;
+      w1[tid] = (tid >= 4 && tid <= 30) ? T.x_interior[tid] * T.x_ninio[tid - 2] * scl[tid + 2] : 0.0;
+    }
+    double *qb_out = qbtri + (size_t)sq * tri_slot;
+    __syncthreads();
+
+    for (int d = BF_TURN + 1; d <= n - 1; d++) {
+      const int ncell = n - d;
+      const int nch = (ncell + 31) >> 5;
+      const int smax = min(BF_MAXLOOP, d - 6);
+      for (int c = 0; c < nch; c++) {
+        const int cell = c * 32 + lane;
+        const int i = min(cell, ncell - 1) + 1;
+        const int j = i + d;
+        const int t = bf_ptype_bases(S[i], S[j]);
+        double accg = 0.0, acc1 = 0.0, accb = 0.0;
+        if (__any_sync(BF_FULL, t != 0)) {
+          for (int s = 2 + warp; s <= smax; s += NW) {
+            const int row = ((d - 2 - s) & (kRing - 1)) * RS + i;
+            accb += (QBB[row + 1] + QBB[row + 1 + s]) * wb[s];
+            if (s >= 4) acc1 += (Q1[row + 2] + Q1[row + s]) * w1[s];
+            if (s >= 6) {
+              const double *qp = QG + row + 3;
+              const double *w = wg + (s << 5);
+              const int kn = s - 3;
+              double a0 = 0.0, a1 = 0.0;
+              int k = 0;
+              for (; k + 1 < kn; k += 2) { a0 = fma(qp[k], w[k], a0); a1 = fma(qp[k + 1], w[k + 1], a1); }
+              if (k < kn) a0 = fma(qp[k], w[k], a0);
+              accg += a0 + a1;
+            }
+          }
+        }
+        double tot = 0.0;
+        if (t) {
+          const int si1 = S[i + 1], sj1 = S[j - 1];
+          tot = accg * T.x_mmI[t][si1][sj1] + acc1 * T.x_mm1nI[t][si1][sj1] + accb * (t > 2 ? T.x_TerminalAU : 1.0);
+        }
+        // ---- qm splits: k = u - i in [1, d-4]; qm1 lives on diagonal d-k (>= 4), qm on diagonal k-1 (>= 4 to be non-zero)
+        double accs = 0.0, accu = 0.0;
+        for (int k = 1 + warp; k <= d - 4; k += NW) {
+          const double r = QM1[tri_off(n, d - k) + i + k - 1];
+          accu = fma(bu[k], r, accu);
+          if (k >= 5) accs = fma(QM[tri_off(n, k - 1) + i - 1], r, accs);
+        }
+        if (warp == (c % NW)) {
+          double e = 0.0;
+          if (t) {
+            const int si1 = S[i + 1], sj1 = S[j - 1];
+            e = bf_x_hairpin(P, T, S, i, j, t) * scl[d + 1];
+            const int cu1[9] = {0, 0, 1, 1, 1, 2, 2, 2, 3}, cu2[9] = {0, 1, 0, 1, 2, 1, 2, 3, 2};
+#pragma unroll
+            for (int k = 0; k < 9; k++) {
+              const int u1 = cu1[k], u2 = cu2[k];
+              const int p = i + 1 + u1, q = j - 1 - u2;
+              if (q - p <= BF_TURN) continue;
+              const int t2 = bf_ptype_bases(S[p], S[q]);
+              if (!t2) continue;
+              // ring holds qb * terminalAU(t2); undo the factor
+              double qv = QBB[((q - p) & (kRing - 1)) * RS + p];
+              if (t2 > 2) qv *= 1.0 / T.x_TerminalAU;
+              e += qv * bf_x_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]) * scl[u1 + u2 + 2];
+            }
+          }
+          if (cell < ncell) HS[cell] = e;
+        }
+        if (cell < ncell) { PI[warp * RS + cell] = tot; PS[warp * RS + cell] = accs; PB[warp * RS + cell] = accu; }
+      }
+      __syncthreads();
+      for (int cell = tid; cell < ncell; cell += blockDim.x) {
+        const int i = cell + 1, j = i + d;
+        const int t = bf_ptype_bases(S[i], S[j]);
+        double qms = 0.0, qmu = 0.0, qb = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) { qms += PS[w * RS + cell]; qmu += PB[w * RS + cell]; }
+        if (t) {
+          qb = HS[cell];
+#pragma unroll
+          for (int w = 0; w < NW; w++) qb += PI[w * RS + cell];
+          qb += QMS[((d - 2) & 3) * RS + i + 1] * (T.x_MLclosing * bf_x_mlstem(T, bf_rtype(t), S[j - 1], S[i + 1]) * scl[2]);
+        }
+        double qm1 = 0.0;
+        if (d > BF_TURN + 1) qm1 = QM1[tri_off(n, d - 1) + i - 1] * bu[1];
+        if (t && i > 1 && j < n) qm1 += qb * bf_x_mlstem(T, t, S[i - 1], S[j + 1]);
+        const double qm = qms + qmu + qm1;
+        const int o = tri_off(n, d) + i - 1;
+        qb_out[o] = qb;
+        QM[o] = qm;
+        QM1[o] = qm1;
+        QMS[(d & 3) * RS + i] = qms;
+        const int row = (d & (kRing - 1)) * RS + i;
+        double g = 0.0, g1 = 0.0, gb = 0.0;
+        if (t) {
+          const int t2 = bf_rtype(t), a = S[j + 1], bb = S[i - 1];
+          g = qb * T.x_mmI[t2][a][bb];
+          g1 = qb * T.x_mm1nI[t2][a][bb];
+          gb = (t > 2) ? qb * T.x_TerminalAU : qb;
+        }
+        QG[row] = g; Q1[row] = g1; QBB[row] = gb;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// exterior pass of the partition function: one warp per sequence on the qb table in HBM
+template <int WPB>
+__global__ void __launch_bounds__(WPB * 32) bf_k_pf_ext(const BfParams *__restrict__ P, BfBatchDev b, const double *__restrict__ qbtri,
+                                                        size_t tri_slot, const double *__restrict__ lnscale, double *out5) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ BfSmallD T;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nmax = b.stride;
+  bf_stage(&T, &P->sd);
+  __syncthreads();
+  const int sq = blockIdx.x * WPB + warp;
+  if (sq >= b.B) return;
+  const size_t per_warp = align_up((nmax + 4) * sizeof(double) + align_up(nmax + 2, 16), 16);
+  unsigned char *base = dyn + per_warp * warp;
+  double *q5 = reinterpret_cast<double *>(base);
+  uint8_t *S = reinterpret_cast<uint8_t *>(q5 + (nmax + 4));
+  const int n = b.len[sq];
+  const char *src = b.seq + (size_t)sq * b.stride;
+  for (int k = lane; k <= n + 1; k += 32) S[k] = (uint8_t)((k >= 1 && k <= n) ? bf_base_code(src[k - 1]) : 0);
+  const double lns = lnscale[sq], sc1 = exp(-lns);
+  const double *qb = qbtri + (size_t)sq * tri_slot;
+  if (lane == 0) q5[0] = 1.0;
+  __syncwarp();
+  for (int j = 1; j <= n; j++) {
+    double sum = 0.0;
+    for (int i = 1 + lane; i < j - BF_TURN; i += 32) {
+      const int t = bf_ptype_bases(S[i], S[j]);
+      if (!t) continue;
+      const int a = (i > 1) ? S[i - 1] : -1, bb = (j < n) ? S[j + 1] : -1;
+      sum += q5[i - 1] * __ldg(qb + tri_off(n, j - i) + i - 1) * bf_x_ext(T, t, a, bb);
+    }
+    sum = bf_warp_sum(sum);
+    if (lane == 0) q5[j] = sum + q5[j - 1] * sc1;
+    __syncwarp();
+  }
+  if (lane == 0 && out5) {
+    double *o = out5 + (size_t)sq * 5;
+    o[0] = o[1] = o[2] = o[3] = 0.0;
+    o[4] = (n > 0) ? -T.kT * (log(q5[n]) + n * lns) / 1000.0 : 0.0;
+  }
+}
+
+constexpr int kTraceWPB = 4;
+
+size_t trace_smem(int nmax) {
+  size_t a = (nmax + 2 + 15) / 16 * 16;
+  size_t per_warp = (2 * a + (nmax + 4) * sizeof(int) + (2 * nmax + 16) * sizeof(Sector) + 15) / 16 * 16;
+  return per_warp * kTraceWPB;
+}
+size_t pfext_smem(int nmax) {
+  size_t a = (nmax + 2 + 15) / 16 * 16;
+  size_t per_warp = ((nmax + 4) * sizeof(double) + a + 15) / 16 * 16;
+  return per_warp * kTraceWPB;
+}
+
+template <typename K>
+cudaError_t set_smem(K kern, size_t sm) {
+  if (sm > 48 * 1024) return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  return cudaSuccess;
+}
+
+constexpr size_t kSmemBudget = 227 * 1024 - 14 * 1024;  // dynamic budget per CTA (static tables + reserve taken off)
+
+}  // namespace
+
+// =====================================================================================================
+//                                            host side
+// =====================================================================================================
+size_t bf_tri_slot(int nmax) { return (tri_size(nmax) + 7) / 8 * 8; }
+
+// 0: not supported by the fill path; 1: fML on chip; 2: fML in HBM
+int bf_fill_mfe_mode(int nmax) {
+  if (nmax < 1 || nmax > 2000) return 0;
+  if (mfe_plan(nmax, 8, true).total <= kSmemBudget) return 1;
+  if (mfe_plan(nmax, 8, false).total <= kSmemBudget) return 2;
+  return 0;
+}
+int bf_fill_pf_mode(int nmax) {
+  if (nmax < 1 || nmax > 2000) return 0;
+  if (pf_plan(nmax, 8, true, true).total <= kSmemBudget) return 1;
+  if (pf_plan(nmax, 8, false, true).total <= kSmemBudget) return 2;
+  if (pf_plan(nmax, 8, false, false).total <= kSmemBudget) return 3;
+  return 0;
+}
+// doubles of per-CTA HBM workspace the PF fill needs in this mode
+size_t bf_pf_ws_slot(int nmax) {
+  const int mode = bf_fill_pf_mode(nmax);
+  const size_t rs = pf_plan(nmax, 8, false, false).rs;
+  if (mode == 2) return 2 * bf_tri_slot(nmax);
+  if (mode == 3) return 2 * bf_tri_slot(nmax) + (2 * kRing * rs + 7) / 8 * 8;
+  return 0;
+}
+
+template <int NW, bool FM>
+static cudaError_t launch_mfe_fill_t(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, size_t slot, int sms, int *counter,
+                                     cudaStream_t st) {
+  auto kern = bf_k_mfe_fill<NW, FM>;
+  const size_t sm = mfe_plan(b.stride, NW, FM).total;
+  cudaError_t e = set_smem(kern, sm);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, sm);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  const int grid = b.B < sms * occ ? b.B : sms * occ;
+  kern<<<grid, NW * 32, sm, st>>>(dP, b, ctri, ftri, slot, counter);
+  return cudaGetLastError();
+}
+
+cudaError_t bf_launch_mfe_fill(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int sms, int *work_counter, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  const size_t slot = bf_tri_slot(b.stride);
+  const int mode = bf_fill_mfe_mode(b.stride);
+  if (mode == 1) return launch_mfe_fill_t<8, true>(dP, b, ctri, ftri, slot, sms, work_counter, st);
+  if (mode == 2) return launch_mfe_fill_t<8, false>(dP, b, ctri, ftri, slot, sms, work_counter, st);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t bf_launch_trace(const BfParams *dP, const BfBatchDev &b, const int *ctri, const int *ftri, int *out_mfe, char *out_ss,
+                            int ss_stride, cudaStream_t st) {
+  auto kern = bf_k_trace<kTraceWPB>;
+  const size_t sm = trace_smem(b.stride);
+  cudaError_t e = set_smem(kern, sm);
+  if (e != cudaSuccess) return e;
+  kern<<<(b.B + kTraceWPB - 1) / kTraceWPB, kTraceWPB * 32, sm, st>>>(dP, b, ctri, ftri, bf_tri_slot(b.stride), out_mfe, out_ss, ss_stride);
+  return cudaGetLastError();
+}
+
+template <int NW, bool QM, bool RG>
+static cudaError_t pf_fill_t(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *qmws, const int *mfe_for_scale, double *lnscale,
+                             int sms, int *grid_out, bool launch, int *counter, cudaStream_t st) {
+  auto kern = bf_k_pf_fill<NW, QM, RG>;
+  const size_t sm = pf_plan(b.stride, NW, QM, RG).total;
+  cudaError_t e = set_smem(kern, sm);
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, sm);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  const int grid = b.B < sms * occ ? b.B : sms * occ;
+  if (grid_out) *grid_out = grid;
+  if (!launch) return cudaSuccess;
+  kern<<<grid, NW * 32, sm, st>>>(dP, b, qbtri, bf_tri_slot(b.stride), qmws, bf_pf_ws_slot(b.stride), mfe_for_scale, lnscale, counter);
+  return cudaGetLastError();
+}
+
+static cudaError_t pf_fill_dispatch(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *qmws, const int *mfe_for_scale,
+                                    double *lnscale, int sms, int *grid_out, bool launch, int *counter, cudaStream_t st) {
+  const int mode = bf_fill_pf_mode(b.stride);
+  if (mode == 1) return pf_fill_t<8, true, true>(dP, b, qbtri, qmws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+  if (mode == 2) return pf_fill_t<8, false, true>(dP, b, qbtri, qmws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+  if (mode == 3) return pf_fill_t<8, false, false>(dP, b, qbtri, qmws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+  return cudaErrorInvalidValue;
+}
+
+// grid size the PF fill will use (the caller sizes the per-CTA workspace with it in modes 2 and 3)
+cudaError_t bf_pf_fill_grid(const BfBatchDev &b, int sms, int *grid) {
+  return pf_fill_dispatch(nullptr, b, nullptr, nullptr, nullptr, nullptr, sms, grid, false, nullptr, nullptr);
+}
+
+cudaError_t bf_launch_pf_fill(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *qmws, const int *mfe_for_scale,
+                              double *lnscale, int sms, int *work_counter, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  return pf_fill_dispatch(dP, b, qbtri, qmws, mfe_for_scale, lnscale, sms, nullptr, true, work_counter, st);
+}
+
+cudaError_t bf_launch_pf_ext(const BfParams *dP, const BfBatchDev &b, const double *qbtri, const double *lnscale, double *out5,
+                             cudaStream_t st) {
+  auto kern = bf_k_pf_ext<kTraceWPB>;
+  const size_t sm = pfext_smem(b.stride);
+  cudaError_t e = set_smem(kern, sm);
+  if (e != cudaSuccess) return e;
+  kern<<<(b.B + kTraceWPB - 1) / kTraceWPB, kTraceWPB * 32, sm, st>>>(dP, b, qbtri, bf_tri_slot(b.stride), lnscale, out5);
+  return cudaGetLastError();
+}

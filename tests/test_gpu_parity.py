@@ -65,7 +65,7 @@ def test_eterna_v1_kats(engine):
         assert out["pf"][k, 4] <= out["mfe_dcal"][k] / 100.0 + 1e-9
 
 
-@pytest.mark.parametrize("L,B", [(50, 256), (100, 128), (200, 48), (400, 12)])
+@pytest.mark.parametrize("L,B", [(50, 256), (100, 128), (150, 64), (200, 48), (300, 16), (400, 12)])
 def test_random_vs_oracle(engine, oracle, L, B):
     seqs = rand_seqs(20240000 + L, B, L)
     out = engine.score_batch(seqs, want=engine.WANT_MFE | engine.WANT_SS | engine.WANT_PF)
