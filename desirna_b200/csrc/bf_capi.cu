@@ -38,7 +38,7 @@ struct Engine {
   BfParams *dP = nullptr;  // device image
   int *d_counters = nullptr;  // work counters (one per kernel kind)
   DevBuf ws_mfe, ws_pf, d_mfe_scratch;
-  DevBuf tri_c, tri_f, tri_qb, ws_qm, d_lnscale;  // diagonal-major fill path (bf_fill.cu)
+  DevBuf tri_c, tri_f, tri_qb, ws_qm, ws_ring, d_lnscale;  // diagonal-major fill path (bf_fill.cu)
   bool force_generic = false;                     // BF_FORCE_GENERIC=1: route single strands through the generic kernels too
   // staging for the host-buffer entry point
   DevBuf d_seq, d_len, d_cut, d_nopair, d_targets, d_mfe, d_ss, d_pf, d_eval;
@@ -97,7 +97,14 @@ int run_device(const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t
       const size_t slot = bf_tri_slot(b->stride) * sizeof(int);
       CU(g.tri_c.reserve((size_t)b->B * slot), "cudaMalloc(c table)");
       CU(g.tri_f.reserve((size_t)b->B * slot), "cudaMalloc(fML table)");
-      CU(bf_launch_mfe_fill(g.dP, db, (int *)g.tri_c.p, (int *)g.tri_f.p, g.sm_count, g.d_counters + 0, st), "launch bf_k_mfe_fill");
+      const size_t wsi = bf_mfe_ws_slot(b->stride) * sizeof(int);
+      if (wsi) {
+        int grid = 0;
+        CU(bf_mfe_fill_grid(db, g.sm_count, &grid), "size bf_k_mfe_fill");
+        CU(g.ws_ring.reserve((size_t)grid * wsi), "cudaMalloc(ring workspace)");
+      }
+      CU(bf_launch_mfe_fill(g.dP, db, (int *)g.tri_c.p, (int *)g.tri_f.p, (int *)g.ws_ring.p, g.sm_count, g.d_counters + 0, st),
+         "launch bf_k_mfe_fill");
       CU(bf_launch_trace(g.dP, db, (const int *)g.tri_c.p, (const int *)g.tri_f.p, out_mfe, (b->want & BF_WANT_SS) ? r->mfe_ss : nullptr,
                          b->stride + 1, st), "launch bf_k_trace");
       g.launches += 2;
@@ -194,7 +201,7 @@ int bf_init(int device) {
 int bf_shutdown(void) {
   if (!g.inited) return BF_OK;
   cudaStreamSynchronize(g.stream);
-  for (DevBuf *b : {&g.tri_c, &g.tri_f, &g.tri_qb, &g.ws_qm, &g.d_lnscale, &g.ws_mfe, &g.ws_pf, &g.d_mfe_scratch, &g.d_seq, &g.d_len, &g.d_cut, &g.d_nopair, &g.d_targets, &g.d_mfe, &g.d_ss, &g.d_pf, &g.d_eval}) b->release();
+  for (DevBuf *b : {&g.tri_c, &g.tri_f, &g.tri_qb, &g.ws_qm, &g.ws_ring, &g.d_lnscale, &g.ws_mfe, &g.ws_pf, &g.d_mfe_scratch, &g.d_seq, &g.d_len, &g.d_cut, &g.d_nopair, &g.d_targets, &g.d_mfe, &g.d_ss, &g.d_pf, &g.d_eval}) b->release();
   if (g.dP) cudaFree(g.dP);
   if (g.d_counters) cudaFree(g.d_counters);
   cudaStreamDestroy(g.stream);

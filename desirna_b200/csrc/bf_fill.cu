@@ -26,6 +26,8 @@
 // backtrack run afterwards in one-warp-per-sequence kernels on the tables written to HBM.
 #include "bf_kernels.h"
 
+#include <cstdlib>
+
 #include "bf_device.cuh"
 
 namespace {
@@ -44,59 +46,92 @@ __device__ __forceinline__ size_t align_up(size_t x, size_t a) { return (x + a -
 __device__ __forceinline__ int ptype_sp(const uint8_t *SP, int i, int j) { return bf_ptype_bases(SP[i], SP[j]); }
 
 // ---------------------------------------------------------------------------------------------
-// shared-memory plan (identical arithmetic on host and device)
+// shared-memory plans (identical arithmetic on host and device)
 // ---------------------------------------------------------------------------------------------
+// placement flags of the MFE fill: where the tables that are re-read every diagonal live
+constexpr int kMfeFmSmem = 1;   // packed fML table on chip (else: the per-sequence HBM copy, L2-resident while in use)
+constexpr int kMfeRgSmem = 2;   // the three 32-deep pair rings on chip (else: per-CTA HBM workspace)
+constexpr int kTabSmem = 8;     // small loop tables (BfSmallI / BfSmallD) staged per CTA (else: read through L1)
+
 struct MfePlan {
   int rs;  // ring row stride (ints)
-  size_t o_S, o_SP, o_pg, o_pb, o_p1, o_fm, o_ring, o_dml, o_pi, o_ps, o_hs, total;
+  size_t o_S, o_SP, o_toff, o_pg, o_pb, o_p1, o_fm, o_ring, o_dml, o_pi, o_ps, o_list, o_tab, total;
 };
-__host__ __device__ inline MfePlan mfe_plan(int nmax, int nw, bool fm_in_smem) {
+__host__ __device__ inline MfePlan mfe_plan(int nmax, int nw, int pl) {
   MfePlan p;
   p.rs = (nmax + 8 + 3) / 4 * 4;
   size_t o = 0;
   p.o_S = o; o += (nmax + 2 + 15) / 16 * 16;
   p.o_SP = o; o += (nmax + 2 + 15) / 16 * 16;
+  p.o_toff = o; o += (size_t)(nmax + 4) / 4 * 4 * sizeof(int);
   p.o_pg = o; o += 31 * 32 * sizeof(int);
   p.o_pb = o; o += 32 * sizeof(int);
   p.o_p1 = o; o += 32 * sizeof(int);
-  p.o_fm = o; o += fm_in_smem ? (tri_size(nmax) + 4) * sizeof(int) : 0;
-  p.o_ring = o; o += (size_t)3 * kRing * p.rs * sizeof(int);
+  p.o_fm = o; o += (pl & kMfeFmSmem) ? (tri_size(nmax) + 4) * sizeof(int) : 0;
+  p.o_ring = o; o += (pl & kMfeRgSmem) ? (size_t)3 * kRing * p.rs * sizeof(int) : 0;
   p.o_dml = o; o += (size_t)4 * p.rs * sizeof(int);
-  p.o_pi = o; o += (size_t)nw * p.rs * sizeof(int);
-  p.o_ps = o; o += (size_t)nw * p.rs * sizeof(int);
-  p.o_hs = o; o += (size_t)p.rs * sizeof(int);
+  p.o_pi = o; o += (size_t)2 * nw * p.rs * sizeof(int);   // double-buffered per-warp partial minima
+  p.o_ps = o; o += (size_t)2 * nw * p.rs * sizeof(int);
+  p.o_list = o; o += (size_t)2 * p.rs * sizeof(unsigned short);  // pairable cells of a diagonal, double-buffered
+  p.o_tab = o; o += (pl & kTabSmem) ? (sizeof(BfSmallI) + 15) / 16 * 16 : 0;
   p.total = o;
   return p;
 }
+
+// Compact the pairable cells of diagonal d into list[0..count): one warp, ballot + popc prefix.
+__device__ __forceinline__ int build_pair_list(const uint8_t *SP, int n, int d, unsigned short *list, int lane) {
+  int count = 0;
+  for (int base = 1; base <= n - d; base += 32) {
+    const int i = base + lane;
+    const bool ok = (i <= n - d) && bf_ptype_bases(SP[i], SP[i + d]) != 0;
+    const unsigned mk = __ballot_sync(BF_FULL, ok);
+    if (ok) list[count + __popc(mk & ((1u << lane) - 1))] = (unsigned short)i;
+    count += __popc(mk);
+  }
+  return count;
+}
+
+// strided share of the loop sizes s = smax .. 2 with the long and the short ones alternating between warps
+// (idx = 0 is s = smax; warp w takes idx = w, 2NW-1-w, 2NW+w, 4NW-1-w, ...)
+#define BF_FOR_MY_S(NW, warp, smax, s)                                                          \
+  for (int idx_ = (warp), flip_ = 0, s = (smax) - idx_; s >= 2;                                  \
+       idx_ += flip_ ? 2 * (warp) + 1 : 2 * ((NW) - 1 - (warp)) + 1, flip_ ^= 1, s = (smax) - idx_)
 
 // =====================================================================================================
 //                                           MFE fill
 // =====================================================================================================
 // ctri / ftri: per-sequence tables in HBM (slot s at s * tri_slot), read later by bf_k_trace.
-template <int NW, bool FM_SMEM>
-__global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restrict__ P, BfBatchDev b, int *ctri,
-                                                         int *ftri, size_t tri_slot, int *work_counter) {
+// Phase d of the diagonal loop: every warp first combines the partial minima of diagonal d-1 for the cells
+// it owns (-> c, fML, ring rows of d-1), then accumulates partial minima for diagonal d.  The heavy part of
+// diagonal d only reads diagonals <= d-2 (interior loops) and <= d-5 (fML splits), so one barrier per
+// diagonal is enough; the partial buffers are double-buffered.
+template <int NW, int PL>
+__global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restrict__ P, BfBatchDev b, int *ctri, int *ftri,
+                                                         size_t tri_slot, int *ws, size_t ws_slot, int *work_counter) {
   extern __shared__ __align__(16) unsigned char dyn[];
-  __shared__ BfSmallI T;
-  __shared__ int s_seq;
+  __shared__ int s_seq, s_np[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nmax = b.stride;
-  const MfePlan pl = mfe_plan(nmax, NW, FM_SMEM);
+  const MfePlan pl = mfe_plan(nmax, NW, PL);
   const int RS = pl.rs;
   uint8_t *S = dyn + pl.o_S;
   uint8_t *SP = dyn + pl.o_SP;
-  int *pg = reinterpret_cast<int *>(dyn + pl.o_pg);   // [s][k], k = u1-2: interior[s] + ninio(|s-2u1|), INF padded
+  int *toff = reinterpret_cast<int *>(dyn + pl.o_toff);
+  int *pg = reinterpret_cast<int *>(dyn + pl.o_pg);   // [s][k], k = u1-2: interior[s] + ninio(|s-2u1|)
   int *pb = reinterpret_cast<int *>(dyn + pl.o_pb);   // bulge[s]
   int *p1 = reinterpret_cast<int *>(dyn + pl.o_p1);   // 1xn: interior[s] + ninio(s-2)
   int *fms = reinterpret_cast<int *>(dyn + pl.o_fm);
-  int *ring = reinterpret_cast<int *>(dyn + pl.o_ring);
+  int *ring = (PL & kMfeRgSmem) ? reinterpret_cast<int *>(dyn + pl.o_ring) : ws + (size_t)blockIdx.x * ws_slot;
   int *CG = ring, *C1 = ring + kRing * RS, *CB = ring + 2 * kRing * RS;
   int *DML = reinterpret_cast<int *>(dyn + pl.o_dml);
   int *PI = reinterpret_cast<int *>(dyn + pl.o_pi);
   int *PS = reinterpret_cast<int *>(dyn + pl.o_ps);
-  int *HS = reinterpret_cast<int *>(dyn + pl.o_hs);
+  unsigned short *LST = reinterpret_cast<unsigned short *>(dyn + pl.o_list);
 
-  bf_stage(&T, &P->si);
+  for (int k = tid; k < (int)(pl.total / 4); k += blockDim.x) reinterpret_cast<int *>(dyn)[k] = 0;
+  __syncthreads();
+  if (PL & kTabSmem) bf_stage(reinterpret_cast<BfSmallI *>(dyn + pl.o_tab), &P->si);
+  const BfSmallI &T = (PL & kTabSmem) ? *reinterpret_cast<const BfSmallI *>(dyn + pl.o_tab) : P->si;
   __syncthreads();
   for (int k = tid; k < 31 * 32; k += blockDim.x) {
     const int s = k >> 5, u1 = (k & 31) + 2;
@@ -126,25 +161,81 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
         SP[k] = (uint8_t)((np && k >= 1 && k <= n && np[k - 1]) ? 0 : code);
       }
     }
+    for (int k = tid; k <= n; k += blockDim.x) toff[k] = (k >= 4) ? tri_off(n, k) : 0;
     for (int k = tid; k < 4 * RS; k += blockDim.x) DML[k] = BF_INF;
     int *cg_out = ctri + (size_t)sq * tri_slot;
     int *fg_out = ftri + (size_t)sq * tri_slot;
-    int *FM = FM_SMEM ? fms : fg_out;
+    int *FM = (PL & kMfeFmSmem) ? fms : fg_out;
+    __syncthreads();
+    if (warp == 0 && n > BF_TURN + 1) {
+      const int cnt = build_pair_list(SP, n, BF_TURN + 1, LST + ((BF_TURN + 1) & 1) * RS, lane);
+      if (lane == 0) s_np[(BF_TURN + 1) & 1] = cnt;
+    }
     __syncthreads();
 
-    for (int d = BF_TURN + 1; d <= n - 1; d++) {
-      const int ncell = n - d;
-      const int nch = (ncell + 31) >> 5;
-      const int smax = min(BF_MAXLOOP, d - 6);  // inner diagonal d-2-s >= 4
-      for (int c = 0; c < nch; c++) {
-        const int cell = c * 32 + lane;           // 0-based cell on the diagonal
-        const int i = min(cell, ncell - 1) + 1;   // clamped: idle lanes repeat the last cell and are dropped at the store
-        const int j = i + d;
-        const int t = ptype_sp(SP, i, j);
-        // ---- interior loops, decomposable classes: this warp's share of the loop sizes
-        int accg = BF_INF, acc1 = BF_INF, accb = BF_INF;
-        if (__any_sync(BF_FULL, t != 0)) {
-          for (int s = 2 + warp; s <= smax; s += NW) {
+    for (int d = BF_TURN + 1; d <= n; d++) {
+      // ------------------------------------------------------------ pairable cells of the next diagonal
+      if (warp == NW - 1 && d + 1 <= n - 1) {
+        const int cnt = build_pair_list(SP, n, d + 1, LST + ((d + 1) & 1) * RS, lane);
+        if (lane == 0) s_np[(d + 1) & 1] = cnt;
+      }
+      // ------------------------------------------------------------ combine diagonal d-1
+      if (d > BF_TURN + 1) {
+        const int dd = d - 1, ncell = n - dd, buf = dd & 1;
+        const int *pi = PI + buf * NW * RS, *ps = PS + buf * NW * RS;
+        for (int cell = tid; cell < ncell; cell += blockDim.x) {
+          const int i = cell + 1, j = i + dd;
+          const int t = ptype_sp(SP, i, j);
+          int e = BF_INF, sp = BF_INF;
+#pragma unroll
+          for (int w = 0; w < NW; w++) sp = min(sp, ps[w * RS + cell]);
+          if (t) {
+#pragma unroll
+            for (int w = 0; w < NW; w++) e = min(e, pi[w * RS + cell]);
+            const int dm = DML[((dd - 2) & 3) * RS + i + 1];
+            if (dm < kInfThr) e = min(e, dm + T.MLclosing + bf_e_mlstem(T, bf_rtype(t), S[j - 1], S[i + 1]));
+            if (e >= kInfThr) e = BF_INF;
+          }
+          if (sp >= kInfThr) sp = BF_INF;
+          int m = sp;
+          if (e < BF_INF && i > 1 && j < n) m = min(m, e + bf_e_mlstem(T, t, S[i - 1], S[j + 1]));
+          if (dd > BF_TURN + 1) {
+            const int o = toff[dd - 1] + i - 1;
+            m = min(m, min(FM[o + 1], FM[o]) + T.MLbase);
+          }
+          if (m >= kInfThr) m = BF_INF;
+          const int o = toff[dd] + i - 1;
+          cg_out[o] = e;
+          fg_out[o] = m;
+          if (PL & kMfeFmSmem) fms[o] = m;
+          DML[(dd & 3) * RS + i] = sp;
+          const int row = (dd & (kRing - 1)) * RS + i;
+          int eg = BF_INF, e1 = BF_INF, eb = BF_INF;
+          if (e < BF_INF) {
+            const int t2 = bf_rtype(t), a = S[j + 1], bb = S[i - 1];  // as an inner pair: sq1 = S[q+1], sp1 = S[p-1]
+            eg = e + T.mmI[t2][a][bb];
+            e1 = e + T.mm1nI[t2][a][bb];
+            eb = e + (t > 2 ? T.TerminalAU : 0);
+          }
+          CG[row] = eg; C1[row] = e1; CB[row] = eb;
+        }
+      }
+      // ------------------------------------------------------------ partial minima of diagonal d
+      if (d <= n - 1) {
+        const int ncell = n - d, buf = d & 1;
+        int *pi = PI + (buf * NW + warp) * RS, *ps = PS + (buf * NW + warp) * RS;
+        const int smax = min(BF_MAXLOOP, d - 6);  // inner diagonal d-2-s >= 4
+        // ---- pair-only work on the compacted list: interior loops, hairpin
+        const int np = s_np[buf];
+        const unsigned short *list = LST + buf * RS;
+        for (int c = 0; c < np; c += 32) {
+          const int kk = c + lane;
+          const int i = list[min(kk, np - 1)];      // idle lanes repeat the last pairable cell and are dropped at the store
+          const int j = i + d;
+          const int t = ptype_sp(SP, i, j);
+          const int si1 = S[i + 1], sj1 = S[j - 1];
+          int accg = BF_INF, acc1 = BF_INF, accb = BF_INF;
+          BF_FOR_MY_S(NW, warp, smax, s) {
             const int row = ((d - 2 - s) & (kRing - 1)) * RS + i;
             accb = min(accb, min(CB[row + 1], CB[row + 1 + s]) + pb[s]);
             if (s >= 4) acc1 = min(acc1, min(C1[row + 2], C1[row + s]) + p1[s]);
@@ -156,80 +247,31 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
               for (int k = 0; k < kn; k++) accg = min(accg, cgp[k] + pen[k]);
             }
           }
-        }
-        int tot = BF_INF;
-        if (t) {
-          const int si1 = S[i + 1], sj1 = S[j - 1];
-          tot = min(accg + T.mmI[t][si1][sj1], min(acc1 + T.mm1nI[t][si1][sj1], accb + (t > 2 ? T.TerminalAU : 0)));
-        }
-        // ---- fML split: k = u - i in [5, d-4]
-        int accs = BF_INF;
-        {
-          const int *left = FM + (i - 1);
-          for (int k = 5 + warp; k <= d - 4; k += NW)
-            accs = min(accs, left[tri_off(n, k - 1)] + FM[tri_off(n, d - k) + i + k - 1]);
-        }
-        // ---- hairpin + the non-decomposable interior candidates: one warp per chunk
-        if (warp == (c % NW)) {
-          int e = BF_INF;
-          if (t) {
-            const int si1 = S[i + 1], sj1 = S[j - 1];
-            e = bf_e_hairpin(P, T, S, i, j, t);
-            const int cu1[9] = {0, 0, 1, 1, 1, 2, 2, 2, 3}, cu2[9] = {0, 1, 0, 1, 2, 1, 2, 3, 2};
-#pragma unroll
-            for (int k = 0; k < 9; k++) {
-              const int u1 = cu1[k], u2 = cu2[k];
-              const int p = i + 1 + u1, q = j - 1 - u2;
-              if (q - p <= BF_TURN) continue;
-              int cc = CB[((q - p) & (kRing - 1)) * RS + p];  // c + terminalAU(inner pair)
-              if (cc >= kInfThr) continue;
-              const int t2 = ptype_sp(SP, p, q);
-              if (t2 > 2) cc -= T.TerminalAU;
-              e = min(e, cc + bf_e_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]));
-            }
+          int tot = min(accg + T.mmI[t][si1][sj1], min(acc1 + T.mm1nI[t][si1][sj1], accb + (t > 2 ? T.TerminalAU : 0)));
+          // the hairpin and the nine non-decomposable interior candidates, dealt round-robin to the warps
+          for (int k = (warp + c + d) % NW; k < 10; k += NW) {
+            if (k == 9) { tot = min(tot, bf_e_hairpin(P, T, S, i, j, t)); continue; }
+            const int u1 = (0x322211100ull >> (4 * k)) & 15, u2 = (0x232121010ull >> (4 * k)) & 15;
+            const int p = i + 1 + u1, q = j - 1 - u2;
+            if (q - p <= BF_TURN) continue;
+            int cc = CB[((q - p) & (kRing - 1)) * RS + p];  // c + terminalAU(inner pair)
+            if (cc >= kInfThr) continue;
+            const int t2 = ptype_sp(SP, p, q);
+            if (t2 > 2) cc -= T.TerminalAU;
+            tot = min(tot, cc + bf_e_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]));
           }
-          if (cell < ncell) HS[cell] = e;
+          if (kk < np) pi[i - 1] = tot;
         }
-        if (cell < ncell) { PI[warp * RS + cell] = tot; PS[warp * RS + cell] = accs; }
-      }
-      __syncthreads();
-      // ---- combine: one thread per cell
-      for (int cell = tid; cell < ncell; cell += blockDim.x) {
-        const int i = cell + 1, j = i + d;
-        const int t = ptype_sp(SP, i, j);
-        int e = BF_INF, sp = BF_INF;
-#pragma unroll
-        for (int w = 0; w < NW; w++) sp = min(sp, PS[w * RS + cell]);
-        if (t) {
-          e = HS[cell];
-#pragma unroll
-          for (int w = 0; w < NW; w++) e = min(e, PI[w * RS + cell]);
-          const int dm = DML[((d - 2) & 3) * RS + i + 1];
-          if (dm < kInfThr) e = min(e, dm + T.MLclosing + bf_e_mlstem(T, bf_rtype(t), S[j - 1], S[i + 1]));
-          if (e >= kInfThr) e = BF_INF;
+        // ---- fML split for every cell: k = u - i in [5, d-4]
+        for (int c = 0; c < ncell; c += 32) {
+          const int cell = c + lane;
+          const int i = min(cell, ncell - 1) + 1;
+          int accs = BF_INF;
+          const int *left = FM + (i - 1);
+#pragma unroll 2
+          for (int k = 5 + warp; k <= d - 4; k += NW) accs = min(accs, left[toff[k - 1]] + left[toff[d - k] + k]);
+          if (cell < ncell) ps[cell] = accs;
         }
-        if (sp >= kInfThr) sp = BF_INF;
-        int m = sp;
-        if (e < BF_INF && i > 1 && j < n) m = min(m, e + bf_e_mlstem(T, t, S[i - 1], S[j + 1]));
-        if (d > BF_TURN + 1) {
-          const int o = tri_off(n, d - 1) + i - 1;
-          m = min(m, min(FM[o + 1], FM[o]) + T.MLbase);
-        }
-        if (m >= kInfThr) m = BF_INF;
-        const int o = tri_off(n, d) + i - 1;
-        cg_out[o] = e;
-        fg_out[o] = m;
-        if (FM_SMEM) fms[o] = m;
-        DML[(d & 3) * RS + i] = sp;
-        const int row = (d & (kRing - 1)) * RS + i;
-        int eg = BF_INF, e1 = BF_INF, eb = BF_INF;
-        if (e < BF_INF) {
-          const int t2 = bf_rtype(t), a = S[j + 1], bb = S[i - 1];  // as an inner pair: sq1 = S[q+1], sp1 = S[p-1]
-          eg = e + T.mmI[t2][a][bb];
-          e1 = e + T.mm1nI[t2][a][bb];
-          eb = e + (t > 2 ? T.TerminalAU : 0);
-        }
-        CG[row] = eg; C1[row] = e1; CB[row] = eb;
       }
       __syncthreads();
     }
@@ -416,12 +458,15 @@ __global__ void __launch_bounds__(WPB * 32) bf_k_trace(const BfParams *__restric
 // =====================================================================================================
 //                                   partition function (inside) fill
 // =====================================================================================================
+constexpr int kPfQmSmem = 1;   // packed qm and qm1 tables on chip (else: per-CTA HBM workspace)
+constexpr int kPfR2Smem = 2;   // the 1xn and bulge rings on chip
+constexpr int kPfQgSmem = 4;   // the generic-interior ring on chip
+
 struct PfPlan {
   int rs;
-  size_t o_S, o_wg, o_wb, o_w1, o_scl, o_bu, o_qm, o_qm1, o_ring, o_qms, o_pi, o_ps, o_pb, o_hs, total;
+  size_t o_S, o_toff, o_wg, o_wb, o_w1, o_scl, o_bu, o_qm, o_qm1, o_qg, o_r2, o_qms, o_au, o_pi, o_ps, o_list, o_tab, total;
 };
-// mode 1: everything on chip; 2: qm/qm1 in HBM; 3: qm/qm1 and the two small rings (1xn, bulge) in HBM
-__host__ __device__ inline PfPlan pf_plan(int nmax, int nw, bool qm_in_smem, bool rings_in_smem) {
+__host__ __device__ inline PfPlan pf_plan(int nmax, int nw, int pl) {
   PfPlan p;
   p.rs = (nmax + 8 + 3) / 4 * 4;
   size_t o = 0;
@@ -430,60 +475,73 @@ __host__ __device__ inline PfPlan pf_plan(int nmax, int nw, bool qm_in_smem, boo
   p.o_w1 = o; o += 32 * sizeof(double);
   p.o_scl = o; o += (size_t)(nmax + 8) * sizeof(double);
   p.o_bu = o; o += (size_t)(nmax + 8) * sizeof(double);
-  p.o_qm = o; o += qm_in_smem ? (tri_size(nmax) + 4) * sizeof(double) : 0;
-  p.o_qm1 = o; o += qm_in_smem ? (tri_size(nmax) + 4) * sizeof(double) : 0;
-  p.o_ring = o; o += (size_t)(rings_in_smem ? 3 : 1) * kRing * p.rs * sizeof(double);
+  p.o_qm = o; o += (pl & kPfQmSmem) ? (tri_size(nmax) + 4) * sizeof(double) : 0;
+  p.o_qm1 = o; o += (pl & kPfQmSmem) ? (tri_size(nmax) + 4) * sizeof(double) : 0;
+  p.o_qg = o; o += (pl & kPfQgSmem) ? (size_t)kRing * p.rs * sizeof(double) : 0;
+  p.o_r2 = o; o += (pl & kPfR2Smem) ? (size_t)2 * kRing * p.rs * sizeof(double) : 0;
   p.o_qms = o; o += (size_t)4 * p.rs * sizeof(double);
-  p.o_pi = o; o += (size_t)nw * p.rs * sizeof(double);
-  p.o_ps = o; o += (size_t)nw * p.rs * sizeof(double);
-  p.o_pb = o; o += (size_t)nw * p.rs * sizeof(double);
-  p.o_hs = o; o += (size_t)p.rs * sizeof(double);
+  p.o_au = o; o += (size_t)2 * p.rs * sizeof(double);
+  p.o_pi = o; o += (size_t)2 * nw * p.rs * sizeof(double);
+  p.o_ps = o; o += (size_t)2 * nw * p.rs * sizeof(double);
+  p.o_tab = o; o += (pl & kTabSmem) ? (sizeof(BfSmallD) + 15) / 16 * 16 : 0;
+  p.o_list = o; o += (size_t)2 * p.rs * sizeof(unsigned short);
+  p.o_toff = o; o += (size_t)(nmax + 4) / 4 * 4 * sizeof(int);
   p.o_S = o; o += (nmax + 2 + 15) / 16 * 16;
   p.total = o;
   return p;
 }
+// doubles of per-CTA HBM workspace for the tables that are not on chip
+__host__ __device__ inline size_t pf_ws_doubles(int nmax, int pl) {
+  const size_t rs = (nmax + 8 + 3) / 4 * 4;
+  size_t o = 0;
+  if (!(pl & kPfQmSmem)) o += 2 * ((tri_size(nmax) + 7) / 8 * 8);
+  if (!(pl & kPfQgSmem)) o += kRing * rs;
+  if (!(pl & kPfR2Smem)) o += 2 * kRing * rs;
+  return (o + 7) / 8 * 8;
+}
 
-// qbtri: per-sequence qb table in HBM (for the exterior pass); qmws: per-CTA qm/qm1 workspace when they do not fit on chip
-template <int NW, bool QM_SMEM, bool RG_SMEM>
-__global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restrict__ P, BfBatchDev b, double *qbtri,
-                                                        size_t tri_slot, double *qmws, size_t ws_slot, const int *mfe_for_scale,
-                                                        double *lnscale_out, int *work_counter) {
+// qbtri: per-sequence qb table in HBM (for the exterior pass).  Same phase structure as bf_k_mfe_fill.
+// qm(i,j) = qm1(i,j) + A(i,j) + sum_k qm[i][i+k-1] qm1[i+k][j] with A(i,j) = sum_{k>=1} bu^k qm1(i+k,j)
+//         = bu (qm1(i+1,j) + A(i+1,j)): the unpaired-prefix part is carried along the diagonals in O(1) per cell.
+template <int NW, int PL>
+__global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restrict__ P, BfBatchDev b, double *qbtri, size_t tri_slot,
+                                                        double *ws, size_t ws_slot, const int *mfe_for_scale, double *lnscale_out,
+                                                        int *work_counter) {
   extern __shared__ __align__(16) unsigned char dyn[];
-  __shared__ BfSmallD T;
-  __shared__ int s_seq;
+  __shared__ int s_seq, s_np[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nmax = b.stride;
-  const PfPlan pl = pf_plan(nmax, NW, QM_SMEM, RG_SMEM);
+  const PfPlan pl = pf_plan(nmax, NW, PL);
   const int RS = pl.rs;
   uint8_t *S = dyn + pl.o_S;
+  int *toff = reinterpret_cast<int *>(dyn + pl.o_toff);
   double *wg = reinterpret_cast<double *>(dyn + pl.o_wg);
   double *wb = reinterpret_cast<double *>(dyn + pl.o_wb);
   double *w1 = reinterpret_cast<double *>(dyn + pl.o_w1);
   double *scl = reinterpret_cast<double *>(dyn + pl.o_scl);
   double *bu = reinterpret_cast<double *>(dyn + pl.o_bu);
-  double *ring = reinterpret_cast<double *>(dyn + pl.o_ring);
-  double *QG = ring, *Q1, *QBB;
   double *QMS = reinterpret_cast<double *>(dyn + pl.o_qms);
+  double *AU = reinterpret_cast<double *>(dyn + pl.o_au);
   double *PI = reinterpret_cast<double *>(dyn + pl.o_pi);
   double *PS = reinterpret_cast<double *>(dyn + pl.o_ps);
-  double *PB = reinterpret_cast<double *>(dyn + pl.o_pb);
-  double *HS = reinterpret_cast<double *>(dyn + pl.o_hs);
-  double *QM, *QM1;
-  if (QM_SMEM) {
+  unsigned short *LST = reinterpret_cast<unsigned short *>(dyn + pl.o_list);
+  double *wsp = ws + (size_t)blockIdx.x * ws_slot;
+  double *QM, *QM1, *QG, *Q1, *QBB;
+  if (PL & kPfQmSmem) {
     QM = reinterpret_cast<double *>(dyn + pl.o_qm);
     QM1 = reinterpret_cast<double *>(dyn + pl.o_qm1);
   } else {
-    QM = qmws + (size_t)blockIdx.x * ws_slot;
-    QM1 = QM + tri_slot;
+    QM = wsp; QM1 = wsp + (tri_size(nmax) + 7) / 8 * 8; wsp += 2 * ((tri_size(nmax) + 7) / 8 * 8);
   }
-  if (RG_SMEM) {
-    Q1 = ring + kRing * RS;
-    QBB = ring + 2 * kRing * RS;
-  } else {
-    Q1 = qmws + (size_t)blockIdx.x * ws_slot + 2 * tri_slot;
-    QBB = Q1 + kRing * RS;
-  }
-  bf_stage(&T, &P->sd);
+  if (PL & kPfQgSmem) QG = reinterpret_cast<double *>(dyn + pl.o_qg);
+  else { QG = wsp; wsp += kRing * RS; }
+  if (PL & kPfR2Smem) { Q1 = reinterpret_cast<double *>(dyn + pl.o_r2); QBB = Q1 + kRing * RS; }
+  else { Q1 = wsp; QBB = wsp + kRing * RS; }
+
+  for (int k = tid; k < (int)(pl.total / 4); k += blockDim.x) reinterpret_cast<int *>(dyn)[k] = 0;
+  __syncthreads();
+  if (PL & kTabSmem) bf_stage(reinterpret_cast<BfSmallD *>(dyn + pl.o_tab), &P->sd);
+  const BfSmallD &T = (PL & kTabSmem) ? *reinterpret_cast<const BfSmallD *>(dyn + pl.o_tab) : P->sd;
   for (int k = tid; k < kRing * RS; k += blockDim.x) { QG[k] = 0.0; Q1[k] = 0.0; QBB[k] = 0.0; }
 
   for (;;) {
@@ -497,6 +555,7 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
       const char *src = b.seq + (size_t)sq * b.stride;
       for (int k = tid; k <= n + 1; k += blockDim.x) S[k] = (uint8_t)((k >= 1 && k <= n) ? bf_base_code(src[k - 1]) : 0);
     }
+    for (int k = tid; k <= n; k += blockDim.x) toff[k] = (k >= 4) ? tri_off(n, k) : 0;
     // per-nucleotide scale (ViennaRNA exp_params_rescale, sfact 1.07; default estimate -185 cal/mol/nt)
     double lns = 185.0 / T.kT;
     if (mfe_for_scale && n > 0) {
@@ -510,6 +569,7 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
     }
     if (tid == 0 && lnscale_out) lnscale_out[sq] = lns;
     for (int k = tid; k < 4 * RS; k += blockDim.x) QMS[k] = 0.0;
+    for (int k = tid; k < 2 * RS; k += blockDim.x) AU[k] = 0.0;
     __syncthreads();
     for (int k = tid; k < 31 * 32; k += blockDim.x) {
       const int s = k >> 5, u1 = (k & 31) + 2;
@@ -520,20 +580,75 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
       w1[tid] = (tid >= 4 && tid <= 30) ? T.x_interior[tid] * T.x_ninio[tid - 2] * scl[tid + 2] : 0.0;
     }
     double *qb_out = qbtri + (size_t)sq * tri_slot;
+    const double bu1 = exp(log(T.x_MLbase) - lns);
+    const double xtau = T.x_TerminalAU, inv_tau = 1.0 / xtau;
+    const double xclose = T.x_MLclosing * exp(-2.0 * lns);
+    if (warp == 0 && n > BF_TURN + 1) {
+      const int cnt = build_pair_list(S, n, BF_TURN + 1, LST + ((BF_TURN + 1) & 1) * RS, lane);
+      if (lane == 0) s_np[(BF_TURN + 1) & 1] = cnt;
+    }
     __syncthreads();
 
-    for (int d = BF_TURN + 1; d <= n - 1; d++) {
-      const int ncell = n - d;
-      const int nch = (ncell + 31) >> 5;
-      const int smax = min(BF_MAXLOOP, d - 6);
-      for (int c = 0; c < nch; c++) {
-        const int cell = c * 32 + lane;
-        const int i = min(cell, ncell - 1) + 1;
-        const int j = i + d;
-        const int t = bf_ptype_bases(S[i], S[j]);
-        double accg = 0.0, acc1 = 0.0, accb = 0.0;
-        if (__any_sync(BF_FULL, t != 0)) {
-          for (int s = 2 + warp; s <= smax; s += NW) {
+    for (int d = BF_TURN + 1; d <= n; d++) {
+      if (warp == NW - 1 && d + 1 <= n - 1) {
+        const int cnt = build_pair_list(S, n, d + 1, LST + ((d + 1) & 1) * RS, lane);
+        if (lane == 0) s_np[(d + 1) & 1] = cnt;
+      }
+      // ------------------------------------------------------------ combine diagonal d-1
+      if (d > BF_TURN + 1) {
+        const int dd = d - 1, ncell = n - dd, buf = dd & 1;
+        const double *pi = PI + buf * NW * RS, *ps = PS + buf * NW * RS;
+        for (int cell = tid; cell < ncell; cell += blockDim.x) {
+          const int i = cell + 1, j = i + dd;
+          const int t = bf_ptype_bases(S[i], S[j]);
+          double qms = 0.0, qb = 0.0;
+#pragma unroll
+          for (int w = 0; w < NW; w++) qms += ps[w * RS + cell];
+          if (t) {
+#pragma unroll
+            for (int w = 0; w < NW; w++) qb += pi[w * RS + cell];
+            qb += QMS[((dd - 2) & 3) * RS + i + 1] * (xclose * bf_x_mlstem(T, bf_rtype(t), S[j - 1], S[i + 1]));
+          }
+          double qm1 = 0.0, au = 0.0;
+          if (dd > BF_TURN + 1) {
+            const int o = toff[dd - 1] + i - 1;
+            qm1 = QM1[o] * bu1;                                        // (i, j-1) plus one unpaired base
+            au = bu1 * (QM1[o + 1] + AU[((dd - 1) & 1) * RS + i + 1]);  // stems starting right of i
+          }
+          if (t && i > 1 && j < n) qm1 += qb * bf_x_mlstem(T, t, S[i - 1], S[j + 1]);
+          const double qm = qms + au + qm1;
+          const int o = toff[dd] + i - 1;
+          qb_out[o] = qb;
+          QM[o] = qm;
+          QM1[o] = qm1;
+          QMS[(dd & 3) * RS + i] = qms;
+          AU[(dd & 1) * RS + i] = au;
+          const int row = (dd & (kRing - 1)) * RS + i;
+          double g = 0.0, g1 = 0.0, gb = 0.0;
+          if (t) {
+            const int t2 = bf_rtype(t), a = S[j + 1], bb = S[i - 1];
+            g = qb * T.x_mmI[t2][a][bb];
+            g1 = qb * T.x_mm1nI[t2][a][bb];
+            gb = (t > 2) ? qb * xtau : qb;
+          }
+          QG[row] = g; Q1[row] = g1; QBB[row] = gb;
+        }
+      }
+      // ------------------------------------------------------------ partial sums of diagonal d
+      if (d <= n - 1) {
+        const int ncell = n - d, buf = d & 1;
+        double *pi = PI + (buf * NW + warp) * RS, *ps = PS + (buf * NW + warp) * RS;
+        const int smax = min(BF_MAXLOOP, d - 6);
+        const int np = s_np[buf];
+        const unsigned short *list = LST + buf * RS;
+        for (int c = 0; c < np; c += 32) {
+          const int kk = c + lane;
+          const int i = list[min(kk, np - 1)];
+          const int j = i + d;
+          const int t = bf_ptype_bases(S[i], S[j]);
+          const int si1 = S[i + 1], sj1 = S[j - 1];
+          double accg = 0.0, acc1 = 0.0, accb = 0.0;
+          BF_FOR_MY_S(NW, warp, smax, s) {
             const int row = ((d - 2 - s) & (kRing - 1)) * RS + i;
             accb += (QBB[row + 1] + QBB[row + 1 + s]) * wb[s];
             if (s >= 4) acc1 += (Q1[row + 2] + Q1[row + s]) * w1[s];
@@ -548,73 +663,30 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
               accg += a0 + a1;
             }
           }
-        }
-        double tot = 0.0;
-        if (t) {
-          const int si1 = S[i + 1], sj1 = S[j - 1];
-          tot = accg * T.x_mmI[t][si1][sj1] + acc1 * T.x_mm1nI[t][si1][sj1] + accb * (t > 2 ? T.x_TerminalAU : 1.0);
-        }
-        // ---- qm splits: k = u - i in [1, d-4]; qm1 lives on diagonal d-k (>= 4), qm on diagonal k-1 (>= 4 to be non-zero)
-        double accs = 0.0, accu = 0.0;
-        for (int k = 1 + warp; k <= d - 4; k += NW) {
-          const double r = QM1[tri_off(n, d - k) + i + k - 1];
-          accu = fma(bu[k], r, accu);
-          if (k >= 5) accs = fma(QM[tri_off(n, k - 1) + i - 1], r, accs);
-        }
-        if (warp == (c % NW)) {
-          double e = 0.0;
-          if (t) {
-            const int si1 = S[i + 1], sj1 = S[j - 1];
-            e = bf_x_hairpin(P, T, S, i, j, t) * scl[d + 1];
-            const int cu1[9] = {0, 0, 1, 1, 1, 2, 2, 2, 3}, cu2[9] = {0, 1, 0, 1, 2, 1, 2, 3, 2};
-#pragma unroll
-            for (int k = 0; k < 9; k++) {
-              const int u1 = cu1[k], u2 = cu2[k];
-              const int p = i + 1 + u1, q = j - 1 - u2;
-              if (q - p <= BF_TURN) continue;
-              const int t2 = bf_ptype_bases(S[p], S[q]);
-              if (!t2) continue;
-              // ring holds qb * terminalAU(t2); undo the factor
-              double qv = QBB[((q - p) & (kRing - 1)) * RS + p];
-              if (t2 > 2) qv *= 1.0 / T.x_TerminalAU;
-              e += qv * bf_x_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]) * scl[u1 + u2 + 2];
-            }
+          double tot = accg * T.x_mmI[t][si1][sj1] + acc1 * T.x_mm1nI[t][si1][sj1] + accb * (t > 2 ? xtau : 1.0);
+          for (int k = (warp + c + d) % NW; k < 10; k += NW) {
+            if (k == 9) { tot += bf_x_hairpin(P, T, S, i, j, t) * scl[d + 1]; continue; }
+            const int u1 = (0x322211100ull >> (4 * k)) & 15, u2 = (0x232121010ull >> (4 * k)) & 15;
+            const int p = i + 1 + u1, q = j - 1 - u2;
+            if (q - p <= BF_TURN) continue;
+            const int t2 = bf_ptype_bases(S[p], S[q]);
+            if (!t2) continue;
+            double qv = QBB[((q - p) & (kRing - 1)) * RS + p];  // qb * terminalAU(t2): undo the factor
+            if (t2 > 2) qv *= inv_tau;
+            tot += qv * bf_x_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]) * scl[u1 + u2 + 2];
           }
-          if (cell < ncell) HS[cell] = e;
+          if (kk < np) pi[i - 1] = tot;
         }
-        if (cell < ncell) { PI[warp * RS + cell] = tot; PS[warp * RS + cell] = accs; PB[warp * RS + cell] = accu; }
-      }
-      __syncthreads();
-      for (int cell = tid; cell < ncell; cell += blockDim.x) {
-        const int i = cell + 1, j = i + d;
-        const int t = bf_ptype_bases(S[i], S[j]);
-        double qms = 0.0, qmu = 0.0, qb = 0.0;
-#pragma unroll
-        for (int w = 0; w < NW; w++) { qms += PS[w * RS + cell]; qmu += PB[w * RS + cell]; }
-        if (t) {
-          qb = HS[cell];
-#pragma unroll
-          for (int w = 0; w < NW; w++) qb += PI[w * RS + cell];
-          qb += QMS[((d - 2) & 3) * RS + i + 1] * (T.x_MLclosing * bf_x_mlstem(T, bf_rtype(t), S[j - 1], S[i + 1]) * scl[2]);
+        // ---- qm split for every cell: k = u - i in [5, d-4] (qm on diagonal k-1 >= 4, qm1 on diagonal d-k >= 4)
+        for (int c = 0; c < ncell; c += 32) {
+          const int cell = c + lane;
+          const int i = min(cell, ncell - 1) + 1;
+          double accs = 0.0;
+          const double *left = QM + (i - 1), *right = QM1 + (i - 1);
+#pragma unroll 2
+          for (int k = 5 + warp; k <= d - 4; k += NW) accs = fma(left[toff[k - 1]], right[toff[d - k] + k], accs);
+          if (cell < ncell) ps[cell] = accs;
         }
-        double qm1 = 0.0;
-        if (d > BF_TURN + 1) qm1 = QM1[tri_off(n, d - 1) + i - 1] * bu[1];
-        if (t && i > 1 && j < n) qm1 += qb * bf_x_mlstem(T, t, S[i - 1], S[j + 1]);
-        const double qm = qms + qmu + qm1;
-        const int o = tri_off(n, d) + i - 1;
-        qb_out[o] = qb;
-        QM[o] = qm;
-        QM1[o] = qm1;
-        QMS[(d & 3) * RS + i] = qms;
-        const int row = (d & (kRing - 1)) * RS + i;
-        double g = 0.0, g1 = 0.0, gb = 0.0;
-        if (t) {
-          const int t2 = bf_rtype(t), a = S[j + 1], bb = S[i - 1];
-          g = qb * T.x_mmI[t2][a][bb];
-          g1 = qb * T.x_mm1nI[t2][a][bb];
-          gb = (t > 2) ? qb * T.x_TerminalAU : qb;
-        }
-        QG[row] = g; Q1[row] = g1; QBB[row] = gb;
       }
       __syncthreads();
     }
@@ -678,11 +750,10 @@ size_t pfext_smem(int nmax) {
 
 template <typename K>
 cudaError_t set_smem(K kern, size_t sm) {
-  if (sm > 48 * 1024) return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-  return cudaSuccess;
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sm > 1024 ? sm : 1024));
 }
 
-constexpr size_t kSmemBudget = 227 * 1024 - 14 * 1024;  // dynamic budget per CTA (static tables + reserve taken off)
+constexpr size_t kSmemBudget = 232448 - 1024 - 256;  // dynamic budget per CTA (static tables + reserve taken off)
 
 }  // namespace
 
@@ -691,34 +762,69 @@ constexpr size_t kSmemBudget = 227 * 1024 - 14 * 1024;  // dynamic budget per CT
 // =====================================================================================================
 size_t bf_tri_slot(int nmax) { return (tri_size(nmax) + 7) / 8 * 8; }
 
-// 0: not supported by the fill path; 1: fML on chip; 2: fML in HBM
+// ---- configuration: warps per CTA and table placement.  Defaults come from the tuning sweep on B200
+// (profiles/); BF_MFE_NW / BF_MFE_PL / BF_PF_NW / BF_PF_PL override them for experiments.
+static int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+struct FillCfg { int nw, pl; };
+
+static bool mfe_fits(int nmax, int nw, int pl) { return mfe_plan(nmax, nw, pl).total <= kSmemBudget; }
+static bool pf_fits(int nmax, int nw, int pl) { return pf_plan(nmax, nw, pl).total <= kSmemBudget; }
+
+static FillCfg mfe_cfg(int nmax) {
+  FillCfg c;
+  c.nw = env_int("BF_MFE_NW", 8);
+  if (c.nw != 2 && c.nw != 4) c.nw = 8;
+  // default (tuning sweep, profiles/r01_sweeps.md): rings on chip while >= 3 CTAs still fit on an SM, else everything through L2
+  const int dflt = mfe_plan(nmax, c.nw, kMfeRgSmem).total <= 74 * 1024 ? kMfeRgSmem : 0;
+  const int want = env_int("BF_MFE_PL", dflt);
+  const int tb = want & kTabSmem;
+  const int order[4] = {want & 11, (want & kMfeRgSmem) | tb, want & kMfeRgSmem, 0};
+  for (int k = 0; k < 4; k++)
+    if (mfe_fits(nmax, c.nw, order[k])) { c.pl = order[k]; return c; }
+  c.pl = -1;
+  return c;
+}
+static FillCfg pf_cfg(int nmax) {
+  FillCfg c;
+  c.nw = env_int("BF_PF_NW", 8);
+  if (c.nw != 2 && c.nw != 4) c.nw = 8;
+  const int dflt = pf_plan(nmax, c.nw, kPfQgSmem).total <= 74 * 1024 ? kPfQgSmem : 0;
+  const int want = env_int("BF_PF_PL", dflt);
+  const int tb = want & kTabSmem;
+  const int order[4] = {want & 15, (want & (kPfQgSmem | kPfR2Smem)) | tb, (want & kPfQgSmem) | tb, 0};
+  for (int k = 0; k < 4; k++)
+    if (pf_fits(nmax, c.nw, order[k])) { c.pl = order[k]; return c; }
+  c.pl = -1;
+  return c;
+}
+
+// 0: length not covered by the fill path (the generic kernels take it); else 1 + placement flags
 int bf_fill_mfe_mode(int nmax) {
   if (nmax < 1 || nmax > 2000) return 0;
-  if (mfe_plan(nmax, 8, true).total <= kSmemBudget) return 1;
-  if (mfe_plan(nmax, 8, false).total <= kSmemBudget) return 2;
-  return 0;
+  return mfe_cfg(nmax).pl + 1;
 }
 int bf_fill_pf_mode(int nmax) {
   if (nmax < 1 || nmax > 2000) return 0;
-  if (pf_plan(nmax, 8, true, true).total <= kSmemBudget) return 1;
-  if (pf_plan(nmax, 8, false, true).total <= kSmemBudget) return 2;
-  if (pf_plan(nmax, 8, false, false).total <= kSmemBudget) return 3;
-  return 0;
+  return pf_cfg(nmax).pl + 1;
 }
-// doubles of per-CTA HBM workspace the PF fill needs in this mode
-size_t bf_pf_ws_slot(int nmax) {
-  const int mode = bf_fill_pf_mode(nmax);
-  const size_t rs = pf_plan(nmax, 8, false, false).rs;
-  if (mode == 2) return 2 * bf_tri_slot(nmax);
-  if (mode == 3) return 2 * bf_tri_slot(nmax) + (2 * kRing * rs + 7) / 8 * 8;
-  return 0;
+size_t bf_mfe_ws_slot(int nmax) {  // ints of per-CTA HBM workspace
+  const FillCfg c = mfe_cfg(nmax);
+  if (c.pl < 0 || (c.pl & kMfeRgSmem)) return 0;
+  return ((size_t)3 * kRing * mfe_plan(nmax, c.nw, c.pl).rs + 7) / 8 * 8;
+}
+size_t bf_pf_ws_slot(int nmax) {  // doubles of per-CTA HBM workspace
+  const FillCfg c = pf_cfg(nmax);
+  return c.pl < 0 ? 0 : pf_ws_doubles(nmax, c.pl);
 }
 
-template <int NW, bool FM>
-static cudaError_t launch_mfe_fill_t(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, size_t slot, int sms, int *counter,
-                                     cudaStream_t st) {
-  auto kern = bf_k_mfe_fill<NW, FM>;
-  const size_t sm = mfe_plan(b.stride, NW, FM).total;
+template <int NW, int PL>
+static cudaError_t mfe_fill_t(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *grid_out, bool launch,
+                              int *counter, cudaStream_t st) {
+  auto kern = bf_k_mfe_fill<NW, PL>;
+  const size_t sm = mfe_plan(b.stride, NW, PL).total;
   cudaError_t e = set_smem(kern, sm);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -726,18 +832,43 @@ static cudaError_t launch_mfe_fill_t(const BfParams *dP, const BfBatchDev &b, in
   if (e != cudaSuccess) return e;
   if (occ < 1) return cudaErrorInvalidConfiguration;
   const int grid = b.B < sms * occ ? b.B : sms * occ;
-  kern<<<grid, NW * 32, sm, st>>>(dP, b, ctri, ftri, slot, counter);
+  if (grid_out) *grid_out = grid;
+  if (!launch) return cudaSuccess;
+  kern<<<grid, NW * 32, sm, st>>>(dP, b, ctri, ftri, bf_tri_slot(b.stride), ws, bf_mfe_ws_slot(b.stride), counter);
   return cudaGetLastError();
 }
 
-cudaError_t bf_launch_mfe_fill(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int sms, int *work_counter, cudaStream_t st) {
+template <int NW>
+static cudaError_t mfe_fill_pl(int pl, const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *grid_out,
+                               bool launch, int *counter, cudaStream_t st) {
+  switch (pl) {
+    case 0: return mfe_fill_t<NW, 0>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
+    case 1: return mfe_fill_t<NW, 1>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
+    case 2: return mfe_fill_t<NW, 2>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
+    case 3: return mfe_fill_t<NW, 3>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
+    case 8: return mfe_fill_t<NW, 8>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
+    case 9: return mfe_fill_t<NW, 9>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
+    case 10: return mfe_fill_t<NW, 10>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
+    case 11: return mfe_fill_t<NW, 11>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
+  }
+  return cudaErrorInvalidValue;
+}
+static cudaError_t mfe_fill_dispatch(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *grid_out,
+                                     bool launch, int *counter, cudaStream_t st) {
+  const FillCfg c = mfe_cfg(b.stride);
+  if (c.pl < 0) return cudaErrorInvalidValue;
+  if (c.nw == 4) return mfe_fill_pl<4>(c.pl, dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
+  if (c.nw == 2) return mfe_fill_pl<2>(c.pl, dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
+  return mfe_fill_pl<8>(c.pl, dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
+}
+cudaError_t bf_mfe_fill_grid(const BfBatchDev &b, int sms, int *grid) {
+  return mfe_fill_dispatch(nullptr, b, nullptr, nullptr, nullptr, sms, grid, false, nullptr, nullptr);
+}
+cudaError_t bf_launch_mfe_fill(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *work_counter,
+                               cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
-  const size_t slot = bf_tri_slot(b.stride);
-  const int mode = bf_fill_mfe_mode(b.stride);
-  if (mode == 1) return launch_mfe_fill_t<8, true>(dP, b, ctri, ftri, slot, sms, work_counter, st);
-  if (mode == 2) return launch_mfe_fill_t<8, false>(dP, b, ctri, ftri, slot, sms, work_counter, st);
-  return cudaErrorInvalidValue;
+  return mfe_fill_dispatch(dP, b, ctri, ftri, ws, sms, nullptr, true, work_counter, st);
 }
 
 cudaError_t bf_launch_trace(const BfParams *dP, const BfBatchDev &b, const int *ctri, const int *ftri, int *out_mfe, char *out_ss,
@@ -750,11 +881,11 @@ cudaError_t bf_launch_trace(const BfParams *dP, const BfBatchDev &b, const int *
   return cudaGetLastError();
 }
 
-template <int NW, bool QM, bool RG>
-static cudaError_t pf_fill_t(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *qmws, const int *mfe_for_scale, double *lnscale,
+template <int NW, int PL>
+static cudaError_t pf_fill_t(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, const int *mfe_for_scale, double *lnscale,
                              int sms, int *grid_out, bool launch, int *counter, cudaStream_t st) {
-  auto kern = bf_k_pf_fill<NW, QM, RG>;
-  const size_t sm = pf_plan(b.stride, NW, QM, RG).total;
+  auto kern = bf_k_pf_fill<NW, PL>;
+  const size_t sm = pf_plan(b.stride, NW, PL).total;
   cudaError_t e = set_smem(kern, sm);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -764,20 +895,34 @@ static cudaError_t pf_fill_t(const BfParams *dP, const BfBatchDev &b, double *qb
   const int grid = b.B < sms * occ ? b.B : sms * occ;
   if (grid_out) *grid_out = grid;
   if (!launch) return cudaSuccess;
-  kern<<<grid, NW * 32, sm, st>>>(dP, b, qbtri, bf_tri_slot(b.stride), qmws, bf_pf_ws_slot(b.stride), mfe_for_scale, lnscale, counter);
+  kern<<<grid, NW * 32, sm, st>>>(dP, b, qbtri, bf_tri_slot(b.stride), ws, bf_pf_ws_slot(b.stride), mfe_for_scale, lnscale, counter);
   return cudaGetLastError();
 }
-
-static cudaError_t pf_fill_dispatch(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *qmws, const int *mfe_for_scale,
-                                    double *lnscale, int sms, int *grid_out, bool launch, int *counter, cudaStream_t st) {
-  const int mode = bf_fill_pf_mode(b.stride);
-  if (mode == 1) return pf_fill_t<8, true, true>(dP, b, qbtri, qmws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
-  if (mode == 2) return pf_fill_t<8, false, true>(dP, b, qbtri, qmws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
-  if (mode == 3) return pf_fill_t<8, false, false>(dP, b, qbtri, qmws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+template <int NW>
+static cudaError_t pf_fill_pl(int pl, const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, const int *mfe_for_scale,
+                              double *lnscale, int sms, int *grid_out, bool launch, int *counter, cudaStream_t st) {
+  switch (pl) {
+    case 0: return pf_fill_t<NW, 0>(dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    case 4: return pf_fill_t<NW, 4>(dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    case 6: return pf_fill_t<NW, 6>(dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    case 7: return pf_fill_t<NW, 7>(dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    case 8: return pf_fill_t<NW, 8>(dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    case 12: return pf_fill_t<NW, 12>(dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    case 14: return pf_fill_t<NW, 14>(dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    case 15: return pf_fill_t<NW, 15>(dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+  }
   return cudaErrorInvalidValue;
 }
+static cudaError_t pf_fill_dispatch(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, const int *mfe_for_scale,
+                                    double *lnscale, int sms, int *grid_out, bool launch, int *counter, cudaStream_t st) {
+  const FillCfg c = pf_cfg(b.stride);
+  if (c.pl < 0) return cudaErrorInvalidValue;
+  if (c.nw == 4) return pf_fill_pl<4>(c.pl, dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+  if (c.nw == 2) return pf_fill_pl<2>(c.pl, dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+  return pf_fill_pl<8>(c.pl, dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+}
 
-// grid size the PF fill will use (the caller sizes the per-CTA workspace with it in modes 2 and 3)
+// grid size the fill will use (the caller sizes the per-CTA workspace with it)
 cudaError_t bf_pf_fill_grid(const BfBatchDev &b, int sms, int *grid) {
   return pf_fill_dispatch(nullptr, b, nullptr, nullptr, nullptr, nullptr, sms, grid, false, nullptr, nullptr);
 }

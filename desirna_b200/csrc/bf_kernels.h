@@ -23,11 +23,14 @@ cudaError_t bf_launch_eval(const BfParams *dP, const BfBatchDev &b, const char *
 
 // ---- diagonal-major fill path for single-strand batches (bf_fill.cu)
 size_t bf_tri_slot(int nmax);      // entries of one packed triangular table (per sequence)
-int bf_fill_mfe_mode(int nmax);    // 0: length not covered (use the generic kernels), 1: fML on chip, 2: fML in HBM
-int bf_fill_pf_mode(int nmax);     // 0 | 1: all on chip | 2: qm/qm1 in HBM | 3: qm/qm1 and the small rings in HBM
+int bf_fill_mfe_mode(int nmax);    // 0: length not covered (the generic kernels take it); else 1 + placement flags
+int bf_fill_pf_mode(int nmax);
+size_t bf_mfe_ws_slot(int nmax);   // ints of per-CTA HBM workspace of the MFE fill
 size_t bf_pf_ws_slot(int nmax);    // doubles of per-CTA HBM workspace of the PF fill
+cudaError_t bf_mfe_fill_grid(const BfBatchDev &b, int sms, int *grid);
 cudaError_t bf_pf_fill_grid(const BfBatchDev &b, int sms, int *grid);
-cudaError_t bf_launch_mfe_fill(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int sms, int *work_counter, cudaStream_t st);
+cudaError_t bf_launch_mfe_fill(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *work_counter,
+                               cudaStream_t st);
 cudaError_t bf_launch_trace(const BfParams *dP, const BfBatchDev &b, const int *ctri, const int *ftri, int *out_mfe, char *out_ss,
                             int ss_stride, cudaStream_t st);
 cudaError_t bf_launch_pf_fill(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *qmws, const int *mfe_for_scale,
