@@ -1,0 +1,161 @@
+"""CPU: the lock-step replica loop makes the same decisions, from the same random draws, as the reference's
+one-process-per-replica loop (utils/replica_exchange_monte_carlo.py:176-271), also when sharded over two ranks."""
+import os
+import random
+import subprocess
+import sys
+import types
+
+import pytest
+
+from conftest import PAR1999, ROOT, load_golden
+
+TARGET = "((((((.((((((((....))))).)).).))))))"
+
+
+class Stats:
+    def __init__(self):
+        self.global_step = self.step = 0
+        self.acc_mc_step = self.acc_mc_better_e = self.rej_mc_step = 0
+        self.acc_re_step = self.acc_re_better_e = self.rej_re_step = 0
+
+    def update_step(self, n): self.step += n
+    def reset_mc_stats(self): self.acc_mc_step = self.acc_mc_better_e = self.rej_mc_step = 0
+    def update_acc_mc_step(self): self.acc_mc_step += 1
+    def update_acc_mc_better_e(self): self.acc_mc_better_e += 1
+    def update_rej_mc_step(self): self.rej_mc_step += 1
+    def update_acc_re_step(self): self.acc_re_step += 1
+    def update_acc_re_better_e(self): self.acc_re_better_e += 1
+    def update_rej_re_step(self): self.rej_re_step += 1
+
+
+def toy_mutate(seq_obj, nt_list, sim_options, input_file):
+    """stand-in for DesiRNA's move generator: a point mutation drawn from the global `random` stream, ending, like
+    sequence_utils.mutate_sequence (:1132-1136), in es.score_sequence + the two stamps"""
+    from desirna_b200.utils import energy_scores as es
+    s = seq_obj.sequence
+    pos = random.randrange(len(s))
+    new = s[:pos] + random.choice("ACGU") + s[pos + 1:]
+    out = es.score_sequence(new, input_file, sim_options)
+    out.get_replica_num(seq_obj.replica_num)
+    out.get_temp_shelf(seq_obj.temp_shelf)
+    return out
+
+
+def setup(R):
+    from desirna_b200 import RNA
+    from desirna_b200.utils import energy_scores as es
+    from oracle_backend import OracleBackend
+    RNA.set_backend(OracleBackend(PAR1999))
+    opt = types.SimpleNamespace(oligo_state="none", pks="off", scoring_f=[("Ed-Epf", 1.0)], subopt="off", motifs={}, RE_attempt=6, L=504.12, replicas=R)
+    inp = types.SimpleNamespace(sec_struct=TARGET, alt_sec_struct=None, alt_sec_structs=None)
+    rows = load_golden("G1")[:R]
+    objs = []
+    for r, row in enumerate(rows):
+        o = es.score_sequence(row["sequence"], inp, opt)
+        o.get_replica_num(r + 1)
+        o.get_temp_shelf(10.0 + 20.0 * r)
+        objs.append(o)
+    return opt, inp, objs
+
+
+def reference_order(objs, opt, inp):
+    """what the reference's pool does: replica after replica, each on random.seed(index)"""
+    from desirna_b200.utils import replica_exchange_monte_carlo as remc
+    out, tot = [], Stats()
+    for idx, o in enumerate(objs):
+        random.seed(idx)
+        ws = Stats()
+        res, ws = remc.single_replica_design(o, None, ws, opt, inp, mutate=toy_mutate)
+        out.append(res)
+        for a in ("acc_mc_step", "acc_mc_better_e", "rej_mc_step"):
+            setattr(tot, a, getattr(tot, a) + getattr(ws, a))
+    return out, tot
+
+
+def test_lockstep_equals_sequential():
+    from desirna_b200 import RNA
+    from desirna_b200.utils import replica_exchange_monte_carlo as remc
+    old = RNA.get_backend()
+    try:
+        opt, inp, objs = setup(5)
+        want, wstats = reference_order(objs, opt, inp)
+        be = RNA.get_backend()
+        calls0 = be.calls
+        random.seed(2137)
+        got, st = remc.mutate_sequence_re(objs, None, Stats(), opt, inp, mutate=toy_mutate)
+        assert random.random() == random.Random(2137).random()  # the parent stream is untouched
+        assert be.calls - calls0 == opt.RE_attempt              # ONE engine call per sub-step for all replicas
+        assert [vars(a) for a in got] == [vars(b) for b in want]
+        assert (st.acc_mc_step, st.acc_mc_better_e, st.rej_mc_step) == (wstats.acc_mc_step, wstats.acc_mc_better_e, wstats.rej_mc_step)
+        assert st.step == opt.RE_attempt
+    finally:
+        RNA.set_backend(old)
+
+
+def test_replica_exchange_swaps_neighbours():
+    from desirna_b200.utils import replica_exchange_monte_carlo as remc
+    old = __import__("desirna_b200").RNA.get_backend()
+    try:
+        opt, inp, objs = setup(5)
+        st = Stats(); st.global_step = 1          # odd step: pairs (0,1), (2,3)
+        objs[0].scoring_function, objs[1].scoring_function = 5.0, 1.0   # colder replica is worse -> certain swap
+        t0, t1 = objs[0].temp_shelf, objs[1].temp_shelf
+        random.seed(1)
+        out, st = remc.replica_exchange(objs, st, opt)
+        assert [o.replica_num for o in out] == [1, 2, 3, 4, 5]
+        assert (out[0].temp_shelf, out[1].temp_shelf) == (t1, t0)
+        assert st.acc_re_step + st.rej_re_step == 2
+    finally:
+        __import__("desirna_b200").RNA.set_backend(old)
+
+
+WORKER = r'''
+import os, sys, random, pickle
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import torch.distributed as dist
+import test_remc_lockstep as T
+from desirna_b200.utils import replica_exchange_monte_carlo as remc
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+opt, inp, objs = T.setup(5)
+random.seed(2137)
+got, st = remc.mutate_sequence_re(objs, None, T.Stats(), opt, inp, mutate=T.toy_mutate)
+st.global_step = 1
+got, st = remc.replica_exchange(got, st, opt)
+pickle.dump(([vars(o) for o in got], vars(st)), open(sys.argv[4] + ".%s" % sys.argv[3], "wb"))
+dist.destroy_process_group()
+'''
+
+
+def test_two_ranks_gloo_match_single_process(tmp_path):
+    import pickle
+    from desirna_b200 import RNA
+    from desirna_b200.utils import replica_exchange_monte_carlo as remc
+    old = RNA.get_backend()
+    try:
+        opt, inp, objs = setup(5)
+        random.seed(2137)
+        want, st = remc.mutate_sequence_re(objs, None, Stats(), opt, inp, mutate=toy_mutate)
+        st.global_step = 1
+        want, st = remc.replica_exchange(want, st, opt)
+    finally:
+        RNA.set_backend(old)
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    out = str(tmp_path / "res")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), out]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=240) == 0
+    for r in range(2):
+        got, gst = pickle.load(open(out + ".%d" % r, "rb"))
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            vb = vars(b)
+            for k, v in a.items():
+                if isinstance(v, float):
+                    assert abs(v - vb[k]) < 1e-12, k
+                else:
+                    assert v == vb[k], k
+        for k in ("acc_mc_step", "acc_mc_better_e", "rej_mc_step", "acc_re_step", "rej_re_step", "step"):
+            assert gst[k] == vars(st)[k], k
