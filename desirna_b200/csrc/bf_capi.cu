@@ -38,10 +38,10 @@ struct Engine {
   BfParams *dP = nullptr;  // device image
   int *d_counters = nullptr;  // work counters (one per kernel kind)
   DevBuf ws_mfe, ws_pf, d_mfe_scratch;
-  DevBuf tri_c, tri_f, tri_qb, ws_qm, ws_ring, d_lnscale;  // diagonal-major fill path (bf_fill.cu)
+  DevBuf tri_c, tri_f, tri_qb, ws_qm, ws_ring, d_lnscale, qm_seq, ws_out;  // diagonal-major fill path (bf_fill.cu)
   bool force_generic = false;                     // BF_FORCE_GENERIC=1: route single strands through the generic kernels too
   // staging for the host-buffer entry point
-  DevBuf d_seq, d_len, d_cut, d_nopair, d_targets, d_mfe, d_ss, d_pf, d_eval;
+  DevBuf d_seq, d_len, d_cut, d_nopair, d_targets, d_mfe, d_ss, d_pf, d_eval, d_defect, d_bpp;
   int64_t launches = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // begin/end of mfe, pf, eval in the last call
   bool ran[3] = {false, false, false};
@@ -75,7 +75,9 @@ int validate(const bf_batch_t *b, const bf_result_t *r) {
   if ((b->want & BF_WANT_MFE) && !r->mfe_dcal) return fail(BF_ERR_ARG, "BF_WANT_MFE without mfe_dcal buffer");
   if ((b->want & BF_WANT_PF) && !r->pf) return fail(BF_ERR_ARG, "BF_WANT_PF without pf buffer");
   if ((b->want & BF_WANT_EVAL) && (!r->eval_dcal || !b->targets || b->n_targets <= 0)) return fail(BF_ERR_ARG, "BF_WANT_EVAL without targets/eval_dcal");
-  if (b->want & (BF_WANT_BPP | BF_WANT_DEFECT)) return fail(BF_ERR_UNAVAILABLE, "bpp / ensemble defect kernels are not built yet");
+  if ((b->want & BF_WANT_DEFECT) && (!r->defect || !b->targets || b->n_targets <= 0)) return fail(BF_ERR_ARG, "BF_WANT_DEFECT without targets/defect buffer");
+  if ((b->want & BF_WANT_BPP) && !r->bpp) return fail(BF_ERR_ARG, "BF_WANT_BPP without bpp buffer");
+  if ((b->want & (BF_WANT_BPP | BF_WANT_DEFECT)) && !r->pf) return fail(BF_ERR_ARG, "BF_WANT_BPP/DEFECT need the pf buffer too");
   return BF_OK;
 }
 
@@ -123,7 +125,10 @@ int run_device(const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t
     g.ran[0] = true;
     mfe_for_scale = out_mfe;
   }
-  if (b->want & BF_WANT_PF) {
+  const bool want_out = (b->want & (BF_WANT_BPP | BF_WANT_DEFECT)) != 0;
+  if (want_out && (two || !fill_pf))
+    return fail(BF_ERR_UNAVAILABLE, "base-pair probabilities / ensemble defect: single-strand sequences within the fill path's length range only");
+  if ((b->want & BF_WANT_PF) || want_out) {
     BfBatchDev dbp = db;
     dbp.nopair = nullptr;  // hard constraints are added after fc.pf() in the reference (sequence_utils.py:1181)
     // a constrained MFE is not a bound on the unconstrained ensemble: only use it for scaling when unconstrained
@@ -137,10 +142,26 @@ int run_device(const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t
       CU(bf_pf_fill_grid(dbp, g.sm_count, &grid), "size bf_k_pf_fill");
       const size_t ws = bf_pf_ws_slot(b->stride) * sizeof(double);
       if (ws) CU(g.ws_qm.reserve((size_t)grid * ws), "cudaMalloc(qm workspace)");
-      CU(bf_launch_pf_fill(g.dP, dbp, (double *)g.tri_qb.p, (double *)g.ws_qm.p, scale_src, (double *)g.d_lnscale.p, g.sm_count,
+      double *qmseq = nullptr;
+      if (want_out) {
+        CU(g.qm_seq.reserve((size_t)b->B * 2 * slot), "cudaMalloc(per-sequence qm/qm1)");
+        qmseq = (double *)g.qm_seq.p;
+      }
+      CU(bf_launch_pf_fill(g.dP, dbp, (double *)g.tri_qb.p, (double *)g.ws_qm.p, qmseq, scale_src, (double *)g.d_lnscale.p, g.sm_count,
                            g.d_counters + 1, st), "launch bf_k_pf_fill");
       CU(bf_launch_pf_ext(g.dP, dbp, (const double *)g.tri_qb.p, (const double *)g.d_lnscale.p, r->pf, st), "launch bf_k_pf_ext");
       g.launches += 2;
+      if (want_out) {
+        int ogrid = 0;
+        CU(bf_out_grid(dbp, g.sm_count, &ogrid), "size bf_k_pf_out");
+        CU(g.ws_out.reserve((size_t)ogrid * bf_out_ws_slot(b->stride) * sizeof(double)), "cudaMalloc(outside workspace)");
+        if (b->want & BF_WANT_BPP) CU(cudaMemsetAsync(r->bpp, 0, (size_t)b->B * b->stride * b->stride * sizeof(double), st), "clear bpp");
+        CU(bf_launch_pf_out(g.dP, dbp, (const double *)g.tri_qb.p, qmseq, (double *)g.ws_out.p, (const double *)g.d_lnscale.p,
+                            (b->want & BF_WANT_DEFECT) ? b->targets : nullptr, b->n_targets, b->stride,
+                            (b->want & BF_WANT_DEFECT) ? r->defect : nullptr, (b->want & BF_WANT_BPP) ? r->bpp : nullptr, ogrid,
+                            g.d_counters + 2, st), "launch bf_k_pf_out");
+        g.launches++;
+      }
     } else {
       int occ = bf_occupancy_pf(two, wstride);
       int grid = std::min(b->B, g.sm_count * occ);
@@ -201,7 +222,7 @@ int bf_init(int device) {
 int bf_shutdown(void) {
   if (!g.inited) return BF_OK;
   cudaStreamSynchronize(g.stream);
-  for (DevBuf *b : {&g.tri_c, &g.tri_f, &g.tri_qb, &g.ws_qm, &g.ws_ring, &g.d_lnscale, &g.ws_mfe, &g.ws_pf, &g.d_mfe_scratch, &g.d_seq, &g.d_len, &g.d_cut, &g.d_nopair, &g.d_targets, &g.d_mfe, &g.d_ss, &g.d_pf, &g.d_eval}) b->release();
+  for (DevBuf *b : {&g.tri_c, &g.tri_f, &g.tri_qb, &g.ws_qm, &g.ws_ring, &g.d_lnscale, &g.qm_seq, &g.ws_out, &g.d_defect, &g.d_bpp, &g.ws_mfe, &g.ws_pf, &g.d_mfe_scratch, &g.d_seq, &g.d_len, &g.d_cut, &g.d_nopair, &g.d_targets, &g.d_mfe, &g.d_ss, &g.d_pf, &g.d_eval}) b->release();
   if (g.dP) cudaFree(g.dP);
   if (g.d_counters) cudaFree(g.d_counters);
   cudaStreamDestroy(g.stream);
@@ -307,7 +328,7 @@ int bf_score_batch(const bf_batch_t *b, bf_result_t *r) {
     CU(cudaMemcpyAsync(g.d_nopair.p, b->nopair, B * S, cudaMemcpyHostToDevice, st), "H2D nopair");
     db.nopair = (const uint8_t *)g.d_nopair.p;
   }
-  if (b->want & BF_WANT_EVAL) {
+  if (b->want & (BF_WANT_EVAL | BF_WANT_DEFECT)) {
     size_t tb = B * (size_t)b->n_targets * S;
     CU(g.d_targets.reserve(tb), "cudaMalloc(targets)");
     CU(cudaMemcpyAsync(g.d_targets.p, b->targets, tb, cudaMemcpyHostToDevice, st), "H2D targets");
@@ -315,15 +336,19 @@ int bf_score_batch(const bf_batch_t *b, bf_result_t *r) {
     CU(g.d_eval.reserve(B * b->n_targets * sizeof(int)), "cudaMalloc(eval)");
     dr.eval_dcal = (int32_t *)g.d_eval.p;
   }
+  if (b->want & BF_WANT_DEFECT) { CU(g.d_defect.reserve(B * sizeof(double)), "cudaMalloc(defect)"); dr.defect = (double *)g.d_defect.p; }
+  if (b->want & BF_WANT_BPP) { CU(g.d_bpp.reserve(B * S * S * sizeof(double)), "cudaMalloc(bpp)"); dr.bpp = (double *)g.d_bpp.p; }
   if (b->want & (BF_WANT_MFE | BF_WANT_SS)) { CU(g.d_mfe.reserve(B * sizeof(int)), "cudaMalloc(mfe)"); dr.mfe_dcal = (int32_t *)g.d_mfe.p; }
   if (b->want & BF_WANT_SS) { CU(g.d_ss.reserve(B * (S + 1)), "cudaMalloc(ss)"); dr.mfe_ss = (char *)g.d_ss.p; }
-  if (b->want & BF_WANT_PF) { CU(g.d_pf.reserve(B * 5 * sizeof(double)), "cudaMalloc(pf)"); dr.pf = (double *)g.d_pf.p; }
+  if (b->want & (BF_WANT_PF | BF_WANT_BPP | BF_WANT_DEFECT)) { CU(g.d_pf.reserve(B * 5 * sizeof(double)), "cudaMalloc(pf)"); dr.pf = (double *)g.d_pf.p; }
   rc = run_device(&db, &dr, two, st);
   if (rc) return rc;
   if ((b->want & BF_WANT_MFE) && r->mfe_dcal) CU(cudaMemcpyAsync(r->mfe_dcal, dr.mfe_dcal, B * sizeof(int), cudaMemcpyDeviceToHost, st), "D2H mfe");
   if (b->want & BF_WANT_SS) CU(cudaMemcpyAsync(r->mfe_ss, dr.mfe_ss, B * (S + 1), cudaMemcpyDeviceToHost, st), "D2H ss");
-  if (b->want & BF_WANT_PF) CU(cudaMemcpyAsync(r->pf, dr.pf, B * 5 * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H pf");
+  if ((b->want & (BF_WANT_PF | BF_WANT_BPP | BF_WANT_DEFECT)) && r->pf) CU(cudaMemcpyAsync(r->pf, dr.pf, B * 5 * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H pf");
   if (b->want & BF_WANT_EVAL) CU(cudaMemcpyAsync(r->eval_dcal, dr.eval_dcal, B * b->n_targets * sizeof(int), cudaMemcpyDeviceToHost, st), "D2H eval");
+  if (b->want & BF_WANT_DEFECT) CU(cudaMemcpyAsync(r->defect, dr.defect, B * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H defect");
+  if (b->want & BF_WANT_BPP) CU(cudaMemcpyAsync(r->bpp, dr.bpp, B * S * S * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H bpp");
   CU(cudaStreamSynchronize(st), "bf_score_batch");
   return BF_OK;
 }

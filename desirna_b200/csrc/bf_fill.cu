@@ -505,8 +505,8 @@ __host__ __device__ inline size_t pf_ws_doubles(int nmax, int pl) {
 //         = bu (qm1(i+1,j) + A(i+1,j)): the unpaired-prefix part is carried along the diagonals in O(1) per cell.
 template <int NW, int PL>
 __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restrict__ P, BfBatchDev b, double *qbtri, size_t tri_slot,
-                                                        double *ws, size_t ws_slot, const int *mfe_for_scale, double *lnscale_out,
-                                                        int *work_counter) {
+                                                        double *ws, size_t ws_slot, double *qm_perseq, const int *mfe_for_scale,
+                                                        double *lnscale_out, int *work_counter) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ int s_seq, s_np[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -580,6 +580,10 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
       w1[tid] = (tid >= 4 && tid <= 30) ? T.x_interior[tid] * T.x_ninio[tid - 2] * scl[tid + 2] : 0.0;
     }
     double *qb_out = qbtri + (size_t)sq * tri_slot;
+    if (qm_perseq) {  // the outside pass needs qm and qm1 of every sequence: keep them per sequence instead of per CTA
+      QM = qm_perseq + (size_t)sq * 2 * tri_slot;
+      QM1 = QM + tri_slot;
+    }
     const double bu1 = exp(log(T.x_MLbase) - lns);
     const double xtau = T.x_TerminalAU, inv_tau = 1.0 / xtau;
     const double xclose = T.x_MLclosing * exp(-2.0 * lns);
@@ -882,7 +886,7 @@ cudaError_t bf_launch_trace(const BfParams *dP, const BfBatchDev &b, const int *
 }
 
 template <int NW, int PL>
-static cudaError_t pf_fill_t(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, const int *mfe_for_scale, double *lnscale,
+static cudaError_t pf_fill_t(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale, double *lnscale,
                              int sms, int *grid_out, bool launch, int *counter, cudaStream_t st) {
   auto kern = bf_k_pf_fill<NW, PL>;
   const size_t sm = pf_plan(b.stride, NW, PL).total;
@@ -895,43 +899,43 @@ static cudaError_t pf_fill_t(const BfParams *dP, const BfBatchDev &b, double *qb
   const int grid = b.B < sms * occ ? b.B : sms * occ;
   if (grid_out) *grid_out = grid;
   if (!launch) return cudaSuccess;
-  kern<<<grid, NW * 32, sm, st>>>(dP, b, qbtri, bf_tri_slot(b.stride), ws, bf_pf_ws_slot(b.stride), mfe_for_scale, lnscale, counter);
+  kern<<<grid, NW * 32, sm, st>>>(dP, b, qbtri, bf_tri_slot(b.stride), ws, bf_pf_ws_slot(b.stride), qmseq, mfe_for_scale, lnscale, counter);
   return cudaGetLastError();
 }
 template <int NW>
-static cudaError_t pf_fill_pl(int pl, const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, const int *mfe_for_scale,
+static cudaError_t pf_fill_pl(int pl, const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale,
                               double *lnscale, int sms, int *grid_out, bool launch, int *counter, cudaStream_t st) {
   switch (pl) {
-    case 0: return pf_fill_t<NW, 0>(dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
-    case 4: return pf_fill_t<NW, 4>(dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
-    case 6: return pf_fill_t<NW, 6>(dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
-    case 7: return pf_fill_t<NW, 7>(dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
-    case 8: return pf_fill_t<NW, 8>(dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
-    case 12: return pf_fill_t<NW, 12>(dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
-    case 14: return pf_fill_t<NW, 14>(dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
-    case 15: return pf_fill_t<NW, 15>(dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    case 0: return pf_fill_t<NW, 0>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    case 4: return pf_fill_t<NW, 4>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    case 6: return pf_fill_t<NW, 6>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    case 7: return pf_fill_t<NW, 7>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    case 8: return pf_fill_t<NW, 8>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    case 12: return pf_fill_t<NW, 12>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    case 14: return pf_fill_t<NW, 14>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    case 15: return pf_fill_t<NW, 15>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
   }
   return cudaErrorInvalidValue;
 }
-static cudaError_t pf_fill_dispatch(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, const int *mfe_for_scale,
+static cudaError_t pf_fill_dispatch(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale,
                                     double *lnscale, int sms, int *grid_out, bool launch, int *counter, cudaStream_t st) {
   const FillCfg c = pf_cfg(b.stride);
   if (c.pl < 0) return cudaErrorInvalidValue;
-  if (c.nw == 4) return pf_fill_pl<4>(c.pl, dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
-  if (c.nw == 2) return pf_fill_pl<2>(c.pl, dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
-  return pf_fill_pl<8>(c.pl, dP, b, qbtri, ws, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+  if (c.nw == 4) return pf_fill_pl<4>(c.pl, dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+  if (c.nw == 2) return pf_fill_pl<2>(c.pl, dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+  return pf_fill_pl<8>(c.pl, dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
 }
 
 // grid size the fill will use (the caller sizes the per-CTA workspace with it)
 cudaError_t bf_pf_fill_grid(const BfBatchDev &b, int sms, int *grid) {
-  return pf_fill_dispatch(nullptr, b, nullptr, nullptr, nullptr, nullptr, sms, grid, false, nullptr, nullptr);
+  return pf_fill_dispatch(nullptr, b, nullptr, nullptr, nullptr, nullptr, nullptr, sms, grid, false, nullptr, nullptr);
 }
 
-cudaError_t bf_launch_pf_fill(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *qmws, const int *mfe_for_scale,
+cudaError_t bf_launch_pf_fill(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *qmws, double *qmseq, const int *mfe_for_scale,
                               double *lnscale, int sms, int *work_counter, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
-  return pf_fill_dispatch(dP, b, qbtri, qmws, mfe_for_scale, lnscale, sms, nullptr, true, work_counter, st);
+  return pf_fill_dispatch(dP, b, qbtri, qmws, qmseq, mfe_for_scale, lnscale, sms, nullptr, true, work_counter, st);
 }
 
 cudaError_t bf_launch_pf_ext(const BfParams *dP, const BfBatchDev &b, const double *qbtri, const double *lnscale, double *out5,

@@ -33,7 +33,15 @@ cudaError_t bf_launch_mfe_fill(const BfParams *dP, const BfBatchDev &b, int *ctr
                                cudaStream_t st);
 cudaError_t bf_launch_trace(const BfParams *dP, const BfBatchDev &b, const int *ctri, const int *ftri, int *out_mfe, char *out_ss,
                             int ss_stride, cudaStream_t st);
-cudaError_t bf_launch_pf_fill(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *qmws, const int *mfe_for_scale,
+// qmseq: optional per-sequence qm/qm1 storage (2 x bf_tri_slot doubles per sequence) for the outside pass
+cudaError_t bf_launch_pf_fill(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *qmws, double *qmseq, const int *mfe_for_scale,
                               double *lnscale, int sms, int *work_counter, cudaStream_t st);
 cudaError_t bf_launch_pf_ext(const BfParams *dP, const BfBatchDev &b, const double *qbtri, const double *lnscale, double *out5,
                              cudaStream_t st);
+
+// ---- outside pass: base-pair probabilities and ensemble defect (bf_outside.cu)
+size_t bf_out_ws_slot(int nmax);   // doubles of per-CTA HBM workspace
+cudaError_t bf_out_grid(const BfBatchDev &b, int sms, int *grid);
+cudaError_t bf_launch_pf_out(const BfParams *dP, const BfBatchDev &b, const double *qbtri, const double *qmseq, double *ws,
+                             const double *lnscale, const char *targets, int n_targets, int tstride, double *out_defect, double *out_bpp,
+                             int grid, int *work_counter, cudaStream_t st);

@@ -1,0 +1,275 @@
+// bf_outside.cu -- outside pass of the partition function: base-pair probabilities and ensemble defect (sm_100a).
+//
+// Replaces md.compute_bpp=1 + fc.pf() + fc.ensemble_defect(target) (utils/energy_scores.py:362-374 in the reference).
+// Formulated as the reverse-mode derivative of the inside recursion of bf_k_pf_fill in GATHER form, so that it runs
+// on the same diagonal-major tables with stride-1 accesses, diagonals d = n-1 down to 4:
+//
+//   bqm(a,b)  = sum_{m>=5} H(a,b+m) qm1(b+1,b+m)                      H(a,j) = bqm(a,j) + G(a-1,j+1)
+//   bqm1(a,b) = bqm(a,b) + bu bqm1(a,b+1) + A(a,b) + sum_{m>=5} H(a-m,b) qm(a-m,a-1)
+//               A(a,b) = sum_{m>=1} bu^m bqm(a-m,b) = bu (bqm(a-1,b) + A(a-1,b))
+//   bqb(a,b)  = q5[a-1] xExt(a,b) q3[b+1] / Z + bqm1(a,b) xMLstem(a,b) + sum_{outer (i,j)} bqb(i,j) B(interior)
+//   G(a,b)    = bqb(a,b) B(MLclosing) xMLstem(closing) scale^2,       P(a,b) = bqb(a,b) qb(a,b)
+//
+// (bq* are d ln Z / d q*; all quantities carry the inside kernel's per-nucleotide scale.)  The outer pair table is kept in
+// the same three "outer-term folded in" variants as the inside rings, so a decomposable enclosing loop is one load + fma.
+// One persistent CTA per sequence, warps own 32-cell chunks of a diagonal, one barrier per diagonal.
+#include "bf_kernels.h"
+
+#include "bf_device.cuh"
+
+namespace {
+
+__host__ __device__ __forceinline__ int tri_off(int n, int d) { return (d - 4) * n - (d * (d - 1) / 2 - 6); }
+__host__ __device__ __forceinline__ size_t tri_size(int n) { return n >= 5 ? (size_t)tri_off(n, n) : 0; }
+
+struct OutPlan {
+  int rs;
+  size_t o_wg, o_wb, o_w1, o_scl, o_q5, o_q3, o_prow, o_ppair, o_ap, o_bqm, o_bqm1, o_g, o_toff, o_pt, o_stk, o_S, total;
+};
+__host__ __device__ inline OutPlan out_plan(int nmax) {
+  OutPlan p;
+  p.rs = (nmax + 8 + 3) / 4 * 4;
+  size_t o = 0;
+  p.o_wg = o; o += 31 * 32 * sizeof(double);
+  p.o_wb = o; o += 32 * sizeof(double);
+  p.o_w1 = o; o += 32 * sizeof(double);
+  p.o_scl = o; o += (size_t)p.rs * sizeof(double);
+  p.o_q5 = o; o += (size_t)p.rs * sizeof(double);
+  p.o_q3 = o; o += (size_t)p.rs * sizeof(double);
+  p.o_prow = o; o += (size_t)p.rs * sizeof(double);
+  p.o_ppair = o; o += (size_t)p.rs * sizeof(double);
+  p.o_ap = o; o += (size_t)2 * p.rs * sizeof(double);
+  p.o_bqm = o; o += (size_t)2 * p.rs * sizeof(double);
+  p.o_bqm1 = o; o += (size_t)2 * p.rs * sizeof(double);
+  p.o_g = o; o += (size_t)4 * p.rs * sizeof(double);
+  p.o_toff = o; o += (size_t)p.rs * sizeof(int);
+  p.o_pt = o; o += (size_t)p.rs * sizeof(short);
+  p.o_stk = o; o += (size_t)p.rs * sizeof(short);
+  p.o_S = o; o += (nmax + 2 + 15) / 16 * 16;
+  p.total = o;
+  return p;
+}
+
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) bf_k_pf_out(const BfParams *__restrict__ P, BfBatchDev b, const double *qbtri, const double *qmseq,
+                                                       size_t tri_slot, double *ws, const double *lnscale, const char *targets,
+                                                       int n_targets, int tstride, double *out_defect, double *out_bpp, int *work_counter) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ int s_seq, s_bad;
+  __shared__ double s_red[NW];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nmax = b.stride;
+  const OutPlan pl = out_plan(nmax);
+  const int RS = pl.rs;
+  const BfSmallD &T = P->sd;
+  double *wg = reinterpret_cast<double *>(dyn + pl.o_wg);
+  double *wb = reinterpret_cast<double *>(dyn + pl.o_wb);
+  double *w1 = reinterpret_cast<double *>(dyn + pl.o_w1);
+  double *scl = reinterpret_cast<double *>(dyn + pl.o_scl);
+  double *q5 = reinterpret_cast<double *>(dyn + pl.o_q5);
+  double *q3 = reinterpret_cast<double *>(dyn + pl.o_q3);
+  double *prow = reinterpret_cast<double *>(dyn + pl.o_prow);
+  double *ppair = reinterpret_cast<double *>(dyn + pl.o_ppair);
+  double *AP = reinterpret_cast<double *>(dyn + pl.o_ap);
+  double *BQM = reinterpret_cast<double *>(dyn + pl.o_bqm);
+  double *BQM1 = reinterpret_cast<double *>(dyn + pl.o_bqm1);
+  double *GR = reinterpret_cast<double *>(dyn + pl.o_g);
+  int *toff = reinterpret_cast<int *>(dyn + pl.o_toff);
+  short *pt = reinterpret_cast<short *>(dyn + pl.o_pt);
+  short *stk = reinterpret_cast<short *>(dyn + pl.o_stk);
+  uint8_t *S = dyn + pl.o_S;
+  // per-CTA workspace: H and the three outer-pair tables, packed triangles
+  double *H = ws + (size_t)blockIdx.x * 4 * tri_slot;
+  double *OG = H + tri_slot, *O1 = OG + tri_slot, *OB = O1 + tri_slot;
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_seq = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int sq = s_seq;
+    if (sq >= b.B) break;
+    const int n = b.len[sq];
+    const char *src = b.seq + (size_t)sq * b.stride;
+    for (int k = tid; k <= n + 1; k += blockDim.x) S[k] = (uint8_t)((k >= 1 && k <= n) ? bf_base_code(src[k - 1]) : 0);
+    for (int k = tid; k <= n; k += blockDim.x) toff[k] = (k >= 4) ? tri_off(n, k) : 0;
+    const double lns = lnscale[sq];
+    for (int k = tid; k <= n + 2; k += blockDim.x) { scl[k] = exp(-lns * k); prow[k] = 0.0; ppair[k] = 0.0; pt[k] = 0; }
+    for (int k = tid; k < 2 * RS; k += blockDim.x) { AP[k] = 0.0; BQM[k] = 0.0; BQM1[k] = 0.0; }
+    for (int k = tid; k < 4 * RS; k += blockDim.x) GR[k] = 0.0;
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
+    for (int k = tid; k < 31 * 32; k += blockDim.x) {
+      const int s = k >> 5, u1 = (k & 31) + 2;
+      wg[k] = (s >= 6 && u1 <= s - 2) ? T.x_interior[s] * T.x_ninio[abs(s - 2 * u1)] * scl[s + 2] : 0.0;
+    }
+    if (tid < 32) {
+      wb[tid] = (tid >= 2 && tid <= 30) ? T.x_bulge[tid] * scl[tid + 2] : 0.0;
+      w1[tid] = (tid >= 4 && tid <= 30) ? T.x_interior[tid] * T.x_ninio[tid - 2] * scl[tid + 2] : 0.0;
+    }
+    const double *qb = qbtri + (size_t)sq * tri_slot;
+    const double *QM = qmseq + (size_t)sq * 2 * tri_slot, *QM1 = QM + tri_slot;
+    const double bu1 = exp(log(T.x_MLbase) - lns), sc1 = scl[1];
+    const double xtau = T.x_TerminalAU, inv_tau = 1.0 / xtau;
+    const double xclose = T.x_MLclosing * scl[2];
+    auto xext = [&](int i, int j, int t) -> double { return bf_x_ext(T, t, (i > 1) ? S[i - 1] : -1, (j < n) ? S[j + 1] : -1); };
+    // target pair table (thread 0) + exterior chains q5 (warp 0) and q3 (warp 1)
+    if (tid == 0 && targets) {
+      const char *db = targets + (size_t)sq * n_targets * tstride;
+      int sp = 0;
+      for (int i = 1; i <= n; i++) {
+        const char ch = db[i - 1];
+        if (ch == '(') stk[sp++] = (short)i;
+        else if (ch == ')') {
+          if (!sp) { s_bad = 1; break; }
+          const int o = stk[--sp];
+          pt[o] = (short)i; pt[i] = (short)o;
+        }
+      }
+      if (sp) s_bad = 1;
+    }
+    if (warp == 0) {
+      if (lane == 0) q5[0] = 1.0;
+      __syncwarp();
+      for (int j = 1; j <= n; j++) {
+        double sum = 0.0;
+        for (int i = 1 + lane; i < j - BF_TURN; i += 32) {
+          const int t = bf_ptype_bases(S[i], S[j]);
+          if (t) sum += q5[i - 1] * qb[toff[j - i] + i - 1] * xext(i, j, t);
+        }
+        sum = bf_warp_sum(sum);
+        if (lane == 0) q5[j] = sum + q5[j - 1] * sc1;
+        __syncwarp();
+      }
+    } else if (warp == 1 || NW == 1) {
+      if (lane == 0) q3[n + 1] = 1.0;
+      __syncwarp();
+      for (int i = n; i >= 1; i--) {
+        double sum = 0.0;
+        for (int j = i + BF_TURN + 1 + lane; j <= n; j += 32) {
+          const int t = bf_ptype_bases(S[i], S[j]);
+          if (t) sum += qb[toff[j - i] + i - 1] * xext(i, j, t) * q3[j + 1];
+        }
+        sum = bf_warp_sum(sum);
+        if (lane == 0) q3[i] = sum + q3[i + 1] * sc1;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    const double invZ = 1.0 / q5[n];
+
+    for (int d = n - 1; d >= BF_TURN + 1; d--) {
+      const int ncell = n - d;
+      const int r0 = (d & 1) * RS, r1 = ((d + 1) & 1) * RS;
+      for (int c = warp * 32; c < ncell; c += NW * 32) {
+        const int a = c + lane + 1;
+        if (a > ncell) continue;
+        const int bb = a + d;
+        const int t = bf_ptype_bases(S[a], S[bb]);
+        // ---- bqm(a,b): (a,b) as the left part of a longer multiloop segment
+        double bqm = 0.0;
+        for (int m = 5; a + d + m <= n; m++) bqm = fma(H[toff[d + m] + a - 1], QM1[toff[m - 1] + a + d], bqm);
+        const double gprev = (a > 1 && bb < n && d + 2 <= n - 1) ? GR[((d + 2) & 3) * RS + a - 1] : 0.0;
+        const double hab = bqm + gprev;
+        // ---- bqm1(a,b)
+        double u2 = 0.0;
+        for (int m = 5; m <= a - 1; m++) u2 = fma(H[toff[d + m] + a - m - 1], QM[toff[m - 1] + a - m - 1], u2);
+        double ap = 0.0, bqm1 = bqm + u2;
+        if (d + 1 <= n - 1) {
+          if (a > 1) ap = bu1 * (BQM[r1 + a - 1] + AP[r1 + a - 1]);
+          if (bb + 1 <= n) bqm1 += BQM1[r1 + a] * bu1;
+        }
+        bqm1 += ap;
+        // ---- bqb(a,b)
+        double bqb = 0.0;
+        if (t) {
+          bqb = q5[a - 1] * xext(a, bb, t) * q3[bb + 1] * invZ;
+          if (a > 1 && bb < n) bqb = fma(bqm1, bf_x_mlstem(T, t, S[a - 1], S[bb + 1]), bqb);
+          const int t2 = bf_rtype(t), sq1 = S[bb + 1], sp1 = S[a - 1];
+          double accg = 0.0, acc1 = 0.0, accb = 0.0, accs = 0.0;
+          const int smax = min(BF_MAXLOOP, n - 1 - d - 2);
+          for (int s = 0; s <= smax; s++) {
+            const int o = toff[d + 2 + s];
+            for (int u1 = 0; u1 <= s; u1++) {
+              const int i = a - 1 - u1, j = bb + 1 + s - u1, u2l = s - u1;
+              if (i < 1 || j > n) continue;
+              const int nl = max(u1, u2l), ns = min(u1, u2l);
+              if (ns == 0 && nl >= 2) accb = fma(OB[o + i - 1], wb[s], accb);
+              else if (ns == 1 && nl >= 3) acc1 = fma(O1[o + i - 1], w1[s], acc1);
+              else if (ns >= 2 && !(ns == 2 && nl <= 3)) accg = fma(OG[o + i - 1], wg[(s << 5) + u1 - 2], accg);
+              else {
+                const int to = bf_ptype_bases(S[i], S[j]);
+                if (!to) continue;
+                double ov = OB[o + i - 1];
+                if (to > 2) ov *= inv_tau;
+                accs = fma(ov, bf_x_intloop(P, T, u1, u2l, to, t2, S[i + 1], S[j - 1], sp1, sq1) * scl[s + 2], accs);
+              }
+            }
+          }
+          bqb += accg * T.x_mmI[t2][sq1][sp1] + acc1 * T.x_mm1nI[t2][sq1][sp1] + accb * (t > 2 ? xtau : 1.0) + accs;
+        }
+        const int o = toff[d] + a - 1;
+        H[o] = hab;
+        BQM[r0 + a] = bqm;
+        AP[r0 + a] = ap;
+        BQM1[r0 + a] = bqm1;
+        double g = 0.0, og = 0.0, o1 = 0.0, ob = 0.0;
+        if (t) {
+          const int si1 = S[a + 1], sj1 = S[bb - 1];
+          g = bqb * xclose * bf_x_mlstem(T, bf_rtype(t), sj1, si1);
+          og = bqb * T.x_mmI[t][si1][sj1];
+          o1 = bqb * T.x_mm1nI[t][si1][sj1];
+          ob = (t > 2) ? bqb * xtau : bqb;
+          const double p = bqb * qb[o];
+          atomicAdd(&prow[a], p);
+          atomicAdd(&prow[bb], p);
+          if (pt[a] == bb) { ppair[a] = p; ppair[bb] = p; }
+          if (out_bpp) out_bpp[((size_t)sq * b.stride + (a - 1)) * b.stride + (bb - 1)] = p;
+        }
+        GR[(d & 3) * RS + a] = g;
+        OG[o] = og; O1[o] = o1; OB[o] = ob;
+      }
+      __syncthreads();
+    }
+    // ---- ensemble defect of target 0: (1/n) sum_i (paired ? 1 - P(i, pt i) : sum_j P(i,j))
+    if (out_defect) {
+      double e = 0.0;
+      for (int i = 1 + tid; i <= n; i += blockDim.x) e += pt[i] ? 1.0 - ppair[i] : prow[i];
+      e = bf_warp_sum(e);
+      if (lane == 0) s_red[warp] = e;
+      __syncthreads();
+      if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < NW; w++) tot += s_red[w];
+        out_defect[sq] = (s_bad || n == 0) ? -1.0 : tot / n;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+size_t bf_out_ws_slot(int nmax) { return 4 * ((tri_size(nmax) + 7) / 8 * 8); }
+
+cudaError_t bf_out_grid(const BfBatchDev &b, int sms, int *grid) {
+  auto kern = bf_k_pf_out<8>;
+  const size_t sm = out_plan(b.stride).total;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sm > 1024 ? sm : 1024));
+  if (e != cudaSuccess) return e;
+  int occ = 0;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, sm);
+  if (e != cudaSuccess) return e;
+  if (occ < 1) return cudaErrorInvalidConfiguration;
+  *grid = b.B < sms * occ ? b.B : sms * occ;
+  return cudaSuccess;
+}
+
+cudaError_t bf_launch_pf_out(const BfParams *dP, const BfBatchDev &b, const double *qbtri, const double *qmseq, double *ws,
+                             const double *lnscale, const char *targets, int n_targets, int tstride, double *out_defect, double *out_bpp,
+                             int grid, int *work_counter, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  const size_t sm = out_plan(b.stride).total;
+  bf_k_pf_out<8><<<grid, 256, sm, st>>>(dP, b, qbtri, qmseq, (tri_size(b.stride) + 7) / 8 * 8, ws, lnscale, targets, n_targets, tstride,
+                                        out_defect, out_bpp, work_counter);
+  return cudaGetLastError();
+}

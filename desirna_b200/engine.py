@@ -202,14 +202,23 @@ def score_batch(seqs, targets=None, nopair=None, want=WANT_MFE | WANT_SS | WANT_
         b.nopair = nopair.ctypes.data
         keep.append(nopair)
     out = {}
-    if targets is not None and (want & WANT_EVAL):
+    if targets is not None and (want & (WANT_EVAL | WANT_DEFECT)):
         tb = pack_targets(targets, stride)
         b.targets, b.n_targets = tb.ctypes.data, tb.shape[1]
-        out["eval_dcal"] = np.zeros((B, tb.shape[1]), np.int32)
-        r.eval_dcal = out["eval_dcal"].ctypes.data
         keep.append(tb)
+        if want & WANT_EVAL:
+            out["eval_dcal"] = np.zeros((B, tb.shape[1]), np.int32)
+            r.eval_dcal = out["eval_dcal"].ctypes.data
     else:
-        want &= ~WANT_EVAL
+        want &= ~(WANT_EVAL | WANT_DEFECT)
+    if want & (WANT_BPP | WANT_DEFECT):
+        want |= WANT_MFE | WANT_PF   # the MFE sets the partition function's scale (energy_scores.py:371-372)
+    if want & WANT_DEFECT:
+        out["defect"] = np.zeros(B, np.float64)
+        r.defect = out["defect"].ctypes.data
+    if want & WANT_BPP:
+        out["bpp"] = np.zeros((B, stride, stride), np.float64)
+        r.bpp = out["bpp"].ctypes.data
     if want & (WANT_MFE | WANT_SS):
         want |= WANT_MFE
         out["mfe_dcal"] = np.zeros(B, np.int32)

@@ -109,3 +109,35 @@ def test_hard_constraints(engine, oracle):
 def test_empty_batch(engine):
     out = engine.score_batch([], want=engine.WANT_MFE)
     assert len(out["len"]) == 0
+
+
+@pytest.mark.parametrize("L,B", [(30, 24), (100, 24), (150, 8)])
+def test_bpp_and_defect_vs_oracle(engine, oracle, L, B):
+    """Outside pass: not pinned by any ViennaRNA value in the reference tree; the oracle's outside recursion is
+    checked against exhaustive enumeration on CPU (tests/test_oracle_golden.py).  Tolerance of north_star: 1e-5 absolute."""
+    seqs = rand_seqs(4242 + L, B, L)
+    mfe, ss, epf, ed = oracle.fold_batch(seqs, nthreads=8)
+    out = engine.score_batch(seqs, [[s] for s in ss], want=engine.WANT_MFE | engine.WANT_PF | engine.WANT_BPP | engine.WANT_DEFECT)
+    for k, s in enumerate(seqs):
+        pf, bpp = oracle.pf(s, bpp=True)
+        assert abs(out["pf"][k, 4] - pf[4]) <= 1e-6 * max(1.0, abs(pf[4]))
+        got = out["bpp"][k][:L, :L]
+        assert np.abs(got - bpp).max() < 1e-9, (L, k, np.abs(got - bpp).max())
+        assert abs(out["defect"][k] - oracle.ensemble_defect(bpp, ss[k])) < 1e-9
+    # row sums are probabilities
+    full = out["bpp"] + out["bpp"].transpose(0, 2, 1)
+    assert full.sum(axis=2).max() <= 1.0 + 1e-9
+
+
+def test_bpp_ragged_and_unavailable_cases(engine, oracle):
+    seqs = ["GGGGAAAACCCC", "ACGUACGUAGCUAGCUAGCUAGCAUCGAUCGAUGCAUCG", "AAAAAA", "GCGCAAAAGCGCAAAAGCGCUUUUGCGC"]
+    tg = [["((((....))))"], ["." * len(seqs[1])], ["......"], ["((((....))))....((((....))))"]]
+    out = engine.score_batch(seqs, tg, want=engine.WANT_DEFECT | engine.WANT_BPP)
+    for k, s in enumerate(seqs):
+        pf, bpp = oracle.pf(s, bpp=True)
+        n = len(s)
+        assert np.abs(out["bpp"][k][:n, :n] - bpp).max() < 1e-9
+        assert abs(out["defect"][k] - oracle.ensemble_defect(bpp, tg[k][0])) < 1e-9
+    with pytest.raises(engine.EngineError) as ei:
+        engine.score_batch(["GGGG&CCCC"], [["((((&))))"]], want=engine.WANT_DEFECT)
+    assert ei.value.code == 4
