@@ -39,10 +39,12 @@ struct Engine {
   int *d_counters = nullptr;  // work counters (one per kernel kind)
   DevBuf ws_mfe, ws_pf, d_mfe_scratch;
   DevBuf tri_c, tri_f, tri_qb, ws_qm, ws_ring, d_lnscale, qm_seq, ws_out;  // diagonal-major fill path (bf_fill.cu)
+  int fill_kind = 0;                              // BF_FILL=tile: tile-wavefront fill kernels (bf_tile.cu); diag: bf_fill.cu
   bool force_generic = false;                     // BF_FORCE_GENERIC=1: route single strands through the generic kernels too
   // staging for the host-buffer entry point
   DevBuf d_seq, d_len, d_cut, d_nopair, d_targets, d_mfe, d_ss, d_pf, d_eval, d_defect, d_bpp;
   int64_t launches = 0;
+  int last_stride = 0;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // begin/end of mfe, pf, eval in the last call
   bool ran[3] = {false, false, false};
   std::string err;
@@ -87,6 +89,7 @@ int run_device(const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t
   BfBatchDev db;
   db.B = b->B; db.stride = b->stride; db.seq = b->seq; db.len = b->len; db.cut = b->cut; db.nopair = b->nopair;
   const int wstride = b->stride + 2;
+  g.last_stride = b->stride;
   const int *mfe_for_scale = nullptr;
   g.ran[0] = g.ran[1] = g.ran[2] = false;
   const bool fill_mfe = !two && !g.force_generic && bf_fill_mfe_mode(b->stride) != 0;
@@ -99,14 +102,25 @@ int run_device(const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t
       const size_t slot = bf_tri_slot(b->stride) * sizeof(int);
       CU(g.tri_c.reserve((size_t)b->B * slot), "cudaMalloc(c table)");
       CU(g.tri_f.reserve((size_t)b->B * slot), "cudaMalloc(fML table)");
-      const size_t wsi = bf_mfe_ws_slot(b->stride) * sizeof(int);
-      if (wsi) {
-        int grid = 0;
-        CU(bf_mfe_fill_grid(db, g.sm_count, &grid), "size bf_k_mfe_fill");
-        CU(g.ws_ring.reserve((size_t)grid * wsi), "cudaMalloc(ring workspace)");
+      if (g.fill_kind == 1 && bf_tile_mfe_ok(b->stride)) {
+        const size_t wsi = bf_mfe_tile_ws_slot(b->stride) * sizeof(int);
+        if (wsi) {
+          int grid = 0;
+          CU(bf_mfe_tile_grid(db, g.sm_count, &grid), "size bf_k_mfe_tile");
+          CU(g.ws_ring.reserve((size_t)grid * wsi), "cudaMalloc(tile workspace)");
+        }
+        CU(bf_launch_mfe_tile(g.dP, db, (int *)g.tri_c.p, (int *)g.tri_f.p, (int *)g.ws_ring.p, g.sm_count, g.d_counters + 0, st),
+           "launch bf_k_mfe_tile");
+      } else {
+        const size_t wsi = bf_mfe_ws_slot(b->stride) * sizeof(int);
+        if (wsi) {
+          int grid = 0;
+          CU(bf_mfe_fill_grid(db, g.sm_count, &grid), "size bf_k_mfe_fill");
+          CU(g.ws_ring.reserve((size_t)grid * wsi), "cudaMalloc(ring workspace)");
+        }
+        CU(bf_launch_mfe_fill(g.dP, db, (int *)g.tri_c.p, (int *)g.tri_f.p, (int *)g.ws_ring.p, g.sm_count, g.d_counters + 0, st),
+           "launch bf_k_mfe_fill");
       }
-      CU(bf_launch_mfe_fill(g.dP, db, (int *)g.tri_c.p, (int *)g.tri_f.p, (int *)g.ws_ring.p, g.sm_count, g.d_counters + 0, st),
-         "launch bf_k_mfe_fill");
       CU(bf_launch_trace(g.dP, db, (const int *)g.tri_c.p, (const int *)g.tri_f.p, out_mfe, (b->want & BF_WANT_SS) ? r->mfe_ss : nullptr,
                          b->stride + 1, st), "launch bf_k_trace");
       g.launches += 2;
@@ -208,6 +222,7 @@ int bf_init(int device) {
   if (prop.major < 10) return fail(BF_ERR_CUDA, std::string("built for sm_100a, found ") + prop.name);
   g.device = device;
   { const char *fg = getenv("BF_FORCE_GENERIC"); g.force_generic = fg && fg[0] == '1'; }
+  { const char *fk = getenv("BF_FILL"); g.fill_kind = (fk && !strcmp(fk, "tile")) ? 1 : 0; }
   g.sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking), "cudaStreamCreate");
   CU(cudaMalloc(&g.d_counters, 8 * sizeof(int)), "cudaMalloc(counters)");
@@ -363,6 +378,26 @@ int bf_last_kernel_ms(double out[3]) {
     CU(cudaEventElapsedTime(&ms, g.ev[2 * k], g.ev[2 * k + 1]), "cudaEventElapsedTime");
     out[k] = ms;
   }
+  return BF_OK;
+}
+
+int bf_set_option(const char *key, int value) {
+  if (!key) return fail(BF_ERR_ARG, "null option key");
+  if (!strcmp(key, "fill")) { g.fill_kind = value ? 1 : 0; return BF_OK; }
+  return fail(BF_ERR_ARG, std::string("unknown option: ") + key);
+}
+
+int bf_debug_copy_table(int which, int32_t n_seq, void *host, size_t host_bytes, size_t *slot_entries) {
+  if (!g.inited) return fail(BF_ERR_NOT_INIT, "bf_init has not been called");
+  if (which < 0 || which > 2) return fail(BF_ERR_ARG, "which must be 0 (c), 1 (fML) or 2 (qb)");
+  const size_t slot = bf_tri_slot(g.last_stride);
+  if (slot_entries) *slot_entries = slot;
+  if (!host) return BF_OK;
+  DevBuf &t = which == 0 ? g.tri_c : which == 1 ? g.tri_f : g.tri_qb;
+  const size_t bytes = (size_t)n_seq * slot * (which == 2 ? sizeof(double) : sizeof(int));
+  if (bytes > host_bytes || bytes > t.cap) return fail(BF_ERR_ARG, "table copy larger than the host buffer or the table");
+  CU(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
+  CU(cudaMemcpy(host, t.p, bytes, cudaMemcpyDeviceToHost), "D2H table");
   return BF_OK;
 }
 

@@ -54,6 +54,8 @@ def lib():
         L.bf_kernel_launches.restype = C.c_int64
         L.bf_last_kernel_ms.argtypes = [C.POINTER(C.c_double)]
         L.bf_microbench.argtypes = [C.POINTER(C.c_double)]
+        L.bf_set_option.argtypes = [C.c_char_p, C.c_int]
+        L.bf_debug_copy_table.argtypes = [C.c_int, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         _lib = L
     return _lib
 
@@ -114,6 +116,21 @@ def last_kernel_ms():
     out = (C.c_double * 3)()
     _check(lib().bf_last_kernel_ms(out))
     return list(out)
+
+
+def set_option(key, value):
+    """Tuning / test hook (bf_set_option): e.g. set_option("fill", 1) selects the tile-wavefront fill kernels."""
+    ensure_ready()
+    _check(lib().bf_set_option(key.encode(), int(value)))
+
+
+def debug_table(which, n_seq):
+    """Test hook: the packed diagonal-major DP table (0 = c, 1 = fML, 2 = qb) of the most recent call, [n_seq, slot]."""
+    slot = C.c_size_t(0)
+    _check(lib().bf_debug_copy_table(which, n_seq, None, 0, C.byref(slot)))
+    out = np.zeros((n_seq, slot.value), np.float64 if which == 2 else np.int32)
+    _check(lib().bf_debug_copy_table(which, n_seq, out.ctypes.data, out.nbytes, C.byref(slot)))
+    return out
 
 
 def microbench():

@@ -93,6 +93,12 @@ int bf_microbench(double out[3]);
 int64_t bf_kernel_launches(void);
 /* SM count of the device in use */
 int bf_sm_count(void);
+/* Tuning / test hook.  key "fill": 0 = diagonal-major fill kernels (bf_fill.cu), 1 = tile-wavefront fill kernels (bf_tile.cu). */
+int bf_set_option(const char *key, int value);
+/* Test hook: copy one engine-internal DP table of the most recent call to host memory.
+ * which: 0 = c (int32), 1 = fML (int32), 2 = qb (double); layout: per sequence a packed, diagonal-major triangle of
+ * *slot_entries entries (entry (i,j), d=j-i>=4, at (d-4)*n - (d*(d-1)/2-6) + i-1).  host may be NULL to query the size. */
+int bf_debug_copy_table(int which, int32_t n_seq, void *host, size_t host_bytes, size_t *slot_entries);
 
 #ifdef __cplusplus
 }
