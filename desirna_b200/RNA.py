@@ -179,7 +179,15 @@ class fold_compound:
         return self._cache[key]
 
     def subopt_cb(self, delta, cb, data=None):
-        raise NotImplementedError("subopt_cb (Wuchty enumeration) is outside the accelerated path: SURVEY.md 8(f) rank 3")
+        """vrna_subopt_cb as DesiRNA calls it (energy_scores.py:465-474, uniq_ML = 1): cb(structure, energy, data) for every
+        structure within `delta` dcal/mol of the MFE, then once more with structure None."""
+        if "&" in self.sequence:
+            raise NotImplementedError("subopt_cb on two-strand compounds is not part of the accelerated path")
+        nopair = np.asarray(self._nopair, np.uint8) if self._nopair is not None and any(self._nopair) else None
+        found, _ = _backend.subopt(self.sequence, int(delta), nopair)
+        for structure, e in found:
+            cb(structure, f32(e / 100.0), data)
+        cb(None, 0.0, data)
 
 
 def fold(sequence):

@@ -368,6 +368,45 @@ int bf_score_batch(const bf_batch_t *b, bf_result_t *r) {
   return BF_OK;
 }
 
+int bf_subopt(const char *seq, int32_t len, const uint8_t *nopair, int32_t delta_dcal, int32_t max_out, char *ss_out, int32_t *e_out,
+              int32_t *n_out, int32_t *truncated) {
+  if (!g.inited) return fail(BF_ERR_NOT_INIT, "bf_init has not been called");
+  if (!g.have_params) return fail(BF_ERR_NOT_INIT, "no energy parameters loaded");
+  if (!seq || len <= 0 || !ss_out || !e_out || !n_out || max_out <= 0 || delta_dcal < 0) return fail(BF_ERR_ARG, "bf_subopt: bad argument");
+  if (g.force_generic || bf_fill_mfe_mode(len) == 0) return fail(BF_ERR_UNAVAILABLE, "bf_subopt: length outside the fill path");
+  // the MFE fill of this one sequence leaves its c / fML tables in the engine's table buffers
+  int32_t l32 = len, mfe = 0;
+  bf_batch_t b;
+  memset(&b, 0, sizeof(b));
+  b.B = 1; b.stride = len; b.seq = seq; b.len = &l32; b.nopair = nopair; b.want = BF_WANT_MFE;
+  bf_result_t r;
+  memset(&r, 0, sizeof(r));
+  r.mfe_dcal = &mfe;
+  int rc = bf_score_batch(&b, &r);
+  if (rc) return rc;
+  const size_t slot = bf_tri_slot(len);
+  std::vector<int> c(slot), fm(slot);
+  CU(cudaMemcpy(c.data(), g.tri_c.p, slot * sizeof(int), cudaMemcpyDeviceToHost), "D2H c table");
+  CU(cudaMemcpy(fm.data(), g.tri_f.p, slot * sizeof(int), cudaMemcpyDeviceToHost), "D2H fML table");
+  std::vector<uint8_t> S(len + 2, 0), SP(len + 2, 0);
+  for (int k = 1; k <= len; k++) {
+    S[k] = (uint8_t)bf_base_code(seq[k - 1]);
+    SP[k] = (nopair && nopair[k - 1]) ? 0 : S[k];
+  }
+  std::vector<std::pair<int, std::string>> out;
+  int mfe_host = 0;
+  bool trunc = false;
+  bf_wuchty_host(g.hP, len, S.data(), SP.data(), c.data(), fm.data(), delta_dcal, max_out, &out, &mfe_host, &trunc);
+  if (mfe_host != mfe) return fail(BF_ERR_CUDA, "bf_subopt: host exterior pass disagrees with the device MFE");
+  for (size_t k = 0; k < out.size(); k++) {
+    e_out[k] = out[k].first;
+    memcpy(ss_out + k * (size_t)(len + 1), out[k].second.c_str(), (size_t)len + 1);
+  }
+  *n_out = (int32_t)out.size();
+  if (truncated) *truncated = trunc ? 1 : 0;
+  return BF_OK;
+}
+
 int bf_last_kernel_ms(double out[3]) {
   if (!g.inited) return fail(BF_ERR_NOT_INIT, "bf_init has not been called");
   for (int k = 0; k < 3; k++) {

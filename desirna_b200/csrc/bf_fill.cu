@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
           const int i = min(cell, ncell - 1) + 1;
           int accs = BF_INF;
           const int *left = FM + (i - 1);
-#pragma unroll 2
+#pragma unroll 4
           for (int k = 5 + warp; k <= d - 4; k += NW) accs = min(accs, left[toff[k - 1]] + left[toff[d - k] + k]);
           if (cell < ncell) ps[cell] = accs;
         }
@@ -687,7 +687,7 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
           const int i = min(cell, ncell - 1) + 1;
           double accs = 0.0;
           const double *left = QM + (i - 1), *right = QM1 + (i - 1);
-#pragma unroll 2
+#pragma unroll 4
           for (int k = 5 + warp; k <= d - 4; k += NW) accs = fma(left[toff[k - 1]], right[toff[d - k] + k], accs);
           if (cell < ncell) ps[cell] = accs;
         }

@@ -52,3 +52,12 @@ cudaError_t bf_out_grid(const BfBatchDev &b, int sms, int *grid);
 cudaError_t bf_launch_pf_out(const BfParams *dP, const BfBatchDev &b, const double *qbtri, const double *qmseq, double *ws,
                              const double *lnscale, const char *targets, int n_targets, int tstride, double *out_defect, double *out_bpp,
                              int grid, int *work_counter, cudaStream_t st);
+
+// ---- suboptimal structures (bf_subopt.cu): host walk over the c / fML tables of the GPU fill
+#ifdef __cplusplus
+#include <string>
+#include <utility>
+#include <vector>
+int bf_wuchty_host(const BfParams *P, int n, const uint8_t *S, const uint8_t *SP, const int *c, const int *fm, int delta, int cap,
+                   std::vector<std::pair<int, std::string>> *out, int *mfe_out, bool *truncated);
+#endif

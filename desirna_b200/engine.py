@@ -54,6 +54,8 @@ def lib():
         L.bf_kernel_launches.restype = C.c_int64
         L.bf_last_kernel_ms.argtypes = [C.POINTER(C.c_double)]
         L.bf_microbench.argtypes = [C.POINTER(C.c_double)]
+        L.bf_subopt.argtypes = [C.c_char_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.bf_set_option.argtypes = [C.c_char_p, C.c_int]
         L.bf_debug_copy_table.argtypes = [C.c_int, C.c_int32, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]
         _lib = L
@@ -116,6 +118,24 @@ def last_kernel_ms():
     out = (C.c_double * 3)()
     _check(lib().bf_last_kernel_ms(out))
     return list(out)
+
+
+def subopt(seq, delta_dcal, nopair=None, max_out=4096):
+    """bf_subopt: every structure of one single-strand sequence within delta_dcal of the MFE, sorted by energy.
+    Returns (list of (structure, energy_dcal), truncated)."""
+    ensure_ready()
+    s = seq.upper().replace("T", "U").encode("ascii")
+    n = len(s)
+    ss = np.zeros((max_out, n + 1), np.uint8)
+    en = np.zeros(max_out, np.int32)
+    cnt, trunc = C.c_int32(0), C.c_int32(0)
+    mask = None
+    if nopair is not None:
+        mask = np.ascontiguousarray(nopair, np.uint8)
+        assert mask.shape == (n,)
+    _check(lib().bf_subopt(s, n, mask.ctypes.data if mask is not None else None, int(delta_dcal), max_out, ss.ctypes.data, en.ctypes.data,
+                           C.byref(cnt), C.byref(trunc)))
+    return [(bytes(ss[k, :n]).decode("ascii"), int(en[k])) for k in range(cnt.value)], bool(trunc.value)
 
 
 def set_option(key, value):

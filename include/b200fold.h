@@ -82,6 +82,14 @@ int bf_score_batch(const bf_batch_t *batch, bf_result_t *result);
  * (a cudaStream_t handle; NULL = the legacy default stream, as in the CUDA runtime) and NOT synchronised. */
 int bf_score_batch_device(const bf_batch_t *batch, bf_result_t *result, void *cuda_stream);
 
+/* fc.subopt_cb(delta, cb, data) with RNA.cvar.uniq_ML = 1                     energy_scores.py:465-474, sequence_utils.py:783
+ * Every secondary structure of ONE single-strand sequence whose energy is within delta_dcal of the MFE, each exactly once,
+ * sorted by energy.  The O(N^3) tables come from the GPU MFE fill; the output-sensitive walk over them runs on the host.
+ * ss_out: max_out x (len+1) chars, e_out: max_out energies in dcal/mol, *n_out: structures written (<= max_out),
+ * *truncated: 1 if the band holds more than max_out structures.  nopair: optional len bytes (hard constraint 'x'). */
+int bf_subopt(const char *seq, int32_t len, const uint8_t *nopair, int32_t delta_dcal, int32_t max_out, char *ss_out, int32_t *e_out,
+              int32_t *n_out, int32_t *truncated);
+
 /* device time (ms, CUDA events on the launch stream) of the mfe, pf and eval kernels of the most recent
  * bf_score_batch[_device] call; -1 for a kernel that did not run.  Blocks until those kernels finished. */
 int bf_last_kernel_ms(double out[3]);

@@ -910,6 +910,7 @@ double orc_ensemble_defect(const double *bpp, int n, const char *db) {
 /* ------------------------------------------------------------------ exhaustive enumeration (tests) */
 typedef struct {
   ctx_t *X; int n; char *db; double Z; double *bpp; int e1, e2; int *pt;
+  int bound, cap, cnt; int *band_e; char *band_ss; /* optional: every structure with energy <= bound */
 } enum_t;
 
 static double struct_weight(enum_t *E, int *e_out) {
@@ -940,6 +941,15 @@ static void enum_rec(enum_t *E, int pos) {
     E->Z += w;
     if (E->bpp) for (int i = 1; i <= n; i++) if (E->pt[i] > i) E->bpp[(size_t)(i - 1) * n + (E->pt[i] - 1)] += w;
     if (en < E->e1) { E->e2 = E->e1; E->e1 = en; } else if (en > E->e1 && en < E->e2) E->e2 = en;
+    if (E->band_e && en <= E->bound) {
+      if (E->cnt < E->cap) {
+        E->band_e[E->cnt] = en;
+        char *o = E->band_ss + (size_t)E->cnt * (n + 1);
+        for (int i = 1; i <= n; i++) o[i - 1] = E->pt[i] > i ? '(' : (E->pt[i] > 0 ? ')' : '.');
+        o[n] = 0;
+      }
+      E->cnt++;
+    }
     return;
   }
   /* pos unpaired (mark with -1) */
@@ -960,6 +970,7 @@ static void enum_rec(enum_t *E, int pos) {
 double orc_enumerate(const orc_params *P, const char *seq, int n, double *bpp, int *emin, int *e2nd) {
   ctx_t X; ctx_init(&X, P, seq, n, 0, NULL);
   enum_t E; E.X = &X; E.n = n; E.Z = 0; E.bpp = bpp; E.e1 = INF; E.e2 = INF; E.pt = (int *)calloc(n + 2, sizeof(int));
+  E.band_e = NULL; E.band_ss = NULL; E.cnt = 0; E.cap = 0; E.bound = 0;
   if (bpp) for (int i = 0; i < n * n; i++) bpp[i] = 0;
   enum_rec(&E, 1);
   /* unpaired markers are -1 inside recursion only */
@@ -969,6 +980,16 @@ double orc_enumerate(const orc_params *P, const char *seq, int n, double *bpp, i
   double F = -P->kT * log(E.Z) / 1000.0;
   free(E.pt); ctx_free(&X);
   return F;
+}
+
+/* every structure with energy <= bound (dcal), brute force; returns how many there are (may exceed cap) */
+int orc_enumerate_band(const orc_params *P, const char *seq, int n, int bound, int cap, int *energies, char *ss) {
+  ctx_t X; ctx_init(&X, P, seq, n, 0, NULL);
+  enum_t E; E.X = &X; E.n = n; E.Z = 0; E.bpp = NULL; E.e1 = INF; E.e2 = INF; E.pt = (int *)calloc(n + 2, sizeof(int));
+  E.band_e = energies; E.band_ss = ss; E.cnt = 0; E.cap = cap; E.bound = bound;
+  enum_rec(&E, 1);
+  free(E.pt); ctx_free(&X);
+  return E.cnt;
 }
 
 /* ------------------------------------------------------------------ batch helper (CPU baseline) */

@@ -42,6 +42,8 @@ def lib():
         L.orc_ensemble_defect.argtypes = [C.POINTER(C.c_double), C.c_int, C.c_char_p]
         L.orc_enumerate.restype = C.c_double
         L.orc_enumerate.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_enumerate_band.restype = C.c_int
+        L.orc_enumerate_band.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_fold_batch.restype = C.c_int
         L.orc_fold_batch.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -106,6 +108,17 @@ class Oracle:
         F = lib().orc_enumerate(self.P, seq.encode(), n, P.ctypes.data_as(C.POINTER(C.c_double)) if bpp else None,
                                 C.byref(e1), C.byref(e2))
         return F, P, e1.value, e2.value
+
+    def enumerate_band(self, seq, bound, cap=20000):
+        """brute force: sorted [(energy_dcal, structure)] of every structure with energy <= bound"""
+        import numpy as np
+        n = len(seq)
+        en = np.zeros(cap, np.int32)
+        ss = C.create_string_buffer(cap * (n + 1))
+        cnt = lib().orc_enumerate_band(self.P, seq.encode(), n, int(bound), cap, en.ctypes.data, C.addressof(ss))
+        assert cnt <= cap, "band larger than cap"
+        raw = ss.raw
+        return sorted((int(en[k]), raw[k * (n + 1): k * (n + 1) + n].decode()) for k in range(cnt))
 
     def fold_batch(self, seqs, targets=None, nthreads=1):
         """seqs: list of equal-length strings -> (mfe[int32], ss[list], epf[f64], ed[int32])"""

@@ -45,3 +45,11 @@ class OracleBackend:
         if targets is not None and (want & self.WANT_EVAL):
             out["eval_dcal"] = np.array([[self.O.eval(s, t) for t in targets[k]] for k, s in enumerate(seqs)], np.int32)
         return out
+
+    def subopt(self, seq, delta_dcal, nopair=None, max_out=4096):
+        """brute force (short sequences only): same contract as engine.subopt"""
+        s = seq.upper().replace("T", "U")
+        assert len(s) <= 20 and nopair is None
+        mfe = self.O.mfe(s)[0]
+        band = self.O.enumerate_band(s, mfe + int(delta_dcal))
+        return [(ss, e) for e, ss in band[:max_out]], len(band) > max_out

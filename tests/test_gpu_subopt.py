@@ -1,0 +1,69 @@
+"""GPU parity of the suboptimal-structure walk (bf_subopt / fold_compound.subopt_cb) against brute-force enumeration.
+
+Reference call sites: utils/energy_scores.py:453-488 (get_first_suboptimal_structure_and_energy, uniq_ML = 1),
+utils/sequence_utils.py:783.  ViennaRNA values for subopt are pinned by nothing the reference ships, so the
+check is exhaustive enumeration under the validated loop model (oracle) for short sequences, and energy consistency
+(every listed structure re-evaluates to its listed energy, no duplicates, first = MFE) for longer ones."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def rand_seq(rng, n):
+    return "".join("ACGU"[x] for x in rng.integers(0, 4, n))
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_band_equals_brute_force(engine, oracle, seed):
+    rng = np.random.default_rng(seed)
+    checked = 0
+    for n in [8, 10, 12, 13, 14, 15, 16, 17, 18]:
+        for _ in range(3):
+            s = rand_seq(rng, n) if rng.random() < 0.5 else "GGG" + rand_seq(rng, n - 6) + "CCC"
+            delta = int(rng.choice([0, 100, 300, 600]))
+            found, trunc = engine.subopt(s, delta, max_out=20000)
+            mfe = oracle.mfe(s)[0]
+            want = oracle.enumerate_band(s, mfe + delta)
+            assert not trunc
+            assert [e for _, e in found] == [e for e, _ in want], (s, delta)
+            assert sorted(ss for ss, _ in found) == sorted(ss for _, ss in want), (s, delta)
+            checked += len(want)
+    assert checked > 50
+
+
+def test_long_sequence_consistency(engine, oracle):
+    rng = np.random.default_rng(11)
+    for n in [60, 120, 300]:
+        s = rand_seq(rng, n)
+        found, trunc = engine.subopt(s, 100, max_out=5000)
+        mfe, ss = oracle.mfe(s)
+        assert found and found[0][1] == mfe
+        assert any(x == ss for x, e in found if e == mfe)
+        assert len({x for x, _ in found}) == len(found)          # each structure once
+        for x, e in found[:200]:
+            assert oracle.eval(s, x) == e                          # the walk's energy is the structure's loop-sum energy
+            assert e <= mfe + 100
+
+
+def test_truncation_flag(engine):
+    s = "GGGGGAAAAACCCCCAAAAAGGGGGAAAAACCCCC"
+    full, trunc = engine.subopt(s, 500, max_out=20000)
+    assert not trunc and len(full) > 5
+    part, trunc = engine.subopt(s, 500, max_out=5)
+    assert trunc and len(part) == 5
+
+
+def test_reference_helper_through_the_shim(engine, oracle):
+    """get_first_suboptimal_structure_and_energy(seq, fc, 1) -> second-best structure and its energy (float32 kcal/mol)."""
+    import struct
+    from desirna_b200 import RNA
+    from desirna_b200.utils import energy_scores as es
+    RNA.set_backend(engine)
+    s = "GGGAAAUCCCGCGAAAGC"
+    fc = RNA.fold_compound(s)
+    ss2, e2 = es.get_first_suboptimal_structure_and_energy(s, fc, 1)
+    mfe = oracle.mfe(s)[0]
+    band = oracle.enumerate_band(s, mfe + 5000)
+    assert e2 == struct.unpack("f", struct.pack("f", band[1][0] / 100.0))[0]
+    assert oracle.eval(s, ss2) == band[1][0]

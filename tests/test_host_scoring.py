@@ -112,3 +112,19 @@ def test_dimer_module_constants():
     assert (dme.KB, dme.RHO, dme.CONC) == (0.001987204259, 55.14, 1e-3) and abs(dme.TEMP - 310.15) < 1e-12
     f = 0.25
     assert abs(dme.kTlog_oligo_fraction(f) + dme.KB * dme.TEMP * __import__("math").log(f)) < 1e-15
+
+
+def test_subopt_term_of_the_score(rna_on_oracle, oracle):
+    """`-nd on`: when the MFE structure IS the target (mcc term 0) the energy gap to the second-best structure enters the score
+    (energy_scores.py:104-107, :406-410): scoring_function -= (E_2nd - Epf)."""
+    import struct
+    from desirna_b200.utils import energy_scores as es
+    seq = "GGGAAAUCCCGCGAAAGC"
+    mfe, ss = oracle.mfe(seq)
+    plain = es.score_sequence(seq, input_file(ss), options())
+    nd = es.score_sequence(seq, input_file(ss), options(subopt="on"))
+    assert plain.mcc == 0
+    band = oracle.enumerate_band(seq, mfe + 5000)
+    e2 = struct.unpack("f", struct.pack("f", band[1][0] / 100.0))[0]
+    assert nd.subopt_e == e2
+    assert abs(nd.scoring_function - (plain.scoring_function - (e2 - plain.Epf))) < 1e-9
