@@ -243,8 +243,13 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
               const int *cgp = CG + row + 3;
               const int *pen = pg + (s << 5);
               const int kn = s - 3;
+              if (PL & kMfeRgSmem) {
 #pragma unroll 4
-              for (int k = 0; k < kn; k++) accg = min(accg, cgp[k] + pen[k]);
+                for (int k = 0; k < kn; k++) accg = min(accg, cgp[k] + pen[k]);
+              } else {  // ring rows come from L2: keep more loads in flight
+#pragma unroll 8
+                for (int k = 0; k < kn; k++) accg = min(accg, cgp[k] + pen[k]);
+              }
             }
           }
           int tot = min(accg + T.mmI[t][si1][sj1], min(acc1 + T.mm1nI[t][si1][sj1], accb + (t > 2 ? T.TerminalAU : 0)));
@@ -268,8 +273,14 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
           const int i = min(cell, ncell - 1) + 1;
           int accs = BF_INF;
           const int *left = FM + (i - 1);
+          // operands come from L2 unless the table is on chip: deep unrolling keeps many loads in flight on long diagonals
+          if (d - 8 >= 16 * NW) {
+#pragma unroll 8
+            for (int k = 5 + warp; k <= d - 4; k += NW) accs = min(accs, left[toff[k - 1]] + left[toff[d - k] + k]);
+          } else {
 #pragma unroll 4
-          for (int k = 5 + warp; k <= d - 4; k += NW) accs = min(accs, left[toff[k - 1]] + left[toff[d - k] + k]);
+            for (int k = 5 + warp; k <= d - 4; k += NW) accs = min(accs, left[toff[k - 1]] + left[toff[d - k] + k]);
+          }
           if (cell < ncell) ps[cell] = accs;
         }
       }
@@ -662,6 +673,13 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
               const int kn = s - 3;
               double a0 = 0.0, a1 = 0.0;
               int k = 0;
+              if (!(PL & kPfQgSmem)) {  // ring rows come from L2: eight loads in flight
+                for (; k + 7 < kn; k += 8) {
+                  const double q0 = qp[k], q1 = qp[k + 1], q2 = qp[k + 2], q3 = qp[k + 3], q4 = qp[k + 4], q5 = qp[k + 5], q6 = qp[k + 6], q7 = qp[k + 7];
+                  a0 = fma(q0, w[k], a0); a1 = fma(q1, w[k + 1], a1); a0 = fma(q2, w[k + 2], a0); a1 = fma(q3, w[k + 3], a1);
+                  a0 = fma(q4, w[k + 4], a0); a1 = fma(q5, w[k + 5], a1); a0 = fma(q6, w[k + 6], a0); a1 = fma(q7, w[k + 7], a1);
+                }
+              }
               for (; k + 1 < kn; k += 2) { a0 = fma(qp[k], w[k], a0); a1 = fma(qp[k + 1], w[k + 1], a1); }
               if (k < kn) a0 = fma(qp[k], w[k], a0);
               accg += a0 + a1;
@@ -687,8 +705,13 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
           const int i = min(cell, ncell - 1) + 1;
           double accs = 0.0;
           const double *left = QM + (i - 1), *right = QM1 + (i - 1);
+          if (d - 8 >= 16 * NW) {
+#pragma unroll 8
+            for (int k = 5 + warp; k <= d - 4; k += NW) accs = fma(left[toff[k - 1]], right[toff[d - k] + k], accs);
+          } else {
 #pragma unroll 4
-          for (int k = 5 + warp; k <= d - 4; k += NW) accs = fma(left[toff[k - 1]], right[toff[d - k] + k], accs);
+            for (int k = 5 + warp; k <= d - 4; k += NW) accs = fma(left[toff[k - 1]], right[toff[d - k] + k], accs);
+          }
           if (cell < ncell) ps[cell] = accs;
         }
       }
