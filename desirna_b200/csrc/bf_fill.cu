@@ -477,7 +477,7 @@ struct PfPlan {
   int rs;
   size_t o_S, o_toff, o_wg, o_wb, o_w1, o_scl, o_bu, o_qm, o_qm1, o_qg, o_r2, o_qms, o_au, o_pi, o_ps, o_list, o_tab, total;
 };
-__host__ __device__ inline PfPlan pf_plan(int nmax, int nw, int pl) {
+__host__ __device__ inline PfPlan pf_plan(int nmax, int nw, int pl, bool half = false) {
   PfPlan p;
   p.rs = (nmax + 8 + 3) / 4 * 4;
   size_t o = 0;
@@ -492,8 +492,9 @@ __host__ __device__ inline PfPlan pf_plan(int nmax, int nw, int pl) {
   p.o_r2 = o; o += (pl & kPfR2Smem) ? (size_t)2 * kRing * p.rs * sizeof(double) : 0;
   p.o_qms = o; o += (size_t)4 * p.rs * sizeof(double);
   p.o_au = o; o += (size_t)2 * p.rs * sizeof(double);
-  p.o_pi = o; o += (size_t)2 * nw * p.rs * sizeof(double);
-  p.o_ps = o; o += (size_t)2 * nw * p.rs * sizeof(double);
+  const int nb = half ? nw / 2 : nw;  // per-warp partial buffers; half: two warps share one (see bf_k_pf_fill)
+  p.o_pi = o; o += (size_t)2 * nb * p.rs * sizeof(double);
+  p.o_ps = o; o += (size_t)2 * nb * p.rs * sizeof(double);
   p.o_tab = o; o += (pl & kTabSmem) ? (sizeof(BfSmallD) + 15) / 16 * 16 : 0;
   p.o_list = o; o += (size_t)2 * p.rs * sizeof(unsigned short);
   p.o_toff = o; o += (size_t)(nmax + 4) / 4 * 4 * sizeof(int);
@@ -511,10 +512,23 @@ __host__ __device__ inline size_t pf_ws_doubles(int nmax, int pl) {
   return (o + 7) / 8 * 8;
 }
 
+// named barrier of a warp pair (ids 1..4; id 0 is __syncthreads)
+__device__ __forceinline__ void pair_barrier(int k) {
+  switch (k) {
+    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+  }
+}
+
 // qbtri: per-sequence qb table in HBM (for the exterior pass).  Same phase structure as bf_k_mfe_fill.
 // qm(i,j) = qm1(i,j) + A(i,j) + sum_k qm[i][i+k-1] qm1[i+k][j] with A(i,j) = sum_{k>=1} bu^k qm1(i+k,j)
 //         = bu (qm1(i+1,j) + A(i+1,j)): the unpaired-prefix part is carried along the diagonals in O(1) per cell.
-template <int NW, int PL>
+// HALF: warps w and w + NW/2 share one partial buffer.  The first of the pair does the interior part, then the split part; the
+// second does them in the opposite order; between the two halves the pair meets at a named barrier, after which each ADDS onto
+// what the other stored.  Halves the reduction buffers (two CTAs per SM at L = 400) at the cost of one 64-thread barrier.
+template <int NW, int PL, bool HALF = false>
 __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restrict__ P, BfBatchDev b, double *qbtri, size_t tri_slot,
                                                         double *ws, size_t ws_slot, double *qm_perseq, const int *mfe_for_scale,
                                                         double *lnscale_out, int *work_counter) {
@@ -522,7 +536,8 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
   __shared__ int s_seq, s_np[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nmax = b.stride;
-  const PfPlan pl = pf_plan(nmax, NW, PL);
+  constexpr int NB = HALF ? NW / 2 : NW;
+  const PfPlan pl = pf_plan(nmax, NW, PL, HALF);
   const int RS = pl.rs;
   uint8_t *S = dyn + pl.o_S;
   int *toff = reinterpret_cast<int *>(dyn + pl.o_toff);
@@ -612,16 +627,16 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
       // ------------------------------------------------------------ combine diagonal d-1
       if (d > BF_TURN + 1) {
         const int dd = d - 1, ncell = n - dd, buf = dd & 1;
-        const double *pi = PI + buf * NW * RS, *ps = PS + buf * NW * RS;
+        const double *pi = PI + buf * NB * RS, *ps = PS + buf * NB * RS;
         for (int cell = tid; cell < ncell; cell += blockDim.x) {
           const int i = cell + 1, j = i + dd;
           const int t = bf_ptype_bases(S[i], S[j]);
           double qms = 0.0, qb = 0.0;
 #pragma unroll
-          for (int w = 0; w < NW; w++) qms += ps[w * RS + cell];
+          for (int w = 0; w < NB; w++) qms += ps[w * RS + cell];
           if (t) {
 #pragma unroll
-            for (int w = 0; w < NW; w++) qb += pi[w * RS + cell];
+            for (int w = 0; w < NB; w++) qb += pi[w * RS + cell];
             qb += QMS[((dd - 2) & 3) * RS + i + 1] * (xclose * bf_x_mlstem(T, bf_rtype(t), S[j - 1], S[i + 1]));
           }
           double qm1 = 0.0, au = 0.0;
@@ -652,10 +667,11 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
       // ------------------------------------------------------------ partial sums of diagonal d
       if (d <= n - 1) {
         const int ncell = n - d, buf = d & 1;
-        double *pi = PI + (buf * NW + warp) * RS, *ps = PS + (buf * NW + warp) * RS;
+        double *pi = PI + (buf * NB + warp % NB) * RS, *ps = PS + (buf * NB + warp % NB) * RS;
         const int smax = min(BF_MAXLOOP, d - 6);
         const int np = s_np[buf];
         const unsigned short *list = LST + buf * RS;
+        auto do_interior = [&](const bool add) {
         for (int c = 0; c < np; c += 32) {
           const int kk = c + lane;
           const int i = list[min(kk, np - 1)];
@@ -697,9 +713,11 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
             if (t2 > 2) qv *= inv_tau;
             tot += qv * bf_x_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]) * scl[u1 + u2 + 2];
           }
-          if (kk < np) pi[i - 1] = tot;
+          if (kk < np) pi[i - 1] = add ? pi[i - 1] + tot : tot;
         }
+        };
         // ---- qm split for every cell: k = u - i in [5, d-4] (qm on diagonal k-1 >= 4, qm1 on diagonal d-k >= 4)
+        auto do_split = [&](const bool add) {
         for (int c = 0; c < ncell; c += 32) {
           const int cell = c + lane;
           const int i = min(cell, ncell - 1) + 1;
@@ -712,7 +730,20 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
 #pragma unroll 4
             for (int k = 5 + warp; k <= d - 4; k += NW) accs = fma(left[toff[k - 1]], right[toff[d - k] + k], accs);
           }
-          if (cell < ncell) ps[cell] = accs;
+          if (cell < ncell) ps[cell] = add ? ps[cell] + accs : accs;
+        }
+        };
+        if (!HALF) {
+          do_interior(false);
+          do_split(false);
+        } else if (warp < NB) {
+          do_interior(false);
+          pair_barrier(warp % NB);
+          do_split(true);
+        } else {
+          do_split(false);
+          pair_barrier(warp % NB);
+          do_interior(true);
         }
       }
       __syncthreads();
@@ -908,11 +939,11 @@ cudaError_t bf_launch_trace(const BfParams *dP, const BfBatchDev &b, const int *
   return cudaGetLastError();
 }
 
-template <int NW, int PL>
+template <int NW, int PL, bool HALF = false>
 static cudaError_t pf_fill_t(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale, double *lnscale,
                              int sms, int *grid_out, bool launch, int *counter, cudaStream_t st) {
-  auto kern = bf_k_pf_fill<NW, PL>;
-  const size_t sm = pf_plan(b.stride, NW, PL).total;
+  auto kern = bf_k_pf_fill<NW, PL, HALF>;
+  const size_t sm = pf_plan(b.stride, NW, PL, HALF).total;
   cudaError_t e = set_smem(kern, sm);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -944,6 +975,10 @@ static cudaError_t pf_fill_dispatch(const BfParams *dP, const BfBatchDev &b, dou
                                     double *lnscale, int sms, int *grid_out, bool launch, int *counter, cudaStream_t st) {
   const FillCfg c = pf_cfg(b.stride);
   if (c.pl < 0) return cudaErrorInvalidValue;
+  // long sequences: with one partial buffer per warp only one CTA fits an SM; sharing buffers between warp pairs fits two
+  if (c.nw == 8 && c.pl == 0 && env_int("BF_PF_HALF", 1) && pf_plan(b.stride, 8, 0, false).total > 113 * 1024 &&
+      pf_plan(b.stride, 8, 0, true).total <= 113 * 1024)
+    return pf_fill_t<8, 0, true>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
   if (c.nw == 4) return pf_fill_pl<4>(c.pl, dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
   if (c.nw == 2) return pf_fill_pl<2>(c.pl, dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
   return pf_fill_pl<8>(c.pl, dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
