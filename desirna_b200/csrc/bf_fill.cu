@@ -43,6 +43,13 @@ __host__ __device__ __forceinline__ size_t tri_size(int n) { return n >= 5 ? (si
 
 __device__ __forceinline__ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// tile-major copy of a triangular table (blocked split): 4x4 tiles, tile (I,J) at tile_off(NT,I) + J-I, entry a*4+b
+__host__ __device__ __forceinline__ int tile_off(int NT, int I) { return I * NT - I * (I - 1) / 2; }
+__host__ __device__ __forceinline__ size_t tile_table_entries(int nmax) {
+  const size_t nt = (nmax + 3) / 4;
+  return nt * (nt + 1) / 2 * 16;
+}
+
 __device__ __forceinline__ int ptype_sp(const uint8_t *SP, int i, int j) { return bf_ptype_bases(SP[i], SP[j]); }
 
 // ---------------------------------------------------------------------------------------------
@@ -55,9 +62,9 @@ constexpr int kTabSmem = 8;     // small loop tables (BfSmallI / BfSmallD) stage
 
 struct MfePlan {
   int rs;  // ring row stride (ints)
-  size_t o_S, o_SP, o_toff, o_pg, o_pb, o_p1, o_fm, o_ring, o_dml, o_pi, o_ps, o_list, o_tab, total;
+  size_t o_S, o_SP, o_toff, o_pg, o_pb, o_p1, o_fm, o_ring, o_dml, o_pi, o_ps, o_list, o_tab, o_sa, total;
 };
-__host__ __device__ inline MfePlan mfe_plan(int nmax, int nw, int pl) {
+__host__ __device__ inline MfePlan mfe_plan(int nmax, int nw, int pl, bool blk = false) {
   MfePlan p;
   p.rs = (nmax + 8 + 3) / 4 * 4;
   size_t o = 0;
@@ -74,6 +81,8 @@ __host__ __device__ inline MfePlan mfe_plan(int nmax, int nw, int pl) {
   p.o_ps = o; o += (size_t)2 * nw * p.rs * sizeof(int);
   p.o_list = o; o += (size_t)2 * p.rs * sizeof(unsigned short);  // pairable cells of a diagonal, double-buffered
   p.o_tab = o; o += (pl & kTabSmem) ? (sizeof(BfSmallI) + 15) / 16 * 16 : 0;
+  o = (o + 15) / 16 * 16;
+  p.o_sa = o; o += blk ? (size_t)3 * ((nmax + 3) / 4) * 16 * sizeof(int) : 0;  // blocked-split minima of three tile-diagonals
   p.total = o;
   return p;
 }
@@ -105,18 +114,28 @@ __device__ __forceinline__ int build_pair_list(const uint8_t *SP, int n, int d, 
 // it owns (-> c, fML, ring rows of d-1), then accumulates partial minima for diagonal d.  The heavy part of
 // diagonal d only reads diagonals <= d-2 (interior loops) and <= d-5 (fML splits), so one barrier per
 // diagonal is enough; the partial buffers are double-buffered.
-template <int NW, int PL>
+//
+// BLK (blocked split): the bulk of  min_u fML[i][u-1] + fML[u][j]  is taken out of the per-diagonal loop.  fML is mirrored
+// TILE-MAJOR (4x4 tiles) in the per-CTA workspace; for the tiles of tile-diagonal D' = J-I the products over the intermediate
+// tiles K = I+3 .. J-3 only need diagonals <= 4D'-9, so they are computed as 4x4 register-tiled (min,+) block products
+// (8 x 128-bit loads per 64 relaxations, lanes = 4 tiles x 8 K-slices) during the four phases d = 4D'-7 .. 4D'-4, one quarter
+// of the tiles per phase, into SA[D' % 3].  The per-diagonal loop keeps only the <= 15 candidates next to either end.
+template <int NW, int PL, bool BLK = false>
 __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restrict__ P, BfBatchDev b, int *ctri, int *ftri,
                                                          size_t tri_slot, int *ws, size_t ws_slot, int *work_counter) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ int s_seq, s_np[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nmax = b.stride;
-  const MfePlan pl = mfe_plan(nmax, NW, PL);
+  const MfePlan pl = mfe_plan(nmax, NW, PL, BLK);
   const int RS = pl.rs;
   uint8_t *S = dyn + pl.o_S;
   uint8_t *SP = dyn + pl.o_SP;
   int *toff = reinterpret_cast<int *>(dyn + pl.o_toff);
+  int *SA = reinterpret_cast<int *>(dyn + pl.o_sa);
+  const int NTS = (nmax + 3) / 4;  // tiles per side at the batch stride (SA row length)
+  // tile-major fML mirror: last part of this CTA's workspace slot
+  int *FMT = BLK ? ws + (size_t)blockIdx.x * ws_slot + (ws_slot - (tile_table_entries(nmax) + 7) / 8 * 8) : nullptr;
   int *pg = reinterpret_cast<int *>(dyn + pl.o_pg);   // [s][k], k = u1-2: interior[s] + ninio(|s-2u1|)
   int *pb = reinterpret_cast<int *>(dyn + pl.o_pb);   // bulge[s]
   int *p1 = reinterpret_cast<int *>(dyn + pl.o_p1);   // 1xn: interior[s] + ninio(s-2)
@@ -163,6 +182,11 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
     }
     for (int k = tid; k <= n; k += blockDim.x) toff[k] = (k >= 4) ? tri_off(n, k) : 0;
     for (int k = tid; k < 4 * RS; k += blockDim.x) DML[k] = BF_INF;
+    const int NT = (n + 3) >> 2;
+    if (BLK) {
+      for (int k = tid; k < (NT * (NT + 1) / 2) * 16; k += blockDim.x) FMT[k] = BF_INF;
+      for (int k = tid; k < 3 * NTS * 16; k += blockDim.x) SA[k] = BF_INF;
+    }
     int *cg_out = ctri + (size_t)sq * tri_slot;
     int *fg_out = ftri + (size_t)sq * tri_slot;
     int *FM = (PL & kMfeFmSmem) ? fms : fg_out;
@@ -196,6 +220,8 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
             if (dm < kInfThr) e = min(e, dm + T.MLclosing + bf_e_mlstem(T, bf_rtype(t), S[j - 1], S[i + 1]));
             if (e >= kInfThr) e = BF_INF;
           }
+          const int tI = (i - 1) >> 2, tJ = (j - 1) >> 2, tab = ((i - 1) & 3) * 4 + ((j - 1) & 3);
+          if (BLK && tJ - tI >= 6) sp = min(sp, SA[((tJ - tI) % 3) * NTS * 16 + tI * 16 + tab]);
           if (sp >= kInfThr) sp = BF_INF;
           int m = sp;
           if (e < BF_INF && i > 1 && j < n) m = min(m, e + bf_e_mlstem(T, t, S[i - 1], S[j + 1]));
@@ -207,6 +233,7 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
           const int o = toff[dd] + i - 1;
           cg_out[o] = e;
           fg_out[o] = m;
+          if (BLK) FMT[(size_t)(tile_off(NT, tI) + tJ - tI) * 16 + tab] = m;
           if (PL & kMfeFmSmem) fms[o] = m;
           DML[(dd & 3) * RS + i] = sp;
           const int row = (dd & (kRing - 1)) * RS + i;
@@ -268,6 +295,7 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
           if (kk < np) pi[i - 1] = tot;
         }
         // ---- fML split for every cell: k = u - i in [5, d-4]
+        if (!BLK) {
         for (int c = 0; c < ncell; c += 32) {
           const int cell = c + lane;
           const int i = min(cell, ncell - 1) + 1;
@@ -282,6 +310,68 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
             for (int k = 5 + warp; k <= d - 4; k += NW) accs = min(accs, left[toff[k - 1]] + left[toff[d - k] + k]);
           }
           if (cell < ncell) ps[cell] = accs;
+        }
+        } else {
+        // blocked split: only the candidates next to either end stay here -- k in [5, 12] and [d-10, d-4] minus what the
+        // block products of tiles K = I+3 .. J-3 cover (left column x+k-1 inside those tiles)
+        for (int c = 0; c < ncell; c += 32) {
+          const int cell = c + lane;
+          const int i = min(cell, ncell - 1) + 1, x = i - 1;
+          const int tI = x >> 2, tJ = (x + d) >> 2;
+          const int klo = (tJ - tI >= 6) ? 4 * (tI + 3) - x + 1 : 1 << 30, khi = 4 * (tJ - 3) + 3 - x + 1;  // covered k range
+          int accs = BF_INF;
+          const int *left = FM + x;
+          for (int slot = warp; slot < 15; slot += NW) {
+            const int k = slot < 8 ? 5 + slot : d - 18 + slot;  // 5..12, d-10..d-4
+            if (k < 5 || k > d - 4 || (slot >= 8 && k <= 12)) continue;  // warp-uniform
+            const int v = left[toff[k - 1]] + left[toff[d - k] + k];
+            if (k < klo || k > khi) accs = min(accs, v);
+          }
+          if (cell < ncell) ps[cell] = accs;
+        }
+        // block products for tile-diagonal D' = (d+7)/4, quarter q = (d+7)%4 of its tiles
+        {
+          const int Dp = (d + 7) >> 2, q = (d + 7) & 3;
+          if (Dp >= 6 && Dp < NT) {
+            const int Tn = NT - Dp;
+            int *dst = SA + (Dp % 3) * NTS * 16;
+            for (int g = warp; q + 16 * g < Tn; g += NW) {
+              const int I = q + 4 * (4 * g + (lane >> 3)), J = I + Dp, sl = lane & 7;
+              int acc[16];
+#pragma unroll
+              for (int k = 0; k < 16; k++) acc[k] = BF_INF;
+              if (I < Tn) {
+                const int *rowI = FMT + (size_t)tile_off(NT, I) * 16;
+                for (int K = I + 3 + sl; K <= J - 3; K += 8) {
+                  const int4 *lp = reinterpret_cast<const int4 *>(rowI + (K - I) * 16);
+                  const int4 *rp = reinterpret_cast<const int4 *>(FMT + (size_t)(tile_off(NT, K) + J - K) * 16);
+                  const int4 *rq = reinterpret_cast<const int4 *>(FMT + (size_t)(tile_off(NT, K + 1) + J - K - 1) * 16);
+                  const int4 r0 = rp[1], r1 = rp[2], r2 = rp[3], r3 = rq[0];  // rows u = 4K+c+1, c = 0..3 (0-based)
+#pragma unroll
+                  for (int a = 0; a < 4; a++) {
+                    const int4 l = lp[a];  // fML[4I+a][4K+c], c = 0..3
+                    acc[a * 4 + 0] = min(acc[a * 4 + 0], min(min(l.x + r0.x, l.y + r1.x), min(l.z + r2.x, l.w + r3.x)));
+                    acc[a * 4 + 1] = min(acc[a * 4 + 1], min(min(l.x + r0.y, l.y + r1.y), min(l.z + r2.y, l.w + r3.y)));
+                    acc[a * 4 + 2] = min(acc[a * 4 + 2], min(min(l.x + r0.z, l.y + r1.z), min(l.z + r2.z, l.w + r3.z)));
+                    acc[a * 4 + 3] = min(acc[a * 4 + 3], min(min(l.x + r0.w, l.y + r1.w), min(l.z + r2.w, l.w + r3.w)));
+                  }
+                }
+              }
+#pragma unroll
+              for (int o = 4; o > 0; o >>= 1) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) acc[k] = min(acc[k], __shfl_xor_sync(BF_FULL, acc[k], o));
+              }
+              if (I < Tn && sl == 0) {
+                int4 *d4 = reinterpret_cast<int4 *>(dst + I * 16);
+                d4[0] = make_int4(acc[0], acc[1], acc[2], acc[3]);
+                d4[1] = make_int4(acc[4], acc[5], acc[6], acc[7]);
+                d4[2] = make_int4(acc[8], acc[9], acc[10], acc[11]);
+                d4[3] = make_int4(acc[12], acc[13], acc[14], acc[15]);
+              }
+            }
+          }
+        }
         }
       }
       __syncthreads();
@@ -528,7 +618,10 @@ __device__ __forceinline__ void pair_barrier(int k) {
 // HALF: warps w and w + NW/2 share one partial buffer.  The first of the pair does the interior part, then the split part; the
 // second does them in the opposite order; between the two halves the pair meets at a named barrier, after which each ADDS onto
 // what the other stored.  Halves the reduction buffers (two CTAs per SM at L = 400) at the cost of one 64-thread barrier.
-template <int NW, int PL, bool HALF = false>
+// BLK: blocked split as in bf_k_mfe_fill.  qm and qm1 are mirrored tile-major in the workspace; the products over tiles
+// K = I+3 .. J-3 of tile-diagonal D' are accumulated during phases d = 4D'-7 .. 4D'-4 (lanes = 4 tiles x 4 K-slices x 2 column
+// halves, 12 x 128-bit loads per 32 DFMA and 4 B of operand traffic per relaxation instead of 16) into SA[D' % 3] (workspace).
+template <int NW, int PL, bool HALF = false, bool BLK = false>
 __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restrict__ P, BfBatchDev b, double *qbtri, size_t tri_slot,
                                                         double *ws, size_t ws_slot, double *qm_perseq, const int *mfe_for_scale,
                                                         double *lnscale_out, int *work_counter) {
@@ -563,6 +656,12 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
   else { QG = wsp; wsp += kRing * RS; }
   if (PL & kPfR2Smem) { Q1 = reinterpret_cast<double *>(dyn + pl.o_r2); QBB = Q1 + kRing * RS; }
   else { Q1 = wsp; QBB = wsp + kRing * RS; }
+  // blocked split: tile-major mirrors of qm / qm1 and the block-product sums of three tile-diagonals, at the end of the slot
+  const int NTS = (nmax + 3) / 4;
+  const size_t tt = (tile_table_entries(nmax) + 7) / 8 * 8;
+  double *QMT = BLK ? ws + (size_t)blockIdx.x * ws_slot + (ws_slot - (2 * tt + (size_t)3 * NTS * 16)) : nullptr;
+  double *QM1T = BLK ? QMT + tt : nullptr;
+  double *SA = BLK ? QM1T + tt : nullptr;
 
   for (int k = tid; k < (int)(pl.total / 4); k += blockDim.x) reinterpret_cast<int *>(dyn)[k] = 0;
   __syncthreads();
@@ -596,6 +695,11 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
     if (tid == 0 && lnscale_out) lnscale_out[sq] = lns;
     for (int k = tid; k < 4 * RS; k += blockDim.x) QMS[k] = 0.0;
     for (int k = tid; k < 2 * RS; k += blockDim.x) AU[k] = 0.0;
+    const int NT = (n + 3) >> 2;
+    if (BLK) {
+      for (int k = tid; k < (NT * (NT + 1) / 2) * 16; k += blockDim.x) { QMT[k] = 0.0; QM1T[k] = 0.0; }
+      for (int k = tid; k < 3 * NTS * 16; k += blockDim.x) SA[k] = 0.0;
+    }
     __syncthreads();
     for (int k = tid; k < 31 * 32; k += blockDim.x) {
       const int s = k >> 5, u1 = (k & 31) + 2;
@@ -634,6 +738,8 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
           double qms = 0.0, qb = 0.0;
 #pragma unroll
           for (int w = 0; w < NB; w++) qms += ps[w * RS + cell];
+          const int tI = (i - 1) >> 2, tJ = (j - 1) >> 2, tab = ((i - 1) & 3) * 4 + ((j - 1) & 3);
+          if (BLK && tJ - tI >= 6) qms += SA[((tJ - tI) % 3) * NTS * 16 + tI * 16 + tab];
           if (t) {
 #pragma unroll
             for (int w = 0; w < NB; w++) qb += pi[w * RS + cell];
@@ -651,6 +757,11 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
           qb_out[o] = qb;
           QM[o] = qm;
           QM1[o] = qm1;
+          if (BLK) {
+            const size_t to = (size_t)(tile_off(NT, tI) + tJ - tI) * 16 + tab;
+            QMT[to] = qm;
+            QM1T[to] = qm1;
+          }
           QMS[(dd & 3) * RS + i] = qms;
           AU[(dd & 1) * RS + i] = au;
           const int row = (dd & (kRing - 1)) * RS + i;
@@ -718,6 +829,7 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
         };
         // ---- qm split for every cell: k = u - i in [5, d-4] (qm on diagonal k-1 >= 4, qm1 on diagonal d-k >= 4)
         auto do_split = [&](const bool add) {
+        if (!BLK) {
         for (int c = 0; c < ncell; c += 32) {
           const int cell = c + lane;
           const int i = min(cell, ncell - 1) + 1;
@@ -731,6 +843,61 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
             for (int k = 5 + warp; k <= d - 4; k += NW) accs = fma(left[toff[k - 1]], right[toff[d - k] + k], accs);
           }
           if (cell < ncell) ps[cell] = add ? ps[cell] + accs : accs;
+        }
+        } else {
+        // only the candidates next to either end stay here: k in [5, 12] and [d-10, d-4] minus what the block products cover
+        for (int c = 0; c < ncell; c += 32) {
+          const int cell = c + lane;
+          const int i = min(cell, ncell - 1) + 1, x = i - 1;
+          const int tI = x >> 2, tJ = (x + d) >> 2;
+          const int klo = (tJ - tI >= 6) ? 4 * (tI + 3) - x + 1 : 1 << 30, khi = 4 * (tJ - 3) + 3 - x + 1;  // covered k range
+          double accs = 0.0;
+          const double *left = QM + x, *right = QM1 + x;
+          for (int slot = warp; slot < 15; slot += NW) {
+            const int k = slot < 8 ? 5 + slot : d - 18 + slot;  // 5..12, d-10..d-4
+            if (k < 5 || k > d - 4 || (slot >= 8 && k <= 12)) continue;  // warp-uniform
+            const double v = left[toff[k - 1]] * right[toff[d - k] + k];
+            if (k < klo || k > khi) accs += v;
+          }
+          if (cell < ncell) ps[cell] = add ? ps[cell] + accs : accs;
+        }
+        // block products for tile-diagonal D' = (d+7)/4, quarter q = (d+7)%4 of its tiles
+        const int Dp = (d + 7) >> 2, q = (d + 7) & 3;
+        if (Dp >= 6 && Dp < NT) {
+          const int Tn = NT - Dp;
+          double *dst = SA + (Dp % 3) * NTS * 16;
+          for (int g = warp; q + 16 * g < Tn; g += NW) {
+            const int I = q + 4 * (4 * g + (lane >> 3)), J = I + Dp, sl = (lane >> 1) & 3, hb = (lane & 1) * 2;  // columns hb, hb+1
+            double acc[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc[k] = 0.0;
+            if (I < Tn) {
+              const double *rowI = QMT + (size_t)tile_off(NT, I) * 16;
+              for (int K = I + 3 + sl; K <= J - 3; K += 4) {
+                const double *lp = rowI + (K - I) * 16;
+                const double *rp = QM1T + (size_t)(tile_off(NT, K) + J - K) * 16 + hb;
+                const double *rq = QM1T + (size_t)(tile_off(NT, K + 1) + J - K - 1) * 16 + hb;
+                const double2 r0 = *reinterpret_cast<const double2 *>(rp + 4), r1 = *reinterpret_cast<const double2 *>(rp + 8),
+                              r2 = *reinterpret_cast<const double2 *>(rp + 12), r3 = *reinterpret_cast<const double2 *>(rq);
+#pragma unroll
+                for (int a = 0; a < 4; a++) {
+                  const double2 l01 = *reinterpret_cast<const double2 *>(lp + a * 4), l23 = *reinterpret_cast<const double2 *>(lp + a * 4 + 2);
+                  acc[a * 2 + 0] = fma(l01.x, r0.x, fma(l01.y, r1.x, fma(l23.x, r2.x, fma(l23.y, r3.x, acc[a * 2 + 0]))));
+                  acc[a * 2 + 1] = fma(l01.x, r0.y, fma(l01.y, r1.y, fma(l23.x, r2.y, fma(l23.y, r3.y, acc[a * 2 + 1]))));
+                }
+              }
+            }
+#pragma unroll
+            for (int o = 4; o > 1; o >>= 1) {
+#pragma unroll
+              for (int k = 0; k < 8; k++) acc[k] += __shfl_xor_sync(BF_FULL, acc[k], o);
+            }
+            if (I < Tn && sl == 0) {
+#pragma unroll
+              for (int a = 0; a < 4; a++) *reinterpret_cast<double2 *>(dst + I * 16 + a * 4 + hb) = make_double2(acc[a * 2], acc[a * 2 + 1]);
+            }
+          }
+        }
         }
         };
         if (!HALF) {
@@ -859,6 +1026,13 @@ static FillCfg pf_cfg(int nmax) {
   return c;
 }
 
+// blocked split (tile-major mirror + block products): for NW = 8 and the two default placements.  It pays once the split
+// operands no longer fit on chip (measured: L=100 3.86 -> 5.18 ms, L=200 16.1 -> 17.8 ms, L=400 143 -> 117 ms): long sequences only
+static bool mfe_blk(int nmax, const FillCfg &c) {
+  return env_int("BF_BLK", 1) && c.nw == 8 && (c.pl == 0 || c.pl == kMfeRgSmem) && nmax >= env_int("BF_BLK_MIN", 350) &&
+         mfe_plan(nmax, c.nw, c.pl, true).total <= kSmemBudget;
+}
+
 // 0: length not covered by the fill path (the generic kernels take it); else 1 + placement flags
 int bf_fill_mfe_mode(int nmax) {
   if (nmax < 1 || nmax > 2000) return 0;
@@ -868,21 +1042,35 @@ int bf_fill_pf_mode(int nmax) {
   if (nmax < 1 || nmax > 2000) return 0;
   return pf_cfg(nmax).pl + 1;
 }
-size_t bf_mfe_ws_slot(int nmax) {  // ints of per-CTA HBM workspace
+size_t bf_mfe_ws_slot(int nmax) {  // ints of per-CTA HBM workspace: [rings when they are not on chip][tile-major fML mirror when blocked]
   const FillCfg c = mfe_cfg(nmax);
-  if (c.pl < 0 || (c.pl & kMfeRgSmem)) return 0;
-  return ((size_t)3 * kRing * mfe_plan(nmax, c.nw, c.pl).rs + 7) / 8 * 8;
+  if (c.pl < 0) return 0;
+  size_t o = 0;
+  if (!(c.pl & kMfeRgSmem)) o += ((size_t)3 * kRing * mfe_plan(nmax, c.nw, c.pl).rs + 7) / 8 * 8;
+  if (mfe_blk(nmax, c)) o += (tile_table_entries(nmax) + 7) / 8 * 8;
+  return o;
 }
-size_t bf_pf_ws_slot(int nmax) {  // doubles of per-CTA HBM workspace
+static bool pf_blk(int nmax, const FillCfg &c) {
+  return env_int("BF_BLK", 1) && c.nw == 8 && c.pl == 0 && nmax >= env_int("BF_BLK_MIN_PF", 250);
+}
+static bool pf_half(int nmax, const FillCfg &c) {
+  // long sequences: with one partial buffer per warp only one CTA fits an SM; sharing buffers between warp pairs fits two
+  return c.nw == 8 && c.pl == 0 && env_int("BF_PF_HALF", 1) && pf_plan(nmax, 8, 0, false).total > 113 * 1024 &&
+         pf_plan(nmax, 8, 0, true).total <= 113 * 1024;
+}
+size_t bf_pf_ws_slot(int nmax) {  // doubles of per-CTA HBM workspace: [tables that are not on chip][blocked split: qm/qm1 mirrors, sums]
   const FillCfg c = pf_cfg(nmax);
-  return c.pl < 0 ? 0 : pf_ws_doubles(nmax, c.pl);
+  if (c.pl < 0) return 0;
+  size_t o = pf_ws_doubles(nmax, c.pl);
+  if (pf_blk(nmax, c)) o += 2 * ((tile_table_entries(nmax) + 7) / 8 * 8) + (size_t)3 * ((nmax + 3) / 4) * 16;
+  return (o + 7) / 8 * 8;
 }
 
-template <int NW, int PL>
+template <int NW, int PL, bool BLK = false>
 static cudaError_t mfe_fill_t(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *grid_out, bool launch,
                               int *counter, cudaStream_t st) {
-  auto kern = bf_k_mfe_fill<NW, PL>;
-  const size_t sm = mfe_plan(b.stride, NW, PL).total;
+  auto kern = bf_k_mfe_fill<NW, PL, BLK>;
+  const size_t sm = mfe_plan(b.stride, NW, PL, BLK).total;
   cudaError_t e = set_smem(kern, sm);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -915,6 +1103,10 @@ static cudaError_t mfe_fill_dispatch(const BfParams *dP, const BfBatchDev &b, in
                                      bool launch, int *counter, cudaStream_t st) {
   const FillCfg c = mfe_cfg(b.stride);
   if (c.pl < 0) return cudaErrorInvalidValue;
+  if (mfe_blk(b.stride, c)) {
+    if (c.pl == 0) return mfe_fill_t<8, 0, true>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
+    return mfe_fill_t<8, kMfeRgSmem, true>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
+  }
   if (c.nw == 4) return mfe_fill_pl<4>(c.pl, dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
   if (c.nw == 2) return mfe_fill_pl<2>(c.pl, dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
   return mfe_fill_pl<8>(c.pl, dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
@@ -939,10 +1131,10 @@ cudaError_t bf_launch_trace(const BfParams *dP, const BfBatchDev &b, const int *
   return cudaGetLastError();
 }
 
-template <int NW, int PL, bool HALF = false>
+template <int NW, int PL, bool HALF = false, bool BLK = false>
 static cudaError_t pf_fill_t(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale, double *lnscale,
                              int sms, int *grid_out, bool launch, int *counter, cudaStream_t st) {
-  auto kern = bf_k_pf_fill<NW, PL, HALF>;
+  auto kern = bf_k_pf_fill<NW, PL, HALF, BLK>;
   const size_t sm = pf_plan(b.stride, NW, PL, HALF).total;
   cudaError_t e = set_smem(kern, sm);
   if (e != cudaSuccess) return e;
@@ -975,10 +1167,10 @@ static cudaError_t pf_fill_dispatch(const BfParams *dP, const BfBatchDev &b, dou
                                     double *lnscale, int sms, int *grid_out, bool launch, int *counter, cudaStream_t st) {
   const FillCfg c = pf_cfg(b.stride);
   if (c.pl < 0) return cudaErrorInvalidValue;
-  // long sequences: with one partial buffer per warp only one CTA fits an SM; sharing buffers between warp pairs fits two
-  if (c.nw == 8 && c.pl == 0 && env_int("BF_PF_HALF", 1) && pf_plan(b.stride, 8, 0, false).total > 113 * 1024 &&
-      pf_plan(b.stride, 8, 0, true).total <= 113 * 1024)
-    return pf_fill_t<8, 0, true>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+  const bool half = pf_half(b.stride, c), blk = pf_blk(b.stride, c);
+  if (half && blk) return pf_fill_t<8, 0, true, true>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+  if (half) return pf_fill_t<8, 0, true, false>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+  if (blk) return pf_fill_t<8, 0, false, true>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
   if (c.nw == 4) return pf_fill_pl<4>(c.pl, dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
   if (c.nw == 2) return pf_fill_pl<2>(c.pl, dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
   return pf_fill_pl<8>(c.pl, dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);

@@ -141,3 +141,20 @@ def test_bpp_ragged_and_unavailable_cases(engine, oracle):
     with pytest.raises(engine.EngineError) as ei:
         engine.score_batch(["GGGG&CCCC"], [["((((&))))"]], want=engine.WANT_DEFECT)
     assert ei.value.code == 4
+
+
+def test_blocked_split_matches_oracle(engine, oracle, monkeypatch):
+    """The blocked split (tile-major mirrors + 4x4 block products, long sequences by default) forced on for every length:
+    MFE energies and structures bit-exact, ensemble free energy within 1e-6 relative of the oracle."""
+    monkeypatch.setenv("BF_BLK", "1")
+    monkeypatch.setenv("BF_BLK_MIN", "1")
+    monkeypatch.setenv("BF_BLK_MIN_PF", "1")
+    rng = np.random.default_rng(77)
+    seqs = ["".join("ACGU"[x] for x in rng.integers(0, 4, int(L))) for L in rng.integers(20, 180, 96)]
+    seqs += rand_seqs(5, 4, 300) + rand_seqs(6, 2, 401)
+    out = engine.score_batch(seqs, want=engine.WANT_MFE | engine.WANT_SS | engine.WANT_PF)
+    for k, s in enumerate(seqs):
+        e, ss = oracle.mfe(s)
+        assert out["mfe_dcal"][k] == e and out["mfe_ss"][k] == ss, (len(s), k)
+        f = oracle.pf(s)[4]
+        assert abs(out["pf"][k, 4] - f) <= 1e-6 * max(1.0, abs(f)), (len(s), k)
