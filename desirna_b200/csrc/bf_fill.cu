@@ -262,10 +262,33 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
           const int t = ptype_sp(SP, i, j);
           const int si1 = S[i + 1], sj1 = S[j - 1];
           int accg = BF_INF, acc1 = BF_INF, accb = BF_INF;
+          constexpr bool kBatchR2 = (NW == 8 && PL == 0 && BLK);  // long-sequence configuration: every ring is read through L2
+          if (kBatchR2) {
+            // bulge and 1xn candidates of this warp's (at most four) loop sizes: all sixteen loads first
+            int sv[4], ns = 0;
+            BF_FOR_MY_S(NW, warp, smax, s) { if (ns < 4) sv[ns] = s; ns++; }
+            int b0[4], b1[4], o0[4], o1[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int s = u < ns ? sv[u] : 2;
+              const int row = ((d - 2 - s) & (kRing - 1)) * RS + i;
+              b0[u] = CB[row + 1]; b1[u] = CB[row + 1 + s];
+              o0[u] = C1[row + 2]; o1[u] = C1[row + s];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              if (u < ns) {
+                accb = min(accb, min(b0[u], b1[u]) + pb[sv[u]]);
+                if (sv[u] >= 4) acc1 = min(acc1, min(o0[u], o1[u]) + p1[sv[u]]);
+              }
+            }
+          }
           BF_FOR_MY_S(NW, warp, smax, s) {
             const int row = ((d - 2 - s) & (kRing - 1)) * RS + i;
-            accb = min(accb, min(CB[row + 1], CB[row + 1 + s]) + pb[s]);
-            if (s >= 4) acc1 = min(acc1, min(C1[row + 2], C1[row + s]) + p1[s]);
+            if (!kBatchR2) {
+              accb = min(accb, min(CB[row + 1], CB[row + 1 + s]) + pb[s]);
+              if (s >= 4) acc1 = min(acc1, min(C1[row + 2], C1[row + s]) + p1[s]);
+            }
             if (s >= 6) {
               const int *cgp = CG + row + 3;
               const int *pen = pg + (s << 5);
@@ -313,21 +336,35 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
         }
         } else {
         // blocked split: only the candidates next to either end stay here -- k in [5, 12] and [d-10, d-4] minus what the
-        // block products of tiles K = I+3 .. J-3 cover (left column x+k-1 inside those tiles)
-        for (int c = 0; c < ncell; c += 32) {
-          const int cell = c + lane;
-          const int i = min(cell, ncell - 1) + 1, x = i - 1;
-          const int tI = x >> 2, tJ = (x + d) >> 2;
-          const int klo = (tJ - tI >= 6) ? 4 * (tI + 3) - x + 1 : 1 << 30, khi = 4 * (tJ - 3) + 3 - x + 1;  // covered k range
-          int accs = BF_INF;
-          const int *left = FM + x;
+        // block products of tiles K = I+3 .. J-3 cover (left column x+k-1 inside those tiles).  Four chunks of 32 cells are
+        // handled together so that eight operand pairs are in flight per thread.
+        for (int c = 0; c < ncell; c += 128) {
+          int xs[4], klo[4], khi[4], accs[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int x = min(c + 32 * u + lane, ncell - 1);
+            const int tI = x >> 2, tJ = (x + d) >> 2;
+            xs[u] = x;
+            klo[u] = (tJ - tI >= 6) ? 4 * (tI + 3) - x + 1 : 1 << 30;  // covered k range
+            khi[u] = 4 * (tJ - 3) + 3 - x + 1;
+            accs[u] = BF_INF;
+          }
           for (int slot = warp; slot < 15; slot += NW) {
             const int k = slot < 8 ? 5 + slot : d - 18 + slot;  // 5..12, d-10..d-4
             if (k < 5 || k > d - 4 || (slot >= 8 && k <= 12)) continue;  // warp-uniform
-            const int v = left[toff[k - 1]] + left[toff[d - k] + k];
-            if (k < klo || k > khi) accs = min(accs, v);
+            const int o1 = toff[k - 1], o2 = toff[d - k] + k;
+            int va[4], vb[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { va[u] = FM[xs[u] + o1]; vb[u] = FM[xs[u] + o2]; }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+              if (k < klo[u] || k > khi[u]) accs[u] = min(accs[u], va[u] + vb[u]);
           }
-          if (cell < ncell) ps[cell] = accs;
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int cell = c + 32 * u + lane;
+            if (cell < ncell) ps[cell] = accs[u];
+          }
         }
         // block products for tile-diagonal D' = (d+7)/4, quarter q = (d+7)%4 of its tiles
         {
@@ -790,10 +827,33 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
           const int t = bf_ptype_bases(S[i], S[j]);
           const int si1 = S[i + 1], sj1 = S[j - 1];
           double accg = 0.0, acc1 = 0.0, accb = 0.0;
+          constexpr bool kBatchR2 = (NW == 8 && PL == 0);  // long-sequence configuration: every ring is read through L2
+          if (kBatchR2) {
+            // bulge and 1xn candidates of this warp's (at most four) loop sizes: all sixteen loads first
+            int sv[4], ns = 0;
+            BF_FOR_MY_S(NW, warp, smax, s) { if (ns < 4) sv[ns] = s; ns++; }
+            double b0[4], b1[4], o0[4], o1[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int s = u < ns ? sv[u] : 2;
+              const int row = ((d - 2 - s) & (kRing - 1)) * RS + i;
+              b0[u] = QBB[row + 1]; b1[u] = QBB[row + 1 + s];
+              o0[u] = Q1[row + 2]; o1[u] = Q1[row + s];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              if (u < ns) {
+                accb += (b0[u] + b1[u]) * wb[sv[u]];
+                if (sv[u] >= 4) acc1 += (o0[u] + o1[u]) * w1[sv[u]];
+              }
+            }
+          }
           BF_FOR_MY_S(NW, warp, smax, s) {
             const int row = ((d - 2 - s) & (kRing - 1)) * RS + i;
-            accb += (QBB[row + 1] + QBB[row + 1 + s]) * wb[s];
-            if (s >= 4) acc1 += (Q1[row + 2] + Q1[row + s]) * w1[s];
+            if (!kBatchR2) {
+              accb += (QBB[row + 1] + QBB[row + 1 + s]) * wb[s];
+              if (s >= 4) acc1 += (Q1[row + 2] + Q1[row + s]) * w1[s];
+            }
             if (s >= 6) {
               const double *qp = QG + row + 3;
               const double *w = wg + (s << 5);
@@ -845,21 +905,36 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
           if (cell < ncell) ps[cell] = add ? ps[cell] + accs : accs;
         }
         } else {
-        // only the candidates next to either end stay here: k in [5, 12] and [d-10, d-4] minus what the block products cover
-        for (int c = 0; c < ncell; c += 32) {
-          const int cell = c + lane;
-          const int i = min(cell, ncell - 1) + 1, x = i - 1;
-          const int tI = x >> 2, tJ = (x + d) >> 2;
-          const int klo = (tJ - tI >= 6) ? 4 * (tI + 3) - x + 1 : 1 << 30, khi = 4 * (tJ - 3) + 3 - x + 1;  // covered k range
-          double accs = 0.0;
-          const double *left = QM + x, *right = QM1 + x;
+        // only the candidates next to either end stay here: k in [5, 12] and [d-10, d-4] minus what the block products cover.
+        // Four chunks of 32 cells are handled together so that eight operand pairs are in flight per thread.
+        for (int c = 0; c < ncell; c += 128) {
+          int xs[4], klo[4], khi[4];
+          double accs[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int x = min(c + 32 * u + lane, ncell - 1);
+            const int tI = x >> 2, tJ = (x + d) >> 2;
+            xs[u] = x;
+            klo[u] = (tJ - tI >= 6) ? 4 * (tI + 3) - x + 1 : 1 << 30;  // covered k range
+            khi[u] = 4 * (tJ - 3) + 3 - x + 1;
+            accs[u] = 0.0;
+          }
           for (int slot = warp; slot < 15; slot += NW) {
             const int k = slot < 8 ? 5 + slot : d - 18 + slot;  // 5..12, d-10..d-4
             if (k < 5 || k > d - 4 || (slot >= 8 && k <= 12)) continue;  // warp-uniform
-            const double v = left[toff[k - 1]] * right[toff[d - k] + k];
-            if (k < klo || k > khi) accs += v;
+            const int o1 = toff[k - 1], o2 = toff[d - k] + k;
+            double va[4], vb[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { va[u] = QM[xs[u] + o1]; vb[u] = QM1[xs[u] + o2]; }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+              if (k < klo[u] || k > khi[u]) accs[u] += va[u] * vb[u];
           }
-          if (cell < ncell) ps[cell] = add ? ps[cell] + accs : accs;
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int cell = c + 32 * u + lane;
+            if (cell < ncell) ps[cell] = add ? ps[cell] + accs[u] : accs[u];
+          }
         }
         // block products for tile-diagonal D' = (d+7)/4, quarter q = (d+7)%4 of its tiles
         const int Dp = (d + 7) >> 2, q = (d + 7) & 3;
