@@ -311,6 +311,13 @@ def run_ours(args):
     hbm_bytes = (2 * L + 1 + 4 + 4 + 40 + 4 + L) * B
     roof["hbm"] = {"achieved_gbs": hbm_bytes / (sum(main["kernel_ms"]) * 1e-3) / 1e9, "peak_gbs": peaks["hbm_gbs"], "peak_src": peaks["hbm_src"], "algorithmic_bytes_per_launch": hbm_bytes}
 
+    # the same two fractions for the other lengths of the sweep (kernel times of this run)
+    roof["by_length"] = {}
+    for l, (m_ms, p_ms, _e) in kern.items():
+        rm, rp = relaxations(int(l))
+        roof["by_length"][l] = {"mfe_int32_frac": 2.0 * rm * B / (m_ms * 1e-3) / 1e12 / peaks["int32_tops"],
+                                "pf_fp64_frac": 2.0 * rp * B / (p_ms * 1e-3) / 1e12 / peaks["fp64_tflops"]}
+
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu:
