@@ -274,6 +274,29 @@ def run_ours(args):
             kern[str(l)] = m["kernel_ms"]; checks[str(l)] = m["ok"]
             del m
 
+    # ---- the "+defect" column: the same step plus the outside pass and the ensemble defect of the target (Edef scoring,
+    # energy_scores.py:362-374), L-workload only
+    WANTD = WANT | eng.WANT_DEFECT
+    bD = main["bufs"]
+    dfc = torch.zeros(B, dtype=torch.float64, device=dev)
+    def stepD():
+        eng.score_batch_device(bD["seq"], bD["lens"], WANTD, targets=bD["targets"], mfe=bD["mfe"], ss=bD["ss"], pf=bD["pf"], ev=bD["ev"],
+                               stream=stream, defect=dfc)
+    for _ in range(3):
+        stepD()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nD = max(2, min(args.steps, 3))
+    e0.record()
+    for _ in range(nD):
+        stepD()
+    e1.record(); e1.synchronize()
+    tD = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tD, op=dist.ReduceOp.MAX)
+    with_defect = {"value": world * B * nD / (float(tD.item()) * 1e-3), "unit": "folds/s", "ms_per_step": float(tD.item()) / nD,
+                   "defect_in_0_1": bool(((dfc >= -1e-9) & (dfc <= 1.0 + 1e-9)).all().item()), "defect_mean": float(dfc.mean().item())}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -299,6 +322,15 @@ def run_ours(args):
         ach = 2.0 * r_mfe * B / (mfe_ms * 1e-3) / 1e12
         roof = {"kernel": names[0], "bound": "int32", "achieved": ach, "peak": peaks["int32_tops"], "unit": "TOP/s", "frac": ach / peaks["int32_tops"],
                 "traffic": None, "algorithmic": f"2 int32 ops x {r_mfe:.4g} relaxations/fold x {B} folds per launch", "peak_src": peaks["chip_src"]}
+    # DRAM traffic of the dominant fill kernel per launch, from the committed `ncu --set full` capture of this workload (if any)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        key = f"{'bf_k_pf_fill' if dom == 1 else 'bf_k_mfe_fill'}@L{L}xB{B}"
+        if key in tr:
+            roof["traffic"] = tr[key]["dram_bytes"]
+            roof["traffic_src"] = tr[key]["src"]
+    except Exception:
+        pass
     roof["kernel_ms"] = dict(zip(names, main["kernel_ms"]))
     roof["share_of_step"] = main["kernel_ms"][dom] / max(1e-9, sum(main["kernel_ms"]))
     # on-chip operand traffic view (4 B per interior candidate, 8 B per split candidate; fp64 doubles it)
@@ -334,7 +366,7 @@ def run_ours(args):
                    "l2": "256 MiB write between timed steps"},
         "e2e": {"value": e2e_val, "unit": "folds/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "timer": "host clock around the synchronous C-ABI call"},
         "gpu_launches": int(launches),
-        "roofline": roof, "cpu_baseline": cpu, "by_length": by, "kernel_ms_by_length": kern,
+        "roofline": roof, "cpu_baseline": cpu, "by_length": by, "kernel_ms_by_length": kern, "with_ensemble_defect": with_defect,
         "checks": {"ed_equals_mfe_and_epf_le_mfe": checks, "e2e_matches_device_path": e2e_ok},
         "clocks": clocks,
     }

@@ -161,7 +161,8 @@ def microbench():
     return {"int32_ops_per_s": out[0], "fp64_flops_per_s": out[1], "smem_bytes_per_s": out[2]}
 
 
-def score_batch_device(seq, lens, want, cut=None, nopair=None, targets=None, mfe=None, ss=None, pf=None, ev=None, stream=0):
+def score_batch_device(seq, lens, want, cut=None, nopair=None, targets=None, mfe=None, ss=None, pf=None, ev=None, stream=0, defect=None,
+                       bpp=None):
     """Device-resident entry point (bf_score_batch_device).  Arguments are torch CUDA tensors:
     seq uint8[B,stride], lens int32[B], cut int32[B], nopair uint8[B,stride], targets uint8[B,T,stride];
     outputs mfe int32[B], ss uint8[B,stride+1], pf float64[B,5], ev int32[B,T].  Enqueues on `stream`
@@ -179,6 +180,8 @@ def score_batch_device(seq, lens, want, cut=None, nopair=None, targets=None, mfe
     r.mfe_ss = ss.data_ptr() if ss is not None else None
     r.pf = pf.data_ptr() if pf is not None else None
     r.eval_dcal = ev.data_ptr() if ev is not None else None
+    r.defect = defect.data_ptr() if defect is not None else None   # float64[B]
+    r.bpp = bpp.data_ptr() if bpp is not None else None            # float64[B,stride,stride]
     _check(lib().bf_score_batch_device(C.byref(b), C.byref(r), C.c_void_p(stream)))
 
 
