@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../include/b200fold.h"
+#include "bf_design.h"
 #include "bf_device.cuh"
 #include "bf_kernels.h"
 #include "bf_params.h"
@@ -30,23 +31,41 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// Engine-internal device memory of one pipeline invocation (DP tables, per-CTA workspaces, work counters, timing events).
+// The engine owns one for the bf_score_batch* entry points; every design loop (bf_design_*) owns its own, so that loops
+// running on different streams never share tables.
+struct Workspace {
+  int *d_counters = nullptr;  // work counters (one per kernel kind)
+  DevBuf ws_mfe, ws_pf, d_mfe_scratch;
+  DevBuf tri_c, tri_f, tri_qb, ws_qm, ws_ring, d_lnscale, qm_seq, ws_out;  // diagonal-major fill path (bf_fill.cu)
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // begin/end of mfe, pf, eval in the last call
+  bool ran[3] = {false, false, false};
+  cudaError_t create() {
+    cudaError_t e = cudaMalloc(&d_counters, 8 * sizeof(int));
+    for (int k = 0; k < 6 && e == cudaSuccess; k++) e = cudaEventCreate(&ev[k]);
+    return e;
+  }
+  void destroy() {
+    for (DevBuf *b : {&ws_mfe, &ws_pf, &d_mfe_scratch, &tri_c, &tri_f, &tri_qb, &ws_qm, &ws_ring, &d_lnscale, &qm_seq, &ws_out}) b->release();
+    if (d_counters) cudaFree(d_counters);
+    d_counters = nullptr;
+    for (int k = 0; k < 6; k++) { if (ev[k]) cudaEventDestroy(ev[k]); ev[k] = nullptr; }
+  }
+};
+
 struct Engine {
   bool inited = false, have_params = false;
   int device = 0, sm_count = 0;
   cudaStream_t stream = nullptr;
   BfParams *hP = nullptr;  // host image
   BfParams *dP = nullptr;  // device image
-  int *d_counters = nullptr;  // work counters (one per kernel kind)
-  DevBuf ws_mfe, ws_pf, d_mfe_scratch;
-  DevBuf tri_c, tri_f, tri_qb, ws_qm, ws_ring, d_lnscale, qm_seq, ws_out;  // diagonal-major fill path (bf_fill.cu)
+  Workspace w;             // tables and workspaces of the bf_score_batch* entry points
   int fill_kind = 0;                              // BF_FILL=tile: tile-wavefront fill kernels (bf_tile.cu); diag: bf_fill.cu
   bool force_generic = false;                     // BF_FORCE_GENERIC=1: route single strands through the generic kernels too
   // staging for the host-buffer entry point
   DevBuf d_seq, d_len, d_cut, d_nopair, d_targets, d_mfe, d_ss, d_pf, d_eval, d_defect, d_bpp;
   int64_t launches = 0;
   int last_stride = 0;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // begin/end of mfe, pf, eval in the last call
-  bool ran[3] = {false, false, false};
   std::string err;
 };
 
@@ -84,44 +103,44 @@ int validate(const bf_batch_t *b, const bf_result_t *r) {
 }
 
 // all pointers are device pointers
-int run_device(const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t st) {
+int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t st) {
   if (b->B == 0) return BF_OK;
   BfBatchDev db;
   db.B = b->B; db.stride = b->stride; db.seq = b->seq; db.len = b->len; db.cut = b->cut; db.nopair = b->nopair;
   const int wstride = b->stride + 2;
-  g.last_stride = b->stride;
+  if (&w == &g.w) g.last_stride = b->stride;
   const int *mfe_for_scale = nullptr;
-  g.ran[0] = g.ran[1] = g.ran[2] = false;
+  w.ran[0] = w.ran[1] = w.ran[2] = false;
   const bool fill_mfe = !two && !g.force_generic && bf_fill_mfe_mode(b->stride) != 0;
   const bool fill_pf = !two && !g.force_generic && bf_fill_pf_mode(b->stride) != 0;
   if (b->want & (BF_WANT_MFE | BF_WANT_SS)) {
     int *out_mfe = r->mfe_dcal;
-    if (!out_mfe) { CU(g.d_mfe_scratch.reserve((size_t)b->B * sizeof(int)), "cudaMalloc(mfe scratch)"); out_mfe = (int *)g.d_mfe_scratch.p; }
-    cudaEventRecord(g.ev[0], st);
+    if (!out_mfe) { CU(w.d_mfe_scratch.reserve((size_t)b->B * sizeof(int)), "cudaMalloc(mfe scratch)"); out_mfe = (int *)w.d_mfe_scratch.p; }
+    cudaEventRecord(w.ev[0], st);
     if (fill_mfe) {
       const size_t slot = bf_tri_slot(b->stride) * sizeof(int);
-      CU(g.tri_c.reserve((size_t)b->B * slot), "cudaMalloc(c table)");
-      CU(g.tri_f.reserve((size_t)b->B * slot), "cudaMalloc(fML table)");
+      CU(w.tri_c.reserve((size_t)b->B * slot), "cudaMalloc(c table)");
+      CU(w.tri_f.reserve((size_t)b->B * slot), "cudaMalloc(fML table)");
       if (g.fill_kind == 1 && bf_tile_mfe_ok(b->stride)) {
         const size_t wsi = bf_mfe_tile_ws_slot(b->stride) * sizeof(int);
         if (wsi) {
           int grid = 0;
           CU(bf_mfe_tile_grid(db, g.sm_count, &grid), "size bf_k_mfe_tile");
-          CU(g.ws_ring.reserve((size_t)grid * wsi), "cudaMalloc(tile workspace)");
+          CU(w.ws_ring.reserve((size_t)grid * wsi), "cudaMalloc(tile workspace)");
         }
-        CU(bf_launch_mfe_tile(g.dP, db, (int *)g.tri_c.p, (int *)g.tri_f.p, (int *)g.ws_ring.p, g.sm_count, g.d_counters + 0, st),
+        CU(bf_launch_mfe_tile(g.dP, db, (int *)w.tri_c.p, (int *)w.tri_f.p, (int *)w.ws_ring.p, g.sm_count, w.d_counters + 0, st),
            "launch bf_k_mfe_tile");
       } else {
         const size_t wsi = bf_mfe_ws_slot(b->stride) * sizeof(int);
         if (wsi) {
           int grid = 0;
           CU(bf_mfe_fill_grid(db, g.sm_count, &grid), "size bf_k_mfe_fill");
-          CU(g.ws_ring.reserve((size_t)grid * wsi), "cudaMalloc(ring workspace)");
+          CU(w.ws_ring.reserve((size_t)grid * wsi), "cudaMalloc(ring workspace)");
         }
-        CU(bf_launch_mfe_fill(g.dP, db, (int *)g.tri_c.p, (int *)g.tri_f.p, (int *)g.ws_ring.p, g.sm_count, g.d_counters + 0, st),
+        CU(bf_launch_mfe_fill(g.dP, db, (int *)w.tri_c.p, (int *)w.tri_f.p, (int *)w.ws_ring.p, g.sm_count, w.d_counters + 0, st),
            "launch bf_k_mfe_fill");
       }
-      CU(bf_launch_trace(g.dP, db, (const int *)g.tri_c.p, (const int *)g.tri_f.p, out_mfe, (b->want & BF_WANT_SS) ? r->mfe_ss : nullptr,
+      CU(bf_launch_trace(g.dP, db, (const int *)w.tri_c.p, (const int *)w.tri_f.p, out_mfe, (b->want & BF_WANT_SS) ? r->mfe_ss : nullptr,
                          b->stride + 1, st), "launch bf_k_trace");
       g.launches += 2;
     } else {
@@ -130,13 +149,13 @@ int run_device(const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t
       size_t slot = bf_mfe_slot_ints(wstride) * sizeof(int);
       // keep the workspace within a sane share of HBM
       while (grid > g.sm_count && (size_t)grid * slot > ((size_t)48 << 30)) grid -= g.sm_count;
-      CU(g.ws_mfe.reserve((size_t)grid * slot), "cudaMalloc(mfe workspace)");
-      CU(bf_launch_mfe(g.dP, db, two, (int *)g.ws_mfe.p, wstride, grid, g.d_counters + 0, out_mfe,
+      CU(w.ws_mfe.reserve((size_t)grid * slot), "cudaMalloc(mfe workspace)");
+      CU(bf_launch_mfe(g.dP, db, two, (int *)w.ws_mfe.p, wstride, grid, w.d_counters + 0, out_mfe,
                        (b->want & BF_WANT_SS) ? r->mfe_ss : nullptr, b->stride + 1, st), "launch bf_k_mfe");
       g.launches++;
     }
-    cudaEventRecord(g.ev[1], st);
-    g.ran[0] = true;
+    cudaEventRecord(w.ev[1], st);
+    w.ran[0] = true;
     mfe_for_scale = out_mfe;
   }
   const bool want_out = (b->want & (BF_WANT_BPP | BF_WANT_DEFECT)) != 0;
@@ -147,33 +166,33 @@ int run_device(const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t
     dbp.nopair = nullptr;  // hard constraints are added after fc.pf() in the reference (sequence_utils.py:1181)
     // a constrained MFE is not a bound on the unconstrained ensemble: only use it for scaling when unconstrained
     const int *scale_src = b->nopair ? nullptr : mfe_for_scale;
-    cudaEventRecord(g.ev[2], st);
+    cudaEventRecord(w.ev[2], st);
     if (fill_pf) {
       const size_t slot = bf_tri_slot(b->stride) * sizeof(double);
-      CU(g.tri_qb.reserve((size_t)b->B * slot), "cudaMalloc(qb table)");
-      CU(g.d_lnscale.reserve((size_t)b->B * sizeof(double)), "cudaMalloc(lnscale)");
+      CU(w.tri_qb.reserve((size_t)b->B * slot), "cudaMalloc(qb table)");
+      CU(w.d_lnscale.reserve((size_t)b->B * sizeof(double)), "cudaMalloc(lnscale)");
       int grid = 0;
       CU(bf_pf_fill_grid(dbp, g.sm_count, &grid), "size bf_k_pf_fill");
       const size_t ws = bf_pf_ws_slot(b->stride) * sizeof(double);
-      if (ws) CU(g.ws_qm.reserve((size_t)grid * ws), "cudaMalloc(qm workspace)");
+      if (ws) CU(w.ws_qm.reserve((size_t)grid * ws), "cudaMalloc(qm workspace)");
       double *qmseq = nullptr;
       if (want_out) {
-        CU(g.qm_seq.reserve((size_t)b->B * 2 * slot), "cudaMalloc(per-sequence qm/qm1)");
-        qmseq = (double *)g.qm_seq.p;
+        CU(w.qm_seq.reserve((size_t)b->B * 2 * slot), "cudaMalloc(per-sequence qm/qm1)");
+        qmseq = (double *)w.qm_seq.p;
       }
-      CU(bf_launch_pf_fill(g.dP, dbp, (double *)g.tri_qb.p, (double *)g.ws_qm.p, qmseq, scale_src, (double *)g.d_lnscale.p, g.sm_count,
-                           g.d_counters + 1, st), "launch bf_k_pf_fill");
-      CU(bf_launch_pf_ext(g.dP, dbp, (const double *)g.tri_qb.p, (const double *)g.d_lnscale.p, r->pf, st), "launch bf_k_pf_ext");
+      CU(bf_launch_pf_fill(g.dP, dbp, (double *)w.tri_qb.p, (double *)w.ws_qm.p, qmseq, scale_src, (double *)w.d_lnscale.p, g.sm_count,
+                           w.d_counters + 1, st), "launch bf_k_pf_fill");
+      CU(bf_launch_pf_ext(g.dP, dbp, (const double *)w.tri_qb.p, (const double *)w.d_lnscale.p, r->pf, st), "launch bf_k_pf_ext");
       g.launches += 2;
       if (want_out) {
         int ogrid = 0;
         CU(bf_out_grid(dbp, g.sm_count, &ogrid), "size bf_k_pf_out");
-        CU(g.ws_out.reserve((size_t)ogrid * bf_out_ws_slot(b->stride) * sizeof(double)), "cudaMalloc(outside workspace)");
+        CU(w.ws_out.reserve((size_t)ogrid * bf_out_ws_slot(b->stride) * sizeof(double)), "cudaMalloc(outside workspace)");
         if (b->want & BF_WANT_BPP) CU(cudaMemsetAsync(r->bpp, 0, (size_t)b->B * b->stride * b->stride * sizeof(double), st), "clear bpp");
-        CU(bf_launch_pf_out(g.dP, dbp, (const double *)g.tri_qb.p, qmseq, (double *)g.ws_out.p, (const double *)g.d_lnscale.p,
+        CU(bf_launch_pf_out(g.dP, dbp, (const double *)w.tri_qb.p, qmseq, (double *)w.ws_out.p, (const double *)w.d_lnscale.p,
                             (b->want & BF_WANT_DEFECT) ? b->targets : nullptr, b->n_targets, b->stride,
                             (b->want & BF_WANT_DEFECT) ? r->defect : nullptr, (b->want & BF_WANT_BPP) ? r->bpp : nullptr, ogrid,
-                            g.d_counters + 2, st), "launch bf_k_pf_out");
+                            w.d_counters + 2, st), "launch bf_k_pf_out");
         g.launches++;
       }
     } else {
@@ -181,18 +200,18 @@ int run_device(const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t
       int grid = std::min(b->B, g.sm_count * occ);
       size_t slot = bf_pf_slot_doubles(wstride) * sizeof(double);
       while (grid > g.sm_count && (size_t)grid * slot > ((size_t)64 << 30)) grid -= g.sm_count;
-      CU(g.ws_pf.reserve((size_t)grid * slot), "cudaMalloc(pf workspace)");
-      CU(bf_launch_pf(g.dP, dbp, two, (double *)g.ws_pf.p, wstride, grid, g.d_counters + 1, scale_src, r->pf, st), "launch bf_k_pf");
+      CU(w.ws_pf.reserve((size_t)grid * slot), "cudaMalloc(pf workspace)");
+      CU(bf_launch_pf(g.dP, dbp, two, (double *)w.ws_pf.p, wstride, grid, w.d_counters + 1, scale_src, r->pf, st), "launch bf_k_pf");
       g.launches++;
     }
-    cudaEventRecord(g.ev[3], st);
-    g.ran[1] = true;
+    cudaEventRecord(w.ev[3], st);
+    w.ran[1] = true;
   }
   if (b->want & BF_WANT_EVAL) {
-    cudaEventRecord(g.ev[4], st);
+    cudaEventRecord(w.ev[4], st);
     CU(bf_launch_eval(g.dP, db, b->targets, b->n_targets, b->stride, r->eval_dcal, st), "launch bf_k_eval");
-    cudaEventRecord(g.ev[5], st);
-    g.ran[2] = true;
+    cudaEventRecord(w.ev[5], st);
+    w.ran[2] = true;
     g.launches++;
   }
   return BF_OK;
@@ -225,9 +244,8 @@ int bf_init(int device) {
   { const char *fk = getenv("BF_FILL"); g.fill_kind = (fk && !strcmp(fk, "tile")) ? 1 : 0; }
   g.sm_count = prop.multiProcessorCount;
   CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking), "cudaStreamCreate");
-  CU(cudaMalloc(&g.d_counters, 8 * sizeof(int)), "cudaMalloc(counters)");
+  CU(g.w.create(), "create engine workspace");
   CU(bf_upload_constants(), "upload candidate table");
-  for (int k = 0; k < 6; k++) CU(cudaEventCreate(&g.ev[k]), "cudaEventCreate");
   if (!g.hP) g.hP = new BfParams;
   g.inited = true;
   if (g.have_params) return upload_params();
@@ -237,11 +255,11 @@ int bf_init(int device) {
 int bf_shutdown(void) {
   if (!g.inited) return BF_OK;
   cudaStreamSynchronize(g.stream);
-  for (DevBuf *b : {&g.tri_c, &g.tri_f, &g.tri_qb, &g.ws_qm, &g.ws_ring, &g.d_lnscale, &g.qm_seq, &g.ws_out, &g.d_defect, &g.d_bpp, &g.ws_mfe, &g.ws_pf, &g.d_mfe_scratch, &g.d_seq, &g.d_len, &g.d_cut, &g.d_nopair, &g.d_targets, &g.d_mfe, &g.d_ss, &g.d_pf, &g.d_eval}) b->release();
+  for (DevBuf *b : {&g.d_defect, &g.d_bpp, &g.d_seq, &g.d_len, &g.d_cut, &g.d_nopair, &g.d_targets, &g.d_mfe, &g.d_ss, &g.d_pf, &g.d_eval}) b->release();
+  g.w.destroy();
   if (g.dP) cudaFree(g.dP);
-  if (g.d_counters) cudaFree(g.d_counters);
   cudaStreamDestroy(g.stream);
-  g.dP = nullptr; g.d_counters = nullptr; g.stream = nullptr;
+  g.dP = nullptr; g.stream = nullptr;
   g.inited = false;
   return BF_OK;
 }
@@ -309,7 +327,7 @@ int bf_score_batch_device(const bf_batch_t *b, bf_result_t *r, void *cuda_stream
   int rc = validate(b, r);
   if (rc) return rc;
   // the cut array lives on the device: the two-strand kernels handle cut == 0 rows as single strands
-  return run_device(b, r, b->cut != nullptr, (cudaStream_t)cuda_stream);
+  return run_device(g.w, b, r, b->cut != nullptr, (cudaStream_t)cuda_stream);
 }
 
 int bf_score_batch(const bf_batch_t *b, bf_result_t *r) {
@@ -356,7 +374,7 @@ int bf_score_batch(const bf_batch_t *b, bf_result_t *r) {
   if (b->want & (BF_WANT_MFE | BF_WANT_SS)) { CU(g.d_mfe.reserve(B * sizeof(int)), "cudaMalloc(mfe)"); dr.mfe_dcal = (int32_t *)g.d_mfe.p; }
   if (b->want & BF_WANT_SS) { CU(g.d_ss.reserve(B * (S + 1)), "cudaMalloc(ss)"); dr.mfe_ss = (char *)g.d_ss.p; }
   if (b->want & (BF_WANT_PF | BF_WANT_BPP | BF_WANT_DEFECT)) { CU(g.d_pf.reserve(B * 5 * sizeof(double)), "cudaMalloc(pf)"); dr.pf = (double *)g.d_pf.p; }
-  rc = run_device(&db, &dr, two, st);
+  rc = run_device(g.w, &db, &dr, two, st);
   if (rc) return rc;
   if ((b->want & BF_WANT_MFE) && r->mfe_dcal) CU(cudaMemcpyAsync(r->mfe_dcal, dr.mfe_dcal, B * sizeof(int), cudaMemcpyDeviceToHost, st), "D2H mfe");
   if (b->want & BF_WANT_SS) CU(cudaMemcpyAsync(r->mfe_ss, dr.mfe_ss, B * (S + 1), cudaMemcpyDeviceToHost, st), "D2H ss");
@@ -386,8 +404,8 @@ int bf_subopt(const char *seq, int32_t len, const uint8_t *nopair, int32_t delta
   if (rc) return rc;
   const size_t slot = bf_tri_slot(len);
   std::vector<int> c(slot), fm(slot);
-  CU(cudaMemcpy(c.data(), g.tri_c.p, slot * sizeof(int), cudaMemcpyDeviceToHost), "D2H c table");
-  CU(cudaMemcpy(fm.data(), g.tri_f.p, slot * sizeof(int), cudaMemcpyDeviceToHost), "D2H fML table");
+  CU(cudaMemcpy(c.data(), g.w.tri_c.p, slot * sizeof(int), cudaMemcpyDeviceToHost), "D2H c table");
+  CU(cudaMemcpy(fm.data(), g.w.tri_f.p, slot * sizeof(int), cudaMemcpyDeviceToHost), "D2H fML table");
   std::vector<uint8_t> S(len + 2, 0), SP(len + 2, 0);
   for (int k = 1; k <= len; k++) {
     S[k] = (uint8_t)bf_base_code(seq[k - 1]);
@@ -411,10 +429,10 @@ int bf_last_kernel_ms(double out[3]) {
   if (!g.inited) return fail(BF_ERR_NOT_INIT, "bf_init has not been called");
   for (int k = 0; k < 3; k++) {
     out[k] = -1.0;
-    if (!g.ran[k]) continue;
-    CU(cudaEventSynchronize(g.ev[2 * k + 1]), "cudaEventSynchronize");
+    if (!g.w.ran[k]) continue;
+    CU(cudaEventSynchronize(g.w.ev[2 * k + 1]), "cudaEventSynchronize");
     float ms = 0.f;
-    CU(cudaEventElapsedTime(&ms, g.ev[2 * k], g.ev[2 * k + 1]), "cudaEventElapsedTime");
+    CU(cudaEventElapsedTime(&ms, g.w.ev[2 * k], g.w.ev[2 * k + 1]), "cudaEventElapsedTime");
     out[k] = ms;
   }
   return BF_OK;
@@ -432,7 +450,7 @@ int bf_debug_copy_table(int which, int32_t n_seq, void *host, size_t host_bytes,
   const size_t slot = bf_tri_slot(g.last_stride);
   if (slot_entries) *slot_entries = slot;
   if (!host) return BF_OK;
-  DevBuf &t = which == 0 ? g.tri_c : which == 1 ? g.tri_f : g.tri_qb;
+  DevBuf &t = which == 0 ? g.w.tri_c : which == 1 ? g.w.tri_f : g.w.tri_qb;
   const size_t bytes = (size_t)n_seq * slot * (which == 2 ? sizeof(double) : sizeof(int));
   if (bytes > host_bytes || bytes > t.cap) return fail(BF_ERR_ARG, "table copy larger than the host buffer or the table");
   CU(cudaDeviceSynchronize(), "cudaDeviceSynchronize");
@@ -442,5 +460,253 @@ int bf_debug_copy_table(int which, int32_t n_seq, void *host, size_t host_bytes,
 
 int64_t bf_kernel_launches(void) { return g.launches; }
 int bf_sm_count(void) { return g.sm_count; }
+
+// =====================================================================================================
+//                      device-resident Replica-Exchange Monte-Carlo design loop
+// =====================================================================================================
+}  // extern "C"
+
+namespace {
+struct DesignLoop {
+  Workspace w;
+  cudaStream_t st = nullptr;
+  BfDesignDev D;
+  BfDesignCfg C;
+  int B = 0, gstep = 0, re_attempt = 0;
+  uint32_t want = 0;
+  std::vector<void *> allocs;
+  std::vector<uint8_t> active;
+  uint8_t *d_active = nullptr;
+  int *d_rowmap = nullptr;
+  template <typename T>
+  cudaError_t alloc(T **p, size_t n) {
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) { allocs.push_back(q); e = cudaMemset(q, 0, std::max<size_t>(n, 1) * sizeof(T)); }
+    *p = (T *)q;
+    return e;
+  }
+  void destroy() {
+    if (st) cudaStreamSynchronize(st);
+    for (void *q : allocs) cudaFree(q);
+    allocs.clear();
+    w.destroy();
+    if (st) cudaStreamDestroy(st);
+    st = nullptr;
+  }
+};
+
+int design_rows(DesignLoop *h) {
+  // batch rows = the replicas of the active jobs, job-major
+  std::vector<int> rows;
+  for (int j = 0; j < h->D.J; j++)
+    if (h->active[j])
+      for (int r = 0; r < h->D.R; r++) rows.push_back(j * h->D.R + r);
+  h->B = (int)rows.size();
+  if (h->B) CU(cudaMemcpyAsync(h->d_rowmap, rows.data(), rows.size() * sizeof(int), cudaMemcpyHostToDevice, h->st), "H2D row map");
+  CU(cudaMemcpyAsync(h->d_active, h->active.data(), h->active.size(), cudaMemcpyHostToDevice, h->st), "H2D active jobs");
+  CU(cudaStreamSynchronize(h->st), "design row map");   // `rows` is a temporary
+  CU(bf_launch_design_gather(h->D, h->B, h->st), "launch bf_k_design_gather");
+  g.launches++;
+  return BF_OK;
+}
+
+// one scoring pass over the rows: the same pipeline bf_score_batch_device runs (MFE fill + backtrack, PF fill + exterior, eval)
+int design_score(DesignLoop *h) {
+  bf_batch_t b;
+  std::memset(&b, 0, sizeof b);
+  b.B = h->B; b.stride = h->D.stride; b.seq = h->D.mut_seq; b.len = h->D.row_len; b.targets = h->D.row_tgt; b.n_targets = 1; b.want = h->want;
+  bf_result_t r;
+  std::memset(&r, 0, sizeof r);
+  r.mfe_dcal = h->D.o_mfe; r.mfe_ss = h->D.o_ss; r.pf = h->D.o_pf; r.eval_dcal = h->D.o_eval; r.defect = h->D.o_defect;
+  return run_device(h->w, &b, &r, false, h->st);
+}
+}  // namespace
+
+extern "C" {
+
+int bf_design_create(const bf_design_t *c, void **handle) {
+  if (!g.inited) return fail(BF_ERR_NOT_INIT, "bf_init has not been called");
+  if (!g.have_params) return fail(BF_ERR_NOT_INIT, "no energy parameters loaded");
+  if (!c || !handle) return fail(BF_ERR_ARG, "null argument");
+  if (c->n_jobs <= 0 || c->replicas <= 0 || c->stride <= 0 || c->stride > 4000) return fail(BF_ERR_ARG, "bf_design_create: bad shape");
+  if (!c->target || !c->len || !c->allowed || !c->init_seq || !c->temps || !c->tm_prob) return fail(BF_ERR_ARG, "bf_design_create: null buffer");
+  if (c->n_terms <= 0 || c->n_terms > 8 || c->re_attempt <= 0) return fail(BF_ERR_ARG, "bf_design_create: bad scoring terms / re_attempt");
+  const int J = c->n_jobs, R = c->replicas, S = c->stride;
+  const size_t G = (size_t)J * R;
+  // host-side preparation: partner tables and the lists of mutable positions
+  std::vector<short> tpt((size_t)J * S, -1);
+  std::vector<unsigned short> avail((size_t)J * S, 0);
+  std::vector<int> n_avail(J, 0);
+  for (int j = 0; j < J; j++) {
+    const int n = c->len[j];
+    if (n <= 0 || n > S) return fail(BF_ERR_ARG, "bf_design_create: length outside (0, stride]");
+    std::vector<int> stk;
+    for (int i = 0; i < n; i++) {
+      const char ch = c->target[(size_t)j * S + i];
+      if (ch == '(') stk.push_back(i);
+      else if (ch == ')') {
+        if (stk.empty()) return fail(BF_ERR_ARG, "bf_design_create: unbalanced target");
+        tpt[(size_t)j * S + i] = (short)stk.back(); tpt[(size_t)j * S + stk.back()] = (short)i; stk.pop_back();
+      } else if (ch != '.') return fail(BF_ERR_ARG, "bf_design_create: targets may contain only . ( )");
+      const uint8_t a = c->allowed[(size_t)j * S + i];
+      if (a == 0 || a > 15) return fail(BF_ERR_ARG, "bf_design_create: allowed-letter mask outside 1..15");
+      if (__builtin_popcount(a) > 1) avail[(size_t)j * S + n_avail[j]++] = (unsigned short)i;
+    }
+    if (!stk.empty()) return fail(BF_ERR_ARG, "bf_design_create: unbalanced target");
+  }
+  if (bf_fill_mfe_mode(S) == 0 || bf_fill_pf_mode(S) == 0) return fail(BF_ERR_UNAVAILABLE, "bf_design_create: stride outside the fill path");
+  DesignLoop *h = new DesignLoop;
+  std::memset(&h->D, 0, sizeof h->D);
+  std::memset(&h->C, 0, sizeof h->C);
+  auto bail = [&](cudaError_t e, const char *what) { h->destroy(); delete h; return cuda_fail(e, what); };
+#define DCU(call, what) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(e_, what); } while (0)
+  DCU(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking), "cudaStreamCreate(design)");
+  DCU(h->w.create(), "create design workspace");
+  BfDesignDev &D = h->D;
+  D.J = J; D.R = R; D.stride = S;
+  char *tgt; short *d_tpt; uint8_t *allowed; int *len; unsigned short *d_avail; int *d_navail; double *temps, *tm_prob;
+  DCU(h->alloc(&tgt, (size_t)J * S), "cudaMalloc(design)"); DCU(h->alloc(&d_tpt, (size_t)J * S), "cudaMalloc(design)");
+  DCU(h->alloc(&allowed, (size_t)J * S), "cudaMalloc(design)"); DCU(h->alloc(&len, J), "cudaMalloc(design)");
+  DCU(h->alloc(&d_avail, (size_t)J * S), "cudaMalloc(design)"); DCU(h->alloc(&d_navail, J), "cudaMalloc(design)");
+  DCU(h->alloc(&temps, R), "cudaMalloc(design)"); DCU(h->alloc(&tm_prob, R), "cudaMalloc(design)");
+  DCU(h->alloc(&D.job_rng, J), "cudaMalloc(design)");
+  DCU(h->alloc(&D.best_seq, (size_t)J * S), "cudaMalloc(design)"); DCU(h->alloc(&D.best_ss, (size_t)J * (S + 1)), "cudaMalloc(design)");
+  DCU(h->alloc(&D.best_rec, (size_t)J * kDesignRec), "cudaMalloc(design)");
+  DCU(h->alloc(&D.solved_step, J), "cudaMalloc(design)"); DCU(h->alloc(&D.n_solved, J), "cudaMalloc(design)");
+  DCU(h->alloc(&D.cur_seq, G * S), "cudaMalloc(design)"); DCU(h->alloc(&D.cur_ss, G * (S + 1)), "cudaMalloc(design)");
+  DCU(h->alloc(&D.rec, G * kDesignRec), "cudaMalloc(design)"); DCU(h->alloc(&D.shelf, G), "cudaMalloc(design)");
+  DCU(h->alloc(&D.rng, G), "cudaMalloc(design)"); DCU(h->alloc(&D.counts, G * 3), "cudaMalloc(design)");
+  DCU(h->alloc(&h->d_rowmap, G), "cudaMalloc(design)"); DCU(h->alloc(&h->d_active, J), "cudaMalloc(design)");
+  DCU(h->alloc(&D.mut_seq, G * S), "cudaMalloc(design)"); DCU(h->alloc(&D.row_len, G), "cudaMalloc(design)");
+  DCU(h->alloc(&D.row_tgt, G * S), "cudaMalloc(design)"); DCU(h->alloc(&D.o_mfe, G), "cudaMalloc(design)");
+  DCU(h->alloc(&D.o_ss, G * (S + 1)), "cudaMalloc(design)"); DCU(h->alloc(&D.o_pf, G * 5), "cudaMalloc(design)");
+  DCU(h->alloc(&D.o_eval, G), "cudaMalloc(design)");
+  h->want = BF_WANT_MFE | BF_WANT_SS | BF_WANT_PF | BF_WANT_EVAL;
+  BfDesignCfg &C = h->C;
+  C.n_terms = c->n_terms;
+  for (int k = 0; k < c->n_terms; k++) {
+    if (c->term[k] < 0 || c->term[k] > kTermEdef) return bail(cudaErrorInvalidValue, "bf_design_create: unknown scoring term");
+    C.term[k] = c->term[k]; C.weight[k] = c->weight[k];
+    if (c->term[k] == kTermEdef) h->want |= BF_WANT_DEFECT;
+  }
+  if (h->want & BF_WANT_DEFECT) DCU(h->alloc(&D.o_defect, G), "cudaMalloc(design)");
+  C.metropolis_L = c->metropolis_L; C.point_mutations = c->point_mutations; C.acgu = c->acgu;
+  for (int k = 0; k < 4; k++) C.nt_weight[k] = c->nt_weight[k];
+  h->re_attempt = c->re_attempt;
+  D.tgt = tgt; D.tpt = d_tpt; D.allowed = allowed; D.len = len; D.avail = d_avail; D.n_avail = d_navail; D.temps = temps; D.tm_prob = tm_prob;
+  D.rowmap = h->d_rowmap;
+  // uploads
+  std::vector<unsigned long long> rng(G), jrng(J);
+  unsigned long long sd = c->seed * 0x9E3779B97F4A7C15ull + 0x2545F4914F6CDD1Dull;
+  auto next = [&sd]() { sd += 0x9E3779B97F4A7C15ull; unsigned long long z = sd; z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; return z ^ (z >> 31); };
+  for (auto &x : rng) x = next();
+  for (auto &x : jrng) x = next();
+  std::vector<int> shelf(G);
+  for (size_t k = 0; k < G; k++) shelf[k] = (int)(k % R);   // replica r starts on shelf r (sequence_utils.py:880-884)
+  std::vector<double> best((size_t)J * kDesignRec, 1e300);
+  std::vector<int> sstep(J, -1);
+  DCU(cudaMemcpy(tgt, c->target, (size_t)J * S, cudaMemcpyHostToDevice), "H2D design"); DCU(cudaMemcpy(d_tpt, tpt.data(), tpt.size() * sizeof(short), cudaMemcpyHostToDevice), "H2D design");
+  DCU(cudaMemcpy(allowed, c->allowed, (size_t)J * S, cudaMemcpyHostToDevice), "H2D design"); DCU(cudaMemcpy(len, c->len, J * sizeof(int), cudaMemcpyHostToDevice), "H2D design");
+  DCU(cudaMemcpy(d_avail, avail.data(), avail.size() * sizeof(unsigned short), cudaMemcpyHostToDevice), "H2D design");
+  DCU(cudaMemcpy(d_navail, n_avail.data(), J * sizeof(int), cudaMemcpyHostToDevice), "H2D design");
+  DCU(cudaMemcpy(temps, c->temps, R * sizeof(double), cudaMemcpyHostToDevice), "H2D design"); DCU(cudaMemcpy(tm_prob, c->tm_prob, R * sizeof(double), cudaMemcpyHostToDevice), "H2D design");
+  DCU(cudaMemcpy(D.rng, rng.data(), G * sizeof(unsigned long long), cudaMemcpyHostToDevice), "H2D design");
+  DCU(cudaMemcpy(D.job_rng, jrng.data(), J * sizeof(unsigned long long), cudaMemcpyHostToDevice), "H2D design");
+  DCU(cudaMemcpy(D.shelf, shelf.data(), G * sizeof(int), cudaMemcpyHostToDevice), "H2D design");
+  DCU(cudaMemcpy(D.best_rec, best.data(), best.size() * sizeof(double), cudaMemcpyHostToDevice), "H2D design");
+  DCU(cudaMemcpy(D.solved_step, sstep.data(), J * sizeof(int), cudaMemcpyHostToDevice), "H2D design");
+  DCU(cudaMemcpy(D.cur_seq, c->init_seq, G * S, cudaMemcpyHostToDevice), "H2D design");
+#undef DCU
+  h->active.assign(J, 1);
+  int rc = design_rows(h);
+  // score the start sequences (sequence_utils.py:862-888) and record them as step 0
+  if (!rc) rc = bf_launch_design_propose(h->D, h->C, h->B, true, h->st) == cudaSuccess ? BF_OK : fail(BF_ERR_CUDA, "launch bf_k_design_propose");
+  if (!rc) rc = design_score(h);
+  if (!rc) rc = bf_launch_design_accept(h->D, h->C, h->B, true, 0, h->st) == cudaSuccess ? BF_OK : fail(BF_ERR_CUDA, "launch bf_k_design_accept");
+  if (!rc) rc = bf_launch_design_exchange(h->D, h->C, h->d_active, 0, h->st) == cudaSuccess ? BF_OK : fail(BF_ERR_CUDA, "launch bf_k_design_exchange");
+  if (!rc && cudaStreamSynchronize(h->st) != cudaSuccess) rc = fail(BF_ERR_CUDA, std::string("design loop start: ") + cudaGetErrorString(cudaGetLastError()));
+  if (rc) { h->destroy(); delete h; return rc; }
+  g.launches += 3;
+  *handle = h;
+  return BF_OK;
+}
+
+int bf_design_run(void *handle, int32_t global_steps) {
+  DesignLoop *h = (DesignLoop *)handle;
+  if (!h || global_steps < 0) return fail(BF_ERR_ARG, "bf_design_run: bad argument");
+  for (int s = 0; s < global_steps; s++) {
+    h->gstep++;
+    for (int k = 0; k < h->re_attempt && h->B > 0; k++) {
+      CU(bf_launch_design_propose(h->D, h->C, h->B, false, h->st), "launch bf_k_design_propose");
+      int rc = design_score(h);
+      if (rc) return rc;
+      CU(bf_launch_design_accept(h->D, h->C, h->B, false, h->gstep, h->st), "launch bf_k_design_accept");
+      g.launches += 2;
+    }
+    CU(bf_launch_design_exchange(h->D, h->C, h->d_active, h->gstep, h->st), "launch bf_k_design_exchange");
+    g.launches++;
+  }
+  return BF_OK;
+}
+
+int bf_design_sync(void *handle) {
+  DesignLoop *h = (DesignLoop *)handle;
+  if (!h) return fail(BF_ERR_ARG, "bf_design_sync: null handle");
+  CU(cudaStreamSynchronize(h->st), "bf_design_sync");
+  return BF_OK;
+}
+
+int bf_design_set_active(void *handle, const uint8_t *active_jobs) {
+  DesignLoop *h = (DesignLoop *)handle;
+  if (!h || !active_jobs) return fail(BF_ERR_ARG, "bf_design_set_active: null argument");
+  CU(cudaStreamSynchronize(h->st), "bf_design_set_active");
+  for (int j = 0; j < h->D.J; j++) h->active[j] = active_jobs[j] ? 1 : 0;
+  return design_rows(h);
+}
+
+int bf_design_read_jobs(void *handle, char *best_seq, char *best_ss, double *best_rec, int32_t *solved_step, uint32_t *n_solved) {
+  DesignLoop *h = (DesignLoop *)handle;
+  if (!h) return fail(BF_ERR_ARG, "bf_design_read_jobs: null handle");
+  CU(cudaStreamSynchronize(h->st), "bf_design_read_jobs");
+  const size_t J = h->D.J, S = h->D.stride;
+  if (best_seq) CU(cudaMemcpy(best_seq, h->D.best_seq, J * S, cudaMemcpyDeviceToHost), "D2H best_seq");
+  if (best_ss) CU(cudaMemcpy(best_ss, h->D.best_ss, J * (S + 1), cudaMemcpyDeviceToHost), "D2H best_ss");
+  if (best_rec) CU(cudaMemcpy(best_rec, h->D.best_rec, J * kDesignRec * sizeof(double), cudaMemcpyDeviceToHost), "D2H best_rec");
+  if (solved_step) CU(cudaMemcpy(solved_step, h->D.solved_step, J * sizeof(int), cudaMemcpyDeviceToHost), "D2H solved_step");
+  if (n_solved) CU(cudaMemcpy(n_solved, h->D.n_solved, J * sizeof(unsigned), cudaMemcpyDeviceToHost), "D2H n_solved");
+  return BF_OK;
+}
+
+int bf_design_read_replicas(void *handle, char *seq, char *ss, double *rec, int32_t *shelf, uint32_t *counts) {
+  DesignLoop *h = (DesignLoop *)handle;
+  if (!h) return fail(BF_ERR_ARG, "bf_design_read_replicas: null handle");
+  CU(cudaStreamSynchronize(h->st), "bf_design_read_replicas");
+  const size_t G = (size_t)h->D.J * h->D.R, S = h->D.stride;
+  if (seq) CU(cudaMemcpy(seq, h->D.cur_seq, G * S, cudaMemcpyDeviceToHost), "D2H cur_seq");
+  if (ss) CU(cudaMemcpy(ss, h->D.cur_ss, G * (S + 1), cudaMemcpyDeviceToHost), "D2H cur_ss");
+  if (rec) CU(cudaMemcpy(rec, h->D.rec, G * kDesignRec * sizeof(double), cudaMemcpyDeviceToHost), "D2H rec");
+  if (shelf) CU(cudaMemcpy(shelf, h->D.shelf, G * sizeof(int), cudaMemcpyDeviceToHost), "D2H shelf");
+  if (counts) CU(cudaMemcpy(counts, h->D.counts, G * 3 * sizeof(unsigned), cudaMemcpyDeviceToHost), "D2H counts");
+  return BF_OK;
+}
+
+int bf_design_propose_only(void *handle, char *mut_seq) {
+  DesignLoop *h = (DesignLoop *)handle;
+  if (!h || !mut_seq) return fail(BF_ERR_ARG, "bf_design_propose_only: null argument");
+  CU(bf_launch_design_propose(h->D, h->C, h->B, false, h->st), "launch bf_k_design_propose");
+  g.launches++;
+  CU(cudaMemcpyAsync(mut_seq, h->D.mut_seq, (size_t)h->B * h->D.stride, cudaMemcpyDeviceToHost, h->st), "D2H mutants");
+  CU(cudaStreamSynchronize(h->st), "bf_design_propose_only");
+  return BF_OK;
+}
+
+int bf_design_destroy(void *handle) {
+  DesignLoop *h = (DesignLoop *)handle;
+  if (!h) return BF_OK;
+  h->destroy();
+  delete h;
+  return BF_OK;
+}
 
 }  // extern "C"

@@ -1,0 +1,337 @@
+// bf_design.cu -- move generator, Metropolis acceptance and replica exchange of the design loop, on the device (sm_100a).
+//
+// What the reference does per Monte-Carlo sub-step on the host, one Python process per replica
+// (utils/replica_exchange_monte_carlo.py:176-210, utils/sequence_utils.py:926-1136), is done here for every replica of
+// every design problem at once; the fold kernels (bf_fill.cu) run between bf_k_design_propose and bf_k_design_accept
+// on the same stream.  One warp per batch row; the few serial pieces (bracket matching, the draw itself) run on lane 0.
+//
+// Random numbers: one splitmix64 stream per replica (moves and Metropolis tests) and one per job (neighbour swaps), the
+// device counterpart of the reference's per-worker `random.seed(replica)` streams (:227-228) and of the parent stream
+// that drives replica_exchange (:113-173).  The draws are the same KIND of draws in the same order as the reference's
+// (choose range, choose position, choose letter(s), Metropolis test only when the mutant is worse); the generator is not
+// Python's Mersenne twister, so trajectories agree in distribution, not bit for bit.
+#include "bf_design.h"
+
+#include "bf_device.cuh"
+
+namespace {
+
+constexpr int kWPB = 4;  // warps (rows) per CTA
+
+__device__ __forceinline__ unsigned long long sm64(unsigned long long &s) {
+  s += 0x9E3779B97F4A7C15ull;
+  unsigned long long z = s;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ double u01(unsigned long long &s) { return (double)(sm64(s) >> 11) * (1.0 / 9007199254740992.0); }
+__device__ __forceinline__ int below(unsigned long long &s, int n) {
+  const int k = (int)(u01(s) * (double)n);
+  return k < n ? k : n - 1;
+}
+
+__device__ __forceinline__ int letter_code(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3; }
+__device__ __forceinline__ char code_letter(int k) { return "ACGU"[k & 3]; }
+// letters that pair with letter k (sequence_utils.py:607-622): A-U, C-G, G-{C,U}, U-{A,G}
+__device__ __forceinline__ unsigned pair_mask(int k) { return k == 0 ? 8u : k == 1 ? 4u : k == 2 ? 10u : 5u; }
+
+// k-th set bit (k < popc(m)) of a 4-bit mask
+__device__ __forceinline__ int kth_bit(unsigned m, int k) {
+  for (int b = 0; b < 4; b++)
+    if (m >> b & 1u) { if (k == 0) return b; k--; }
+  return 0;
+}
+// random.choice over the letters of m, or random.choices with the nucleotide weights (letters in sorted order A C G U)
+__device__ int pick_letter(unsigned m, bool weighted, const BfDesignCfg &C, unsigned long long &rng) {
+  if (!weighted) return kth_bit(m, below(rng, __popc(m)));
+  double tot = 0.0;
+  for (int b = 0; b < 4; b++) if (m >> b & 1u) tot += C.nt_weight[b];
+  const double x = u01(rng) * tot;
+  double cum = 0.0;
+  int last = 0;
+  for (int b = 0; b < 4; b++)
+    if (m >> b & 1u) { cum += C.nt_weight[b]; last = b; if (x < cum) return b; }
+  return last;
+}
+
+// dot-bracket -> partner table (lane 0; balanced strings as produced by bf_k_trace); characters other than ( ) are unpaired
+__device__ void pair_table(const char *ss, int n, short *pt, short *stk) {
+  int sp = 0;
+  for (int i = 0; i < n; i++) {
+    const char ch = ss[i];
+    pt[i] = -1;
+    if (ch == '(') stk[sp++] = (short)i;
+    else if (ch == ')' && sp > 0) { const int j = stk[--sp]; pt[i] = (short)j; pt[j] = (short)i; }
+  }
+}
+
+struct WarpScratch { short *pt, *stk; uint8_t *fl; };
+__device__ __forceinline__ WarpScratch scratch(unsigned char *dyn, int stride, int warp) {
+  const size_t per = ((size_t)5 * stride + 15) / 16 * 16;
+  unsigned char *b = dyn + per * warp;
+  WarpScratch w;
+  w.pt = reinterpret_cast<short *>(b);
+  w.stk = w.pt + stride;
+  w.fl = reinterpret_cast<uint8_t *>(w.stk + stride);
+  return w;
+}
+size_t scratch_bytes(int stride) { return ((size_t)5 * stride + 15) / 16 * 16 * kWPB; }
+
+// uniform choice among the positions v in [lo, hi] with flag(v) set; cnt = number of such positions (> 0)
+template <typename F>
+__device__ int choose_flagged(F flag, int lo, int hi, int cnt, unsigned long long &rng, int lane) {
+  int k = below(rng, cnt);
+  for (int base = lo; base <= hi; base += 32) {
+    const int v = base + lane;
+    const unsigned mk = __ballot_sync(BF_FULL, v <= hi && flag(v));
+    const int c = __popc(mk);
+    if (k < c) {
+      unsigned m = mk;
+      for (int t = 0; t < k; t++) m &= m - 1;
+      return base + __ffs(m) - 1;
+    }
+    k -= c;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------------------ gather
+// row_len / row_tgt of the active rows (after the set of active jobs changed)
+__global__ void bf_k_design_gather(BfDesignDev D, int B) {
+  const int lane = threadIdx.x & 31, row = blockIdx.x * kWPB + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const int job = D.rowmap[row] / D.R;
+  if (lane == 0) D.row_len[row] = D.len[job];
+  for (int k = lane; k < D.stride; k += 32) D.row_tgt[(size_t)row * D.stride + k] = D.tgt[(size_t)job * D.stride + k];
+}
+
+// ------------------------------------------------------------------------------------------------ propose
+// mutate_sequence + get_mutation_position (sequence_utils.py:926-1136) without the scoring call at its end
+__global__ void __launch_bounds__(kWPB * 32) bf_k_design_propose(BfDesignDev D, BfDesignCfg C, int B, int copy_only) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, row = blockIdx.x * kWPB + warp;
+  if (row >= B) return;
+  const int g = D.rowmap[row], job = g / D.R, n = D.len[job], S = D.stride;
+  const char *cur = D.cur_seq + (size_t)g * S;
+  char *mut = D.mut_seq + (size_t)row * S;
+  for (int k = lane; k < S; k += 32) mut[k] = cur[k];
+  if (copy_only) return;   // initial scoring: the "mutant" is the start sequence itself
+  const short *tpt = D.tpt + (size_t)job * S;
+  const uint8_t *allowed = D.allowed + (size_t)job * S;
+  const unsigned short *avail = D.avail + (size_t)job * S;
+  const int n_avail = D.n_avail[job];
+  if (n_avail == 0) return;
+  unsigned long long rng = D.rng[g];   // every lane advances an identical copy; lane 0 writes it back
+  WarpScratch w = scratch(dyn, S, warp);
+
+  int pos;
+  if (!C.point_mutations) {
+    pos = avail[below(rng, n_avail)];
+  } else {
+    if (lane == 0) pair_table(D.cur_ss + (size_t)g * (S + 1), n, w.pt, w.stk);
+    __syncwarp();
+    // positions of pairs present in only one of {target, MFE structure}, if mutable (sequence_utils.py:951-962)
+    int nfalse = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const bool f = i < n && tpt[i] != w.pt[i] && __popc(allowed[i]) > 1;
+      if (i < n) w.fl[i] = f;
+      nfalse += __popc(__ballot_sync(BF_FULL, f));
+    }
+    __syncwarp();
+    bool targeted = false;
+    int cnt = 0;
+    // expand_cases(false_cases, len - 1, 3): every v in [1, n-1] within 3 of a flagged position (sequence_utils.py:983-1005)
+    auto near = [&](int v) {
+      bool e = false;
+      for (int o = -3; o <= 3; o++) { const int u = v + o; e |= (u >= 0 && u < n && w.fl[u]); }
+      return e;
+    };
+    if (nfalse > 0) {
+      for (int base = 1; base <= n - 1; base += 32) {
+        const int v = base + lane;
+        cnt += __popc(__ballot_sync(BF_FULL, v <= n - 1 && near(v)));
+      }
+      // random.choices([false_cases, available_positions], weights=[p, 1-p])
+      targeted = u01(rng) < D.tm_prob[D.shelf[g]];
+    }
+    if (targeted && cnt > 0) pos = choose_flagged(near, 1, n - 1, cnt, rng, lane);
+    else pos = avail[below(rng, n_avail)];
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const int curl = letter_code(cur[pos]);
+    const unsigned a1 = allowed[pos];
+    const int partner = tpt[pos];
+    if (partner < 0) {
+      if (__popc(a1) > 1) {
+        unsigned m = a1 & ~(1u << curl);
+        if (!m) m = a1;
+        mut[pos] = code_letter(pick_letter(m, false, C, rng));
+      }
+    } else {
+      unsigned m1 = a1;
+      if ((m1 >> curl & 1u) && __popc(m1) != 1) m1 &= ~(1u << curl);
+      const int l1 = pick_letter(m1, C.acgu != 0, C, rng);
+      const unsigned m2 = allowed[partner] & pair_mask(l1);
+      mut[pos] = code_letter(l1);
+      if (m2) mut[partner] = code_letter(pick_letter(m2, C.acgu != 0, C, rng));
+    }
+    D.rng[g] = rng;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ accept
+// score record of the mutant (energy_scores.py:31-125 with the float32 conventions of the ViennaRNA API, sim_score.py:62-147)
+// and the Metropolis test (replica_exchange_monte_carlo.py:26-77)
+__global__ void __launch_bounds__(kWPB * 32) bf_k_design_accept(BfDesignDev D, BfDesignCfg C, int B, int init, int gstep) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, row = blockIdx.x * kWPB + warp;
+  if (row >= B) return;
+  const int g = D.rowmap[row], job = g / D.R, n = D.len[job], S = D.stride;
+  const short *tpt = D.tpt + (size_t)job * S;
+  const char *nss = D.o_ss + (size_t)row * (S + 1);
+  WarpScratch w = scratch(dyn, S, warp);
+  if (lane == 0) pair_table(nss, n, w.pt, w.stk);
+  __syncwarp();
+  // per-position confusion matrix (sim_score.py:104-119)
+  int tp = 0, fp = 0, fn = 0, tn = 0;
+  for (int i = lane; i < n; i += 32) {
+    const int r = tpt[i], q = w.pt[i];
+    if (r == q) { if (r != -1) tp++; else tn++; }
+    else if (r == -1) fp++;
+    else fn++;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    tp += __shfl_xor_sync(BF_FULL, tp, o); fp += __shfl_xor_sync(BF_FULL, fp, o);
+    fn += __shfl_xor_sync(BF_FULL, fn, o); tn += __shfl_xor_sync(BF_FULL, tn, o);
+  }
+  int ok = 0;
+  double rec[kDesignRec];
+  if (lane == 0) {
+    double num, den;
+    if (tp == 0 && fp == 0 && fn == 0 && tn != 0) { num = 1.0; den = 1.0; }
+    else {
+      num = (double)tp * tn - (double)fp * fn;
+      den = sqrt((double)(tp + fp) * (double)(tp + fn) * (double)(tn + fn) * (double)(tn + fp));
+    }
+    const double mcc = rint(num / (den + 0.00001) * 1000.0) / 1000.0;
+    const double recall = rint((double)tp / ((double)(tp + fn) + 0.001) * 1000.0) / 1000.0;
+    const double precision = rint((double)tp / ((double)(tp + fp) + 0.001) * 1000.0) / 1000.0;
+    const double Ed = (double)(float)((double)D.o_eval[row] / 100.0);
+    const double Epf = (double)(float)D.o_pf[(size_t)row * 5 + 4];
+    const double MFE = (double)(float)((double)D.o_mfe[row] / 100.0);
+    rec[kRecEd] = Ed; rec[kRecEpf] = Epf; rec[kRecMcc] = 1.0 - mcc; rec[kRecPrecision] = 1.0 - precision; rec[kRecRecall] = 1.0 - recall;
+    rec[kRecMFE] = MFE; rec[kRecEdef] = D.o_defect ? D.o_defect[row] : 0.0; rec[kRecDist] = (double)(fp + fn); rec[kRecStep] = (double)gstep;
+    double total = 0.0;
+    for (int k = 0; k < C.n_terms; k++) {
+      const double wgt = C.weight[k];
+      switch (C.term[k]) {
+        case kTermEdEpf: total += (Ed - Epf) * wgt; break;
+        case kTermMcc: total += rec[kRecMcc] * 10 * wgt; break;
+        case kTermSlnEpf: total += (Epf + 0.3759 * n + 5.7534) / 10 * wgt; break;
+        case kTermEdMfe: total += (Ed - MFE) * wgt; break;
+        case kTermPrecision: total += rec[kRecPrecision] * 10 * wgt; break;
+        case kTermRecall: total += rec[kRecRecall] * 10 * wgt; break;
+        case kTermEdef: total += rec[kRecEdef] * wgt; break;
+      }
+    }
+    rec[kRecScore] = total;
+    if (init) ok = 1;
+    else {
+      const double old = D.rec[(size_t)g * kDesignRec + kRecScore];
+      unsigned int *cn = D.counts + (size_t)g * 3;
+      if (total <= old) { ok = 1; cn[0]++; cn[1]++; }
+      else {
+        unsigned long long rng = D.rng[g];
+        const double T = D.temps[D.shelf[g]];
+        ok = exp((-C.metropolis_L / T) * (total - old)) > u01(rng);
+        D.rng[g] = rng;
+        if (ok) cn[0]++; else cn[2]++;
+      }
+    }
+    if (ok)
+      for (int k = 0; k < kDesignRec; k++) D.rec[(size_t)g * kDesignRec + k] = rec[k];
+  }
+  ok = __shfl_sync(BF_FULL, ok, 0);
+  if (ok) {
+    const char *mut = D.mut_seq + (size_t)row * S;
+    char *cs = D.cur_seq + (size_t)g * S, *css = D.cur_ss + (size_t)g * (S + 1);
+    for (int k = lane; k < S; k += 32) cs[k] = mut[k];
+    for (int k = lane; k <= S; k += 32) css[k] = nss[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ exchange
+// End of a global step: record the best state of every job, then the neighbour swaps in temperature order
+// (replica_exchange_monte_carlo.py:113-173: pairs (1,2),(3,4).. on even global steps, (0,1),(2,3).. on odd ones).
+__global__ void bf_k_design_exchange(BfDesignDev D, BfDesignCfg C, const uint8_t *active, int gstep) {
+  const int job = blockIdx.x * blockDim.x + threadIdx.x;
+  if (job >= D.J || (active && !active[job])) return;
+  const int R = D.R, S = D.stride;
+  double *best = D.best_rec + (size_t)job * kDesignRec;
+  int pick = -1;
+  unsigned solved = 0;
+  for (int r = 0; r < R; r++) {
+    const double *rec = D.rec + (size_t)(job * R + r) * kDesignRec;
+    if (rec[kRecDist] == 0.0) solved++;
+    const double bm = pick < 0 ? best[kRecDist] : D.rec[(size_t)(job * R + pick) * kDesignRec + kRecDist];
+    const double bs = pick < 0 ? best[kRecScore] : D.rec[(size_t)(job * R + pick) * kDesignRec + kRecScore];
+    if (rec[kRecDist] < bm || (rec[kRecDist] == bm && rec[kRecScore] < bs)) pick = r;
+  }
+  if (pick >= 0) {
+    const size_t g = (size_t)job * R + pick;
+    for (int k = 0; k < kDesignRec; k++) best[k] = D.rec[g * kDesignRec + k];
+    best[kRecStep] = (double)gstep;
+    for (int k = 0; k < S; k++) D.best_seq[(size_t)job * S + k] = D.cur_seq[g * S + k];
+    for (int k = 0; k <= S; k++) D.best_ss[(size_t)job * (S + 1) + k] = D.cur_ss[g * (S + 1) + k];
+  }
+  if (solved) {
+    D.n_solved[job] += solved;
+    if (D.solved_step[job] < 0) D.solved_step[job] = gstep;
+  }
+  // neighbour swaps: replicas of a job hold a permutation of the shelves
+  if (gstep <= 0) return;   // initial scoring: nothing to exchange yet
+  unsigned long long rng = D.job_rng[job];
+  for (int a = (gstep % 2 == 0) ? 1 : 0; a + 1 < R; a += 2) {
+    int ra = -1, rb = -1;
+    for (int r = 0; r < R; r++) {
+      const int sh = D.shelf[job * R + r];
+      if (sh == a) ra = r;
+      if (sh == a + 1) rb = r;
+    }
+    if (ra < 0 || rb < 0) continue;
+    const double e0 = D.rec[(size_t)(job * R + ra) * kDesignRec + kRecScore], e1 = D.rec[(size_t)(job * R + rb) * kDesignRec + kRecScore];
+    bool ok = e1 <= e0;
+    if (!ok) {
+      const double T0 = D.temps[a], T1 = D.temps[a + 1];
+      ok = exp(C.metropolis_L * (1.0 / T0 - 1.0 / T1) * (e0 - e1)) > u01(rng);
+    }
+    if (ok) { D.shelf[job * R + ra] = a + 1; D.shelf[job * R + rb] = a; }
+  }
+  D.job_rng[job] = rng;
+}
+
+}  // namespace
+
+cudaError_t bf_launch_design_gather(const BfDesignDev &D, int B, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  bf_k_design_gather<<<(B + kWPB - 1) / kWPB, kWPB * 32, 0, st>>>(D, B);
+  return cudaGetLastError();
+}
+cudaError_t bf_launch_design_propose(const BfDesignDev &D, const BfDesignCfg &C, int B, bool copy_only, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  bf_k_design_propose<<<(B + kWPB - 1) / kWPB, kWPB * 32, scratch_bytes(D.stride), st>>>(D, C, B, copy_only ? 1 : 0);
+  return cudaGetLastError();
+}
+cudaError_t bf_launch_design_accept(const BfDesignDev &D, const BfDesignCfg &C, int B, bool init, int gstep, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  bf_k_design_accept<<<(B + kWPB - 1) / kWPB, kWPB * 32, scratch_bytes(D.stride), st>>>(D, C, B, init ? 1 : 0, gstep);
+  return cudaGetLastError();
+}
+cudaError_t bf_launch_design_exchange(const BfDesignDev &D, const BfDesignCfg &C, const uint8_t *active, int gstep, cudaStream_t st) {
+  if (D.J <= 0) return cudaSuccess;
+  bf_k_design_exchange<<<(D.J + 63) / 64, 64, 0, st>>>(D, C, active, gstep);
+  return cudaGetLastError();
+}

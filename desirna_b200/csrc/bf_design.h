@@ -1,0 +1,64 @@
+// bf_design.h -- device side of the Replica-Exchange Monte-Carlo design loop (bf_design.cu).
+//
+// The reference runs this loop on the host: utils/replica_exchange_monte_carlo.py:176-271 (Metropolis sub-steps and
+// neighbour swaps) around utils/sequence_utils.py:926-1136 (move generator).  Here the state of every replica of every
+// design problem ("job") stays in HBM; one sub-step is  propose -> MFE fill + backtrack -> PF fill + exterior -> eval ->
+// accept  on one stream, with no host round trip.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+constexpr int kDesignRec = 10;   // doubles per replica record
+// record slots (names of the reference's ScoreSeq fields, utils/energy_scores.py:176-195)
+enum { kRecScore = 0, kRecEd = 1, kRecEpf = 2, kRecMcc = 3, kRecPrecision = 4, kRecRecall = 5, kRecMFE = 6, kRecEdef = 7, kRecDist = 8, kRecStep = 9 };
+// scoring terms (-sf), in the order of ScoreSeq.get_scoring_function (utils/energy_scores.py:376-398)
+enum { kTermEdEpf = 0, kTermMcc = 1, kTermSlnEpf = 2, kTermEdMfe = 3, kTermPrecision = 4, kTermRecall = 5, kTermEdef = 6 };
+
+struct BfDesignCfg {
+  int n_terms;
+  int term[8];
+  double weight[8];
+  double metropolis_L;   // sim_options.L
+  int point_mutations;   // -tm on/off
+  int acgu;              // -acgu on: paired letters drawn with nt_weight
+  double nt_weight[4];   // A C G U
+};
+
+struct BfDesignDev {
+  int J, R, stride;
+  // per job
+  const char *tgt;               // J x stride   target dot-bracket
+  const short *tpt;              // J x stride   partner in the target (0-based) or -1
+  const uint8_t *allowed;        // J x stride   letters_allowed, bit 0..3 = A C G U  (sequence_utils.py:454-525)
+  const int *len;                // J
+  const unsigned short *avail;   // J x stride   positions with more than one allowed letter (sequence_utils.py:1026-1029)
+  const int *n_avail;            // J
+  unsigned long long *job_rng;   // J            stream of the neighbour swaps
+  char *best_seq, *best_ss;      // J x stride, J x (stride+1)
+  double *best_rec;              // J x kDesignRec
+  int *solved_step;              // J            first global step at whose end a replica folds into the target, -1 before
+  unsigned int *n_solved;        // J            replica states (at global-step ends) that fold into the target
+  // per replica g = job * R + r
+  char *cur_seq, *cur_ss;        // G x stride, G x (stride+1)
+  double *rec;                   // G x kDesignRec
+  int *shelf;                    // G            index into temps
+  unsigned long long *rng;       // G
+  unsigned int *counts;          // G x 3        accepted, accepted because not worse, rejected
+  const double *temps;           // R            temperature shelves, ascending
+  const double *tm_prob;         // R            probability of a targeted move per shelf (sequence_utils.py:963)
+  // per batch row (active jobs only)
+  const int *rowmap;             // B -> g
+  char *mut_seq;                 // B x stride
+  int *row_len;                  // B
+  char *row_tgt;                 // B x stride
+  int *o_mfe;                    // B
+  char *o_ss;                    // B x (stride+1)
+  double *o_pf;                  // B x 5
+  int *o_eval;                   // B
+  double *o_defect;              // B (only with the Edef term)
+};
+
+cudaError_t bf_launch_design_gather(const BfDesignDev &D, int B, cudaStream_t st);
+cudaError_t bf_launch_design_propose(const BfDesignDev &D, const BfDesignCfg &C, int B, bool copy_only, cudaStream_t st);
+cudaError_t bf_launch_design_accept(const BfDesignDev &D, const BfDesignCfg &C, int B, bool init, int gstep, cudaStream_t st);
+cudaError_t bf_launch_design_exchange(const BfDesignDev &D, const BfDesignCfg &C, const uint8_t *active, int gstep, cudaStream_t st);

@@ -1,0 +1,252 @@
+"""Many design problems x replicas in ONE device-resident Replica-Exchange Monte-Carlo loop (C-ABI bf_design_*).
+
+The reference designs one target per process: `DesiRNA.py:331-383` runs, per global step, `remc.mutate_sequence_re`
+(R worker processes x RE_attempt Metropolis sub-steps, utils/replica_exchange_monte_carlo.py:233-271) and
+`remc.replica_exchange` (:113-173).  With R = 10..64 mutants per sub-step a B200 idles (finding 6), so
+this driver advances ALL targets of a benchmark (e.g. the 100 Eterna puzzles) together: jobs are bucketed by length,
+each bucket is one `bf_design_*` loop on its own CUDA stream, and a sub-step of a bucket is
+propose -> MFE fill + backtrack -> PF fill -> eval -> accept for (jobs x replicas) sequences without leaving the GPU.
+
+Host work per poll: read the per-job best records, retire solved jobs (`-sws on`), check the clock.
+"""
+import ctypes as C
+import random
+import time
+
+import numpy as np
+
+from . import engine
+from .utils import sequence_utils as seq_utils
+
+TERM_ID = {"Ed-Epf": 0, "1-MCC": 1, "sln_Epf": 2, "Ed-MFE": 3, "1-precision": 4, "1-recall": 5, "Edef": 6}
+REC_FIELDS = ("scoring_function", "edesired", "Epf", "mcc", "precision", "recall", "MFE", "ensemble_defect", "distance", "global_step")
+REC = len(REC_FIELDS)
+
+
+class DesignOptions:
+    """The fields of DesiRNA.py's DesignOptions (:520-633) the loop reads, with the CLI defaults (:92-139)."""
+
+    def __init__(self, replicas=10, RE_attempt=100, T_min=10.0, T_max=150.0, scoring_f=(("Ed-Epf", 1.0),), point_mutations="on",
+                 tm_max=0.7, tm_min=0.0, acgu_percentages="off", nt_percentages=None, diff_start_replicas="one"):
+        self.replicas = replicas
+        self.RE_attempt = RE_attempt
+        self.T_min, self.T_max = T_min, T_max
+        self.scoring_f = list(scoring_f)
+        self.point_mutations = point_mutations
+        self.tm_max, self.tm_min = tm_max, tm_min
+        self.acgu_percentages = acgu_percentages
+        self.nt_percentages = nt_percentages or {"A": 15, "C": 30, "G": 30, "U": 15}
+        self.diff_start_replicas = diff_start_replicas
+        self.L = 504.12
+        self.oligo_state, self.pks, self.subopt, self.motifs = "none", "off", "off", None
+        self.rep_temps_shelfs = seq_utils.get_rep_temps(self)
+
+
+class bf_design_t(C.Structure):
+    _fields_ = [("n_jobs", C.c_int32), ("replicas", C.c_int32), ("stride", C.c_int32), ("target", C.c_void_p), ("len", C.c_void_p),
+                ("allowed", C.c_void_p), ("init_seq", C.c_void_p), ("temps", C.c_void_p), ("tm_prob", C.c_void_p),
+                ("n_terms", C.c_int32), ("term", C.c_int32 * 8), ("weight", C.c_double * 8), ("metropolis_L", C.c_double),
+                ("point_mutations", C.c_int32), ("re_attempt", C.c_int32), ("acgu", C.c_int32), ("nt_weight", C.c_double * 4),
+                ("seed", C.c_uint64)]
+
+
+def _bind():
+    L = engine.lib()
+    if not getattr(L, "_design_bound", False):
+        L.bf_design_create.argtypes = [C.POINTER(bf_design_t), C.POINTER(C.c_void_p)]
+        L.bf_design_run.argtypes = [C.c_void_p, C.c_int32]
+        L.bf_design_sync.argtypes = [C.c_void_p]
+        L.bf_design_set_active.argtypes = [C.c_void_p, C.c_void_p]
+        L.bf_design_read_jobs.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.bf_design_read_replicas.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.bf_design_propose_only.argtypes = [C.c_void_p, C.c_void_p]
+        L.bf_design_destroy.argtypes = [C.c_void_p]
+        L._design_bound = True
+    return L
+
+
+def _chars(rows, stride):
+    out = np.zeros((len(rows), stride), np.uint8)
+    for k, s in enumerate(rows):
+        out[k, :len(s)] = np.frombuffer(s.encode("ascii"), np.uint8)
+    return out
+
+
+def _strings(buf, lens):
+    return [bytes(buf[k, :lens[k]]).decode("ascii") for k in range(buf.shape[0])]
+
+
+class DesignLoop:
+    """One bf_design_* loop: the jobs of one length bucket."""
+
+    def __init__(self, inputs, sim_options, seed=0, init_seqs=None):
+        engine.ensure_ready()
+        self.lib = _bind()
+        self.inputs = list(inputs)
+        self.J, self.R = len(self.inputs), sim_options.replicas
+        for inp in self.inputs:
+            if set(inp.sec_struct) - set(".()"):
+                raise ValueError("the device design loop takes single-strand targets made of . ( ) only: %r" % (inp.name,))
+        self.lens = np.array([len(i.sec_struct) for i in self.inputs], np.int32)
+        self.stride = int(self.lens.max())
+        nt_lists = [seq_utils.get_nt_list(i) for i in self.inputs]
+        allowed = np.full((self.J, self.stride), 15, np.uint8)
+        for j, nts in enumerate(nt_lists):
+            allowed[j, :self.lens[j]] = seq_utils.allowed_masks(nts)
+        if init_seqs is None:
+            init_seqs = []
+            for inp, nts in zip(self.inputs, nt_lists):
+                first = seq_utils.initial_sequence_generator(nts, inp, sim_options)
+                for _ in range(self.R):
+                    init_seqs.append(seq_utils.initial_sequence_generator(nts, inp, sim_options)
+                                     if sim_options.diff_start_replicas == "different" else first)
+        assert len(init_seqs) == self.J * self.R
+        terms = [(TERM_ID[f], float(w)) for f, w in sim_options.scoring_f]
+        cfg = bf_design_t()
+        self._keep = [_chars([i.sec_struct for i in self.inputs], self.stride), self.lens, allowed, _chars(init_seqs, self.stride),
+                      np.array(sim_options.rep_temps_shelfs, np.float64), np.array(seq_utils.targeted_move_probabilities(sim_options), np.float64)]
+        cfg.n_jobs, cfg.replicas, cfg.stride = self.J, self.R, self.stride
+        cfg.target, cfg.len, cfg.allowed, cfg.init_seq, cfg.temps, cfg.tm_prob = (a.ctypes.data for a in self._keep)
+        cfg.n_terms = len(terms)
+        for k, (t, w) in enumerate(terms):
+            cfg.term[k], cfg.weight[k] = t, w
+        cfg.metropolis_L = sim_options.L
+        cfg.point_mutations = int(sim_options.point_mutations == "on")
+        cfg.re_attempt = sim_options.RE_attempt
+        cfg.acgu = int(sim_options.acgu_percentages == "on")
+        for k, l in enumerate("ACGU"):
+            cfg.nt_weight[k] = float(sim_options.nt_percentages[l])
+        cfg.seed = seed
+        self.h = C.c_void_p()
+        engine._check(self.lib.bf_design_create(C.byref(cfg), C.byref(self.h)))
+        self.active = np.ones(self.J, np.uint8)
+
+    # -- stepping
+    def run(self, global_steps=1):
+        engine._check(self.lib.bf_design_run(self.h, int(global_steps)))
+
+    def sync(self):
+        engine._check(self.lib.bf_design_sync(self.h))
+
+    def set_active(self, mask):
+        self.active = np.ascontiguousarray(mask, np.uint8)
+        engine._check(self.lib.bf_design_set_active(self.h, self.active.ctypes.data))
+
+    # -- reading
+    def jobs(self):
+        seq = np.zeros((self.J, self.stride), np.uint8)
+        ss = np.zeros((self.J, self.stride + 1), np.uint8)
+        rec = np.zeros((self.J, REC))
+        step = np.zeros(self.J, np.int32)
+        nsol = np.zeros(self.J, np.uint32)
+        engine._check(self.lib.bf_design_read_jobs(self.h, seq.ctypes.data, ss.ctypes.data, rec.ctypes.data, step.ctypes.data, nsol.ctypes.data))
+        return {"sequence": _strings(seq, self.lens), "mfe_ss": _strings(ss, self.lens), "rec": rec, "solved_step": step, "n_solved": nsol}
+
+    def replicas(self):
+        G = self.J * self.R
+        seq = np.zeros((G, self.stride), np.uint8)
+        ss = np.zeros((G, self.stride + 1), np.uint8)
+        rec = np.zeros((G, REC))
+        shelf = np.zeros(G, np.int32)
+        counts = np.zeros((G, 3), np.uint32)
+        engine._check(self.lib.bf_design_read_replicas(self.h, seq.ctypes.data, ss.ctypes.data, rec.ctypes.data, shelf.ctypes.data, counts.ctypes.data))
+        lens = np.repeat(self.lens, self.R)
+        return {"sequence": _strings(seq, lens), "mfe_ss": _strings(ss, lens), "rec": rec, "shelf": shelf.reshape(self.J, self.R),
+                "counts": counts}
+
+    def propose_only(self):
+        """test hook: one draw of the move generator for every replica of every active job, not scored, not accepted"""
+        rows = int(self.active.sum()) * self.R
+        out = np.zeros((rows, self.stride), np.uint8)
+        engine._check(self.lib.bf_design_propose_only(self.h, out.ctypes.data))
+        lens = np.repeat(self.lens[self.active.astype(bool)], self.R)
+        return _strings(out, lens)
+
+    def close(self):
+        if self.h:
+            self.lib.bf_design_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+BUCKET_EDGES = (40, 72, 104, 136, 200, 304, 400, 600, 1000, 2000)
+
+
+def bucket_jobs(lengths, edges=BUCKET_EDGES):
+    """indices of the jobs per length bucket (jobs of one loop share a table stride, so similar lengths go together)"""
+    out = {}
+    for k, n in enumerate(lengths):
+        for e in edges:
+            if n <= e:
+                out.setdefault(e, []).append(k)
+                break
+        else:
+            raise ValueError("target longer than %d nt" % edges[-1])
+    return [out[e] for e in sorted(out)]
+
+
+def design_batch(inputs, sim_options, time_limit=None, global_steps=None, stop_when_solved=True, seed=0, poll_steps=1,
+                 edges=BUCKET_EDGES, verbose=False):
+    """Design every target of `inputs` (InputFile objects, utils/stats_inputs_outputs.py) concurrently.
+
+    Stops when every job is solved (stop_when_solved, the reference's `-sws on` with `-r 1`), after `global_steps` global
+    steps (`-s`), or after `time_limit` seconds (`-t`), whichever comes first.  Returns (results, info): one dict per input
+    (REC_FIELDS + name, sequence, mfe_ss, solved, solved_step, solved_after_s) and run statistics."""
+    if time_limit is None and global_steps is None:
+        raise ValueError("give time_limit and/or global_steps")
+    random.seed(seed)
+    inputs = list(inputs)
+    groups = bucket_jobs([len(i.sec_struct) for i in inputs], edges)
+    t_start = time.time()
+    loops = [DesignLoop([inputs[k] for k in grp], sim_options, seed=seed * 1000003 + b) for b, grp in enumerate(groups)]
+    results = [None] * len(inputs)
+    solved_at = [None] * len(inputs)
+    steps = 0
+    folds = sum(l.J * l.R for l in loops)   # start sequences
+
+    def harvest(now):
+        left = 0
+        for grp, loop in zip(groups, loops):
+            jb = loop.jobs()
+            mask = loop.active.copy()
+            for pos, k in enumerate(grp):
+                solved = jb["solved_step"][pos] >= 0
+                if solved and solved_at[k] is None:
+                    solved_at[k] = now
+                res = {"name": inputs[k].name, "sequence": jb["sequence"][pos], "mfe_ss": jb["mfe_ss"][pos], "solved": bool(solved),
+                       "solved_step": int(jb["solved_step"][pos]), "solved_after_s": solved_at[k]}
+                res.update({f: float(jb["rec"][pos, c]) for c, f in enumerate(REC_FIELDS)})
+                results[k] = res
+                if solved and stop_when_solved:
+                    mask[pos] = 0
+            if (mask != loop.active).any():
+                loop.set_active(mask)
+            left += int(loop.active.sum())
+        return left
+
+    left = harvest(time.time() - t_start)
+    while left > 0:
+        if global_steps is not None and steps >= global_steps:
+            break
+        if time_limit is not None and time.time() - t_start >= time_limit:
+            break
+        n = poll_steps if global_steps is None else min(poll_steps, global_steps - steps)
+        for loop in loops:
+            if loop.active.any():
+                loop.run(n)
+                folds += int(loop.active.sum()) * loop.R * sim_options.RE_attempt * n
+        steps += n
+        left = harvest(time.time() - t_start)   # read_jobs waits for each loop's stream
+        if verbose:
+            print("global step %d: %d jobs unsolved, %.1f s" % (steps, left, time.time() - t_start), flush=True)
+    elapsed = time.time() - t_start
+    info = {"global_steps": steps, "seconds": elapsed, "folds": folds, "folds_per_s": folds / max(elapsed, 1e-9),
+            "solved": sum(1 for r in results if r["solved"]), "jobs": len(inputs), "buckets": [(l.stride, l.J) for l in loops]}
+    for loop in loops:
+        loop.close()
+    return results, info

@@ -108,6 +108,58 @@ int bf_set_option(const char *key, int value);
  * *slot_entries entries (entry (i,j), d=j-i>=4, at (d-4)*n - (d*(d-1)/2-6) + i-1).  host may be NULL to query the size. */
 int bf_debug_copy_table(int which, int32_t n_seq, void *host, size_t host_bytes, size_t *slot_entries);
 
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Device-resident Replica-Exchange Monte-Carlo design loop: many design problems ("jobs") x replicas advance
+ * in lock step with sequences, scores, temperature shelves and random streams resident in HBM.  Replaces,
+ * for single-strand targets made of . ( ):
+ *   remc.mutate_sequence_re / single_replica_design / mc_delta      utils/replica_exchange_monte_carlo.py:26-110,176-271
+ *   remc.replica_exchange / replica_exchange_attempt                utils/replica_exchange_monte_carlo.py:80-173
+ *   seq_utils.mutate_sequence / get_mutation_position / expand_cases  utils/sequence_utils.py:926-1136
+ *   es.score_sequence arithmetic (Ed-Epf, 1-MCC, sln_Epf, Ed-MFE, 1-precision, 1-recall, Edef)  utils/energy_scores.py:31-125,376-398
+ * The random generator is per-replica splitmix64, not Python's: trajectories match in distribution only.
+ * All jobs of one loop share `stride`; callers bucket jobs of similar length into one loop each. */
+typedef struct {
+  int32_t n_jobs, replicas, stride;
+  const char *target;      /* n_jobs x stride dot-bracket, only . ( )                          input_file.sec_struct */
+  const int32_t *len;      /* n_jobs */
+  const uint8_t *allowed;  /* n_jobs x stride: Nucleotide.letters_allowed as bits A=1 C=2 G=4 U=8  sequence_utils.py:454-525 */
+  const char *init_seq;    /* n_jobs x replicas x stride start sequences                         sequence_utils.py:862-888 */
+  const double *temps;     /* replicas: temperature shelves, ascending                           sequence_utils.py:811-859 */
+  const double *tm_prob;   /* replicas: probability of a targeted move on each shelf             sequence_utils.py:963 */
+  int32_t n_terms;         /* scoring function terms in -sf order */
+  int32_t term[8];         /* 0 Ed-Epf, 1 1-MCC, 2 sln_Epf, 3 Ed-MFE, 4 1-precision, 5 1-recall, 6 Edef */
+  double weight[8];
+  double metropolis_L;     /* sim_options.L (DesiRNA.py:568) */
+  int32_t point_mutations; /* -tm on: targeted mutations */
+  int32_t re_attempt;      /* Monte-Carlo sub-steps per global step (-e) */
+  int32_t acgu;            /* -acgu on: paired letters drawn with nt_weight */
+  double nt_weight[4];     /* A C G U */
+  uint64_t seed;
+} bf_design_t;
+
+enum { BF_DESIGN_REC = 10 }; /* doubles per record: scoring_function, edesired, Epf, 1-mcc, 1-precision, 1-recall, MFE,
+                                ensemble_defect, positions whose partner differs from the target's (0 = solved), global step */
+
+/* Allocates the loop on the engine's GPU, scores the start sequences (global step 0). */
+int bf_design_create(const bf_design_t *cfg, void **handle);
+/* Enqueue `global_steps` global steps (each: re_attempt sub-steps of propose/fold/accept, then neighbour swaps) on the
+ * loop's own stream and return without waiting; loops of different handles overlap on the GPU. */
+int bf_design_run(void *handle, int32_t global_steps);
+int bf_design_sync(void *handle);
+/* active[j] = 0 drops job j from the following steps (-sws on: stop when solved); waits for enqueued steps first. */
+int bf_design_set_active(void *handle, const uint8_t *active);
+/* Best state per job seen at global-step ends (fewest mismatching positions, then lowest scoring function):
+ * best_seq n_jobs x stride, best_ss n_jobs x (stride+1), best_rec n_jobs x BF_DESIGN_REC, solved_step (first global step
+ * that ended with a replica folding into the target, -1 = none), n_solved (such replica states so far).  NULL = skip. */
+int bf_design_read_jobs(void *handle, char *best_seq, char *best_ss, double *best_rec, int32_t *solved_step, uint32_t *n_solved);
+/* Current state of every replica (job-major): seq G x stride, ss G x (stride+1), rec G x BF_DESIGN_REC, shelf G,
+ * counts G x 3 (accepted, accepted because not worse, rejected).  NULL = skip. */
+int bf_design_read_replicas(void *handle, char *seq, char *ss, double *rec, int32_t *shelf, uint32_t *counts);
+/* Test hook: run the move generator once for every active replica without scoring; mut_seq: rows x stride. */
+int bf_design_propose_only(void *handle, char *mut_seq);
+int bf_design_destroy(void *handle);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,128 @@
+"""CPU: host side of the design loop -- restraints, start sequences, temperature shelves, the move generator's mirror
+(desirna_b200/utils/sequence_utils.py) and the input reader, checked against the reference's documented behaviour
+(utils/sequence_utils.py:454-1136, utils/stats_inputs_outputs.py:183-237) and its shipped example input."""
+import random
+from collections import Counter
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from desirna_b200.utils import sequence_utils as su
+from desirna_b200.utils import stats_inputs_outputs as sio
+
+PAIR_OK = {("A", "U"), ("U", "A"), ("G", "C"), ("C", "G"), ("G", "U"), ("U", "G")}
+
+
+def opts(**kw):
+    o = SimpleNamespace(replicas=10, T_min=10.0, T_max=150.0, acgu_percentages="off", nt_percentages={"A": 15, "C": 30, "G": 30, "U": 15},
+                        point_mutations="on", tm_max=0.7, tm_min=0.0, oligo_state="none", diff_start_replicas="one")
+    o.__dict__.update(kw)
+    o.rep_temps_shelfs = su.get_rep_temps(o)
+    return o
+
+
+def test_check_dot_bracket_families_and_errors():
+    assert su.check_dot_bracket("((..))") == [[1, 4], [0, 5]]
+    assert su.check_dot_bracket("([.)]") == [[0, 3], [1, 4]]
+    with pytest.raises(ValueError):
+        su.check_dot_bracket("(()")
+    with pytest.raises(ValueError):
+        su.check_dot_bracket("())")
+    with pytest.raises(ValueError):
+        su.check_dot_bracket("(x)")
+
+
+def test_allowed_letters_follow_the_partner_restraint():
+    inp = sio.make_input("t", "((...))", "NANNNNS")
+    nts = su.get_nt_list(inp)
+    # position 0 pairs with 6 (S = C/G): letters that pair with C or G are G, C, U
+    assert sorted(nts[0].letters_allowed) == ["C", "G", "U"]
+    assert sorted(nts[6].letters_allowed) == ["C", "G"]
+    # position 1 is a fixed A: its partner 5 must be U
+    assert nts[1].letters_allowed == ["A"] and nts[5].letters_allowed == ["U"]
+    assert sorted(nts[3].letters_allowed) == ["A", "C", "G", "U"] and nts[3].pairs_with is None
+    assert list(su.allowed_masks(nts)) == [2 | 4 | 8, 1, 15, 15, 15, 8, 2 | 4]
+    with pytest.raises(ValueError):
+        su.get_nt_list(sio.make_input("bad", "(...)", "ANNNC"))
+
+
+def test_rep_temps_defaults():
+    t = su.get_rep_temps(opts())
+    assert t[0] == 10.0 and t[-1] == 150.0 and len(t) == 10
+    assert t[1] == round(10 + 140 / 9, 3)
+    assert su.get_rep_temps(opts(replicas=1)) == [150.0]
+    assert su.targeted_move_probabilities(opts())[0] == 0.7 and su.targeted_move_probabilities(opts())[-1] == 0.0
+
+
+def test_initial_sequence_rules():
+    random.seed(3)
+    inp = sio.make_input("t", "((((....))))..((...))", None)
+    nts = su.get_nt_list(inp)
+    s = su.initial_sequence_generator(nts, inp, opts())
+    for a, b in inp.pairs:
+        assert {s[a], s[b]} == {"C", "G"}            # strongest pair where the restraints allow it
+    assert s[4] == "G" and s[5:8] == "AAA"            # loop boosting, A elsewhere in loops
+    assert s[12] == "G" and s[13] == "A"
+    inp2 = sio.make_input("t2", "((.((...))))", "NNNNNNNNNNNN")
+    s2 = su.initial_sequence_generator(su.get_nt_list(inp2), inp2, opts())
+    assert s2[2] == "A"                                # a one-nucleotide bulge stays A
+    inp3 = sio.make_input("t3", "((...))", "WNNNNNW")
+    s3 = su.initial_sequence_generator(su.get_nt_list(inp3), inp3, opts())
+    assert {s3[0], s3[6]} == {"A", "U"}
+
+
+def test_expand_cases_bounds():
+    assert su.expand_cases([0, 9], 9) == [1, 2, 3, 6, 7, 8, 9]
+    assert su.expand_cases([], 9) == []
+
+
+def test_move_generator_respects_restraints_and_targets_wrong_pairs():
+    random.seed(11)
+    inp = sio.make_input("t", "((((....))))....", "NNNNNNNNNNNNNNNA")
+    nts = su.get_nt_list(inp)
+    o = opts(replicas=4)
+    cur = SimpleNamespace(sequence="GGGGAAAACCCCAAAA", mfe_ss="((((....))))....", temp_shelf=o.rep_temps_shelfs[0])
+    hits = Counter()
+    for _ in range(4000):
+        m = su.propose_mutation(cur, nts, o, inp)
+        diff = [i for i in range(16) if m[i] != cur.sequence[i]]
+        assert 1 <= len(diff) <= 2 and 15 not in diff
+        for a, b in inp.pairs:
+            assert (m[a], m[b]) in PAIR_OK
+        hits.update(diff)
+    # MFE structure == target: no wrong pairs, moves are uniform over the 15 mutable positions (pairs move together)
+    assert min(hits[i] for i in range(15)) > 150
+    # one wrong pair at (0, 11): on the coldest shelf 70 % of the moves fall within 3 of position 0 or 11, never on 0 itself
+    cur.mfe_ss = ".(((....)))....."
+    def first_moved(n_draws):
+        out = []
+        for _ in range(n_draws):
+            m = su.propose_mutation(cur, nts, o, inp)
+            out.append([i for i in range(16) if m[i] != cur.sequence[i]][0])
+        return out
+
+    moved = first_moved(4000)
+    assert sum(1 for i in moved if min(abs(i - 0), abs(i - 11)) <= 3) / 4000 > 0.7
+    # hottest shelf: tm_min = 0 -> uniform over the mutable positions again
+    cur.temp_shelf = o.rep_temps_shelfs[-1]
+    moved = first_moved(2000)
+    assert sum(1 for i in moved if i in (4, 5, 6, 7)) > 300
+
+
+def test_read_input_and_sf_parser(tmp_path):
+    p = tmp_path / "in.txt"
+    p.write_text(">name\nEte_1\n>seq_restr\nNNNNNNNNNNNNNNNN\n>sec_struct\n(((((......)))))\n")
+    inp = sio.read_input(str(p))
+    assert inp.name == "Ete_1" and inp.sec_struct == "(((((......)))))" and len(inp.pairs) == 5
+    assert (0, 15) in inp.target_pairs_tupl
+    assert sio.parse_scoring_functions("Ed-Epf:0.5,1-MCC:0.5") == [("Ed-Epf", 0.5)]      # the reference keeps the first term
+    assert sio.parse_scoring_functions_all("Ed-Epf:0.5,1-MCC:0.5") == [("Ed-Epf", 0.5), ("1-MCC", 0.5)]
+    with pytest.raises(ValueError):
+        sio.parse_scoring_functions("Ed-Epf")
+
+
+def test_bucketing():
+    from desirna_b200.design import bucket_jobs
+    g = bucket_jobs([12, 36, 400, 104, 105, 41])
+    assert g == [[0, 1], [5], [3], [4], [2]]

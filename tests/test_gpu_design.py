@@ -1,0 +1,137 @@
+"""GPU: the device-resident design loop (bf_design_*, csrc/bf_design.cu) -- its on-device score records against the
+host mirror of the reference's scoring (golden-pinned in test_host_scoring.py / test_gpu_parity.py), its move generator
+against the host mirror of the reference's mutate_sequence in distribution, and the loop's invariants."""
+import random
+from collections import Counter
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+PAIR_OK = {("A", "U"), ("U", "A"), ("G", "C"), ("C", "G"), ("G", "U"), ("U", "G")}
+
+
+def small_inputs(max_len=48, limit=8):
+    from desirna_b200.utils import stats_inputs_outputs as sio
+    rows = [r for r in load_golden("E1") if len(r["target"]) <= max_len and not set(r["target"]) - set(".()")]
+    return [sio.make_input(r["file"], r["target"]) for r in rows[:limit]]
+
+
+def host_opts(o):
+    """sim_options as the host scoring mirror wants them"""
+    return o
+
+
+@pytest.mark.parametrize("scoring", [[("Ed-Epf", 1.0)], [("Ed-Epf", 0.5), ("1-MCC", 0.5)],
+                                     [("sln_Epf", 1.0), ("Ed-MFE", 0.7), ("1-precision", 0.2), ("1-recall", 0.1)], [("Edef", 5.0), ("Ed-Epf", 0.3)]])
+def test_records_match_host_scoring_and_invariants_hold(engine, scoring):
+    from desirna_b200 import design
+    from desirna_b200.utils import energy_scores as es
+    inputs = small_inputs()
+    o = design.DesignOptions(replicas=6, RE_attempt=15, scoring_f=scoring)
+    random.seed(5)
+    loop = design.DesignLoop(inputs, o, seed=7)
+    loop.run(4)
+    rep = loop.replicas()
+    jobs = loop.jobs()
+    J, R = loop.J, loop.R
+    # every replica made RE_attempt decisions per global step
+    assert (rep["counts"][:, 0] + rep["counts"][:, 2] == 4 * 15).all()
+    assert (rep["counts"][:, 1] <= rep["counts"][:, 0]).all()
+    # shelves stay a permutation within a job
+    assert (np.sort(rep["shelf"], axis=1) == np.arange(R)).all()
+    for j, inp in enumerate(inputs):
+        seqs = rep["sequence"][j * R:(j + 1) * R]
+        ref = es.score_sequences(seqs, inp, o)
+        for r, (s, h) in enumerate(zip(seqs, ref)):
+            g = j * R + r
+            rec = dict(zip(design.REC_FIELDS, rep["rec"][g]))
+            for a, b in inp.pairs:
+                assert (s[a], s[b]) in PAIR_OK, (inp.name, s)
+            assert rep["mfe_ss"][g] == h.mfe_ss
+            assert rec["edesired"] == h.edesired and rec["Epf"] == h.Epf           # float32-rounded API values, bit for bit
+            assert rec["mcc"] == pytest.approx(h.mcc, abs=1e-12) and rec["precision"] == pytest.approx(h.precision, abs=1e-12)
+            assert rec["recall"] == pytest.approx(h.recall, abs=1e-12)
+            assert rec["scoring_function"] == pytest.approx(h.scoring_function, abs=1e-9)
+            if any(f == "Ed-MFE" for f, _ in scoring):
+                assert rec["MFE"] == h.MFE
+            if any(f == "Edef" for f, _ in scoring):
+                assert rec["ensemble_defect"] == pytest.approx(h.ensemble_defect, abs=1e-9)
+            assert (rec["distance"] == 0) == (h.mfe_ss == inp.sec_struct)
+        # the per-job best is one of the states seen, and is at least as good as every current state
+        cur_key = min((rep["rec"][j * R + r][8], rep["rec"][j * R + r][0]) for r in range(R))
+        assert (jobs["rec"][j][8], jobs["rec"][j][0]) <= cur_key
+        if jobs["solved_step"][j] >= 0:
+            assert jobs["mfe_ss"][j] == inp.sec_struct and jobs["rec"][j][8] == 0
+    loop.close()
+
+
+def test_same_seed_same_trajectory(engine):
+    from desirna_b200 import design
+    inputs = small_inputs(limit=4)
+    o = design.DesignOptions(replicas=4, RE_attempt=10)
+    out = []
+    for seed in (3, 3, 4):
+        random.seed(1)
+        loop = design.DesignLoop(inputs, o, seed=seed)
+        loop.run(3)
+        out.append(loop.replicas()["sequence"])
+        loop.close()
+    assert out[0] == out[1]
+    assert out[0] != out[2]
+
+
+def test_move_generator_matches_host_mirror_in_distribution(engine):
+    """bf_k_design_propose against desirna_b200.utils.sequence_utils.propose_mutation (the reference's move,
+    utils/sequence_utils.py:926-1100): same distribution of mutants per temperature shelf."""
+    from desirna_b200 import design
+    from desirna_b200.utils import sequence_utils as su
+    from desirna_b200.utils import stats_inputs_outputs as sio
+    inp = sio.make_input("t", "((((....))))...((...))", "NNNNNNNNSNNNNNANNNNNNN")
+    o = design.DesignOptions(replicas=3, RE_attempt=1, tm_max=0.8, tm_min=0.1)
+    start = "GGGAAAAACCCCAAAGGAAACC"      # folds into something else than the target: targeted moves are active
+    loop = design.DesignLoop([inp], o, seed=11, init_seqs=[start] * 3)
+    cur_ss = loop.replicas()["mfe_ss"][0]
+    assert cur_ss != inp.sec_struct
+    N = 6000
+    dev = [Counter() for _ in range(3)]
+    for _ in range(N):
+        for r, m in enumerate(loop.propose_only()):
+            dev[r][m] += 1
+    loop.close()
+    nts = su.get_nt_list(inp)
+    random.seed(2)
+    for r in range(3):
+        cur = SimpleNamespace(sequence=start, mfe_ss=cur_ss, temp_shelf=o.rep_temps_shelfs[r])
+        host = Counter(su.propose_mutation(cur, nts, o, inp) for _ in range(N))
+        assert set(dev[r]) <= set(host) | {k for k in dev[r] if dev[r][k] < 5}, "device proposes mutants the reference cannot"
+
+        def where(counter):   # marginal over the mutated positions (<= ~25 categories: sampling noise ~0.03 at N = 6000)
+            out = Counter()
+            for m, c in counter.items():
+                out[tuple(i for i in range(len(start)) if m[i] != start[i])] += c
+            return out
+
+        hw, dw = where(host), where(dev[r])
+        tv_pos = 0.5 * sum(abs(hw[k] - dw[k]) for k in set(hw) | set(dw)) / N
+        tv_all = 0.5 * sum(abs(host[k] - dev[r][k]) for k in set(host) | set(dev[r])) / N
+        assert tv_pos < 0.06, (r, tv_pos)
+        assert tv_all < 0.15, (r, tv_all)
+
+
+def test_design_batch_solves_short_eterna_targets(engine, oracle):
+    from desirna_b200 import design
+    inputs = small_inputs(max_len=40, limit=10)
+    o = design.DesignOptions(replicas=10, RE_attempt=100)
+    results, info = design.design_batch(inputs, o, global_steps=30, seed=1)
+    assert info["solved"] >= len(inputs) - 1, info
+    for inp, res in zip(inputs, results):
+        if res["solved"]:
+            e, ss = oracle.mfe(res["sequence"])
+            assert ss == inp.sec_struct, (inp.name, res["sequence"])
+            assert res["mfe_ss"] == inp.sec_struct and res["distance"] == 0
+            assert oracle.eval(res["sequence"], inp.sec_struct) == e
