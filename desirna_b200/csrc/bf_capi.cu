@@ -131,7 +131,7 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
         CU(bf_launch_mfe_tile(g.dP, db, (int *)w.tri_c.p, (int *)w.tri_f.p, (int *)w.ws_ring.p, g.sm_count, w.d_counters + 0, st),
            "launch bf_k_mfe_tile");
       } else {
-        const size_t wsi = bf_mfe_ws_slot(b->stride) * sizeof(int);
+        const size_t wsi = bf_mfe_ws_slot(b->stride, b->B) * sizeof(int);
         if (wsi) {
           int grid = 0;
           CU(bf_mfe_fill_grid(db, g.sm_count, &grid), "size bf_k_mfe_fill");
@@ -173,7 +173,7 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
       CU(w.d_lnscale.reserve((size_t)b->B * sizeof(double)), "cudaMalloc(lnscale)");
       int grid = 0;
       CU(bf_pf_fill_grid(dbp, g.sm_count, &grid), "size bf_k_pf_fill");
-      const size_t ws = bf_pf_ws_slot(b->stride) * sizeof(double);
+      const size_t ws = bf_pf_ws_slot(b->stride, b->B) * sizeof(double);
       if (ws) CU(w.ws_qm.reserve((size_t)grid * ws), "cudaMalloc(qm workspace)");
       double *qmseq = nullptr;
       if (want_out) {
@@ -243,6 +243,7 @@ int bf_init(int device) {
   { const char *fg = getenv("BF_FORCE_GENERIC"); g.force_generic = fg && fg[0] == '1'; }
   { const char *fk = getenv("BF_FILL"); g.fill_kind = (fk && !strcmp(fk, "tile")) ? 1 : 0; }
   g.sm_count = prop.multiProcessorCount;
+  bf_fill_set_sms(g.sm_count);
   CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking), "cudaStreamCreate");
   CU(g.w.create(), "create engine workspace");
   CU(bf_upload_constants(), "upload candidate table");

@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
           const int t = ptype_sp(SP, i, j);
           const int si1 = S[i + 1], sj1 = S[j - 1];
           int accg = BF_INF, acc1 = BF_INF, accb = BF_INF;
-          constexpr bool kBatchR2 = (NW == 8 && PL == 0 && BLK);  // long-sequence configuration: every ring is read through L2
+          constexpr bool kBatchR2 = (NW >= 8 && PL == 0 && BLK);  // long-sequence configuration: every ring is read through L2
           if (kBatchR2) {
             // bulge and 1xn candidates of this warp's (at most four) loop sizes: all sixteen loads first
             int sv[4], ns = 0;
@@ -639,14 +639,9 @@ __host__ __device__ inline size_t pf_ws_doubles(int nmax, int pl) {
   return (o + 7) / 8 * 8;
 }
 
-// named barrier of a warp pair (ids 1..4; id 0 is __syncthreads)
+// named barrier of a warp pair (ids 1..8; id 0 is __syncthreads)
 __device__ __forceinline__ void pair_barrier(int k) {
-  switch (k) {
-    case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
-    case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
-    case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-    default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
-  }
+  asm volatile("bar.sync %0, 64;" ::"r"(k + 1) : "memory");
 }
 
 // qbtri: per-sequence qb table in HBM (for the exterior pass).  Same phase structure as bf_k_mfe_fill.
@@ -827,7 +822,7 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restri
           const int t = bf_ptype_bases(S[i], S[j]);
           const int si1 = S[i + 1], sj1 = S[j - 1];
           double accg = 0.0, acc1 = 0.0, accb = 0.0;
-          constexpr bool kBatchR2 = (NW == 8 && PL == 0);  // long-sequence configuration: every ring is read through L2
+          constexpr bool kBatchR2 = (NW >= 8 && PL == 0);  // long-sequence configuration: every ring is read through L2
           if (kBatchR2) {
             // bulge and 1xn candidates of this warp's (at most four) loop sizes: all sixteen loads first
             int sv[4], ns = 0;
@@ -1070,13 +1065,26 @@ static int env_int(const char *name, int dflt) {
 }
 struct FillCfg { int nw, pl; };
 
+// Small batches (a replica-exchange sub-step: B = replicas x targets, often far fewer sequences than the 148 x 2..3 CTA slots):
+// what matters is the latency of ONE sequence, so a CTA gets 16 warps instead of 8 when every sequence still gets its own SM.
+static int g_fill_sms = 148;
+void bf_fill_set_sms(int sms) { if (sms > 0) g_fill_sms = sms; }
+static bool want_wide(int B) { return B > 0 && B <= g_fill_sms && env_int("BF_WIDE", 1) != 0; }
+
 static bool mfe_fits(int nmax, int nw, int pl) { return mfe_plan(nmax, nw, pl).total <= kSmemBudget; }
 static bool pf_fits(int nmax, int nw, int pl) { return pf_plan(nmax, nw, pl).total <= kSmemBudget; }
 
-static FillCfg mfe_cfg(int nmax) {
+static bool mfe_blk(int nmax, const FillCfg &c);
+static FillCfg mfe_cfg(int nmax, int B = 0) {
   FillCfg c;
   c.nw = env_int("BF_MFE_NW", 8);
   if (c.nw != 2 && c.nw != 4) c.nw = 8;
+  if (c.nw == 8 && want_wide(B)) {   // same placement rule, 16 warps; only the combinations instantiated below
+    FillCfg w;
+    w.nw = 16;
+    w.pl = mfe_plan(nmax, 8, kMfeRgSmem).total <= 74 * 1024 ? kMfeRgSmem : 0;
+    if (env_int("BF_MFE_PL", w.pl) == w.pl && mfe_plan(nmax, 16, w.pl, mfe_blk(nmax, w)).total <= kSmemBudget) return w;
+  }
   // default (tuning sweep, profiles/r01_sweeps.md): rings on chip while >= 3 CTAs still fit on an SM, else everything through L2
   const int dflt = mfe_plan(nmax, c.nw, kMfeRgSmem).total <= 74 * 1024 ? kMfeRgSmem : 0;
   const int want = env_int("BF_MFE_PL", dflt);
@@ -1087,10 +1095,18 @@ static FillCfg mfe_cfg(int nmax) {
   c.pl = -1;
   return c;
 }
-static FillCfg pf_cfg(int nmax) {
+static bool pf_blk(int nmax, const FillCfg &c);
+static bool pf_half(int nmax, const FillCfg &c);
+static FillCfg pf_cfg(int nmax, int B = 0) {
   FillCfg c;
   c.nw = env_int("BF_PF_NW", 8);
   if (c.nw != 2 && c.nw != 4) c.nw = 8;
+  if (c.nw == 8 && want_wide(B)) {
+    FillCfg w;
+    w.nw = 16;
+    w.pl = pf_plan(nmax, 8, kPfQgSmem).total <= 74 * 1024 ? kPfQgSmem : 0;
+    if (env_int("BF_PF_PL", w.pl) == w.pl && pf_plan(nmax, 16, w.pl, pf_half(nmax, w)).total <= kSmemBudget) return w;
+  }
   const int dflt = pf_plan(nmax, c.nw, kPfQgSmem).total <= 74 * 1024 ? kPfQgSmem : 0;
   const int want = env_int("BF_PF_PL", dflt);
   const int tb = want & kTabSmem;
@@ -1104,7 +1120,7 @@ static FillCfg pf_cfg(int nmax) {
 // blocked split (tile-major mirror + block products): for NW = 8 and the two default placements.  It pays once the split
 // operands no longer fit on chip (measured: L=100 3.86 -> 5.18 ms, L=200 16.1 -> 17.8 ms, L=400 143 -> 117 ms): long sequences only
 static bool mfe_blk(int nmax, const FillCfg &c) {
-  return env_int("BF_BLK", 1) && c.nw == 8 && (c.pl == 0 || c.pl == kMfeRgSmem) && nmax >= env_int("BF_BLK_MIN", 350) &&
+  return env_int("BF_BLK", 1) && c.nw >= 8 && (c.pl == 0 || c.pl == kMfeRgSmem) && nmax >= env_int("BF_BLK_MIN", 350) &&
          mfe_plan(nmax, c.nw, c.pl, true).total <= kSmemBudget;
 }
 
@@ -1117,8 +1133,8 @@ int bf_fill_pf_mode(int nmax) {
   if (nmax < 1 || nmax > 2000) return 0;
   return pf_cfg(nmax).pl + 1;
 }
-size_t bf_mfe_ws_slot(int nmax) {  // ints of per-CTA HBM workspace: [rings when they are not on chip][tile-major fML mirror when blocked]
-  const FillCfg c = mfe_cfg(nmax);
+size_t bf_mfe_ws_slot(int nmax, int B) {  // ints of per-CTA HBM workspace: [rings when they are not on chip][tile-major fML mirror when blocked]
+  const FillCfg c = mfe_cfg(nmax, B);
   if (c.pl < 0) return 0;
   size_t o = 0;
   if (!(c.pl & kMfeRgSmem)) o += ((size_t)3 * kRing * mfe_plan(nmax, c.nw, c.pl).rs + 7) / 8 * 8;
@@ -1126,15 +1142,17 @@ size_t bf_mfe_ws_slot(int nmax) {  // ints of per-CTA HBM workspace: [rings when
   return o;
 }
 static bool pf_blk(int nmax, const FillCfg &c) {
-  return env_int("BF_BLK", 1) && c.nw == 8 && c.pl == 0 && nmax >= env_int("BF_BLK_MIN_PF", 250);
+  return env_int("BF_BLK", 1) && c.nw >= 8 && c.pl == 0 && nmax >= env_int("BF_BLK_MIN_PF", 250);
 }
 static bool pf_half(int nmax, const FillCfg &c) {
   // long sequences: with one partial buffer per warp only one CTA fits an SM; sharing buffers between warp pairs fits two
+  if (c.nw == 16)   // one CTA per SM: share buffers between warp pairs only when the full set does not fit
+    return c.pl == 0 && env_int("BF_PF_HALF", 1) && pf_plan(nmax, 16, 0, false).total > kSmemBudget;
   return c.nw == 8 && c.pl == 0 && env_int("BF_PF_HALF", 1) && pf_plan(nmax, 8, 0, false).total > 113 * 1024 &&
          pf_plan(nmax, 8, 0, true).total <= 113 * 1024;
 }
-size_t bf_pf_ws_slot(int nmax) {  // doubles of per-CTA HBM workspace: [tables that are not on chip][blocked split: qm/qm1 mirrors, sums]
-  const FillCfg c = pf_cfg(nmax);
+size_t bf_pf_ws_slot(int nmax, int B) {  // doubles of per-CTA HBM workspace: [tables that are not on chip][blocked split: qm/qm1 mirrors, sums]
+  const FillCfg c = pf_cfg(nmax, B);
   if (c.pl < 0) return 0;
   size_t o = pf_ws_doubles(nmax, c.pl);
   if (pf_blk(nmax, c)) o += 2 * ((tile_table_entries(nmax) + 7) / 8 * 8) + (size_t)3 * ((nmax + 3) / 4) * 16;
@@ -1155,7 +1173,7 @@ static cudaError_t mfe_fill_t(const BfParams *dP, const BfBatchDev &b, int *ctri
   const int grid = b.B < sms * occ ? b.B : sms * occ;
   if (grid_out) *grid_out = grid;
   if (!launch) return cudaSuccess;
-  kern<<<grid, NW * 32, sm, st>>>(dP, b, ctri, ftri, bf_tri_slot(b.stride), ws, bf_mfe_ws_slot(b.stride), counter);
+  kern<<<grid, NW * 32, sm, st>>>(dP, b, ctri, ftri, bf_tri_slot(b.stride), ws, bf_mfe_ws_slot(b.stride, b.B), counter);
   return cudaGetLastError();
 }
 
@@ -1176,8 +1194,15 @@ static cudaError_t mfe_fill_pl(int pl, const BfParams *dP, const BfBatchDev &b, 
 }
 static cudaError_t mfe_fill_dispatch(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *grid_out,
                                      bool launch, int *counter, cudaStream_t st) {
-  const FillCfg c = mfe_cfg(b.stride);
+  const FillCfg c = mfe_cfg(b.stride, b.B);
   if (c.pl < 0) return cudaErrorInvalidValue;
+  if (c.nw == 16) {
+    const bool blk = mfe_blk(b.stride, c);
+    if (c.pl == 0) return blk ? mfe_fill_t<16, 0, true>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st)
+                              : mfe_fill_t<16, 0, false>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
+    return blk ? mfe_fill_t<16, kMfeRgSmem, true>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st)
+               : mfe_fill_t<16, kMfeRgSmem, false>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
+  }
   if (mfe_blk(b.stride, c)) {
     if (c.pl == 0) return mfe_fill_t<8, 0, true>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
     return mfe_fill_t<8, kMfeRgSmem, true>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
@@ -1220,7 +1245,7 @@ static cudaError_t pf_fill_t(const BfParams *dP, const BfBatchDev &b, double *qb
   const int grid = b.B < sms * occ ? b.B : sms * occ;
   if (grid_out) *grid_out = grid;
   if (!launch) return cudaSuccess;
-  kern<<<grid, NW * 32, sm, st>>>(dP, b, qbtri, bf_tri_slot(b.stride), ws, bf_pf_ws_slot(b.stride), qmseq, mfe_for_scale, lnscale, counter);
+  kern<<<grid, NW * 32, sm, st>>>(dP, b, qbtri, bf_tri_slot(b.stride), ws, bf_pf_ws_slot(b.stride, b.B), qmseq, mfe_for_scale, lnscale, counter);
   return cudaGetLastError();
 }
 template <int NW>
@@ -1240,9 +1265,16 @@ static cudaError_t pf_fill_pl(int pl, const BfParams *dP, const BfBatchDev &b, d
 }
 static cudaError_t pf_fill_dispatch(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale,
                                     double *lnscale, int sms, int *grid_out, bool launch, int *counter, cudaStream_t st) {
-  const FillCfg c = pf_cfg(b.stride);
+  const FillCfg c = pf_cfg(b.stride, b.B);
   if (c.pl < 0) return cudaErrorInvalidValue;
   const bool half = pf_half(b.stride, c), blk = pf_blk(b.stride, c);
+  if (c.nw == 16) {
+    if (c.pl == kPfQgSmem) return pf_fill_t<16, kPfQgSmem>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    if (half && blk) return pf_fill_t<16, 0, true, true>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    if (half) return pf_fill_t<16, 0, true, false>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    if (blk) return pf_fill_t<16, 0, false, true>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    return pf_fill_t<16, 0>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+  }
   if (half && blk) return pf_fill_t<8, 0, true, true>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
   if (half) return pf_fill_t<8, 0, true, false>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
   if (blk) return pf_fill_t<8, 0, false, true>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);

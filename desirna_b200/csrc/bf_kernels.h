@@ -25,8 +25,9 @@ cudaError_t bf_launch_eval(const BfParams *dP, const BfBatchDev &b, const char *
 size_t bf_tri_slot(int nmax);      // entries of one packed triangular table (per sequence)
 int bf_fill_mfe_mode(int nmax);    // 0: length not covered (the generic kernels take it); else 1 + placement flags
 int bf_fill_pf_mode(int nmax);
-size_t bf_mfe_ws_slot(int nmax);   // ints of per-CTA HBM workspace of the MFE fill
-size_t bf_pf_ws_slot(int nmax);    // doubles of per-CTA HBM workspace of the PF fill
+size_t bf_mfe_ws_slot(int nmax, int B);   // ints of per-CTA HBM workspace of the MFE fill (B: batch size, selects the 16-warp variant)
+size_t bf_pf_ws_slot(int nmax, int B);    // doubles of per-CTA HBM workspace of the PF fill
+void bf_fill_set_sms(int sms);    // SM count of the device (batches of at most that many sequences use 16-warp CTAs)
 cudaError_t bf_mfe_fill_grid(const BfBatchDev &b, int sms, int *grid);
 cudaError_t bf_pf_fill_grid(const BfBatchDev &b, int sms, int *grid);
 cudaError_t bf_launch_mfe_fill(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *work_counter,

@@ -82,12 +82,19 @@ def main():
     for ver in ("V1", "V2"):
         rows = []
         p = os.path.join(REF, f"eterna_benchmark/Eterna100{ver}_benchmark_results/Eterna100{ver}_all_results.txt")
+        # which time budget of the reference's benchmark solved the puzzle (*_1min_, *_1h_, *_24h_results.txt)
+        tier = {}
+        for name in ("1min", "1h", "24h"):
+            q = os.path.join(REF, f"eterna_benchmark/Eterna100{ver}_benchmark_results/Eterna100{ver}_{name}_results.txt")
+            for line in open(q):
+                if line.strip():
+                    tier.setdefault(line.strip().split(",")[0][1:], name)
         for line in open(p):
             f = line.strip().split(",")
             if len(f) == 3:
-                rows.append({"set": "E" + ver[1], "file": f[0][1:], "sequence": f[1], "target": f[2]})
+                rows.append({"set": "E" + ver[1], "file": f[0][1:], "sequence": f[1], "target": f[2], "ref_solved_within": tier.get(f[0][1:])})
             elif len(f) >= 6:
-                rows.append({"set": "E" + ver[1], "file": f[0][1:], "sequence": f[3], "target": f[4]})
+                rows.append({"set": "E" + ver[1], "file": f[0][1:], "sequence": f[3], "target": f[4], "ref_solved_within": tier.get(f[0][1:])})
         with open(os.path.join(HERE, f"E{ver[1]}.jsonl"), "w") as fo:
             for r in rows:
                 fo.write(json.dumps(r) + "\n")

@@ -158,3 +158,23 @@ def test_blocked_split_matches_oracle(engine, oracle, monkeypatch):
         assert out["mfe_dcal"][k] == e and out["mfe_ss"][k] == ss, (len(s), k)
         f = oracle.pf(s)[4]
         assert abs(out["pf"][k, 4] - f) <= 1e-6 * max(1.0, abs(f)), (len(s), k)
+
+
+@pytest.mark.parametrize("L", [30, 100, 260, 400])
+def test_small_batch_16_warp_variant_matches_8_warp(engine, oracle, monkeypatch, L):
+    """Batches of at most one sequence per SM run the fill kernels with 16 warps per CTA (latency of a replica-exchange
+    sub-step); same tables, same results as the 8-warp configuration, and as the oracle."""
+    seqs = rand_seqs(77 + L, 24, L) + rand_seqs(78 + L, 6, max(5, L // 2))
+    want = engine.WANT_MFE | engine.WANT_SS | engine.WANT_PF
+    monkeypatch.setenv("BF_WIDE", "1")
+    wide = engine.score_batch(seqs, want=want)
+    monkeypatch.setenv("BF_WIDE", "0")
+    narrow = engine.score_batch(seqs, want=want)
+    assert (wide["mfe_dcal"] == narrow["mfe_dcal"]).all()
+    assert wide["mfe_ss"] == narrow["mfe_ss"]
+    assert np.allclose(wide["pf"][:, 4], narrow["pf"][:, 4], rtol=1e-12, atol=0)
+    for k in range(0, len(seqs), 5 if L > 100 else 1):
+        e, ss = oracle.mfe(seqs[k])
+        assert wide["mfe_dcal"][k] == e and wide["mfe_ss"][k] == ss
+        f = oracle.pf(seqs[k])[4]
+        assert abs(wide["pf"][k, 4] - f) <= 1e-6 * max(1.0, abs(f))
