@@ -297,6 +297,9 @@ def run_ours(args):
     with_defect = {"value": world * B * nD / (float(tD.item()) * 1e-3), "unit": "folds/s", "ms_per_step": float(tD.item()) / nD,
                    "defect_in_0_1": bool(((dfc >= -1e-9) & (dfc <= 1.0 + 1e-9)).all().item()), "defect_mean": float(dfc.mean().item())}
 
+    # ---- the path's caller: Monte-Carlo sub-steps of the device-resident replica-exchange design loop (N=1 only)
+    design_blk = bench_design_loop() if world == 1 else None
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -367,12 +370,55 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": "folds/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "timer": "host clock around the synchronous C-ABI call"},
         "gpu_launches": int(launches),
         "roofline": roof, "cpu_baseline": cpu, "by_length": by, "kernel_ms_by_length": kern, "with_ensemble_defect": with_defect,
+        "design_loop": design_blk,
         "checks": {"ed_equals_mfe_and_epf_le_mfe": checks, "e2e_matches_device_path": e2e_ok},
         "clocks": clocks,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_design_loop():
+    """Sub-step cost of the replica-exchange design loop (bf_design_*: propose -> MFE + backtrack -> PF -> eval -> accept,
+    all on the device).  (a) the shape of BASELINE.json's config 3 on one target: 64 replicas of one median-length Eterna
+    puzzle; (b) the 100 Eterna V1 targets x 10 replicas advanced together, one loop per length bucket on its own stream."""
+    import random
+    from desirna_b200 import design
+    from desirna_b200.utils import stats_inputs_outputs as sio
+    rows = [json.loads(l) for l in open(os.path.join(ROOT, "tests", "golden", "E1.jsonl"))]
+    one = min(rows, key=lambda r: (abs(len(r["target"]) - 104), r["file"]))
+    random.seed(0)
+    out = {}
+    o = design.DesignOptions(replicas=64, RE_attempt=100)
+    loop = design.DesignLoop([sio.make_input(one["file"], one["target"])], o, seed=1)
+    loop.run(1); loop.sync()
+    t0 = time.perf_counter()
+    loop.run(2); loop.sync()
+    dt = time.perf_counter() - t0
+    loop.close()
+    out["one_target_64_replicas"] = {"target": one["file"], "L": len(one["target"]), "ms_per_substep": dt / 200 * 1e3,
+                                     "sequences_scored_per_s": 64 * 200 / dt}
+    o = design.DesignOptions(replicas=10, RE_attempt=100)
+    inputs = [sio.make_input(r["file"], r["target"]) for r in rows]
+    groups = design.bucket_jobs([len(i.sec_struct) for i in inputs])
+    loops = [design.DesignLoop([inputs[k] for k in g], o, seed=2 + b) for b, g in enumerate(groups)]
+    for l in loops:
+        l.run(1)
+    for l in loops:
+        l.sync()
+    t0 = time.perf_counter()
+    for l in loops:
+        l.run(1)
+    for l in loops:
+        l.sync()
+    dt = time.perf_counter() - t0
+    for l in loops:
+        l.close()
+    out["eterna100_x_10_replicas"] = {"jobs": len(inputs), "buckets_stride_jobs": [(l.stride, l.J) for l in loops], "s_per_global_step": dt,
+                                      "ms_per_substep": dt / 100 * 1e3, "sequences_scored_per_s": len(inputs) * 10 * 100 / dt}
+    out["timer"] = "host clock around enqueue + stream synchronisation; sequences stay on the device"
+    return out
 
 
 def main():

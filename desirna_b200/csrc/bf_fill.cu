@@ -1120,7 +1120,7 @@ static FillCfg pf_cfg(int nmax, int B = 0) {
 // blocked split (tile-major mirror + block products): for NW = 8 and the two default placements.  It pays once the split
 // operands no longer fit on chip (measured: L=100 3.86 -> 5.18 ms, L=200 16.1 -> 17.8 ms, L=400 143 -> 117 ms): long sequences only
 static bool mfe_blk(int nmax, const FillCfg &c) {
-  return env_int("BF_BLK", 1) && c.nw >= 8 && (c.pl == 0 || c.pl == kMfeRgSmem) && nmax >= env_int("BF_BLK_MIN", 350) &&
+  return env_int("BF_BLK", 1) && c.nw >= 8 && (c.pl == 0 || c.pl == kMfeRgSmem) && nmax >= env_int("BF_BLK_MIN", 280) &&
          mfe_plan(nmax, c.nw, c.pl, true).total <= kSmemBudget;
 }
 

@@ -190,6 +190,55 @@ def bucket_jobs(lengths, edges=BUCKET_EDGES):
     return [out[e] for e in sorted(out)]
 
 
+def shard_jobs(lengths, world):
+    """Job indices per rank: longest first, each to the least loaded rank, load ~ L^3 (the fold's cost).  Every rank computes
+    the same assignment; nothing is exchanged until the results are gathered (independent units)."""
+    load = [0.0] * world
+    out = [[] for _ in range(world)]
+    for k in sorted(range(len(lengths)), key=lambda k: (-lengths[k], k)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        out[r].append(k)
+        load[r] += float(lengths[k]) ** 3
+    return [sorted(x) for x in out]
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist
+    except Exception:
+        pass
+    return None
+
+
+def design_batch_sharded(inputs, sim_options, **kw):
+    """design_batch with the jobs sharded over the ranks of torch.distributed (one process per GPU): each rank designs its
+    own targets; the per-job results are all-gathered at the end.  Returns (results in input order, info of this rank with
+    the job-weighted totals of all ranks) on every rank."""
+    dist = _dist()
+    inputs = list(inputs)
+    if dist is None:
+        return design_batch(inputs, sim_options, **kw)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    mine = shard_jobs([len(i.sec_struct) for i in inputs], world)[rank]
+    kw = dict(kw)
+    kw["seed"] = kw.get("seed", 0) * 131 + rank
+    res, info = design_batch([inputs[k] for k in mine], sim_options, **kw) if mine else ([], {"folds": 0, "seconds": 0.0, "solved": 0, "jobs": 0, "global_steps": 0, "buckets": []})
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (mine, res, info))
+    results = [None] * len(inputs)
+    for idx, rr, _ in gathered:
+        for k, r in zip(idx, rr):
+            results[k] = r
+    infos = [g[2] for g in gathered]
+    total = dict(info)
+    total.update(folds=sum(i["folds"] for i in infos), solved=sum(i["solved"] for i in infos), jobs=len(inputs),
+                 seconds=max(i["seconds"] for i in infos), per_rank=[{"jobs": i["jobs"], "solved": i["solved"], "folds": i["folds"], "seconds": i["seconds"]} for i in infos])
+    total["folds_per_s"] = total["folds"] / max(total["seconds"], 1e-9)
+    return results, total
+
+
 def design_batch(inputs, sim_options, time_limit=None, global_steps=None, stop_when_solved=True, seed=0, poll_steps=1,
                  edges=BUCKET_EDGES, verbose=False):
     """Design every target of `inputs` (InputFile objects, utils/stats_inputs_outputs.py) concurrently.

@@ -38,14 +38,26 @@ def main():
     rows = [json.loads(l) for l in open(os.path.join(ROOT, "tests", "golden", "E1.jsonl"))]
     rows = [r for r in rows if len(r["target"]) <= a.max_len]
     inputs = [sio.make_input(r["file"], r["target"]) for r in rows]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:   # one process per GPU (torchrun): targets sharded over the ranks, results gathered at the end
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
     engine.init()
     engine.params_builtin(1999)
     o = design.DesignOptions(replicas=a.replicas, RE_attempt=a.exchange, scoring_f=sio.parse_scoring_functions_all(a.sf))
     l0 = engine.kernel_launches()
     t0 = time.time()
-    results, info = design.design_batch(inputs, o, time_limit=None if a.steps else a.time, global_steps=a.steps, seed=a.seed,
-                                        poll_steps=a.poll, verbose=a.verbose)
+    results, info = design.design_batch_sharded(inputs, o, time_limit=None if a.steps else a.time, global_steps=a.steps, seed=a.seed,
+                                                poll_steps=a.poll, verbose=a.verbose and rank == 0)
     wall = time.time() - t0
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return 0
     solved = [(r, res) for r, res in zip(rows, results) if res["solved"]]
     verified = 0
     if solved:
@@ -62,7 +74,8 @@ def main():
         t["solved_here"] += int(res["solved"])
     times = sorted(res["solved_after_s"] for _, res in solved)
     line = {
-        "benchmark": "Eterna100 V1 targets, Turner 1999, all puzzles designed concurrently on one GPU",
+        "benchmark": "Eterna100 V1 targets, Turner 1999, all puzzles designed concurrently, targets sharded over %d GPU(s)" % world,
+        "n_gpus": world, "per_rank": info.get("per_rank"),
         "puzzles": len(rows), "solved": len(solved), "solved_and_refolded_ok": verified, "wall_s": round(wall, 2),
         "budget_s": None if a.steps else a.time, "global_steps": info["global_steps"], "replicas": a.replicas, "re_attempt": a.exchange,
         "scoring_function": a.sf, "sequences_scored": info["folds"], "scored_per_s": round(info["folds"] / wall, 1),

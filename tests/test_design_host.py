@@ -126,3 +126,15 @@ def test_bucketing():
     from desirna_b200.design import bucket_jobs
     g = bucket_jobs([12, 36, 400, 104, 105, 41])
     assert g == [[0, 1], [5], [3], [4], [2]]
+
+
+def test_job_sharding_is_balanced_and_deterministic():
+    from desirna_b200.design import shard_jobs
+    lengths = [12, 400, 36, 104, 398, 250, 300, 90, 385, 120, 60, 399]
+    for world in (1, 2, 4, 8):
+        sh = shard_jobs(lengths, world)
+        assert sorted(k for s in sh for k in s) == list(range(len(lengths)))
+        assert sh == shard_jobs(lengths, world)
+        loads = [sum(lengths[k] ** 3 for k in s) for s in sh]
+        if world <= 4:
+            assert max(loads) <= 1.5 * (sum(loads) / world)
