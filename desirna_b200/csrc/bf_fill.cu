@@ -64,7 +64,7 @@ struct MfePlan {
   int rs;  // ring row stride (ints)
   size_t o_S, o_SP, o_toff, o_pg, o_pb, o_p1, o_fm, o_ring, o_dml, o_pi, o_ps, o_list, o_tab, o_sa, total;
 };
-__host__ __device__ inline MfePlan mfe_plan(int nmax, int nw, int pl, bool blk = false) {
+__host__ __device__ inline MfePlan mfe_plan(int nmax, int nw, int pl, bool blk = false, bool atom = false) {
   MfePlan p;
   p.rs = (nmax + 8 + 3) / 4 * 4;
   size_t o = 0;
@@ -77,8 +77,9 @@ __host__ __device__ inline MfePlan mfe_plan(int nmax, int nw, int pl, bool blk =
   p.o_fm = o; o += (pl & kMfeFmSmem) ? (tri_size(nmax) + 4) * sizeof(int) : 0;
   p.o_ring = o; o += (pl & kMfeRgSmem) ? (size_t)3 * kRing * p.rs * sizeof(int) : 0;
   p.o_dml = o; o += (size_t)4 * p.rs * sizeof(int);
-  p.o_pi = o; o += (size_t)2 * nw * p.rs * sizeof(int);   // double-buffered per-warp partial minima
-  p.o_ps = o; o += (size_t)2 * nw * p.rs * sizeof(int);
+  const int nbuf = atom ? 1 : nw;   // double-buffered partial minima: one buffer per warp, or one shared by all warps (atomicMin)
+  p.o_pi = o; o += (size_t)2 * nbuf * p.rs * sizeof(int);
+  p.o_ps = o; o += (size_t)2 * nbuf * p.rs * sizeof(int);
   p.o_list = o; o += (size_t)2 * p.rs * sizeof(unsigned short);  // pairable cells of a diagonal, double-buffered
   p.o_tab = o; o += (pl & kTabSmem) ? (sizeof(BfSmallI) + 15) / 16 * 16 : 0;
   o = (o + 15) / 16 * 16;
@@ -120,14 +121,17 @@ __device__ __forceinline__ int build_pair_list(const uint8_t *SP, int n, int d, 
 // tiles K = I+3 .. J-3 only need diagonals <= 4D'-9, so they are computed as 4x4 register-tiled (min,+) block products
 // (8 x 128-bit loads per 64 relaxations, lanes = 4 tiles x 8 K-slices) during the four phases d = 4D'-7 .. 4D'-4, one quarter
 // of the tiles per phase, into SA[D' % 3].  The per-diagonal loop keeps only the <= 15 candidates next to either end.
-template <int NW, int PL, bool BLK = false>
+// ATOM: the warps share one partial buffer per kind and merge with atomicMin (shared memory): smaller footprint, more CTAs per SM
+// where the per-warp buffers were what limited occupancy (short sequences with the rings on chip, long sequences).
+template <int NW, int PL, bool BLK = false, bool ATOM = false>
 __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restrict__ P, BfBatchDev b, int *ctri, int *ftri,
                                                          size_t tri_slot, int *ws, size_t ws_slot, int *work_counter) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ int s_seq, s_np[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nmax = b.stride;
-  const MfePlan pl = mfe_plan(nmax, NW, PL, BLK);
+  const MfePlan pl = mfe_plan(nmax, NW, PL, BLK, ATOM);
+  constexpr int NBUF = ATOM ? 1 : NW;
   const int RS = pl.rs;
   uint8_t *S = dyn + pl.o_S;
   uint8_t *SP = dyn + pl.o_SP;
@@ -163,6 +167,7 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
     p1[tid] = (tid >= 4 && tid <= 30) ? T.interior[tid] + min(T.ninio_max, (tid - 2) * T.ninio_m) : BF_INF;
   }
   for (int k = tid; k < 3 * kRing * RS; k += blockDim.x) ring[k] = BF_INF;
+  if (ATOM) for (int k = tid; k < 2 * RS; k += blockDim.x) { PI[k] = BF_INF; PS[k] = BF_INF; }
 
   for (;;) {
     __syncthreads();
@@ -206,16 +211,22 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
       // ------------------------------------------------------------ combine diagonal d-1
       if (d > BF_TURN + 1) {
         const int dd = d - 1, ncell = n - dd, buf = dd & 1;
-        const int *pi = PI + buf * NW * RS, *ps = PS + buf * NW * RS;
+        int *pi = PI + buf * NBUF * RS, *ps = PS + buf * NBUF * RS;
         for (int cell = tid; cell < ncell; cell += blockDim.x) {
           const int i = cell + 1, j = i + dd;
           const int t = ptype_sp(SP, i, j);
           int e = BF_INF, sp = BF_INF;
+          if (ATOM) { sp = ps[cell]; ps[cell] = BF_INF; }   // the buffer is used again two phases later
+          else {
 #pragma unroll
-          for (int w = 0; w < NW; w++) sp = min(sp, ps[w * RS + cell]);
+            for (int w = 0; w < NW; w++) sp = min(sp, ps[w * RS + cell]);
+          }
           if (t) {
+            if (ATOM) { e = pi[cell]; pi[cell] = BF_INF; }
+            else {
 #pragma unroll
-            for (int w = 0; w < NW; w++) e = min(e, pi[w * RS + cell]);
+              for (int w = 0; w < NW; w++) e = min(e, pi[w * RS + cell]);
+            }
             const int dm = DML[((dd - 2) & 3) * RS + i + 1];
             if (dm < kInfThr) e = min(e, dm + T.MLclosing + bf_e_mlstem(T, bf_rtype(t), S[j - 1], S[i + 1]));
             if (e >= kInfThr) e = BF_INF;
@@ -250,7 +261,7 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
       // ------------------------------------------------------------ partial minima of diagonal d
       if (d <= n - 1) {
         const int ncell = n - d, buf = d & 1;
-        int *pi = PI + (buf * NW + warp) * RS, *ps = PS + (buf * NW + warp) * RS;
+        int *pi = PI + (buf * NBUF + (ATOM ? 0 : warp)) * RS, *ps = PS + (buf * NBUF + (ATOM ? 0 : warp)) * RS;
         const int smax = min(BF_MAXLOOP, d - 6);  // inner diagonal d-2-s >= 4
         // ---- pair-only work on the compacted list: interior loops, hairpin
         const int np = s_np[buf];
@@ -315,7 +326,7 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
             if (t2 > 2) cc -= T.TerminalAU;
             tot = min(tot, cc + bf_e_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]));
           }
-          if (kk < np) pi[i - 1] = tot;
+          if (kk < np) { if (ATOM) { if (tot < kInfThr) atomicMin(&pi[i - 1], tot); } else pi[i - 1] = tot; }
         }
         // ---- fML split for every cell: k = u - i in [5, d-4]
         if (!BLK) {
@@ -332,7 +343,7 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
 #pragma unroll 4
             for (int k = 5 + warp; k <= d - 4; k += NW) accs = min(accs, left[toff[k - 1]] + left[toff[d - k] + k]);
           }
-          if (cell < ncell) ps[cell] = accs;
+          if (cell < ncell) { if (ATOM) { if (accs < kInfThr) atomicMin(&ps[cell], accs); } else ps[cell] = accs; }
         }
         } else {
         // blocked split: only the candidates next to either end stay here -- k in [5, 12] and [d-10, d-4] minus what the
@@ -363,7 +374,7 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
 #pragma unroll
           for (int u = 0; u < 4; u++) {
             const int cell = c + 32 * u + lane;
-            if (cell < ncell) ps[cell] = accs[u];
+            if (cell < ncell) { if (ATOM) { if (accs[u] < kInfThr) atomicMin(&ps[cell], accs[u]); } else ps[cell] = accs[u]; }
           }
         }
         // block products for tile-diagonal D' = (d+7)/4, quarter q = (d+7)%4 of its tiles
@@ -1075,6 +1086,18 @@ static bool mfe_fits(int nmax, int nw, int pl) { return mfe_plan(nmax, nw, pl).t
 static bool pf_fits(int nmax, int nw, int pl) { return pf_plan(nmax, nw, pl).total <= kSmemBudget; }
 
 static bool mfe_blk(int nmax, const FillCfg &c);
+// shared partial buffers (atomicMin) where they buy occupancy: CTAs per SM by shared memory, capped by the register limit (4 x 256 threads)
+static bool mfe_atom(int nmax, const FillCfg &c, bool blk) {
+  const int a = env_int("BF_MFE_ATOM", -1);
+  if (a >= 0) return a != 0;
+  auto occ = [&](bool atom) {
+    const size_t t = mfe_plan(nmax, c.nw, c.pl, blk, atom).total + 1024;
+    const int cap = c.nw == 16 ? 2 : 4;
+    const int o = (int)(kSmemBudget / t);
+    return t > kSmemBudget ? 0 : (o < cap ? o : cap);
+  };
+  return occ(true) > occ(false);
+}
 static FillCfg mfe_cfg(int nmax, int B = 0) {
   FillCfg c;
   c.nw = env_int("BF_MFE_NW", 8);
@@ -1082,11 +1105,11 @@ static FillCfg mfe_cfg(int nmax, int B = 0) {
   if (c.nw == 8 && want_wide(B)) {   // same placement rule, 16 warps; only the combinations instantiated below
     FillCfg w;
     w.nw = 16;
-    w.pl = mfe_plan(nmax, 8, kMfeRgSmem).total <= 74 * 1024 ? kMfeRgSmem : 0;
-    if (env_int("BF_MFE_PL", w.pl) == w.pl && mfe_plan(nmax, 16, w.pl, mfe_blk(nmax, w)).total <= kSmemBudget) return w;
+    w.pl = mfe_plan(nmax, 8, kMfeRgSmem, false, true).total <= (size_t)env_int("BF_MFE_RING_KB", 70) * 1024 ? kMfeRgSmem : 0;
+    if (env_int("BF_MFE_PL", w.pl) == w.pl && mfe_plan(nmax, 16, w.pl, mfe_blk(nmax, w), true).total <= kSmemBudget) return w;
   }
   // default (tuning sweep, profiles/r01_sweeps.md): rings on chip while >= 3 CTAs still fit on an SM, else everything through L2
-  const int dflt = mfe_plan(nmax, c.nw, kMfeRgSmem).total <= 74 * 1024 ? kMfeRgSmem : 0;
+  const int dflt = mfe_plan(nmax, c.nw, kMfeRgSmem, false, true).total <= (size_t)env_int("BF_MFE_RING_KB", 70) * 1024 ? kMfeRgSmem : 0;
   const int want = env_int("BF_MFE_PL", dflt);
   const int tb = want & kTabSmem;
   const int order[4] = {want & 11, (want & kMfeRgSmem) | tb, want & kMfeRgSmem, 0};
@@ -1159,11 +1182,11 @@ size_t bf_pf_ws_slot(int nmax, int B) {  // doubles of per-CTA HBM workspace: [t
   return (o + 7) / 8 * 8;
 }
 
-template <int NW, int PL, bool BLK = false>
+template <int NW, int PL, bool BLK = false, bool ATOM = false>
 static cudaError_t mfe_fill_t(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *grid_out, bool launch,
                               int *counter, cudaStream_t st) {
-  auto kern = bf_k_mfe_fill<NW, PL, BLK>;
-  const size_t sm = mfe_plan(b.stride, NW, PL, BLK).total;
+  auto kern = bf_k_mfe_fill<NW, PL, BLK, ATOM>;
+  const size_t sm = mfe_plan(b.stride, NW, PL, BLK, ATOM).total;
   cudaError_t e = set_smem(kern, sm);
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -1196,17 +1219,31 @@ static cudaError_t mfe_fill_dispatch(const BfParams *dP, const BfBatchDev &b, in
                                      bool launch, int *counter, cudaStream_t st) {
   const FillCfg c = mfe_cfg(b.stride, b.B);
   if (c.pl < 0) return cudaErrorInvalidValue;
-  if (c.nw == 16) {
-    const bool blk = mfe_blk(b.stride, c);
-    if (c.pl == 0) return blk ? mfe_fill_t<16, 0, true>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st)
-                              : mfe_fill_t<16, 0, false>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
-    return blk ? mfe_fill_t<16, kMfeRgSmem, true>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st)
-               : mfe_fill_t<16, kMfeRgSmem, false>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
+  const bool blk = mfe_blk(b.stride, c);
+  const bool atom = (c.nw >= 8) && (c.pl == 0 || c.pl == kMfeRgSmem) && mfe_atom(b.stride, c, blk);
+#define BF_MFE_GO(NW_, PL_, BLK_, ATOM_) return mfe_fill_t<NW_, PL_, BLK_, ATOM_>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st)
+  if (c.nw == 16 || atom || blk) {
+    const int key = (c.nw == 16 ? 8 : 0) | (c.pl == 0 ? 0 : 4) | (blk ? 2 : 0) | (atom ? 1 : 0);
+    switch (key) {
+      case 0: break;   // <8, 0, false, false>: the generic switch below
+      case 1: BF_MFE_GO(8, 0, false, true);
+      case 2: BF_MFE_GO(8, 0, true, false);
+      case 3: BF_MFE_GO(8, 0, true, true);
+      case 4: break;
+      case 5: BF_MFE_GO(8, kMfeRgSmem, false, true);
+      case 6: BF_MFE_GO(8, kMfeRgSmem, true, false);
+      case 7: BF_MFE_GO(8, kMfeRgSmem, true, true);
+      case 8: BF_MFE_GO(16, 0, false, false);
+      case 9: BF_MFE_GO(16, 0, false, true);
+      case 10: BF_MFE_GO(16, 0, true, false);
+      case 11: BF_MFE_GO(16, 0, true, true);
+      case 12: BF_MFE_GO(16, kMfeRgSmem, false, false);
+      case 13: BF_MFE_GO(16, kMfeRgSmem, false, true);
+      case 14: BF_MFE_GO(16, kMfeRgSmem, true, false);
+      case 15: BF_MFE_GO(16, kMfeRgSmem, true, true);
+    }
   }
-  if (mfe_blk(b.stride, c)) {
-    if (c.pl == 0) return mfe_fill_t<8, 0, true>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
-    return mfe_fill_t<8, kMfeRgSmem, true>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
-  }
+#undef BF_MFE_GO
   if (c.nw == 4) return mfe_fill_pl<4>(c.pl, dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
   if (c.nw == 2) return mfe_fill_pl<2>(c.pl, dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
   return mfe_fill_pl<8>(c.pl, dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
