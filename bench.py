@@ -399,6 +399,16 @@ def bench_design_loop():
     loop.close()
     out["one_target_64_replicas"] = {"target": one["file"], "L": len(one["target"]), "ms_per_substep": dt / 200 * 1e3,
                                      "sequences_scored_per_s": 64 * 200 / dt}
+    # (c) BASELINE config 4: the reference's two-strand example (17 & 18 nt), heterodimer scoring with the oligomerisation term
+    o = design.DesignOptions(replicas=64, RE_attempt=100, oligo_state="heterodimer")
+    loop = design.DesignLoop([sio.make_input("RNA_RNA_complex", "(((.(((((....))..&(((....)))..))))))", "NNNNNNNNNNNNNNNNN&NNNNNNNNNNNNNNNNNN")], o, seed=3)
+    loop.run(1); loop.sync()
+    t0 = time.perf_counter()
+    loop.run(2); loop.sync()
+    dt = time.perf_counter() - t0
+    loop.close()
+    out["heterodimer_17_18nt_64_replicas"] = {"ms_per_substep": dt / 200 * 1e3, "sequences_scored_per_s": 64 * 200 / dt,
+                                              "reference_example_run": "933 score calls/s on 10 processes (example_files/outputs/RNA_RNA_complex*/*_stats)"}
     o = design.DesignOptions(replicas=10, RE_attempt=100)
     inputs = [sio.make_input(r["file"], r["target"]) for r in rows]
     groups = design.bucket_jobs([len(i.sec_struct) for i in inputs])

@@ -475,6 +475,7 @@ struct DesignLoop {
   BfDesignCfg C;
   int B = 0, gstep = 0, re_attempt = 0;
   uint32_t want = 0;
+  bool two = false;   // some job has two strands: the loop folds with the two-strand kernels
   std::vector<void *> allocs;
   std::vector<uint8_t> active;
   uint8_t *d_active = nullptr;
@@ -517,10 +518,11 @@ int design_score(DesignLoop *h) {
   bf_batch_t b;
   std::memset(&b, 0, sizeof b);
   b.B = h->B; b.stride = h->D.stride; b.seq = h->D.mut_seq; b.len = h->D.row_len; b.targets = h->D.row_tgt; b.n_targets = 1; b.want = h->want;
+  b.cut = h->two ? h->D.row_cut : nullptr;
   bf_result_t r;
   std::memset(&r, 0, sizeof r);
   r.mfe_dcal = h->D.o_mfe; r.mfe_ss = h->D.o_ss; r.pf = h->D.o_pf; r.eval_dcal = h->D.o_eval; r.defect = h->D.o_defect;
-  return run_device(h->w, &b, &r, false, h->st);
+  return run_device(h->w, &b, &r, h->two, h->st);
 }
 }  // namespace
 
@@ -538,10 +540,16 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   // host-side preparation: partner tables and the lists of mutable positions
   std::vector<short> tpt((size_t)J * S, -1);
   std::vector<unsigned short> avail((size_t)J * S, 0);
-  std::vector<int> n_avail(J, 0);
+  std::vector<int> n_avail(J, 0), len_a(J, 0);
+  bool two = false;
   for (int j = 0; j < J; j++) {
     const int n = c->len[j];
     if (n <= 0 || n > S) return fail(BF_ERR_ARG, "bf_design_create: length outside (0, stride]");
+    if (c->len_a) {
+      if (c->len_a[j] < 0 || c->len_a[j] >= n) return fail(BF_ERR_ARG, "bf_design_create: strand A length outside [0, len)");
+      len_a[j] = c->len_a[j];
+      two = two || len_a[j] > 0;
+    }
     std::vector<int> stk;
     for (int i = 0; i < n; i++) {
       const char ch = c->target[(size_t)j * S + i];
@@ -556,8 +564,9 @@ int bf_design_create(const bf_design_t *c, void **handle) {
     }
     if (!stk.empty()) return fail(BF_ERR_ARG, "bf_design_create: unbalanced target");
   }
-  if (bf_fill_mfe_mode(S) == 0 || bf_fill_pf_mode(S) == 0) return fail(BF_ERR_UNAVAILABLE, "bf_design_create: stride outside the fill path");
+  if (!two && (bf_fill_mfe_mode(S) == 0 || bf_fill_pf_mode(S) == 0)) return fail(BF_ERR_UNAVAILABLE, "bf_design_create: stride outside the fill path");
   DesignLoop *h = new DesignLoop;
+  h->two = two;
   std::memset(&h->D, 0, sizeof h->D);
   std::memset(&h->C, 0, sizeof h->C);
   auto bail = [&](cudaError_t e, const char *what) { h->destroy(); delete h; return cuda_fail(e, what); };
@@ -566,9 +575,9 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   DCU(h->w.create(), "create design workspace");
   BfDesignDev &D = h->D;
   D.J = J; D.R = R; D.stride = S;
-  char *tgt; short *d_tpt; uint8_t *allowed; int *len; unsigned short *d_avail; int *d_navail; double *temps, *tm_prob;
+  char *tgt; short *d_tpt; uint8_t *allowed; int *len, *d_len_a; unsigned short *d_avail; int *d_navail; double *temps, *tm_prob;
   DCU(h->alloc(&tgt, (size_t)J * S), "cudaMalloc(design)"); DCU(h->alloc(&d_tpt, (size_t)J * S), "cudaMalloc(design)");
-  DCU(h->alloc(&allowed, (size_t)J * S), "cudaMalloc(design)"); DCU(h->alloc(&len, J), "cudaMalloc(design)");
+  DCU(h->alloc(&allowed, (size_t)J * S), "cudaMalloc(design)"); DCU(h->alloc(&len, J), "cudaMalloc(design)"); DCU(h->alloc(&d_len_a, J), "cudaMalloc(design)");
   DCU(h->alloc(&d_avail, (size_t)J * S), "cudaMalloc(design)"); DCU(h->alloc(&d_navail, J), "cudaMalloc(design)");
   DCU(h->alloc(&temps, R), "cudaMalloc(design)"); DCU(h->alloc(&tm_prob, R), "cudaMalloc(design)");
   DCU(h->alloc(&D.job_rng, J), "cudaMalloc(design)");
@@ -579,7 +588,7 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   DCU(h->alloc(&D.rec, G * kDesignRec), "cudaMalloc(design)"); DCU(h->alloc(&D.shelf, G), "cudaMalloc(design)");
   DCU(h->alloc(&D.rng, G), "cudaMalloc(design)"); DCU(h->alloc(&D.counts, G * 3), "cudaMalloc(design)");
   DCU(h->alloc(&h->d_rowmap, G), "cudaMalloc(design)"); DCU(h->alloc(&h->d_active, J), "cudaMalloc(design)");
-  DCU(h->alloc(&D.mut_seq, G * S), "cudaMalloc(design)"); DCU(h->alloc(&D.row_len, G), "cudaMalloc(design)");
+  DCU(h->alloc(&D.mut_seq, G * S), "cudaMalloc(design)"); DCU(h->alloc(&D.row_len, G), "cudaMalloc(design)"); DCU(h->alloc(&D.row_cut, G), "cudaMalloc(design)");
   DCU(h->alloc(&D.row_tgt, G * S), "cudaMalloc(design)"); DCU(h->alloc(&D.o_mfe, G), "cudaMalloc(design)");
   DCU(h->alloc(&D.o_ss, G * (S + 1)), "cudaMalloc(design)"); DCU(h->alloc(&D.o_pf, G * 5), "cudaMalloc(design)");
   DCU(h->alloc(&D.o_eval, G), "cudaMalloc(design)");
@@ -594,8 +603,10 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   if (h->want & BF_WANT_DEFECT) DCU(h->alloc(&D.o_defect, G), "cudaMalloc(design)");
   C.metropolis_L = c->metropolis_L; C.point_mutations = c->point_mutations; C.acgu = c->acgu;
   for (int k = 0; k < 4; k++) C.nt_weight[k] = c->nt_weight[k];
+  C.oligo = c->oligo;
+  if (two && (h->want & BF_WANT_DEFECT)) return bail(cudaErrorInvalidValue, "bf_design_create: the Edef term needs single-strand jobs");
   h->re_attempt = c->re_attempt;
-  D.tgt = tgt; D.tpt = d_tpt; D.allowed = allowed; D.len = len; D.avail = d_avail; D.n_avail = d_navail; D.temps = temps; D.tm_prob = tm_prob;
+  D.tgt = tgt; D.tpt = d_tpt; D.allowed = allowed; D.len = len; D.len_a = d_len_a; D.avail = d_avail; D.n_avail = d_navail; D.temps = temps; D.tm_prob = tm_prob;
   D.rowmap = h->d_rowmap;
   // uploads
   std::vector<unsigned long long> rng(G), jrng(J);
@@ -608,7 +619,7 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   std::vector<double> best((size_t)J * kDesignRec, 1e300);
   std::vector<int> sstep(J, -1);
   DCU(cudaMemcpy(tgt, c->target, (size_t)J * S, cudaMemcpyHostToDevice), "H2D design"); DCU(cudaMemcpy(d_tpt, tpt.data(), tpt.size() * sizeof(short), cudaMemcpyHostToDevice), "H2D design");
-  DCU(cudaMemcpy(allowed, c->allowed, (size_t)J * S, cudaMemcpyHostToDevice), "H2D design"); DCU(cudaMemcpy(len, c->len, J * sizeof(int), cudaMemcpyHostToDevice), "H2D design");
+  DCU(cudaMemcpy(allowed, c->allowed, (size_t)J * S, cudaMemcpyHostToDevice), "H2D design"); DCU(cudaMemcpy(len, c->len, J * sizeof(int), cudaMemcpyHostToDevice), "H2D design"); DCU(cudaMemcpy(d_len_a, len_a.data(), J * sizeof(int), cudaMemcpyHostToDevice), "H2D design");
   DCU(cudaMemcpy(d_avail, avail.data(), avail.size() * sizeof(unsigned short), cudaMemcpyHostToDevice), "H2D design");
   DCU(cudaMemcpy(d_navail, n_avail.data(), J * sizeof(int), cudaMemcpyHostToDevice), "H2D design");
   DCU(cudaMemcpy(temps, c->temps, R * sizeof(double), cudaMemcpyHostToDevice), "H2D design"); DCU(cudaMemcpy(tm_prob, c->tm_prob, R * sizeof(double), cudaMemcpyHostToDevice), "H2D design");

@@ -102,7 +102,7 @@ __global__ void bf_k_design_gather(BfDesignDev D, int B) {
   const int lane = threadIdx.x & 31, row = blockIdx.x * kWPB + (threadIdx.x >> 5);
   if (row >= B) return;
   const int job = D.rowmap[row] / D.R;
-  if (lane == 0) D.row_len[row] = D.len[job];
+  if (lane == 0) { D.row_len[row] = D.len[job]; D.row_cut[row] = D.len_a[job] > 0 ? D.len_a[job] + 1 : 0; }
   for (int k = lane; k < D.stride; k += 32) D.row_tgt[(size_t)row * D.stride + k] = D.tgt[(size_t)job * D.stride + k];
 }
 
@@ -142,25 +142,37 @@ __global__ void __launch_bounds__(kWPB * 32) bf_k_design_propose(BfDesignDev D, 
     __syncwarp();
     bool targeted = false;
     int cnt = 0;
-    // expand_cases(false_cases, len - 1, 3): every v in [1, n-1] within 3 of a flagged position (sequence_utils.py:983-1005)
+    // expand_cases(false_cases, len - 1, 3): every v in [1, len-1] within 3 of a flagged position (sequence_utils.py:983-1005).
+    // The reference's strings carry the '&' of a two-strand design: positions are compared in those coordinates (A = index of
+    // the '&'), and the '&' itself can be drawn -- a move that changes nothing (its restraint allows one letter).
+    const int A = D.len_a[job];
+    const int hi = A > 0 ? n : n - 1;
     auto near = [&](int v) {
       bool e = false;
-      for (int o = -3; o <= 3; o++) { const int u = v + o; e |= (u >= 0 && u < n && w.fl[u]); }
+      for (int o = -3; o <= 3; o++) {
+        const int ua = v + o;                       // '&' coordinates
+        if (ua < 0 || (A > 0 && ua == A)) continue;
+        const int u = ua - (A > 0 && ua > A);       // nucleotide index
+        e |= (u < n && w.fl[u]);
+      }
       return e;
     };
     if (nfalse > 0) {
-      for (int base = 1; base <= n - 1; base += 32) {
+      for (int base = 1; base <= hi; base += 32) {
         const int v = base + lane;
-        cnt += __popc(__ballot_sync(BF_FULL, v <= n - 1 && near(v)));
+        cnt += __popc(__ballot_sync(BF_FULL, v <= hi && near(v)));
       }
       // random.choices([false_cases, available_positions], weights=[p, 1-p])
       targeted = u01(rng) < D.tm_prob[D.shelf[g]];
     }
-    if (targeted && cnt > 0) pos = choose_flagged(near, 1, n - 1, cnt, rng, lane);
-    else pos = avail[below(rng, n_avail)];
+    if (targeted && cnt > 0) {
+      const int va = choose_flagged(near, 1, hi, cnt, rng, lane);
+      pos = (A > 0 && va == A) ? -1 : va - (A > 0 && va > A);
+    } else pos = avail[below(rng, n_avail)];
   }
   __syncwarp();
-  if (lane == 0) {
+  if (lane == 0 && pos < 0) D.rng[g] = rng;
+  if (lane == 0 && pos >= 0) {
     const int curl = letter_code(cur[pos]);
     const unsigned a1 = allowed[pos];
     const int partner = tpt[pos];
@@ -207,6 +219,8 @@ __global__ void __launch_bounds__(kWPB * 32) bf_k_design_accept(BfDesignDev D, B
     tp += __shfl_xor_sync(BF_FULL, tp, o); fp += __shfl_xor_sync(BF_FULL, fp, o);
     fn += __shfl_xor_sync(BF_FULL, fn, o); tn += __shfl_xor_sync(BF_FULL, tn, o);
   }
+  const bool two = D.len_a[job] > 0;
+  if (two) tp += 2;   // '&' becomes the always-matching pair "Ee" for the similarity scores (energy_scores.py:79)
   int ok = 0;
   double rec[kDesignRec];
   if (lane == 0) {
@@ -220,22 +234,33 @@ __global__ void __launch_bounds__(kWPB * 32) bf_k_design_accept(BfDesignDev D, B
     const double recall = rint((double)tp / ((double)(tp + fn) + 0.001) * 1000.0) / 1000.0;
     const double precision = rint((double)tp / ((double)(tp + fp) + 0.001) * 1000.0) / 1000.0;
     const double Ed = (double)(float)((double)D.o_eval[row] / 100.0);
-    const double Epf = (double)(float)D.o_pf[(size_t)row * 5 + 4];
+    const double Epf = (double)(float)D.o_pf[(size_t)row * 5 + (two ? 3 : 4)];   // two strands: FAB (energy_scores.py:157)
     const double MFE = (double)(float)((double)D.o_mfe[row] / 100.0);
     rec[kRecEd] = Ed; rec[kRecEpf] = Epf; rec[kRecMcc] = 1.0 - mcc; rec[kRecPrecision] = 1.0 - precision; rec[kRecRecall] = 1.0 - recall;
     rec[kRecMFE] = MFE; rec[kRecEdef] = D.o_defect ? D.o_defect[row] : 0.0; rec[kRecDist] = (double)(fp + fn); rec[kRecStep] = (double)gstep;
+    rec[kRecOligoFraction] = 0.0; rec[kRecOligoBonus] = 0.0;
     double total = 0.0;
     for (int k = 0; k < C.n_terms; k++) {
       const double wgt = C.weight[k];
       switch (C.term[k]) {
         case kTermEdEpf: total += (Ed - Epf) * wgt; break;
         case kTermMcc: total += rec[kRecMcc] * 10 * wgt; break;
-        case kTermSlnEpf: total += (Epf + 0.3759 * n + 5.7534) / 10 * wgt; break;
+        case kTermSlnEpf: total += (Epf + 0.3759 * (n + (two ? 1 : 0)) + 5.7534) / 10 * wgt; break;   // len(sequence) counts the '&'
         case kTermEdMfe: total += (Ed - MFE) * wgt; break;
         case kTermPrecision: total += rec[kRecPrecision] * 10 * wgt; break;
         case kTermRecall: total += rec[kRecRecall] * 10 * wgt; break;
         case kTermEdef: total += rec[kRecEdef] * wgt; break;
       }
+    }
+    if (two && C.oligo == 1) {
+      // equilibrium dimer fraction at 1 mM from FcAB - FA - FB (dimer_multichain_energy.py:36-63), float32 API values first
+      const double kT = 0.001987204259 * (273.15 + 37);
+      const double dF = (double)(float)D.o_pf[(size_t)row * 5 + 2] - (double)(float)D.o_pf[(size_t)row * 5 + 0] - (double)(float)D.o_pf[(size_t)row * 5 + 1];
+      const double rhs = 1e-3 / 55.14 * exp(-dF / kT);
+      const double frac = 1 - (sqrt(1 + 4 * rhs) - 1) / (2 * rhs);
+      rec[kRecOligoFraction] = frac;
+      rec[kRecOligoBonus] = -kT * log(frac);
+      total += rec[kRecOligoBonus];
     }
     rec[kRecScore] = total;
     if (init) ok = 1;

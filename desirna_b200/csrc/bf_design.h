@@ -8,9 +8,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-constexpr int kDesignRec = 10;   // doubles per replica record
+constexpr int kDesignRec = 12;   // doubles per replica record
 // record slots (names of the reference's ScoreSeq fields, utils/energy_scores.py:176-195)
-enum { kRecScore = 0, kRecEd = 1, kRecEpf = 2, kRecMcc = 3, kRecPrecision = 4, kRecRecall = 5, kRecMFE = 6, kRecEdef = 7, kRecDist = 8, kRecStep = 9 };
+enum { kRecScore = 0, kRecEd = 1, kRecEpf = 2, kRecMcc = 3, kRecPrecision = 4, kRecRecall = 5, kRecMFE = 6, kRecEdef = 7, kRecDist = 8, kRecStep = 9, kRecOligoFraction = 10, kRecOligoBonus = 11 };
 // scoring terms (-sf), in the order of ScoreSeq.get_scoring_function (utils/energy_scores.py:376-398)
 enum { kTermEdEpf = 0, kTermMcc = 1, kTermSlnEpf = 2, kTermEdMfe = 3, kTermPrecision = 4, kTermRecall = 5, kTermEdef = 6 };
 
@@ -22,6 +22,7 @@ struct BfDesignCfg {
   int point_mutations;   // -tm on/off
   int acgu;              // -acgu on: paired letters drawn with nt_weight
   double nt_weight[4];   // A C G U
+  int oligo;             // 1: two-strand jobs add -kT ln(dimer fraction) (energy_scores.py:421-430, dimer_multichain_energy.py:36-63)
 };
 
 struct BfDesignDev {
@@ -30,7 +31,8 @@ struct BfDesignDev {
   const char *tgt;               // J x stride   target dot-bracket
   const short *tpt;              // J x stride   partner in the target (0-based) or -1
   const uint8_t *allowed;        // J x stride   letters_allowed, bit 0..3 = A C G U  (sequence_utils.py:454-525)
-  const int *len;                // J
+  const int *len;                // J            nucleotides (both strands, no '&')
+  const int *len_a;              // J            length of strand A, 0 = single strand ('&' sits after it in the reference's strings)
   const unsigned short *avail;   // J x stride   positions with more than one allowed letter (sequence_utils.py:1026-1029)
   const int *n_avail;            // J
   unsigned long long *job_rng;   // J            stream of the neighbour swaps
@@ -50,6 +52,7 @@ struct BfDesignDev {
   const int *rowmap;             // B -> g
   char *mut_seq;                 // B x stride
   int *row_len;                  // B
+  int *row_cut;                  // B            1-based first nucleotide of strand B, 0 = single strand (bf_batch_t.cut)
   char *row_tgt;                 // B x stride
   int *o_mfe;                    // B
   char *o_ss;                    // B x (stride+1)

@@ -19,7 +19,8 @@ from . import engine
 from .utils import sequence_utils as seq_utils
 
 TERM_ID = {"Ed-Epf": 0, "1-MCC": 1, "sln_Epf": 2, "Ed-MFE": 3, "1-precision": 4, "1-recall": 5, "Edef": 6}
-REC_FIELDS = ("scoring_function", "edesired", "Epf", "mcc", "precision", "recall", "MFE", "ensemble_defect", "distance", "global_step")
+REC_FIELDS = ("scoring_function", "edesired", "Epf", "mcc", "precision", "recall", "MFE", "ensemble_defect", "distance", "global_step",
+              "oligo_fraction", "oligomer_bonus")
 REC = len(REC_FIELDS)
 
 
@@ -27,7 +28,7 @@ class DesignOptions:
     """The fields of DesiRNA.py's DesignOptions (:520-633) the loop reads, with the CLI defaults (:92-139)."""
 
     def __init__(self, replicas=10, RE_attempt=100, T_min=10.0, T_max=150.0, scoring_f=(("Ed-Epf", 1.0),), point_mutations="on",
-                 tm_max=0.7, tm_min=0.0, acgu_percentages="off", nt_percentages=None, diff_start_replicas="one"):
+                 tm_max=0.7, tm_min=0.0, acgu_percentages="off", nt_percentages=None, diff_start_replicas="one", oligo_state="none"):
         self.replicas = replicas
         self.RE_attempt = RE_attempt
         self.T_min, self.T_max = T_min, T_max
@@ -38,16 +39,16 @@ class DesignOptions:
         self.nt_percentages = nt_percentages or {"A": 15, "C": 30, "G": 30, "U": 15}
         self.diff_start_replicas = diff_start_replicas
         self.L = 504.12
-        self.oligo_state, self.pks, self.subopt, self.motifs = "none", "off", "off", None
+        self.oligo_state, self.pks, self.subopt, self.motifs = oligo_state, "off", "off", None   # "none" | "heterodimer"
         self.rep_temps_shelfs = seq_utils.get_rep_temps(self)
 
 
 class bf_design_t(C.Structure):
     _fields_ = [("n_jobs", C.c_int32), ("replicas", C.c_int32), ("stride", C.c_int32), ("target", C.c_void_p), ("len", C.c_void_p),
-                ("allowed", C.c_void_p), ("init_seq", C.c_void_p), ("temps", C.c_void_p), ("tm_prob", C.c_void_p),
+                ("len_a", C.c_void_p), ("allowed", C.c_void_p), ("init_seq", C.c_void_p), ("temps", C.c_void_p), ("tm_prob", C.c_void_p),
                 ("n_terms", C.c_int32), ("term", C.c_int32 * 8), ("weight", C.c_double * 8), ("metropolis_L", C.c_double),
                 ("point_mutations", C.c_int32), ("re_attempt", C.c_int32), ("acgu", C.c_int32), ("nt_weight", C.c_double * 4),
-                ("seed", C.c_uint64)]
+                ("oligo", C.c_int32), ("seed", C.c_uint64)]
 
 
 def _bind():
@@ -72,8 +73,12 @@ def _chars(rows, stride):
     return out
 
 
-def _strings(buf, lens):
-    return [bytes(buf[k, :lens[k]]).decode("ascii") for k in range(buf.shape[0])]
+def _strings(buf, lens, len_a=None):
+    """rows of a char buffer -> str; two-strand rows get their '&' back after strand A"""
+    out = [bytes(buf[k, :lens[k]]).decode("ascii") for k in range(buf.shape[0])]
+    if len_a is not None:
+        out = [s[:a] + "&" + s[a:] if a > 0 else s for s, a in zip(out, len_a)]
+    return out
 
 
 class DesignLoop:
@@ -85,14 +90,18 @@ class DesignLoop:
         self.inputs = list(inputs)
         self.J, self.R = len(self.inputs), sim_options.replicas
         for inp in self.inputs:
-            if set(inp.sec_struct) - set(".()"):
-                raise ValueError("the device design loop takes single-strand targets made of . ( ) only: %r" % (inp.name,))
-        self.lens = np.array([len(i.sec_struct) for i in self.inputs], np.int32)
+            if set(inp.sec_struct) - set(".()&") or inp.sec_struct.count("&") > 1:
+                raise ValueError("the device design loop takes targets made of . ( ), one strand or 'A&B': %r" % (inp.name,))
+            if "&" in inp.sec_struct and sim_options.oligo_state != "heterodimer":
+                raise ValueError("two-strand targets need oligo_state='heterodimer' (homodimer designs run on the lock-step path)")
+        # the reference's strings carry the '&'; the engine's do not: len_a remembers where it sat
+        self.len_a = np.array([i.sec_struct.index("&") if "&" in i.sec_struct else 0 for i in self.inputs], np.int32)
+        self.lens = np.array([len(i.sec_struct.replace("&", "")) for i in self.inputs], np.int32)
         self.stride = int(self.lens.max())
         nt_lists = [seq_utils.get_nt_list(i) for i in self.inputs]
         allowed = np.full((self.J, self.stride), 15, np.uint8)
         for j, nts in enumerate(nt_lists):
-            allowed[j, :self.lens[j]] = seq_utils.allowed_masks(nts)
+            allowed[j, :self.lens[j]] = seq_utils.allowed_masks([nt for nt in nts if nt.letters != ["&"]])
         if init_seqs is None:
             init_seqs = []
             for inp, nts in zip(self.inputs, nt_lists):
@@ -100,13 +109,15 @@ class DesignLoop:
                 for _ in range(self.R):
                     init_seqs.append(seq_utils.initial_sequence_generator(nts, inp, sim_options)
                                      if sim_options.diff_start_replicas == "different" else first)
+        init_seqs = [x.replace("&", "") for x in init_seqs]
         assert len(init_seqs) == self.J * self.R
         terms = [(TERM_ID[f], float(w)) for f, w in sim_options.scoring_f]
         cfg = bf_design_t()
-        self._keep = [_chars([i.sec_struct for i in self.inputs], self.stride), self.lens, allowed, _chars(init_seqs, self.stride),
+        self._keep = [_chars([i.sec_struct.replace("&", "") for i in self.inputs], self.stride), self.lens, self.len_a, allowed, _chars(init_seqs, self.stride),
                       np.array(sim_options.rep_temps_shelfs, np.float64), np.array(seq_utils.targeted_move_probabilities(sim_options), np.float64)]
         cfg.n_jobs, cfg.replicas, cfg.stride = self.J, self.R, self.stride
-        cfg.target, cfg.len, cfg.allowed, cfg.init_seq, cfg.temps, cfg.tm_prob = (a.ctypes.data for a in self._keep)
+        cfg.target, cfg.len, cfg.len_a, cfg.allowed, cfg.init_seq, cfg.temps, cfg.tm_prob = (a.ctypes.data for a in self._keep)
+        cfg.oligo = int(sim_options.oligo_state == "heterodimer")
         cfg.n_terms = len(terms)
         for k, (t, w) in enumerate(terms):
             cfg.term[k], cfg.weight[k] = t, w
@@ -140,7 +151,8 @@ class DesignLoop:
         step = np.zeros(self.J, np.int32)
         nsol = np.zeros(self.J, np.uint32)
         engine._check(self.lib.bf_design_read_jobs(self.h, seq.ctypes.data, ss.ctypes.data, rec.ctypes.data, step.ctypes.data, nsol.ctypes.data))
-        return {"sequence": _strings(seq, self.lens), "mfe_ss": _strings(ss, self.lens), "rec": rec, "solved_step": step, "n_solved": nsol}
+        return {"sequence": _strings(seq, self.lens, self.len_a), "mfe_ss": _strings(ss, self.lens, self.len_a), "rec": rec,
+                "solved_step": step, "n_solved": nsol}
 
     def replicas(self):
         G = self.J * self.R
@@ -150,8 +162,8 @@ class DesignLoop:
         shelf = np.zeros(G, np.int32)
         counts = np.zeros((G, 3), np.uint32)
         engine._check(self.lib.bf_design_read_replicas(self.h, seq.ctypes.data, ss.ctypes.data, rec.ctypes.data, shelf.ctypes.data, counts.ctypes.data))
-        lens = np.repeat(self.lens, self.R)
-        return {"sequence": _strings(seq, lens), "mfe_ss": _strings(ss, lens), "rec": rec, "shelf": shelf.reshape(self.J, self.R),
+        lens, la = np.repeat(self.lens, self.R), np.repeat(self.len_a, self.R)
+        return {"sequence": _strings(seq, lens, la), "mfe_ss": _strings(ss, lens, la), "rec": rec, "shelf": shelf.reshape(self.J, self.R),
                 "counts": counts}
 
     def propose_only(self):
@@ -159,8 +171,8 @@ class DesignLoop:
         rows = int(self.active.sum()) * self.R
         out = np.zeros((rows, self.stride), np.uint8)
         engine._check(self.lib.bf_design_propose_only(self.h, out.ctypes.data))
-        lens = np.repeat(self.lens[self.active.astype(bool)], self.R)
-        return _strings(out, lens)
+        act = self.active.astype(bool)
+        return _strings(out, np.repeat(self.lens[act], self.R), np.repeat(self.len_a[act], self.R))
 
     def close(self):
         if self.h:
@@ -250,7 +262,10 @@ def design_batch(inputs, sim_options, time_limit=None, global_steps=None, stop_w
         raise ValueError("give time_limit and/or global_steps")
     random.seed(seed)
     inputs = list(inputs)
-    groups = bucket_jobs([len(i.sec_struct) for i in inputs], edges)
+    # two-strand jobs fold with the two-strand kernels: they get loops of their own
+    one = [k for k, i in enumerate(inputs) if "&" not in i.sec_struct]
+    two = [k for k, i in enumerate(inputs) if "&" in i.sec_struct]
+    groups = [[sub[k] for k in grp] for sub in (one, two) if sub for grp in bucket_jobs([len(inputs[k].sec_struct) for k in sub], edges)]
     t_start = time.time()
     loops = [DesignLoop([inputs[k] for k in grp], sim_options, seed=seed * 1000003 + b) for b, grp in enumerate(groups)]
     results = [None] * len(inputs)

@@ -112,7 +112,7 @@ int bf_debug_copy_table(int which, int32_t n_seq, void *host, size_t host_bytes,
 /* ---------------------------------------------------------------------------------------------------------
  * Device-resident Replica-Exchange Monte-Carlo design loop: many design problems ("jobs") x replicas advance
  * in lock step with sequences, scores, temperature shelves and random streams resident in HBM.  Replaces,
- * for single-strand targets made of . ( ):
+ * for targets made of . ( ), one strand or two (heterodimer):
  *   remc.mutate_sequence_re / single_replica_design / mc_delta      utils/replica_exchange_monte_carlo.py:26-110,176-271
  *   remc.replica_exchange / replica_exchange_attempt                utils/replica_exchange_monte_carlo.py:80-173
  *   seq_utils.mutate_sequence / get_mutation_position / expand_cases  utils/sequence_utils.py:926-1136
@@ -122,7 +122,8 @@ int bf_debug_copy_table(int which, int32_t n_seq, void *host, size_t host_bytes,
 typedef struct {
   int32_t n_jobs, replicas, stride;
   const char *target;      /* n_jobs x stride dot-bracket, only . ( )                          input_file.sec_struct */
-  const int32_t *len;      /* n_jobs */
+  const int32_t *len;      /* n_jobs: nucleotides (both strands) */
+  const int32_t *len_a;    /* n_jobs or NULL: length of strand A of a two-strand job (the reference's 'A&B' strings), 0 = one strand */
   const uint8_t *allowed;  /* n_jobs x stride: Nucleotide.letters_allowed as bits A=1 C=2 G=4 U=8  sequence_utils.py:454-525 */
   const char *init_seq;    /* n_jobs x replicas x stride start sequences                         sequence_utils.py:862-888 */
   const double *temps;     /* replicas: temperature shelves, ascending                           sequence_utils.py:811-859 */
@@ -135,11 +136,13 @@ typedef struct {
   int32_t re_attempt;      /* Monte-Carlo sub-steps per global step (-e) */
   int32_t acgu;            /* -acgu on: paired letters drawn with nt_weight */
   double nt_weight[4];     /* A C G U */
+  int32_t oligo;           /* 1: heterodimer design, adds -kT ln(dimer fraction)   energy_scores.py:421-430 */
   uint64_t seed;
 } bf_design_t;
 
-enum { BF_DESIGN_REC = 10 }; /* doubles per record: scoring_function, edesired, Epf, 1-mcc, 1-precision, 1-recall, MFE,
-                                ensemble_defect, positions whose partner differs from the target's (0 = solved), global step */
+enum { BF_DESIGN_REC = 12 }; /* doubles per record: scoring_function, edesired, Epf, 1-mcc, 1-precision, 1-recall, MFE,
+                                ensemble_defect, positions whose partner differs from the target's (0 = solved), global step,
+                                oligo_fraction, oligomer_bonus */
 
 /* Allocates the loop on the engine's GPU, scores the start sequences (global step 0). */
 int bf_design_create(const bf_design_t *cfg, void **handle);

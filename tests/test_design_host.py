@@ -138,3 +138,50 @@ def test_job_sharding_is_balanced_and_deterministic():
         loads = [sum(lengths[k] ** 3 for k in s) for s in sh]
         if world <= 4:
             assert max(loads) <= 1.5 * (sum(loads) / world)
+
+
+SHARD_WORKER = r'''
+import os, sys, pickle
+sys.path.insert(0, sys.argv[1])
+import torch.distributed as dist
+from desirna_b200 import design
+from desirna_b200.utils import stats_inputs_outputs as sio
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+seen = []
+def fake_design_batch(inputs, sim_options, **kw):   # stands in for the GPU loop: the sharding and the gather are host code
+    seen.extend(i.name for i in inputs)
+    res = [{"name": i.name, "sequence": "A" * len(i.sec_struct), "solved": len(i.sec_struct) % 2 == 0, "seed": kw["seed"]} for i in inputs]
+    return res, {"folds": 10 * len(inputs), "seconds": 1.0 + dist.get_rank(), "solved": sum(r["solved"] for r in res), "jobs": len(inputs),
+                 "global_steps": 3, "buckets": []}
+design.design_batch = fake_design_batch
+inputs = [sio.make_input("job%d" % k, "(" * 3 + "." * n + ")" * 3) for k, n in enumerate([3, 30, 4, 90, 5, 60, 7, 8])]
+results, info = design.design_batch_sharded(inputs, None, seed=5, global_steps=3)
+pickle.dump((seen, results, info), open(sys.argv[4] + ".%s" % sys.argv[3], "wb"))
+dist.destroy_process_group()
+'''
+
+
+def test_design_sharding_two_ranks_gloo(tmp_path):
+    import os
+    import pickle
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(SHARD_WORKER)
+    port = str(31500 + os.getpid() % 2000)
+    out = str(tmp_path / "res")
+    procs = [subprocess.Popen([sys.executable, str(script), root, port, str(r), out]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=240) == 0
+    got = [pickle.load(open(out + ".%d" % r, "rb")) for r in range(2)]
+    # disjoint shards covering every job; both ranks return the same, complete, input-ordered result list
+    assert sorted(got[0][0] + got[1][0]) == sorted("job%d" % k for k in range(8))
+    assert not set(got[0][0]) & set(got[1][0])
+    assert got[0][1] == got[1][1]
+    assert [r["name"] for r in got[0][1]] == ["job%d" % k for k in range(8)]
+    assert {r["seed"] for r in got[0][1]} == {5 * 131, 5 * 131 + 1}      # per-rank seeds
+    for r in range(2):
+        info = got[r][2]
+        assert info["jobs"] == 8 and info["folds"] == 80 and info["seconds"] == 2.0 and len(info["per_rank"]) == 2
+        assert info["solved"] == sum(1 for x in got[0][1] if x["solved"])

@@ -135,3 +135,74 @@ def test_design_batch_solves_short_eterna_targets(engine, oracle):
             assert ss == inp.sec_struct, (inp.name, res["sequence"])
             assert res["mfe_ss"] == inp.sec_struct and res["distance"] == 0
             assert oracle.eval(res["sequence"], inp.sec_struct) == e
+
+
+HETERO = ("(((.(((((....))..&(((....)))..))))))", "NNNNNNNNNNNNNNNNN&NNNNNNNNNNNNNNNNNN")   # example_files/inputs/RNA_RNA_complex_design_input.txt
+
+
+def test_heterodimer_records_match_host_scoring(engine):
+    """two-strand jobs: FAB as Epf, eval with the nick, '&' -> 'Ee' in the similarity scores, -kT ln(dimer fraction) bonus
+    (utils/energy_scores.py:79,153-158,421-430; utils/dimer_multichain_energy.py:36-63)"""
+    from desirna_b200 import design
+    from desirna_b200.utils import energy_scores as es
+    from desirna_b200.utils import stats_inputs_outputs as sio
+    inp = sio.make_input("complex", *HETERO)
+    o = design.DesignOptions(replicas=8, RE_attempt=20, oligo_state="heterodimer", scoring_f=[("Ed-Epf", 1.0), ("1-MCC", 0.3), ("sln_Epf", 0.2)])
+    random.seed(4)
+    loop = design.DesignLoop([inp], o, seed=9)
+    loop.run(5)
+    rep = loop.replicas()
+    ref = es.score_sequences(rep["sequence"], inp, o)
+    assert (np.sort(rep["shelf"], axis=1) == np.arange(8)).all()
+    moved = 0
+    for g, (s, h) in enumerate(zip(rep["sequence"], ref)):
+        rec = dict(zip(design.REC_FIELDS, rep["rec"][g]))
+        assert s.index("&") == 17 and rep["mfe_ss"][g] == h.mfe_ss
+        for a, b in inp.pairs:
+            assert (s[a], s[b]) in PAIR_OK
+        assert rec["edesired"] == h.edesired and rec["Epf"] == h.Epf
+        assert rec["mcc"] == pytest.approx(h.mcc, abs=1e-12) and rec["recall"] == pytest.approx(h.recall, abs=1e-12)
+        assert rec["oligo_fraction"] == pytest.approx(h.oligo_fraction, rel=1e-9)
+        assert rec["oligomer_bonus"] == pytest.approx(h.oligomer_bonus, abs=1e-9)
+        assert rec["scoring_function"] == pytest.approx(h.scoring_function, abs=1e-9)
+        moved += s != rep["sequence"][0]
+    assert moved > 0
+    jb = loop.jobs()
+    if jb["solved_step"][0] >= 0:
+        assert jb["mfe_ss"][0] == inp.sec_struct
+    loop.close()
+
+
+def test_heterodimer_moves_match_host_mirror(engine):
+    from desirna_b200 import design
+    from desirna_b200.utils import sequence_utils as su
+    from desirna_b200.utils import stats_inputs_outputs as sio
+    inp = sio.make_input("complex", *HETERO)
+    o = design.DesignOptions(replicas=2, RE_attempt=1, tm_max=0.9, tm_min=0.5, oligo_state="heterodimer")
+    start = "AACUGAGGGGAAACCAA&GUCUAGUGACCACUCGUU"    # a shipped trajectory point: folds close to, not into, the target
+    loop = design.DesignLoop([inp], o, seed=3, init_seqs=[start] * 2)
+    cur_ss = loop.replicas()["mfe_ss"][0]
+    assert "&" in cur_ss and cur_ss != inp.sec_struct
+    N = 6000
+    dev = [Counter() for _ in range(2)]
+    for _ in range(N):
+        for r, m in enumerate(loop.propose_only()):
+            dev[r][m] += 1
+    loop.close()
+    nts = su.get_nt_list(inp)
+    random.seed(8)
+    for r in range(2):
+        cur = SimpleNamespace(sequence=start, mfe_ss=cur_ss, temp_shelf=o.rep_temps_shelfs[r])
+        host = Counter(su.propose_mutation(cur, nts, o, inp) for _ in range(N))
+        assert set(dev[r]) <= set(host) | {k for k in dev[r] if dev[r][k] < 5}
+
+        def where(counter):
+            out = Counter()
+            for m, c in counter.items():
+                out[tuple(i for i in range(len(start)) if m[i] != start[i])] += c
+            return out
+
+        hw, dw = where(host), where(dev[r])
+        assert abs(hw[()] - dw[()]) / N < 0.02          # the '&' itself is drawn equally often (a move that changes nothing)
+        tv = 0.5 * sum(abs(hw[k] - dw[k]) for k in set(hw) | set(dw)) / N
+        assert tv < 0.06, (r, tv)
