@@ -206,3 +206,59 @@ def test_heterodimer_moves_match_host_mirror(engine):
         assert abs(hw[()] - dw[()]) / N < 0.02          # the '&' itself is drawn equally often (a move that changes nothing)
         tv = 0.5 * sum(abs(hw[k] - dw[k]) for k in set(hw) | set(dw)) / N
         assert tv < 0.06, (r, tv)
+
+
+@pytest.mark.parametrize("acgu,tm", [("on", "on"), ("off", "off")])
+def test_move_generator_options_match_host_mirror(engine, acgu, tm):
+    """-acgu on (weighted letters for paired positions) and -tm off (uniform positions): device draws vs host mirror"""
+    from desirna_b200 import design
+    from desirna_b200.utils import sequence_utils as su
+    from desirna_b200.utils import stats_inputs_outputs as sio
+    inp = sio.make_input("t", "((((....))))...((...))", "NNNNNNNNSNNNNNANNNNNNN")
+    o = design.DesignOptions(replicas=2, RE_attempt=1, acgu_percentages=acgu, point_mutations=tm)
+    start = "GGGAAAAACCCCAAAGGAAACC"
+    loop = design.DesignLoop([inp], o, seed=21, init_seqs=[start] * 2)
+    cur_ss = loop.replicas()["mfe_ss"][0]
+    N = 5000
+    dev = Counter()
+    for _ in range(N):
+        dev[loop.propose_only()[0]] += 1
+    loop.close()
+    nts = su.get_nt_list(inp)
+    random.seed(6)
+    cur = SimpleNamespace(sequence=start, mfe_ss=cur_ss, temp_shelf=o.rep_temps_shelfs[0])
+    host = Counter(su.propose_mutation(cur, nts, o, inp) for _ in range(N))
+    assert set(dev) <= set(host) | {k for k in dev if dev[k] < 5}
+
+    def letters(counter):   # marginal over (first mutated position, its new letter): <= ~70 categories
+        out = Counter()
+        for m, c in counter.items():
+            d = [i for i in range(len(start)) if m[i] != start[i]]
+            out[(d[0], m[d[0]]) if d else ()] += c
+        return out
+
+    hl, dl = letters(host), letters(dev)
+    tv = 0.5 * sum(abs(hl[k] - dl[k]) for k in set(hl) | set(dl)) / N
+    assert tv < 0.09, tv
+    gc_dev = sum(c for (k, c) in dl.items() if k and k[1] in "CG")
+    gc_host = sum(c for (k, c) in hl.items() if k and k[1] in "CG")
+    assert abs(gc_dev - gc_host) / N < 0.03   # -acgu on: C/G weighted 30:15 against A/U at paired positions, on both sides
+
+
+def test_fixed_sequence_and_single_replica(engine):
+    """nothing mutable: the loop keeps scoring the same sequence; one replica: no exchange partner"""
+    from desirna_b200 import design
+    from desirna_b200.utils import stats_inputs_outputs as sio
+    fixed = sio.make_input("fixed", "((((....))))", "GGGGAAAACCCC")
+    free = sio.make_input("free", "((((....))))")
+    o = design.DesignOptions(replicas=1, RE_attempt=10)
+    assert o.rep_temps_shelfs == [150.0]
+    random.seed(0)
+    loop = design.DesignLoop([fixed, free], o, seed=1)
+    loop.run(3)
+    rep = loop.replicas()
+    assert rep["sequence"][0] == "GGGGAAAACCCC" and rep["mfe_ss"][0] == "((((....))))"
+    assert rep["rec"][0][8] == 0 and loop.jobs()["solved_step"][0] == 0       # solved by its start sequence, recorded at step 0
+    assert (rep["shelf"] == 0).all()
+    assert rep["counts"][1][0] + rep["counts"][1][2] == 30
+    loop.close()
