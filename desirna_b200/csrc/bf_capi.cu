@@ -584,6 +584,7 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   DCU(h->alloc(&D.best_seq, (size_t)J * S), "cudaMalloc(design)"); DCU(h->alloc(&D.best_ss, (size_t)J * (S + 1)), "cudaMalloc(design)");
   DCU(h->alloc(&D.best_rec, (size_t)J * kDesignRec), "cudaMalloc(design)");
   DCU(h->alloc(&D.solved_step, J), "cudaMalloc(design)"); DCU(h->alloc(&D.n_solved, J), "cudaMalloc(design)");
+  DCU(h->alloc(&D.re_counts, (size_t)J * 3), "cudaMalloc(design)");
   DCU(h->alloc(&D.cur_seq, G * S), "cudaMalloc(design)"); DCU(h->alloc(&D.cur_ss, G * (S + 1)), "cudaMalloc(design)");
   DCU(h->alloc(&D.rec, G * kDesignRec), "cudaMalloc(design)"); DCU(h->alloc(&D.shelf, G), "cudaMalloc(design)");
   DCU(h->alloc(&D.rng, G), "cudaMalloc(design)"); DCU(h->alloc(&D.counts, G * 3), "cudaMalloc(design)");
@@ -675,6 +676,14 @@ int bf_design_set_active(void *handle, const uint8_t *active_jobs) {
   CU(cudaStreamSynchronize(h->st), "bf_design_set_active");
   for (int j = 0; j < h->D.J; j++) h->active[j] = active_jobs[j] ? 1 : 0;
   return design_rows(h);
+}
+
+int bf_design_read_swaps(void *handle, uint32_t *re_counts) {
+  DesignLoop *h = (DesignLoop *)handle;
+  if (!h || !re_counts) return fail(BF_ERR_ARG, "bf_design_read_swaps: null argument");
+  CU(cudaStreamSynchronize(h->st), "bf_design_read_swaps");
+  CU(cudaMemcpy(re_counts, h->D.re_counts, (size_t)h->D.J * 3 * sizeof(unsigned), cudaMemcpyDeviceToHost), "D2H re_counts");
+  return BF_OK;
 }
 
 int bf_design_read_jobs(void *handle, char *best_seq, char *best_ss, double *best_rec, int32_t *solved_step, uint32_t *n_solved) {

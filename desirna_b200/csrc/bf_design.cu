@@ -329,11 +329,14 @@ __global__ void bf_k_design_exchange(BfDesignDev D, BfDesignCfg C, const uint8_t
     if (ra < 0 || rb < 0) continue;
     const double e0 = D.rec[(size_t)(job * R + ra) * kDesignRec + kRecScore], e1 = D.rec[(size_t)(job * R + rb) * kDesignRec + kRecScore];
     bool ok = e1 <= e0;
-    if (!ok) {
+    unsigned int *rc = D.re_counts + (size_t)job * 3;
+    if (ok) rc[1]++;
+    else {
       const double T0 = D.temps[a], T1 = D.temps[a + 1];
       ok = exp(C.metropolis_L * (1.0 / T0 - 1.0 / T1) * (e0 - e1)) > u01(rng);
     }
-    if (ok) { D.shelf[job * R + ra] = a + 1; D.shelf[job * R + rb] = a; }
+    if (ok) { D.shelf[job * R + ra] = a + 1; D.shelf[job * R + rb] = a; rc[0]++; }
+    else rc[2]++;
   }
   D.job_rng[job] = rng;
 }

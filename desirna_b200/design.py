@@ -60,6 +60,7 @@ def _bind():
         L.bf_design_set_active.argtypes = [C.c_void_p, C.c_void_p]
         L.bf_design_read_jobs.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         L.bf_design_read_replicas.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        L.bf_design_read_swaps.argtypes = [C.c_void_p, C.c_void_p]
         L.bf_design_propose_only.argtypes = [C.c_void_p, C.c_void_p]
         L.bf_design_destroy.argtypes = [C.c_void_p]
         L._design_bound = True
@@ -166,6 +167,39 @@ class DesignLoop:
         return {"sequence": _strings(seq, lens, la), "mfe_ss": _strings(ss, lens, la), "rec": rec, "shelf": shelf.reshape(self.J, self.R),
                 "counts": counts}
 
+    def swaps(self):
+        """neighbour-swap counters per job: accepted, accepted because not worse, rejected"""
+        out = np.zeros((self.J, 3), np.uint32)
+        engine._check(self.lib.bf_design_read_swaps(self.h, out.ctypes.data))
+        return out
+
+    def records(self, sim_options, sim_step):
+        """the current replica states as the dicts DesiRNA.py appends to `simulation_data` (vars(ScoreSeq), DesiRNA.py:373-375),
+        one list per job"""
+        rep = self.replicas()
+        out = []
+        for j in range(self.J):
+            rows = []
+            for r in range(self.R):
+                g = j * self.R + r
+                v = dict(zip(REC_FIELDS, rep["rec"][g]))
+                n = len(rep["sequence"][g])
+                row = {"sequence": rep["sequence"][g], "scoring_function": v["scoring_function"], "replica_num": r + 1,
+                       "temp_shelf": sim_options.rep_temps_shelfs[rep["shelf"][j, r]], "sim_step": sim_step,
+                       "edesired_minus_Epf": v["edesired"] - v["Epf"], "Epf": v["Epf"], "edesired": v["edesired"], "mcc": v["mcc"], "mcc_alt": 0,
+                       "mfe_ss": rep["mfe_ss"][g], "subopt_e": 0, "esubopt_minus_Epf": 0,
+                       "sln_Epf": (v["Epf"] + 0.3759 * n + 5.7534) / 10 if any(f == "sln_Epf" for f, _ in sim_options.scoring_f) else 0,
+                       "MFE": v["MFE"] if any(f == "Ed-MFE" for f, _ in sim_options.scoring_f) else 0,
+                       "edesired_minus_MFE": v["edesired"] - v["MFE"] if any(f == "Ed-MFE" for f, _ in sim_options.scoring_f) else 0,
+                       "recall": v["recall"], "precision": v["precision"], "edesired2": 0, "edesired2_minus_Epf": 0}
+                if any(f == "Edef" for f, _ in sim_options.scoring_f):
+                    row["ensemble_defect"] = v["ensemble_defect"]
+                if self.len_a[j] > 0:
+                    row["oligo_fraction"], row["oligomer_bonus"] = v["oligo_fraction"], v["oligomer_bonus"]
+                rows.append(row)
+            out.append(rows)
+        return out
+
     def propose_only(self):
         """test hook: one draw of the move generator for every replica of every active job, not scored, not accepted"""
         rows = int(self.active.sum()) * self.R
@@ -252,12 +286,16 @@ def design_batch_sharded(inputs, sim_options, **kw):
 
 
 def design_batch(inputs, sim_options, time_limit=None, global_steps=None, stop_when_solved=True, seed=0, poll_steps=1,
-                 edges=BUCKET_EDGES, verbose=False):
+                 edges=BUCKET_EDGES, verbose=False, trajectory=False):
     """Design every target of `inputs` (InputFile objects, utils/stats_inputs_outputs.py) concurrently.
 
     Stops when every job is solved (stop_when_solved, the reference's `-sws on` with `-r 1`), after `global_steps` global
     steps (`-s`), or after `time_limit` seconds (`-t`), whichever comes first.  Returns (results, info): one dict per input
-    (REC_FIELDS + name, sequence, mfe_ss, solved, solved_step, solved_after_s) and run statistics."""
+    (REC_FIELDS + name, sequence, mfe_ss, solved, solved_step, solved_after_s) and run statistics.
+
+    trajectory=True (use poll_steps=1) also records, per job, what DesiRNA.py keeps as `simulation_data` -- the state of every
+    replica after each global step -- and a Stats object, as info["simulation_data"][k] / info["stats"][k]: the inputs of
+    utils.stats_inputs_outputs.parse_and_output_results, which writes the reference's result files."""
     if time_limit is None and global_steps is None:
         raise ValueError("give time_limit and/or global_steps")
     random.seed(seed)
@@ -273,11 +311,18 @@ def design_batch(inputs, sim_options, time_limit=None, global_steps=None, stop_w
     steps = 0
     folds = sum(l.J * l.R for l in loops)   # start sequences
 
+    sim_data = [[] for _ in inputs] if trajectory else None
+
     def harvest(now):
         left = 0
         for grp, loop in zip(groups, loops):
             jb = loop.jobs()
             mask = loop.active.copy()
+            if trajectory:
+                recs = loop.records(sim_options, steps * sim_options.RE_attempt)
+                for pos, k in enumerate(grp):
+                    if loop.active[pos]:
+                        sim_data[k].extend(recs[pos])
             for pos, k in enumerate(grp):
                 solved = jb["solved_step"][pos] >= 0
                 if solved and solved_at[k] is None:
@@ -311,6 +356,19 @@ def design_batch(inputs, sim_options, time_limit=None, global_steps=None, stop_w
     elapsed = time.time() - t_start
     info = {"global_steps": steps, "seconds": elapsed, "folds": folds, "folds_per_s": folds / max(elapsed, 1e-9),
             "solved": sum(1 for r in results if r["solved"]), "jobs": len(inputs), "buckets": [(l.stride, l.J) for l in loops]}
+    if trajectory:
+        from .utils.stats_inputs_outputs import Stats
+        stats = [None] * len(inputs)
+        for grp, loop in zip(groups, loops):
+            counts, swaps = loop.replicas()["counts"].reshape(loop.J, loop.R, 3).sum(axis=1), loop.swaps()
+            for pos, k in enumerate(grp):
+                st = Stats()
+                st.acc_mc_step, st.acc_mc_better_e, st.rej_mc_step = (int(x) for x in counts[pos])
+                st.acc_re_step, st.acc_re_better_e, st.rej_re_step = (int(x) for x in swaps[pos])
+                st.step = (st.acc_mc_step + st.rej_mc_step) // loop.R
+                st.global_step = st.step // sim_options.RE_attempt
+                stats[k] = st
+        info["simulation_data"], info["stats"] = sim_data, stats
     for loop in loops:
         loop.close()
     return results, info

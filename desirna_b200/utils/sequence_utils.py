@@ -172,6 +172,15 @@ def generate_initial_list(nt_list, input_file, sim_options):
     return out
 
 
+def round_floats(obj):
+    """floats and dict values to 3 decimals (:1254-1274); like the reference, a LIST passes through unchanged"""
+    if isinstance(obj, float):
+        return round(obj, 3)
+    if isinstance(obj, dict):
+        return {k: round_floats(v) for k, v in obj.items()}
+    return obj
+
+
 def expand_cases(cases, max_value, range_expansion=3):
     out = set()
     for c in cases:

@@ -159,6 +159,8 @@ int bf_design_read_jobs(void *handle, char *best_seq, char *best_ss, double *bes
 /* Current state of every replica (job-major): seq G x stride, ss G x (stride+1), rec G x BF_DESIGN_REC, shelf G,
  * counts G x 3 (accepted, accepted because not worse, rejected).  NULL = skip. */
 int bf_design_read_replicas(void *handle, char *seq, char *ss, double *rec, int32_t *shelf, uint32_t *counts);
+/* Neighbour-swap counters per job, n_jobs x 3: accepted, accepted because not worse, rejected (stats_inputs_outputs.py:740-756). */
+int bf_design_read_swaps(void *handle, uint32_t *re_counts);
 /* Test hook: run the move generator once for every active replica without scoring; mut_seq: rows x stride. */
 int bf_design_propose_only(void *handle, char *mut_seq);
 int bf_design_destroy(void *handle);

@@ -185,3 +185,29 @@ def test_design_sharding_two_ranks_gloo(tmp_path):
         info = got[r][2]
         assert info["jobs"] == 8 and info["folds"] == 80 and info["seconds"] == 2.0 and len(info["per_rank"]) == 2
         assert info["solved"] == sum(1 for x in got[0][1] if x["solved"])
+
+
+def test_result_files_have_the_reference_layout(tmp_path):
+    """*_traj.csv / *_results.csv / *_best_str / *_stats / fasta files (utils/stats_inputs_outputs.py:308-633)"""
+    from types import SimpleNamespace
+    inp = sio.make_input("Ete_1", "(((((......)))))")
+    o = SimpleNamespace(infile="in.txt", outname=str(tmp_path / "run"), num_results=2, oligo="off", dimer="off", subopt="off", timlim=60)
+    rows = []
+    for step, (seq, ss, mcc, s) in enumerate([("GCCUGGAUUAACAGGC", "(((((......)))))", 0.0, 1.25), ("GCCUGGAUUAACAGGU", "((((........))))", 0.123, 2.5),
+                                            ("GCCUGGAUUAACAGGC", "(((((......)))))", 0.0, 1.2504), ("ACCUGGAUUAACAGGU", "(((((......)))))", 0.0, 0.9)]):
+        rows.append({"sequence": seq, "scoring_function": s, "replica_num": 1 + step % 2, "temp_shelf": 10.0, "sim_step": 100 * (step // 2),
+                     "edesired_minus_Epf": s, "Epf": -7.1234567, "edesired": -7.1234567 + s, "mcc": mcc, "mfe_ss": ss})
+    st = sio.Stats()
+    st.acc_mc_step, st.acc_mc_better_e, st.rej_mc_step, st.step, st.global_step, st.acc_re_step, st.rej_re_step = 120, 80, 80, 200, 2, 3, 1
+    best, solved = sio.parse_and_output_results(rows, inp, st, 61.0, o, "20260101.000000")
+    assert solved and [r["sequence"] for r in best] == ["ACCUGGAUUAACAGGU", "GCCUGGAUUAACAGGC"]   # distinct, 1-MCC then Ed-Epf
+    assert best[1]["scoring_function"] == 1.2504     # the last record of a sequence wins; round_floats leaves LISTS unrounded (reference quirk)
+    traj = (tmp_path / "run_traj.csv").read_text().splitlines()
+    assert traj[0].startswith("sequence,scoring_function,replica_num,temp_shelf,sim_step") and len(traj) == 5
+    assert (tmp_path / "run_best_str").read_text() == ">Ete_1,True,2,ACCUGGAUUAACAGGU,(((((......)))))"
+    assert (tmp_path / "run_best_fasta.fas").read_text().startswith(">in.txt|20260101.000000|2|100|0.9\nACCUGGAUUAACAGGU\n")
+    stats = (tmp_path / "run_stats").read_text()
+    assert "Acc_ratio=0.6, Iterations=200, Accepted=120/200, Rejected=80/200" in stats
+    assert "Accepted Metropolis=40/120, Rejected Metropolis=80/120" in stats
+    assert "Replica swaps accepted: 3" in stats and "Design solved succesfully!" in stats and "Simulation time: 00:01:01" in stats
+    assert len((tmp_path / "run_results.csv").read_text().splitlines()) == 3

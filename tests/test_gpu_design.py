@@ -262,3 +262,25 @@ def test_fixed_sequence_and_single_replica(engine):
     assert (rep["shelf"] == 0).all()
     assert rep["counts"][1][0] + rep["counts"][1][2] == 30
     loop.close()
+
+
+def test_trajectory_and_result_files(engine, tmp_path):
+    """design_batch(trajectory=True) yields what DesiRNA.py keeps as simulation_data; the reference-format writers run on it"""
+    from desirna_b200 import design
+    from desirna_b200.utils import stats_inputs_outputs as sio
+    inputs = small_inputs(max_len=30, limit=3)
+    o = design.DesignOptions(replicas=4, RE_attempt=25)
+    results, info = design.design_batch(inputs, o, global_steps=3, seed=2, stop_when_solved=False, trajectory=True)
+    for k, inp in enumerate(inputs):
+        data, st = info["simulation_data"][k], info["stats"][k]
+        assert len(data) == 4 * (3 + 1)                      # start records + one per replica per global step
+        assert sorted({d["sim_step"] for d in data}) == [0, 25, 50, 75]
+        assert {d["replica_num"] for d in data} == {1, 2, 3, 4}
+        assert all(d["temp_shelf"] in o.rep_temps_shelfs for d in data)
+        assert st.acc_mc_step + st.rej_mc_step == 4 * 75 and st.step == 75 and st.global_step == 3
+        assert st.acc_re_step + st.rej_re_step == 2 + 1 + 2      # odd steps: pairs (0,1),(2,3); even step: pair (1,2)
+        so = SimpleNamespace(infile=inp.name, outname=str(tmp_path / ("run%d" % k)), num_results=10, oligo="off", dimer="off", subopt="off", timlim=60)
+        best, solved = sio.parse_and_output_results(data, inp, st, info["seconds"], so, "now")
+        assert solved == any(d["mcc"] == 0.0 for d in data)
+        assert best[0]["mcc"] == min(d["mcc"] for d in data)
+        assert (tmp_path / ("run%d_traj.csv" % k)).read_text().count("\n") == len(data) + 1
