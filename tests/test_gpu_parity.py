@@ -65,8 +65,11 @@ def test_eterna_v1_kats(engine):
         assert out["pf"][k, 4] <= out["mfe_dcal"][k] / 100.0 + 1e-9
 
 
+@pytest.mark.parametrize("wide", ["1", "0"])
 @pytest.mark.parametrize("L,B", [(50, 256), (100, 128), (150, 64), (200, 48), (300, 16), (400, 12)])
-def test_random_vs_oracle(engine, oracle, L, B):
+def test_random_vs_oracle(engine, oracle, monkeypatch, L, B, wide):
+    """wide = 0 forces the 8-warp kernels big batches use (batches of <= 148 sequences otherwise take the 16-warp variants)"""
+    monkeypatch.setenv("BF_WIDE", wide)
     seqs = rand_seqs(20240000 + L, B, L)
     out = engine.score_batch(seqs, want=engine.WANT_MFE | engine.WANT_SS | engine.WANT_PF)
     mfe, ss, epf, ed = oracle.fold_batch(seqs, nthreads=8)
@@ -178,3 +181,32 @@ def test_small_batch_16_warp_variant_matches_8_warp(engine, oracle, monkeypatch,
         assert wide["mfe_dcal"][k] == e and wide["mfe_ss"][k] == ss
         f = oracle.pf(seqs[k])[4]
         assert abs(wide["pf"][k, 4] - f) <= 1e-6 * max(1.0, abs(f))
+
+
+@pytest.mark.parametrize("L", [100, 400])
+def test_full_size_batch_invariants(engine, L):
+    """BASELINE.json's sweep size (4096 sequences per launch): properties that need no CPU reference -- the energy of the
+    backtracked structure equals the MFE (bit-exact), the structure is a valid pairing of pairable bases with loops >= 3,
+    the ensemble free energy lies below the MFE, results do not depend on the batch a sequence travels in."""
+    B = 4096 if L == 100 else 1024
+    seqs = rand_seqs(20240000 + L, B, L)
+    want = engine.WANT_MFE | engine.WANT_SS | engine.WANT_PF
+    out = engine.score_batch(seqs, want=want)
+    ev = engine.score_batch(seqs, [[s] for s in out["mfe_ss"]], want=engine.WANT_EVAL)["eval_dcal"][:, 0]
+    assert (ev == out["mfe_dcal"]).all()
+    assert (out["pf"][:, 4] * 100.0 <= out["mfe_dcal"] + 1e-6).all()
+    ok = {("A", "U"), ("U", "A"), ("G", "C"), ("C", "G"), ("G", "U"), ("U", "G")}
+    for k in range(0, B, 37):
+        stack = []
+        for i, ch in enumerate(out["mfe_ss"][k]):
+            if ch == "(":
+                stack.append(i)
+            elif ch == ")":
+                j = stack.pop()
+                assert i - j > 3 and (seqs[k][j], seqs[k][i]) in ok
+        assert not stack
+    sub = list(range(0, B, 41))
+    again = engine.score_batch([seqs[k] for k in sub], want=want)     # a small batch: other kernel variants, same answers
+    assert (again["mfe_dcal"] == out["mfe_dcal"][sub]).all()
+    assert again["mfe_ss"] == [out["mfe_ss"][k] for k in sub]
+    assert np.allclose(again["pf"][:, 4], out["pf"][sub, 4], rtol=1e-12, atol=0)
