@@ -664,8 +664,10 @@ __device__ __forceinline__ void pair_barrier(int k) {
 // BLK: blocked split as in bf_k_mfe_fill.  qm and qm1 are mirrored tile-major in the workspace; the products over tiles
 // K = I+3 .. J-3 of tile-diagonal D' are accumulated during phases d = 4D'-7 .. 4D'-4 (lanes = 4 tiles x 4 K-slices x 2 column
 // halves, 12 x 128-bit loads per 32 DFMA and 4 B of operand traffic per relaxation instead of 16) into SA[D' % 3] (workspace).
-template <int NW, int PL, bool HALF = false, bool BLK = false>
-__global__ void __launch_bounds__(NW * 32) bf_k_pf_fill(const BfParams *__restrict__ P, BfBatchDev b, double *qbtri, size_t tri_slot,
+// MINB: CTAs per SM the build is capped for (__launch_bounds__; 0 = the compiler's choice).  The compiler takes 128 registers when
+// it may; 80 (3 CTAs) or 64 (4 CTAs) cost a few bytes of spill and buy occupancy where shared memory and L2 capacity allow it.
+template <int NW, int PL, bool HALF = false, bool BLK = false, int MINB = 0>
+__global__ void __launch_bounds__(NW * 32, MINB) bf_k_pf_fill(const BfParams *__restrict__ P, BfBatchDev b, double *qbtri, size_t tri_slot,
                                                         double *ws, size_t ws_slot, double *qm_perseq, const int *mfe_for_scale,
                                                         double *lnscale_out, int *work_counter) {
   extern __shared__ __align__(16) unsigned char dyn[];
@@ -1268,10 +1270,10 @@ cudaError_t bf_launch_trace(const BfParams *dP, const BfBatchDev &b, const int *
   return cudaGetLastError();
 }
 
-template <int NW, int PL, bool HALF = false, bool BLK = false>
+template <int NW, int PL, bool HALF = false, bool BLK = false, int MINB = 0>
 static cudaError_t pf_fill_t(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale, double *lnscale,
                              int sms, int *grid_out, bool launch, int *counter, cudaStream_t st) {
-  auto kern = bf_k_pf_fill<NW, PL, HALF, BLK>;
+  auto kern = bf_k_pf_fill<NW, PL, HALF, BLK, MINB>;
   const size_t sm = pf_plan(b.stride, NW, PL, HALF).total;
   cudaError_t e = set_smem(kern, sm);
   if (e != cudaSuccess) return e;
@@ -1315,6 +1317,13 @@ static cudaError_t pf_fill_dispatch(const BfParams *dP, const BfBatchDev &b, dou
   if (half && blk) return pf_fill_t<8, 0, true, true>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
   if (half) return pf_fill_t<8, 0, true, false>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
   if (blk) return pf_fill_t<8, 0, false, true>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+  if (c.nw == 8 && c.pl == 0) {   // everything through L2: occupancy is a register question
+    // measured (profiles/r01_s4_sweep_pf_minb.log): 4 CTAs per SM pay up to ~135 nt, 3 up to ~185 nt; beyond, the tables of more
+    // sequences in flight no longer fit in L2 and the 2-CTA build wins
+    const int mb = env_int("BF_PF_MINB", b.stride <= 135 ? 4 : b.stride <= 185 ? 3 : 0);
+    if (mb == 3) return pf_fill_t<8, 0, false, false, 3>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+    if (mb == 4) return pf_fill_t<8, 0, false, false, 4>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
+  }
   if (c.nw == 4) return pf_fill_pl<4>(c.pl, dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
   if (c.nw == 2) return pf_fill_pl<2>(c.pl, dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
   return pf_fill_pl<8>(c.pl, dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
