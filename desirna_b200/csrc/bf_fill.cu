@@ -27,6 +27,7 @@
 #include "bf_kernels.h"
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "bf_device.cuh"
 
@@ -473,6 +474,44 @@ __global__ void __launch_bounds__(WPB * 32) bf_k_trace(const BfParams *__restric
 
   if (lane == 0) f5[0] = 0;
   __syncwarp();
+  // f5[j] = min(f5[j-1], min_i f5[i-1] + c(i,j) + Ext(i,j)): a serial chain over j whose table look-ups do not depend on f5.
+  // The terms of column j+1 are fetched (L2 latency) while column j is reduced; K = 32-wide chunks of i per lane.
+  auto chain = [&](auto kc) {
+    constexpr int K = decltype(kc)::value;
+    int cur[K], nxt[K];
+    auto fetch = [&](int j, int *v) {
+#pragma unroll
+      for (int c = 0; c < K; c++) {
+        const int i = 1 + lane + 32 * c;
+        int val = BF_INF;
+        if (i < j - BF_TURN) {
+          const int t = ptype_sp(SP, i, j);
+          if (t) {
+            const int cc = C_(i, j);
+            if (cc < BF_INF) val = cc + ext_e(i, j, t);
+          }
+        }
+        v[c] = val;
+      }
+    };
+    fetch(1, cur);
+    for (int j = 1; j <= n; j++) {
+      if (j < n) fetch(j + 1, nxt);
+      int e = BF_INF;
+#pragma unroll
+      for (int c = 0; c < K; c++)
+        if (cur[c] < BF_INF) e = min(e, f5[lane + 32 * c] + cur[c]);
+      e = bf_warp_min(e);
+      if (lane == 0) f5[j] = min(e, f5[j - 1]);
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < K; c++) cur[c] = nxt[c];
+    }
+  };
+  if (n <= 64) chain(std::integral_constant<int, 2>());
+  else if (n <= 128) chain(std::integral_constant<int, 4>());
+  else if (n <= 256) chain(std::integral_constant<int, 8>());
+  else
   for (int j = 1; j <= n; j++) {
     int e = BF_INF;
     for (int i = 1 + lane; i < j - BF_TURN; i += 32) {
@@ -1024,6 +1063,45 @@ __global__ void __launch_bounds__(WPB * 32) bf_k_pf_ext(const BfParams *__restri
   const double *qb = qbtri + (size_t)sq * tri_slot;
   if (lane == 0) q5[0] = 1.0;
   __syncwarp();
+  // q5[j] = q5[j-1] * scale + sum_i q5[i-1] * qb(i,j) * xExt(i,j): as in bf_k_trace the weights of column j+1 are fetched while
+  // column j is reduced.  The products are formed in the order of the plain loop (q5 * qb, then * xExt): same bits.
+  auto chain = [&](auto kc) {
+    constexpr int K = decltype(kc)::value;
+    double curq[K], curx[K], nxtq[K], nxtx[K];
+    auto fetch = [&](int j, double *vq, double *vx) {
+#pragma unroll
+      for (int c = 0; c < K; c++) {
+        const int i = 1 + lane + 32 * c;
+        double q = 0.0, x = 0.0;
+        if (i < j - BF_TURN) {
+          const int t = bf_ptype_bases(S[i], S[j]);
+          if (t) {
+            const int a = (i > 1) ? S[i - 1] : -1, bb = (j < n) ? S[j + 1] : -1;
+            q = __ldg(qb + tri_off(n, j - i) + i - 1);
+            x = bf_x_ext(T, t, a, bb);
+          }
+        }
+        vq[c] = q; vx[c] = x;
+      }
+    };
+    fetch(1, curq, curx);
+    for (int j = 1; j <= n; j++) {
+      if (j < n) fetch(j + 1, nxtq, nxtx);
+      double sum = 0.0;
+#pragma unroll
+      for (int c = 0; c < K; c++)
+        if (curx[c] != 0.0) sum += q5[lane + 32 * c] * curq[c] * curx[c];
+      sum = bf_warp_sum(sum);
+      if (lane == 0) q5[j] = sum + q5[j - 1] * sc1;
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < K; c++) { curq[c] = nxtq[c]; curx[c] = nxtx[c]; }
+    }
+  };
+  if (n <= 64) chain(std::integral_constant<int, 2>());
+  else if (n <= 128) chain(std::integral_constant<int, 4>());
+  else if (n <= 256) chain(std::integral_constant<int, 8>());
+  else
   for (int j = 1; j <= n; j++) {
     double sum = 0.0;
     for (int i = 1 + lane; i < j - BF_TURN; i += 32) {

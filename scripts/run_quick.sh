@@ -1,3 +1,6 @@
-timeout 1200 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -3
-run() { L=$1; shift; r=$(env "$@" python bench.py --steps 2 --warmup 2 --no-sweep --no-cpu --L $L 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['roofline']['kernel_ms']['bf_k_pf'], d['checks']['ed_equals_mfe_and_epf_le_mfe'])"); echo "L=$L $* -> pf $r"; }
-for L in 250 300 350 400; do for o in 1 0; do run $L BF_PF_BLK3=$o; done; done
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/quick_bench.json 2>gpurun_out/quick_bench.err; python -c "
+import json; d=json.load(open('gpurun_out/quick_bench.json')); print(d['by_length']); print(d['kernel_ms_by_length']); print(json.dumps(d['design_loop']))"
+python scripts/latency.py > gpurun_out/quick_latency.json 2>/dev/null; python -c "
+import json; d=json.load(open('gpurun_out/quick_latency.json'))['latency']; print({k:v['call_ms'] for k,v in d.items()})"
