@@ -1183,10 +1183,17 @@ static FillCfg mfe_cfg(int nmax, int B = 0) {
   c.nw = env_int("BF_MFE_NW", 8);
   if (c.nw != 2 && c.nw != 4) c.nw = 8;
   if (c.nw == 8 && want_wide(B)) {   // same placement rule, 16 warps; only the combinations instantiated below
+    // one CTA per SM: nothing is gained by a small footprint, and with nothing else resident L2 latency is fully exposed --
+    // keep on chip whatever fits (fML table + rings, else the rings), shared partial buffers if that is what makes it fit
     FillCfg w;
     w.nw = 16;
-    w.pl = mfe_plan(nmax, 8, kMfeRgSmem, false, true).total <= (size_t)env_int("BF_MFE_RING_KB", 70) * 1024 ? kMfeRgSmem : 0;
-    if (env_int("BF_MFE_PL", w.pl) == w.pl && mfe_plan(nmax, 16, w.pl, mfe_blk(nmax, w), true).total <= kSmemBudget) return w;
+    if (env_int("BF_MFE_PL", -1) < 0)
+      for (int pl : {kMfeFmSmem | kMfeRgSmem, kMfeRgSmem, 0}) {
+        w.pl = pl;
+        const bool blk = mfe_blk(nmax, w);
+        if (pl != 0 && nmax >= env_int("BF_BLK_MIN", 280)) continue;   // blocked split: the through-L2 layout measured faster (L=400)
+        if (mfe_plan(nmax, 16, pl, blk, true).total <= kSmemBudget) return w;
+      }
   }
   // default (tuning sweep, profiles/r01_sweeps.md): rings on chip while >= 3 CTAs still fit on an SM, else everything through L2
   const int dflt = mfe_plan(nmax, c.nw, kMfeRgSmem, false, true).total <= (size_t)env_int("BF_MFE_RING_KB", 70) * 1024 ? kMfeRgSmem : 0;
@@ -1205,10 +1212,14 @@ static FillCfg pf_cfg(int nmax, int B = 0) {
   c.nw = env_int("BF_PF_NW", 8);
   if (c.nw != 2 && c.nw != 4) c.nw = 8;
   if (c.nw == 8 && want_wide(B)) {
-    FillCfg w;
+    FillCfg w;   // as for the MFE: one CTA per SM, keep on chip what fits (qm/qm1 + generic ring, else the ring)
     w.nw = 16;
-    w.pl = pf_plan(nmax, 8, kPfQgSmem).total <= 74 * 1024 ? kPfQgSmem : 0;
-    if (env_int("BF_PF_PL", w.pl) == w.pl && pf_plan(nmax, 16, w.pl, pf_half(nmax, w)).total <= kSmemBudget) return w;
+    if (env_int("BF_PF_PL", -1) < 0)
+      for (int pl : {kPfQmSmem | kPfQgSmem, kPfQgSmem, 0}) {
+        w.pl = pl;
+        if (pl != 0 && nmax >= env_int("BF_BLK_MIN_PF", 250)) continue;   // blocked split: through-L2 layout only
+        if (pf_plan(nmax, 16, pl, pf_half(nmax, w)).total <= kSmemBudget) return w;
+      }
   }
   const int dflt = pf_plan(nmax, c.nw, kPfQgSmem).total <= 74 * 1024 ? kPfQgSmem : 0;
   const int want = env_int("BF_PF_PL", dflt);
@@ -1302,6 +1313,10 @@ static cudaError_t mfe_fill_dispatch(const BfParams *dP, const BfBatchDev &b, in
   const bool blk = mfe_blk(b.stride, c);
   const bool atom = (c.nw >= 8) && (c.pl == 0 || c.pl == kMfeRgSmem) && mfe_atom(b.stride, c, blk);
 #define BF_MFE_GO(NW_, PL_, BLK_, ATOM_) return mfe_fill_t<NW_, PL_, BLK_, ATOM_>(dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st)
+  if (c.nw == 16 && c.pl == (kMfeFmSmem | kMfeRgSmem)) {
+    if (mfe_atom(b.stride, c, false)) BF_MFE_GO(16, kMfeFmSmem | kMfeRgSmem, false, true);
+    BF_MFE_GO(16, kMfeFmSmem | kMfeRgSmem, false, false);
+  }
   if (c.nw == 16 || atom || blk) {
     const int key = (c.nw == 16 ? 8 : 0) | (c.pl == 0 ? 0 : 4) | (blk ? 2 : 0) | (atom ? 1 : 0);
     switch (key) {
@@ -1386,6 +1401,7 @@ static cudaError_t pf_fill_dispatch(const BfParams *dP, const BfBatchDev &b, dou
   if (c.pl < 0) return cudaErrorInvalidValue;
   const bool half = pf_half(b.stride, c), blk = pf_blk(b.stride, c);
   if (c.nw == 16) {
+    if (c.pl == (kPfQmSmem | kPfQgSmem)) return pf_fill_t<16, kPfQmSmem | kPfQgSmem>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
     if (c.pl == kPfQgSmem) return pf_fill_t<16, kPfQgSmem>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
     if (half && blk) return pf_fill_t<16, 0, true, true>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
     if (half) return pf_fill_t<16, 0, true, false>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, grid_out, launch, counter, st);
