@@ -353,6 +353,22 @@ def run_ours(args):
         roof["by_length"][l] = {"mfe_int32_frac": 2.0 * rm * B / (m_ms * 1e-3) / 1e12 / peaks["int32_tops"],
                                 "pf_fp64_frac": 2.0 * rp * B / (p_ms * 1e-3) / 1e12 / peaks["fp64_tflops"]}
 
+    # relaxations the CPU restatement actually evaluates on sequences of THIS workload (it skips candidates whose inner pair cannot
+    # form, the GPU kernels read them as +inf / 0 from the ring): reported next to the closed form the roofline uses
+    if not args.no_cpu:
+        try:
+            from oracle.pyoracle import Oracle, build
+            build()
+            O = Oracle(os.path.join(ROOT, "desirna_b200", "params", "turner1999_37C.par"))
+            cnt = np.array([O.mfe(sq, counts=True)[2] for sq in to_strings(synth(L, 32, rank=0))], dtype=np.float64)
+            counted = float(cnt.sum(axis=1).mean())
+            roof["relaxations_per_fold"] = {"closed_form_mfe": r_mfe, "closed_form_pf": r_pf, "counted_by_cpu_port_mfe": counted,
+                                            "counted_parts": dict(zip(["interior", "ml_closing", "fml_split", "f5"], cnt.mean(axis=0).tolist())),
+                                            "sample": "first 32 sequences of the workload",
+                                            "mfe_int32_frac_on_counted": 2.0 * counted * B / (mfe_ms * 1e-3) / 1e12 / peaks["int32_tops"]}
+        except Exception as exc:  # the count is auxiliary
+            roof["relaxations_per_fold"] = {"error": str(exc)}
+
     # ---- CPU baseline on a bounded sample (rank 0, N=1 only)
     cpu = None
     if world == 1 and not args.no_cpu:

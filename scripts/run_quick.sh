@@ -1,6 +1,2 @@
-mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/quick_bench.json 2>gpurun_out/quick_bench.err; python -c "
-import json; d=json.load(open('gpurun_out/quick_bench.json')); print(d['by_length']); print(d['kernel_ms_by_length']); print(json.dumps(d['design_loop']))"
-python scripts/latency.py > gpurun_out/quick_latency.json 2>/dev/null; python -c "
-import json; d=json.load(open('gpurun_out/quick_latency.json'))['latency']; print({k:v['call_ms'] for k,v in d.items()})"
+run() { L=$1; shift; r=$(env "$@" python bench.py --steps 3 --warmup 3 --no-sweep --no-cpu --L $L 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['roofline']['kernel_ms'], round(d['value']))"); echo "L=$L $* -> $r"; }
+for L in 36 50 70; do run $L BF_X=0; run $L BF_MFE_NW=4 BF_PF_NW=4; run $L BF_MFE_NW=2 BF_PF_NW=2; done
