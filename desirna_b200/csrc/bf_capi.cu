@@ -663,6 +663,15 @@ int bf_design_run(void *handle, int32_t global_steps) {
   return BF_OK;
 }
 
+int bf_design_busy(void *handle, int32_t *busy) {
+  DesignLoop *h = (DesignLoop *)handle;
+  if (!h || !busy) return fail(BF_ERR_ARG, "bf_design_busy: null argument");
+  const cudaError_t e = cudaStreamQuery(h->st);
+  if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "bf_design_busy");
+  *busy = e == cudaErrorNotReady ? 1 : 0;
+  return BF_OK;
+}
+
 int bf_design_sync(void *handle) {
   DesignLoop *h = (DesignLoop *)handle;
   if (!h) return fail(BF_ERR_ARG, "bf_design_sync: null handle");

@@ -57,6 +57,7 @@ def _bind():
         L.bf_design_create.argtypes = [C.POINTER(bf_design_t), C.POINTER(C.c_void_p)]
         L.bf_design_run.argtypes = [C.c_void_p, C.c_int32]
         L.bf_design_sync.argtypes = [C.c_void_p]
+        L.bf_design_busy.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
         L.bf_design_set_active.argtypes = [C.c_void_p, C.c_void_p]
         L.bf_design_read_jobs.argtypes = [C.c_void_p] + [C.c_void_p] * 5
         L.bf_design_read_replicas.argtypes = [C.c_void_p] + [C.c_void_p] * 5
@@ -139,6 +140,11 @@ class DesignLoop:
 
     def sync(self):
         engine._check(self.lib.bf_design_sync(self.h))
+
+    def busy(self):
+        flag = C.c_int32(0)
+        engine._check(self.lib.bf_design_busy(self.h, C.byref(flag)))
+        return bool(flag.value)
 
     def set_active(self, mask):
         self.active = np.ascontiguousarray(mask, np.uint8)
@@ -308,53 +314,72 @@ def design_batch(inputs, sim_options, time_limit=None, global_steps=None, stop_w
     loops = [DesignLoop([inputs[k] for k in grp], sim_options, seed=seed * 1000003 + b) for b, grp in enumerate(groups)]
     results = [None] * len(inputs)
     solved_at = [None] * len(inputs)
-    steps = 0
+    done = [0] * len(loops)          # global steps finished, per loop
     folds = sum(l.J * l.R for l in loops)   # start sequences
-
     sim_data = [[] for _ in inputs] if trajectory else None
 
-    def harvest(now):
-        left = 0
-        for grp, loop in zip(groups, loops):
-            jb = loop.jobs()
-            mask = loop.active.copy()
-            if trajectory:
-                recs = loop.records(sim_options, steps * sim_options.RE_attempt)
-                for pos, k in enumerate(grp):
-                    if loop.active[pos]:
-                        sim_data[k].extend(recs[pos])
+    def harvest(b, now):
+        """read loop b (waits for its stream), record results, retire solved jobs; returns its number of unsolved jobs"""
+        grp, loop = groups[b], loops[b]
+        jb = loop.jobs()
+        mask = loop.active.copy()
+        if trajectory:
+            recs = loop.records(sim_options, done[b] * sim_options.RE_attempt)
             for pos, k in enumerate(grp):
-                solved = jb["solved_step"][pos] >= 0
-                if solved and solved_at[k] is None:
-                    solved_at[k] = now
-                res = {"name": inputs[k].name, "sequence": jb["sequence"][pos], "mfe_ss": jb["mfe_ss"][pos], "solved": bool(solved),
-                       "solved_step": int(jb["solved_step"][pos]), "solved_after_s": solved_at[k]}
-                res.update({f: float(jb["rec"][pos, c]) for c, f in enumerate(REC_FIELDS)})
-                results[k] = res
-                if solved and stop_when_solved:
-                    mask[pos] = 0
-            if (mask != loop.active).any():
-                loop.set_active(mask)
-            left += int(loop.active.sum())
-        return left
+                if loop.active[pos]:
+                    sim_data[k].extend(recs[pos])
+        for pos, k in enumerate(grp):
+            solved = jb["solved_step"][pos] >= 0
+            if solved and solved_at[k] is None:
+                solved_at[k] = now
+            res = {"name": inputs[k].name, "sequence": jb["sequence"][pos], "mfe_ss": jb["mfe_ss"][pos], "solved": bool(solved),
+                   "solved_step": int(jb["solved_step"][pos]), "solved_after_s": solved_at[k]}
+            res.update({f: float(jb["rec"][pos, c]) for c, f in enumerate(REC_FIELDS)})
+            results[k] = res
+            if solved and stop_when_solved:
+                mask[pos] = 0
+        if (mask != loop.active).any():
+            loop.set_active(mask)
+        return int(loop.active.sum())
 
-    left = harvest(time.time() - t_start)
-    while left > 0:
-        if global_steps is not None and steps >= global_steps:
-            break
-        if time_limit is not None and time.time() - t_start >= time_limit:
-            break
-        n = poll_steps if global_steps is None else min(poll_steps, global_steps - steps)
-        for loop in loops:
-            if loop.active.any():
+    # Every loop advances at its own pace: a bucket of short targets makes hundreds of global steps while the 400-nt bucket makes
+    # one.  A loop gets `batch[b]` global steps at a time, sized from its measured pace to ~poll_seconds of GPU time (the host
+    # reads results and retires solved jobs in between); with trajectory=True every poll_steps-th state must be seen instead.
+    poll_seconds = 0.5
+    batch = [poll_steps] * len(loops)
+    pending = [None] * len(loops)     # (steps enqueued, enqueue time) of a running batch
+    left = [harvest(b, time.time() - t_start) for b in range(len(loops))]
+    while True:
+        now = time.time() - t_start
+        out_of_time = time_limit is not None and now >= time_limit
+        progressed = False
+        for b, loop in enumerate(loops):
+            if pending[b] is not None:
+                if loop.busy():
+                    continue
+                n, t0 = pending[b]
+                pending[b] = None
+                done[b] += n
+                left[b] = harvest(b, time.time() - t_start)
+                if not trajectory:
+                    pace = max((time.time() - t_start - t0) / n, 1e-4)     # seconds per global step, as last observed
+                    batch[b] = int(min(64, max(1, poll_seconds / pace)))
+                progressed = True
+                if verbose:
+                    print("loop %d (stride %d): %d global steps, %d jobs unsolved, %.1f s" % (b, loop.stride, done[b], left[b], time.time() - t_start), flush=True)
+            if left[b] > 0 and not out_of_time and (global_steps is None or done[b] < global_steps):
+                n = batch[b] if global_steps is None else min(batch[b], global_steps - done[b])
                 loop.run(n)
-                folds += int(loop.active.sum()) * loop.R * sim_options.RE_attempt * n
-        steps += n
-        left = harvest(time.time() - t_start)   # read_jobs waits for each loop's stream
-        if verbose:
-            print("global step %d: %d jobs unsolved, %.1f s" % (steps, left, time.time() - t_start), flush=True)
+                pending[b] = (n, time.time() - t_start)
+                folds += left[b] * loop.R * sim_options.RE_attempt * n
+                progressed = True
+        if all(p is None for p in pending):
+            break     # nothing running and nothing could be started: solved, out of steps or out of time
+        if not progressed:
+            time.sleep(0.001)
+    steps = max(done) if done else 0
     elapsed = time.time() - t_start
-    info = {"global_steps": steps, "seconds": elapsed, "folds": folds, "folds_per_s": folds / max(elapsed, 1e-9),
+    info = {"global_steps": steps, "global_steps_per_loop": list(done), "seconds": elapsed, "folds": folds, "folds_per_s": folds / max(elapsed, 1e-9),
             "solved": sum(1 for r in results if r["solved"]), "jobs": len(inputs), "buckets": [(l.stride, l.J) for l in loops]}
     if trajectory:
         from .utils.stats_inputs_outputs import Stats

@@ -150,6 +150,8 @@ int bf_design_create(const bf_design_t *cfg, void **handle);
  * loop's own stream and return without waiting; loops of different handles overlap on the GPU. */
 int bf_design_run(void *handle, int32_t global_steps);
 int bf_design_sync(void *handle);
+/* *busy = 1 while enqueued steps are still running (does not wait): lets a host advance many loops at their own pace. */
+int bf_design_busy(void *handle, int32_t *busy);
 /* active[j] = 0 drops job j from the following steps (-sws on: stop when solved); waits for enqueued steps first. */
 int bf_design_set_active(void *handle, const uint8_t *active);
 /* Best state per job seen at global-step ends (fewest mismatching positions, then lowest scoring function):
