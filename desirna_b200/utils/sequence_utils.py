@@ -212,10 +212,8 @@ def get_mutation_position(seq_obj, available_positions, sim_options, input_file)
     return random.choice(pool)
 
 
-def propose_mutation(sequence_obj, nt_list, sim_options, input_file):
-    """The move of mutate_sequence (:1008-1100) up to, not including, the scoring call: returns the mutant string.
-    Unpaired position: another allowed letter.  Paired position: another allowed letter, then a partner letter that
-    pairs with it (G-U wobbles included)."""
+def _point_move(sequence_obj, nt_list, sim_options, input_file):
+    """one draw of the move (:1023-1083): (mutant string, mutated position, partner position or None)"""
     seq = list(sequence_obj.sequence)
     mutable = [i for i in range(len(seq)) if len(nt_list[i].letters_allowed) != 1]
     pos = get_mutation_position(sequence_obj, mutable, sim_options, input_file)
@@ -226,7 +224,7 @@ def propose_mutation(sequence_obj, nt_list, sim_options, input_file):
         if len(nt.letters_allowed) != 1:
             options = [l for l in nt.letters_allowed if l != seq[pos]] if seq[pos] in nt.letters_allowed else list(nt.letters_allowed)
             seq[pos] = random.choice(options)
-        return "".join(seq)
+        return "".join(seq), pos, None
     options = list(nt.letters_allowed)
     if seq[pos] in options and len(options) != 1:
         options.remove(seq[pos])
@@ -238,13 +236,36 @@ def propose_mutation(sequence_obj, nt_list, sim_options, input_file):
     second = (random.choices(second_options, weights=allowed_choice(second_options, sim_options.nt_percentages))[0] if weighted
               else random.choice(second_options))
     seq[pos], seq[partner.number] = first, second
-    return "".join(seq)
+    return "".join(seq), pos, partner.number
+
+
+def propose_mutation(sequence_obj, nt_list, sim_options, input_file):
+    """The move of mutate_sequence (:1008-1128) up to, not including, the scoring call: returns the mutant string.
+    Unpaired position: another allowed letter.  Paired position: another allowed letter, then a partner letter that
+    pairs with it (G-U wobbles included).  Homodimer designs keep the two strands identical: with identical target halves
+    the strand that changed is copied over the other; with different halves the two changed letters are mirrored onto the
+    other strand (:1102-1128)."""
+    mutant, pos, partner = _point_move(sequence_obj, nt_list, sim_options, input_file)
+    if sim_options.oligo_state != "homodimer":
+        return mutant
+    half_a, half_b = input_file.sec_struct.split("&")[:2]
+    old_a, old_b = sequence_obj.sequence.split("&")[:2]
+    new_a, new_b = mutant.split("&")[:2]
+    if half_a != half_b:
+        if partner is not None:
+            lo, hi = sorted((pos, partner))
+            in_a, in_b = lo, hi - len(old_a) - 1        # the reference reads the pair as (strand A, strand B)
+            new_a, new_b = (new_a[:in_b] + new_b[in_b] + new_a[in_b + 1:], new_b[:in_a] + new_a[in_a] + new_b[in_a + 1:])
+        return new_a + "&" + new_b
+    if new_a != old_a:
+        return new_a + "&" + new_a
+    if new_b != old_b:
+        return new_b + "&" + new_b
+    return mutant
 
 
 def mutate_sequence(sequence_obj, nt_list, sim_options, input_file):
-    """mutate_sequence (:1008-1136) for single-strand designs: move, score, stamp replica number and shelf."""
-    if sim_options.oligo_state == "homodimer":
-        raise NotImplementedError("homodimer strand mirroring (:1102-1128) is outside the accelerated path")
+    """mutate_sequence (:1008-1136): move, score, stamp replica number and shelf."""
     out = es.score_sequence(propose_mutation(sequence_obj, nt_list, sim_options, input_file), input_file, sim_options)
     out.get_replica_num(sequence_obj.replica_num)
     out.get_temp_shelf(sequence_obj.temp_shelf)

@@ -211,3 +211,29 @@ def test_result_files_have_the_reference_layout(tmp_path):
     assert "Accepted Metropolis=40/120, Rejected Metropolis=80/120" in stats
     assert "Replica swaps accepted: 3" in stats and "Design solved succesfully!" in stats and "Simulation time: 00:01:01" in stats
     assert len((tmp_path / "run_results.csv").read_text().splitlines()) == 3
+
+
+def test_homodimer_moves_keep_the_strands_in_step():
+    """utils/sequence_utils.py:1102-1128: identical target halves -> identical strands after every move"""
+    random.seed(5)
+    inp = sio.make_input("homo", "((((....))))&((((....))))", "NNNNNNNNNNNN&NNNNNNNNNNNN")
+    nts = su.get_nt_list(inp)
+    o = opts(replicas=3, oligo_state="homodimer")
+    cur = SimpleNamespace(sequence="GGGGAAAACCCC&GGGGAAAACCCC", mfe_ss="((((....))))&((((....))))", temp_shelf=o.rep_temps_shelfs[1])
+    changed = 0
+    for _ in range(300):
+        m = su.propose_mutation(cur, nts, o, inp)
+        a, b = m.split("&")
+        assert a == b and len(a) == 12
+        for i, j in ((0, 11), (1, 10), (2, 9), (3, 8)):
+            assert (a[i], a[j]) in PAIR_OK
+        changed += m != cur.sequence
+    assert changed > 250
+    # different halves: an inter-strand pair's two letters are mirrored onto the other strand (same length strands)
+    inp2 = sio.make_input("homo2", "((((....&....))))", "NNNNNNNN&NNNNNNNN")
+    nts2 = su.get_nt_list(inp2)
+    cur2 = SimpleNamespace(sequence="GGGGAAAA&AAAACCCC", mfe_ss="((((....&....))))", temp_shelf=o.rep_temps_shelfs[1])
+    for _ in range(200):
+        m = su.propose_mutation(cur2, nts2, o, inp2)
+        a, b = m.split("&")
+        assert len(a) == len(b) == 8 and set(m) <= set("ACGU&")
