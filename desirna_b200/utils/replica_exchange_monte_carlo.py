@@ -88,9 +88,9 @@ def single_replica_design(sequence_o, nt_list, worker_stats, sim_options, input_
 
 def _default_mutate():
     try:
-        from utils import sequence_utils as seq_utils  # DesiRNA's move generator, when running inside DesiRNA
-    except Exception as exc:  # pragma: no cover
-        raise RuntimeError("pass mutate=<DesiRNA's sequence_utils.mutate_sequence> (the move generator is not part of this package)") from exc
+        from utils import sequence_utils as seq_utils  # DesiRNA's own move generator, when running inside DesiRNA
+    except Exception:
+        from . import sequence_utils as seq_utils       # its mirror here (same draws, utils/sequence_utils.py:926-1136)
     return seq_utils.mutate_sequence
 
 

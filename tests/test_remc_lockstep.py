@@ -159,3 +159,33 @@ def test_two_ranks_gloo_match_single_process(tmp_path):
                     assert v == vb[k], k
         for k in ("acc_mc_step", "acc_mc_better_e", "rej_mc_step", "acc_re_step", "rej_re_step", "step"):
             assert gst[k] == vars(st)[k], k
+
+
+def test_lockstep_with_the_mirrored_move_generator():
+    """the lock-step loop driven by desirna_b200.utils.sequence_utils.mutate_sequence (targeted moves, paired letters)
+    takes the same decisions from the same draws as replica-after-replica execution"""
+    from desirna_b200 import RNA
+    from desirna_b200.utils import replica_exchange_monte_carlo as remc
+    from desirna_b200.utils import sequence_utils as su
+    from desirna_b200.utils import stats_inputs_outputs as sio
+    old = RNA.get_backend()
+    try:
+        opt, _, objs = setup(4)
+        inp = sio.make_input("t", TARGET)
+        opt.__dict__.update(point_mutations="on", tm_max=0.7, tm_min=0.0, acgu_percentages="off", nt_percentages={"A": 15, "C": 30, "G": 30, "U": 15},
+                            rep_temps_shelfs=[o.temp_shelf for o in objs])
+        nts = su.get_nt_list(inp)
+        want = []
+        for idx, o in enumerate(objs):
+            random.seed(idx)
+            res, _ = remc.single_replica_design(o, nts, Stats(), opt, inp, mutate=su.mutate_sequence)
+            want.append(res)
+        random.seed(1)
+        got, st = remc.mutate_sequence_re(objs, nts, Stats(), opt, inp)      # default move generator = the mirror
+        assert [vars(a) for a in got] == [vars(b) for b in want]
+        assert any(a.sequence != b.sequence for a, b in zip(got, objs))
+        for o in got:
+            for a, b in inp.pairs:
+                assert (o.sequence[a], o.sequence[b]) in {("A", "U"), ("U", "A"), ("G", "C"), ("C", "G"), ("G", "U"), ("U", "G")}
+    finally:
+        RNA.set_backend(old)
