@@ -1,2 +1,4 @@
-run() { L=$1; shift; r=$(env "$@" python bench.py --steps 3 --warmup 3 --no-sweep --no-cpu --L $L 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['roofline']['kernel_ms'], round(d['value']))"); echo "L=$L $* -> $r"; }
-for L in 36 50 70; do run $L BF_X=0; run $L BF_MFE_NW=4 BF_PF_NW=4; run $L BF_MFE_NW=2 BF_PF_NW=2; done
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -3
+for w in 1 0; do BF_PF_WIDE_RING=$w python scripts/latency.py > gpurun_out/quick_latency_$w.json 2>/dev/null; python -c "
+import json; d=json.load(open('gpurun_out/quick_latency_$w.json'))['latency']; print('WIDE_RING=$w', {k:(v['call_ms'],v['pf_ms']) for k,v in d.items() if k.startswith('L400') or k.startswith('L200')})"; done
