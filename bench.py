@@ -415,6 +415,16 @@ def bench_design_loop():
     loop.close()
     out["one_target_64_replicas"] = {"target": one["file"], "L": len(one["target"]), "ms_per_substep": dt / 200 * 1e3,
                                      "sequences_scored_per_s": 64 * 200 / dt}
+    # (d) BASELINE config 1: the reference's standard example target (36 nt) with its default 10 replicas
+    o = design.DesignOptions(replicas=10, RE_attempt=100)
+    loop = design.DesignLoop([sio.make_input("Standard_design", "((((((.((((((((....))))).)).).))))))")], o, seed=4)
+    loop.run(1); loop.sync()
+    t0 = time.perf_counter()
+    loop.run(3); loop.sync()
+    dt = time.perf_counter() - t0
+    loop.close()
+    out["standard_36nt_10_replicas"] = {"ms_per_substep": dt / 300 * 1e3, "sequences_scored_per_s": 10 * 300 / dt,
+                                        "reference_example_run": "1033 score calls/s on 10 processes (example_files/outputs/Standard_design*/*_stats)"}
     # (c) BASELINE config 4: the reference's two-strand example (17 & 18 nt), heterodimer scoring with the oligomerisation term
     o = design.DesignOptions(replicas=64, RE_attempt=100, oligo_state="heterodimer")
     loop = design.DesignLoop([sio.make_input("RNA_RNA_complex", "(((.(((((....))..&(((....)))..))))))", "NNNNNNNNNNNNNNNNN&NNNNNNNNNNNNNNNNNN")], o, seed=3)
