@@ -40,9 +40,15 @@ struct Workspace {
   DevBuf tri_c, tri_f, tri_qb, ws_qm, ws_ring, d_lnscale, qm_seq, ws_out;  // diagonal-major fill path (bf_fill.cu)
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // begin/end of mfe, pf, eval in the last call
   bool ran[3] = {false, false, false};
+  // the partition function of a small batch can run beside the MFE fill on SMs of its own (run_device: scale_override)
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaError_t create() {
     cudaError_t e = cudaMalloc(&d_counters, 8 * sizeof(int));
     for (int k = 0; k < 6 && e == cudaSuccess; k++) e = cudaEventCreate(&ev[k]);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
     return e;
   }
   void destroy() {
@@ -50,6 +56,10 @@ struct Workspace {
     if (d_counters) cudaFree(d_counters);
     d_counters = nullptr;
     for (int k = 0; k < 6; k++) { if (ev[k]) cudaEventDestroy(ev[k]); ev[k] = nullptr; }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (st2) cudaStreamDestroy(st2);
+    ev_fork = ev_join = nullptr; st2 = nullptr;
   }
 };
 
@@ -103,12 +113,16 @@ int validate(const bf_batch_t *b, const bf_result_t *r) {
 }
 
 // all pointers are device pointers
-int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t st) {
+// scale_override (device, B ints, dcal/mol): energies that set the partition function's per-nucleotide scale instead of this
+// call's own MFE.  The result does not depend on the scale beyond rounding, and without that dependency the partition function
+// runs on the workspace's second stream beside the MFE fill -- worth it when both grids fit the GPU together (small batches).
+int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t st, const int *scale_override = nullptr) {
   if (b->B == 0) return BF_OK;
   BfBatchDev db;
   db.B = b->B; db.stride = b->stride; db.seq = b->seq; db.len = b->len; db.cut = b->cut; db.nopair = b->nopair;
   const int wstride = b->stride + 2;
   if (&w == &g.w) g.last_stride = b->stride;
+  if (scale_override) CU(cudaEventRecord(w.ev_fork, st), "fork");   // what the second stream has to wait for: the work before this call
   const int *mfe_for_scale = nullptr;
   w.ran[0] = w.ran[1] = w.ran[2] = false;
   const bool fill_mfe = !two && !g.force_generic && bf_fill_mfe_mode(b->stride) != 0;
@@ -165,8 +179,11 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
     BfBatchDev dbp = db;
     dbp.nopair = nullptr;  // hard constraints are added after fc.pf() in the reference (sequence_utils.py:1181)
     // a constrained MFE is not a bound on the unconstrained ensemble: only use it for scaling when unconstrained
-    const int *scale_src = b->nopair ? nullptr : mfe_for_scale;
-    cudaEventRecord(w.ev[2], st);
+    const bool beside = scale_override && !want_out && !b->nopair && fill_pf;
+    cudaStream_t sp = beside ? w.st2 : st;
+    if (beside) CU(cudaStreamWaitEvent(sp, w.ev_fork, 0), "fork");
+    const int *scale_src = beside ? scale_override : (b->nopair ? nullptr : mfe_for_scale);
+    cudaEventRecord(w.ev[2], sp);
     if (fill_pf) {
       const size_t slot = bf_tri_slot(b->stride) * sizeof(double);
       CU(w.tri_qb.reserve((size_t)b->B * slot), "cudaMalloc(qb table)");
@@ -181,8 +198,8 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
         qmseq = (double *)w.qm_seq.p;
       }
       CU(bf_launch_pf_fill(g.dP, dbp, (double *)w.tri_qb.p, (double *)w.ws_qm.p, qmseq, scale_src, (double *)w.d_lnscale.p, g.sm_count,
-                           w.d_counters + 1, st), "launch bf_k_pf_fill");
-      CU(bf_launch_pf_ext(g.dP, dbp, (const double *)w.tri_qb.p, (const double *)w.d_lnscale.p, r->pf, st), "launch bf_k_pf_ext");
+                           w.d_counters + 1, sp), "launch bf_k_pf_fill");
+      CU(bf_launch_pf_ext(g.dP, dbp, (const double *)w.tri_qb.p, (const double *)w.d_lnscale.p, r->pf, sp), "launch bf_k_pf_ext");
       g.launches += 2;
       if (want_out) {
         int ogrid = 0;
@@ -204,7 +221,8 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
       CU(bf_launch_pf(g.dP, dbp, two, (double *)w.ws_pf.p, wstride, grid, w.d_counters + 1, scale_src, r->pf, st), "launch bf_k_pf");
       g.launches++;
     }
-    cudaEventRecord(w.ev[3], st);
+    cudaEventRecord(w.ev[3], sp);
+    if (beside) { CU(cudaEventRecord(w.ev_join, sp), "join"); CU(cudaStreamWaitEvent(st, w.ev_join, 0), "join"); }
     w.ran[1] = true;
   }
   if (b->want & BF_WANT_EVAL) {
@@ -476,6 +494,9 @@ struct DesignLoop {
   int B = 0, gstep = 0, re_attempt = 0;
   uint32_t want = 0;
   bool two = false;   // some job has two strands: the loop folds with the two-strand kernels
+  bool overlap = true;  // BF_DESIGN_OVERLAP=0: always fold MFE, then PF
+  int overlap_x2 = 16;  // BF_DESIGN_OVERLAP_X: batch size up to which the two fills run side by side, in units of half the SM count
+                        // (measured: pays at every size tried, 0.76 -> 0.42 ms per sub-step at 64 x 104 nt, 15.5 -> 14.4 ms at 296 x 400 nt)
   std::vector<void *> allocs;
   std::vector<uint8_t> active;
   uint8_t *d_active = nullptr;
@@ -514,7 +535,7 @@ int design_rows(DesignLoop *h) {
 }
 
 // one scoring pass over the rows: the same pipeline bf_score_batch_device runs (MFE fill + backtrack, PF fill + exterior, eval)
-int design_score(DesignLoop *h) {
+int design_score(DesignLoop *h, bool init = false) {
   bf_batch_t b;
   std::memset(&b, 0, sizeof b);
   b.B = h->B; b.stride = h->D.stride; b.seq = h->D.mut_seq; b.len = h->D.row_len; b.targets = h->D.row_tgt; b.n_targets = 1; b.want = h->want;
@@ -522,7 +543,9 @@ int design_score(DesignLoop *h) {
   bf_result_t r;
   std::memset(&r, 0, sizeof r);
   r.mfe_dcal = h->D.o_mfe; r.mfe_ss = h->D.o_ss; r.pf = h->D.o_pf; r.eval_dcal = h->D.o_eval; r.defect = h->D.o_defect;
-  return run_device(h->w, &b, &r, h->two, h->st);
+  // small batches: partition function beside the MFE fill, scaled by the parent sequence's MFE (kept per replica)
+  const bool beside = !init && !h->two && h->overlap && h->B * 2 <= g.sm_count * h->overlap_x2 && !(h->want & BF_WANT_DEFECT);
+  return run_device(h->w, &b, &r, h->two, h->st, beside ? h->D.row_scale : nullptr);
 }
 }  // namespace
 
@@ -567,6 +590,8 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   if (!two && (bf_fill_mfe_mode(S) == 0 || bf_fill_pf_mode(S) == 0)) return fail(BF_ERR_UNAVAILABLE, "bf_design_create: stride outside the fill path");
   DesignLoop *h = new DesignLoop;
   h->two = two;
+  { const char *ov = getenv("BF_DESIGN_OVERLAP"); h->overlap = !(ov && ov[0] == '0'); }
+  { const char *ox = getenv("BF_DESIGN_OVERLAP_X"); h->overlap_x2 = (ox && atoi(ox) > 0) ? atoi(ox) : 16; }
   std::memset(&h->D, 0, sizeof h->D);
   std::memset(&h->C, 0, sizeof h->C);
   auto bail = [&](cudaError_t e, const char *what) { h->destroy(); delete h; return cuda_fail(e, what); };
@@ -590,6 +615,7 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   DCU(h->alloc(&D.rng, G), "cudaMalloc(design)"); DCU(h->alloc(&D.counts, G * 3), "cudaMalloc(design)");
   DCU(h->alloc(&h->d_rowmap, G), "cudaMalloc(design)"); DCU(h->alloc(&h->d_active, J), "cudaMalloc(design)");
   DCU(h->alloc(&D.mut_seq, G * S), "cudaMalloc(design)"); DCU(h->alloc(&D.row_len, G), "cudaMalloc(design)"); DCU(h->alloc(&D.row_cut, G), "cudaMalloc(design)");
+  DCU(h->alloc(&D.row_scale, G), "cudaMalloc(design)"); DCU(h->alloc(&D.cur_mfe, G), "cudaMalloc(design)");
   DCU(h->alloc(&D.row_tgt, G * S), "cudaMalloc(design)"); DCU(h->alloc(&D.o_mfe, G), "cudaMalloc(design)");
   DCU(h->alloc(&D.o_ss, G * (S + 1)), "cudaMalloc(design)"); DCU(h->alloc(&D.o_pf, G * 5), "cudaMalloc(design)");
   DCU(h->alloc(&D.o_eval, G), "cudaMalloc(design)");
@@ -635,7 +661,7 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   int rc = design_rows(h);
   // score the start sequences (sequence_utils.py:862-888) and record them as step 0
   if (!rc) rc = bf_launch_design_propose(h->D, h->C, h->B, true, h->st) == cudaSuccess ? BF_OK : fail(BF_ERR_CUDA, "launch bf_k_design_propose");
-  if (!rc) rc = design_score(h);
+  if (!rc) rc = design_score(h, true);
   if (!rc) rc = bf_launch_design_accept(h->D, h->C, h->B, true, 0, h->st) == cudaSuccess ? BF_OK : fail(BF_ERR_CUDA, "launch bf_k_design_accept");
   if (!rc) rc = bf_launch_design_exchange(h->D, h->C, h->d_active, 0, h->st) == cudaSuccess ? BF_OK : fail(BF_ERR_CUDA, "launch bf_k_design_exchange");
   if (!rc && cudaStreamSynchronize(h->st) != cudaSuccess) rc = fail(BF_ERR_CUDA, std::string("design loop start: ") + cudaGetErrorString(cudaGetLastError()));

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(kWPB * 32) bf_k_design_propose(BfDesignDev D, 
   const char *cur = D.cur_seq + (size_t)g * S;
   char *mut = D.mut_seq + (size_t)row * S;
   for (int k = lane; k < S; k += 32) mut[k] = cur[k];
+  if (lane == 0) D.row_scale[row] = D.cur_mfe[g];
   if (copy_only) return;   // initial scoring: the "mutant" is the start sequence itself
   const short *tpt = D.tpt + (size_t)job * S;
   const uint8_t *allowed = D.allowed + (size_t)job * S;
@@ -276,8 +277,10 @@ __global__ void __launch_bounds__(kWPB * 32) bf_k_design_accept(BfDesignDev D, B
         if (ok) cn[0]++; else cn[2]++;
       }
     }
-    if (ok)
+    if (ok) {
       for (int k = 0; k < kDesignRec; k++) D.rec[(size_t)g * kDesignRec + k] = rec[k];
+      D.cur_mfe[g] = D.o_mfe[row];
+    }
   }
   ok = __shfl_sync(BF_FULL, ok, 0);
   if (ok) {

@@ -45,6 +45,7 @@ struct BfDesignDev {
   char *cur_seq, *cur_ss;        // G x stride, G x (stride+1)
   double *rec;                   // G x kDesignRec
   int *shelf;                    // G            index into temps
+  int *cur_mfe;                  // G            MFE (dcal/mol) of the current sequence: scale of its mutant's partition function
   unsigned long long *rng;       // G
   unsigned int *counts;          // G x 3        accepted, accepted because not worse, rejected
   const double *temps;           // R            temperature shelves, ascending
@@ -54,6 +55,7 @@ struct BfDesignDev {
   char *mut_seq;                 // B x stride
   int *row_len;                  // B
   int *row_cut;                  // B            1-based first nucleotide of strand B, 0 = single strand (bf_batch_t.cut)
+  int *row_scale;                // B            cur_mfe of the row's replica (written by bf_k_design_propose)
   char *row_tgt;                 // B x stride
   int *o_mfe;                    // B
   char *o_ss;                    // B x (stride+1)

@@ -26,9 +26,15 @@ def host_opts(o):
     return o
 
 
+@pytest.mark.parametrize("overlap", ["0", "1"])
 @pytest.mark.parametrize("scoring", [[("Ed-Epf", 1.0)], [("Ed-Epf", 0.5), ("1-MCC", 0.5)],
                                      [("sln_Epf", 1.0), ("Ed-MFE", 0.7), ("1-precision", 0.2), ("1-recall", 0.1)], [("Edef", 5.0), ("Ed-Epf", 0.3)]])
-def test_records_match_host_scoring_and_invariants_hold(engine, scoring):
+def test_records_match_host_scoring_and_invariants_hold(engine, monkeypatch, scoring, overlap):
+    """overlap = 1 (default): in small batches the partition function runs beside the MFE fill, scaled by the PARENT sequence's MFE
+    instead of the mutant's own; the ensemble energy then agrees with the host path to rounding (<= 1 float32 ulp after the API's
+    float32 rounding) instead of bit for bit."""
+    monkeypatch.setenv("BF_DESIGN_OVERLAP", overlap)
+    exact = overlap == "0"
     from desirna_b200 import design
     from desirna_b200.utils import energy_scores as es
     inputs = small_inputs()
@@ -53,10 +59,11 @@ def test_records_match_host_scoring_and_invariants_hold(engine, scoring):
             for a, b in inp.pairs:
                 assert (s[a], s[b]) in PAIR_OK, (inp.name, s)
             assert rep["mfe_ss"][g] == h.mfe_ss
-            assert rec["edesired"] == h.edesired and rec["Epf"] == h.Epf           # float32-rounded API values, bit for bit
+            assert rec["edesired"] == h.edesired                                   # float32-rounded API values, bit for bit
+            assert rec["Epf"] == h.Epf if exact else abs(rec["Epf"] - h.Epf) <= 4e-6
             assert rec["mcc"] == pytest.approx(h.mcc, abs=1e-12) and rec["precision"] == pytest.approx(h.precision, abs=1e-12)
             assert rec["recall"] == pytest.approx(h.recall, abs=1e-12)
-            assert rec["scoring_function"] == pytest.approx(h.scoring_function, abs=1e-9)
+            assert rec["scoring_function"] == pytest.approx(h.scoring_function, abs=1e-9 if exact else 1e-5)
             if any(f == "Ed-MFE" for f, _ in scoring):
                 assert rec["MFE"] == h.MFE
             if any(f == "Edef" for f, _ in scoring):
