@@ -198,9 +198,12 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
         qmseq = (double *)w.qm_seq.p;
       }
       CU(bf_launch_pf_fill(g.dP, dbp, (double *)w.tri_qb.p, (double *)w.ws_qm.p, qmseq, scale_src, (double *)w.d_lnscale.p, g.sm_count,
-                           w.d_counters + 1, sp), "launch bf_k_pf_fill");
-      CU(bf_launch_pf_ext(g.dP, dbp, (const double *)w.tri_qb.p, (const double *)w.d_lnscale.p, r->pf, sp), "launch bf_k_pf_ext");
-      g.launches += 2;
+                           w.d_counters + 1, sp, r->pf), "launch bf_k_pf_fill");
+      g.launches++;
+      if (!bf_pf_fill_does_ext(b->stride, b->B)) {
+        CU(bf_launch_pf_ext(g.dP, dbp, (const double *)w.tri_qb.p, (const double *)w.d_lnscale.p, r->pf, sp), "launch bf_k_pf_ext");
+        g.launches++;
+      }
       if (want_out) {
         int ogrid = 0;
         CU(bf_out_grid(dbp, g.sm_count, &ogrid), "size bf_k_pf_out");

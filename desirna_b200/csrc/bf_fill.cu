@@ -652,7 +652,7 @@ constexpr int kPfQgSmem = 4;   // the generic-interior ring on chip
 
 struct PfPlan {
   int rs;
-  size_t o_S, o_toff, o_wg, o_wb, o_w1, o_scl, o_bu, o_qm, o_qm1, o_qg, o_r2, o_qms, o_au, o_pi, o_ps, o_list, o_tab, total;
+  size_t o_S, o_toff, o_wg, o_wb, o_w1, o_scl, o_bu, o_qm, o_qm1, o_qg, o_r2, o_qms, o_au, o_pi, o_ps, o_list, o_tab, o_q5, total;
 };
 __host__ __device__ inline PfPlan pf_plan(int nmax, int nw, int pl, bool half = false) {
   PfPlan p;
@@ -676,6 +676,7 @@ __host__ __device__ inline PfPlan pf_plan(int nmax, int nw, int pl, bool half = 
   p.o_list = o; o += (size_t)2 * p.rs * sizeof(unsigned short);
   p.o_toff = o; o += (size_t)(nmax + 4) / 4 * 4 * sizeof(int);
   p.o_S = o; o += (nmax + 2 + 15) / 16 * 16;
+  p.o_q5 = o; o += nw == 16 ? (size_t)(nmax + 8) * sizeof(double) : 0;   // exterior recursion inside the fill (16-warp variants)
   p.total = o;
   return p;
 }
@@ -708,7 +709,7 @@ __device__ __forceinline__ void pair_barrier(int k) {
 template <int NW, int PL, bool HALF = false, bool BLK = false, int MINB = 0>
 __global__ void __launch_bounds__(NW * 32, MINB) bf_k_pf_fill(const BfParams *__restrict__ P, BfBatchDev b, double *qbtri, size_t tri_slot,
                                                         double *ws, size_t ws_slot, double *qm_perseq, const int *mfe_for_scale,
-                                                        double *lnscale_out, int *work_counter) {
+                                                        double *lnscale_out, int *work_counter, double *out5) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ int s_seq, s_np[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -777,6 +778,26 @@ __global__ void __launch_bounds__(NW * 32, MINB) bf_k_pf_fill(const BfParams *__
       for (int k = tid; k <= n + 2; k += blockDim.x) { scl[k] = exp(-lns * k); bu[k] = exp(bl * k); }
     }
     if (tid == 0 && lnscale_out) lnscale_out[sq] = lns;
+    // 16-warp variants (a CTA owns its SM, latency is what counts): the exterior recursion q5 (bf_k_pf_ext) advances inside the
+    // fill, one column per phase on warp NW-2 -- q5[j] needs the diagonals up to j-1, complete and visible from phase j+1 on
+    constexpr bool EXTQ = (NW == 16);
+    double *q5s = reinterpret_cast<double *>(dyn + pl.o_q5);
+    const double *qb_out_ext = qbtri + (size_t)sq * tri_slot;
+    if (EXTQ && out5 && tid == (NW - 2) * 32) q5s[0] = 1.0;
+    const double sc1 = exp(-lns);
+    int q5_next = 1;
+    auto q5_step = [&](int j) {
+      double sum = 0.0;
+      for (int i = 1 + lane; i < j - BF_TURN; i += 32) {
+        const int t = bf_ptype_bases(S[i], S[j]);
+        if (!t) continue;
+        const int a = (i > 1) ? S[i - 1] : -1, bb = (j < n) ? S[j + 1] : -1;
+        sum += q5s[i - 1] * qb_out_ext[toff[j - i] + i - 1] * bf_x_ext(T, t, a, bb);
+      }
+      sum = bf_warp_sum(sum);
+      if (lane == 0) q5s[j] = sum + q5s[j - 1] * sc1;
+      __syncwarp();
+    };
     for (int k = tid; k < 4 * RS; k += blockDim.x) QMS[k] = 0.0;
     for (int k = tid; k < 2 * RS; k += blockDim.x) AU[k] = 0.0;
     const int NT = (n + 3) >> 2;
@@ -812,6 +833,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) bf_k_pf_fill(const BfParams *__
         const int cnt = build_pair_list(S, n, d + 1, LST + ((d + 1) & 1) * RS, lane);
         if (lane == 0) s_np[(d + 1) & 1] = cnt;
       }
+      if (EXTQ && out5 && warp == NW - 2)
+        while (q5_next <= d - 1) q5_step(q5_next++);
       // ------------------------------------------------------------ combine diagonal d-1
       if (d > BF_TURN + 1) {
         const int dd = d - 1, ncell = n - dd, buf = dd & 1;
@@ -1036,6 +1059,14 @@ __global__ void __launch_bounds__(NW * 32, MINB) bf_k_pf_fill(const BfParams *__
         }
       }
       __syncthreads();
+    }
+    if (EXTQ && out5 && warp == NW - 2) {
+      while (q5_next <= n) q5_step(q5_next++);
+      if (lane == 0) {
+        double *o = out5 + (size_t)sq * 5;
+        o[0] = o[1] = o[2] = o[3] = 0.0;
+        o[4] = (n > 0) ? -T.kT * (log(q5s[n]) + n * lns) / 1000.0 : 0.0;
+      }
     }
   }
 }
@@ -1363,6 +1394,7 @@ cudaError_t bf_launch_trace(const BfParams *dP, const BfBatchDev &b, const int *
   return cudaGetLastError();
 }
 
+static double *g_pf_out5 = nullptr;   // where a 16-warp fill leaves the ensemble energies (set around the launch by bf_launch_pf_fill)
 template <int NW, int PL, bool HALF = false, bool BLK = false, int MINB = 0>
 static cudaError_t pf_fill_t(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale, double *lnscale,
                              int sms, int *grid_out, bool launch, int *counter, cudaStream_t st) {
@@ -1377,7 +1409,7 @@ static cudaError_t pf_fill_t(const BfParams *dP, const BfBatchDev &b, double *qb
   const int grid = b.B < sms * occ ? b.B : sms * occ;
   if (grid_out) *grid_out = grid;
   if (!launch) return cudaSuccess;
-  kern<<<grid, NW * 32, sm, st>>>(dP, b, qbtri, bf_tri_slot(b.stride), ws, bf_pf_ws_slot(b.stride, b.B), qmseq, mfe_for_scale, lnscale, counter);
+  kern<<<grid, NW * 32, sm, st>>>(dP, b, qbtri, bf_tri_slot(b.stride), ws, bf_pf_ws_slot(b.stride, b.B), qmseq, mfe_for_scale, lnscale, counter, NW == 16 ? g_pf_out5 : nullptr);
   return cudaGetLastError();
 }
 template <int NW>
@@ -1428,11 +1460,17 @@ cudaError_t bf_pf_fill_grid(const BfBatchDev &b, int sms, int *grid) {
   return pf_fill_dispatch(nullptr, b, nullptr, nullptr, nullptr, nullptr, nullptr, sms, grid, false, nullptr, nullptr);
 }
 
+// true: the fill kernel chosen for this batch also runs the exterior recursion and writes out5 (no bf_launch_pf_ext needed)
+bool bf_pf_fill_does_ext(int nmax, int B) { return pf_cfg(nmax, B).nw == 16; }
+
 cudaError_t bf_launch_pf_fill(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *qmws, double *qmseq, const int *mfe_for_scale,
-                              double *lnscale, int sms, int *work_counter, cudaStream_t st) {
+                              double *lnscale, int sms, int *work_counter, cudaStream_t st, double *out5) {
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
-  return pf_fill_dispatch(dP, b, qbtri, qmws, qmseq, mfe_for_scale, lnscale, sms, nullptr, true, work_counter, st);
+  g_pf_out5 = out5;
+  e = pf_fill_dispatch(dP, b, qbtri, qmws, qmseq, mfe_for_scale, lnscale, sms, nullptr, true, work_counter, st);
+  g_pf_out5 = nullptr;
+  return e;
 }
 
 cudaError_t bf_launch_pf_ext(const BfParams *dP, const BfBatchDev &b, const double *qbtri, const double *lnscale, double *out5,

@@ -36,7 +36,9 @@ cudaError_t bf_launch_trace(const BfParams *dP, const BfBatchDev &b, const int *
                             int ss_stride, cudaStream_t st);
 // qmseq: optional per-sequence qm/qm1 storage (2 x bf_tri_slot doubles per sequence) for the outside pass
 cudaError_t bf_launch_pf_fill(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *qmws, double *qmseq, const int *mfe_for_scale,
-                              double *lnscale, int sms, int *work_counter, cudaStream_t st);
+                              double *lnscale, int sms, int *work_counter, cudaStream_t st, double *out5 = nullptr);
+// true: the fill kernel chosen for (nmax, B) runs the exterior recursion itself and writes out5 (16-warp variants)
+bool bf_pf_fill_does_ext(int nmax, int B);
 cudaError_t bf_launch_pf_ext(const BfParams *dP, const BfBatchDev &b, const double *qbtri, const double *lnscale, double *out5,
                              cudaStream_t st);
 
