@@ -38,6 +38,7 @@ struct Workspace {
   int *d_counters = nullptr;  // work counters (one per kernel kind)
   DevBuf ws_mfe, ws_pf, d_mfe_scratch;
   DevBuf tri_c, tri_f, tri_qb, ws_qm, ws_ring, d_lnscale, qm_seq, ws_out;  // diagonal-major fill path (bf_fill.cu)
+  DevBuf f5buf;  // f5 of every sequence when the fill kernel runs the exterior recursion (16-warp variants)
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // begin/end of mfe, pf, eval in the last call
   bool ran[3] = {false, false, false};
   // the partition function of a small batch can run beside the MFE fill on SMs of its own (run_device: scale_override)
@@ -52,7 +53,7 @@ struct Workspace {
     return e;
   }
   void destroy() {
-    for (DevBuf *b : {&ws_mfe, &ws_pf, &d_mfe_scratch, &tri_c, &tri_f, &tri_qb, &ws_qm, &ws_ring, &d_lnscale, &qm_seq, &ws_out}) b->release();
+    for (DevBuf *b : {&ws_mfe, &ws_pf, &d_mfe_scratch, &tri_c, &tri_f, &tri_qb, &ws_qm, &ws_ring, &d_lnscale, &qm_seq, &ws_out, &f5buf}) b->release();
     if (d_counters) cudaFree(d_counters);
     d_counters = nullptr;
     for (int k = 0; k < 6; k++) { if (ev[k]) cudaEventDestroy(ev[k]); ev[k] = nullptr; }
@@ -135,6 +136,7 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
       const size_t slot = bf_tri_slot(b->stride) * sizeof(int);
       CU(w.tri_c.reserve((size_t)b->B * slot), "cudaMalloc(c table)");
       CU(w.tri_f.reserve((size_t)b->B * slot), "cudaMalloc(fML table)");
+      int *f5 = nullptr;
       if (g.fill_kind == 1 && bf_tile_mfe_ok(b->stride)) {
         const size_t wsi = bf_mfe_tile_ws_slot(b->stride) * sizeof(int);
         if (wsi) {
@@ -151,11 +153,15 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
           CU(bf_mfe_fill_grid(db, g.sm_count, &grid), "size bf_k_mfe_fill");
           CU(w.ws_ring.reserve((size_t)grid * wsi), "cudaMalloc(ring workspace)");
         }
-        CU(bf_launch_mfe_fill(g.dP, db, (int *)w.tri_c.p, (int *)w.tri_f.p, (int *)w.ws_ring.p, g.sm_count, w.d_counters + 0, st),
+        if (bf_mfe_fill_does_ext(b->stride, b->B)) {
+          CU(w.f5buf.reserve((size_t)b->B * (b->stride + 4) * sizeof(int)), "cudaMalloc(f5)");
+          f5 = (int *)w.f5buf.p;
+        }
+        CU(bf_launch_mfe_fill(g.dP, db, (int *)w.tri_c.p, (int *)w.tri_f.p, (int *)w.ws_ring.p, g.sm_count, w.d_counters + 0, st, f5),
            "launch bf_k_mfe_fill");
       }
       CU(bf_launch_trace(g.dP, db, (const int *)w.tri_c.p, (const int *)w.tri_f.p, out_mfe, (b->want & BF_WANT_SS) ? r->mfe_ss : nullptr,
-                         b->stride + 1, st), "launch bf_k_trace");
+                         b->stride + 1, st, f5), "launch bf_k_trace");
       g.launches += 2;
     } else {
       int occ = bf_occupancy_mfe(two, wstride);

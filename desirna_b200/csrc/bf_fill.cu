@@ -63,7 +63,7 @@ constexpr int kTabSmem = 8;     // small loop tables (BfSmallI / BfSmallD) stage
 
 struct MfePlan {
   int rs;  // ring row stride (ints)
-  size_t o_S, o_SP, o_toff, o_pg, o_pb, o_p1, o_fm, o_ring, o_dml, o_pi, o_ps, o_list, o_tab, o_sa, total;
+  size_t o_S, o_SP, o_toff, o_pg, o_pb, o_p1, o_fm, o_ring, o_dml, o_pi, o_ps, o_list, o_tab, o_sa, o_f5, total;
 };
 __host__ __device__ inline MfePlan mfe_plan(int nmax, int nw, int pl, bool blk = false, bool atom = false) {
   MfePlan p;
@@ -85,6 +85,7 @@ __host__ __device__ inline MfePlan mfe_plan(int nmax, int nw, int pl, bool blk =
   p.o_tab = o; o += (pl & kTabSmem) ? (sizeof(BfSmallI) + 15) / 16 * 16 : 0;
   o = (o + 15) / 16 * 16;
   p.o_sa = o; o += blk ? (size_t)3 * ((nmax + 3) / 4) * 16 * sizeof(int) : 0;  // blocked-split minima of three tile-diagonals
+  p.o_f5 = o; o += nw == 16 ? (size_t)(nmax + 8) * sizeof(int) : 0;   // exterior recursion inside the fill (16-warp variants)
   p.total = o;
   return p;
 }
@@ -126,7 +127,7 @@ __device__ __forceinline__ int build_pair_list(const uint8_t *SP, int n, int d, 
 // where the per-warp buffers were what limited occupancy (short sequences with the rings on chip, long sequences).
 template <int NW, int PL, bool BLK = false, bool ATOM = false>
 __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restrict__ P, BfBatchDev b, int *ctri, int *ftri,
-                                                         size_t tri_slot, int *ws, size_t ws_slot, int *work_counter) {
+                                                         size_t tri_slot, int *ws, size_t ws_slot, int *work_counter, int *f5_out) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ int s_seq, s_np[2];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -196,6 +197,25 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
     int *cg_out = ctri + (size_t)sq * tri_slot;
     int *fg_out = ftri + (size_t)sq * tri_slot;
     int *FM = (PL & kMfeFmSmem) ? fms : fg_out;
+    // 16-warp variants: the exterior recursion f5 (bf_k_trace) advances inside the fill, one column per phase on warp NW-2 --
+    // f5[j] needs the diagonals up to j-1, complete and visible from phase j+1 on; bf_k_trace then only backtracks
+    constexpr bool EXTF = (NW == 16);
+    int *f5s = reinterpret_cast<int *>(dyn + pl.o_f5);
+    int f5_next = 1;
+    if (EXTF && f5_out && tid == (NW - 2) * 32) f5s[0] = 0;
+    auto f5_step = [&](int j) {
+      int e = BF_INF;
+      for (int i = 1 + lane; i < j - BF_TURN; i += 32) {
+        const int t = ptype_sp(SP, i, j);
+        if (!t) continue;
+        const int cc = cg_out[toff[j - i] + i - 1];
+        if (cc >= BF_INF) continue;
+        e = min(e, f5s[i - 1] + cc + bf_e_ext(T, t, i > 1 ? (int)S[i - 1] : -1, j < n ? (int)S[j + 1] : -1));
+      }
+      e = bf_warp_min(e);
+      if (lane == 0) f5s[j] = min(e, f5s[j - 1]);
+      __syncwarp();
+    };
     __syncthreads();
     if (warp == 0 && n > BF_TURN + 1) {
       const int cnt = build_pair_list(SP, n, BF_TURN + 1, LST + ((BF_TURN + 1) & 1) * RS, lane);
@@ -209,6 +229,8 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
         const int cnt = build_pair_list(SP, n, d + 1, LST + ((d + 1) & 1) * RS, lane);
         if (lane == 0) s_np[(d + 1) & 1] = cnt;
       }
+      if (EXTF && f5_out && warp == NW - 2)
+        while (f5_next <= d - 1) f5_step(f5_next++);
       // ------------------------------------------------------------ combine diagonal d-1
       if (d > BF_TURN + 1) {
         const int dd = d - 1, ncell = n - dd, buf = dd & 1;
@@ -425,6 +447,10 @@ __global__ void __launch_bounds__(NW * 32) bf_k_mfe_fill(const BfParams *__restr
       }
       __syncthreads();
     }
+    if (EXTF && f5_out && warp == NW - 2) {
+      while (f5_next <= n) f5_step(f5_next++);
+      for (int k = lane; k <= n; k += 32) f5_out[(size_t)sq * (nmax + 4) + k] = f5s[k];
+    }
   }
 }
 
@@ -436,7 +462,7 @@ struct __align__(8) Sector { short i, j; int kind; };  // 0 exterior (f5 up to j
 template <int WPB>
 __global__ void __launch_bounds__(WPB * 32) bf_k_trace(const BfParams *__restrict__ P, BfBatchDev b, const int *__restrict__ ctri,
                                                        const int *__restrict__ ftri, size_t tri_slot, int *out_mfe, char *out_ss,
-                                                       int ss_stride) {
+                                                       int ss_stride, const int *__restrict__ f5_in) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ BfSmallI T;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -508,7 +534,11 @@ __global__ void __launch_bounds__(WPB * 32) bf_k_trace(const BfParams *__restric
       for (int c = 0; c < K; c++) cur[c] = nxt[c];
     }
   };
-  if (n <= 64) chain(std::integral_constant<int, 2>());
+  if (f5_in) {   // the 16-warp fill already ran the recursion
+    for (int k = lane; k <= n; k += 32) f5[k] = __ldg(f5_in + (size_t)sq * (nmax + 4) + k);
+    __syncwarp();
+  }
+  else if (n <= 64) chain(std::integral_constant<int, 2>());
   else if (n <= 128) chain(std::integral_constant<int, 4>());
   else if (n <= 256) chain(std::integral_constant<int, 8>());
   else
@@ -1304,6 +1334,7 @@ size_t bf_pf_ws_slot(int nmax, int B) {  // doubles of per-CTA HBM workspace: [t
   return (o + 7) / 8 * 8;
 }
 
+static int *g_f5_out = nullptr;   // where a 16-warp fill leaves f5 (set around the launch by bf_launch_mfe_fill)
 template <int NW, int PL, bool BLK = false, bool ATOM = false>
 static cudaError_t mfe_fill_t(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *grid_out, bool launch,
                               int *counter, cudaStream_t st) {
@@ -1318,7 +1349,7 @@ static cudaError_t mfe_fill_t(const BfParams *dP, const BfBatchDev &b, int *ctri
   const int grid = b.B < sms * occ ? b.B : sms * occ;
   if (grid_out) *grid_out = grid;
   if (!launch) return cudaSuccess;
-  kern<<<grid, NW * 32, sm, st>>>(dP, b, ctri, ftri, bf_tri_slot(b.stride), ws, bf_mfe_ws_slot(b.stride, b.B), counter);
+  kern<<<grid, NW * 32, sm, st>>>(dP, b, ctri, ftri, bf_tri_slot(b.stride), ws, bf_mfe_ws_slot(b.stride, b.B), counter, NW == 16 ? g_f5_out : nullptr);
   return cudaGetLastError();
 }
 
@@ -1377,20 +1408,26 @@ static cudaError_t mfe_fill_dispatch(const BfParams *dP, const BfBatchDev &b, in
 cudaError_t bf_mfe_fill_grid(const BfBatchDev &b, int sms, int *grid) {
   return mfe_fill_dispatch(nullptr, b, nullptr, nullptr, nullptr, sms, grid, false, nullptr, nullptr);
 }
+// true: the fill kernel chosen for this batch also runs the exterior recursion and leaves f5 (B x (stride + 4) ints) for bf_k_trace
+bool bf_mfe_fill_does_ext(int nmax, int B) { return mfe_cfg(nmax, B).nw == 16; }
+
 cudaError_t bf_launch_mfe_fill(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *work_counter,
-                               cudaStream_t st) {
+                               cudaStream_t st, int *f5_out) {
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
-  return mfe_fill_dispatch(dP, b, ctri, ftri, ws, sms, nullptr, true, work_counter, st);
+  g_f5_out = f5_out;
+  e = mfe_fill_dispatch(dP, b, ctri, ftri, ws, sms, nullptr, true, work_counter, st);
+  g_f5_out = nullptr;
+  return e;
 }
 
 cudaError_t bf_launch_trace(const BfParams *dP, const BfBatchDev &b, const int *ctri, const int *ftri, int *out_mfe, char *out_ss,
-                            int ss_stride, cudaStream_t st) {
+                            int ss_stride, cudaStream_t st, const int *f5_in) {
   auto kern = bf_k_trace<kTraceWPB>;
   const size_t sm = trace_smem(b.stride);
   cudaError_t e = set_smem(kern, sm);
   if (e != cudaSuccess) return e;
-  kern<<<(b.B + kTraceWPB - 1) / kTraceWPB, kTraceWPB * 32, sm, st>>>(dP, b, ctri, ftri, bf_tri_slot(b.stride), out_mfe, out_ss, ss_stride);
+  kern<<<(b.B + kTraceWPB - 1) / kTraceWPB, kTraceWPB * 32, sm, st>>>(dP, b, ctri, ftri, bf_tri_slot(b.stride), out_mfe, out_ss, ss_stride, f5_in);
   return cudaGetLastError();
 }
 

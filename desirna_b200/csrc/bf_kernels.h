@@ -30,10 +30,12 @@ size_t bf_pf_ws_slot(int nmax, int B);    // doubles of per-CTA HBM workspace of
 void bf_fill_set_sms(int sms);    // SM count of the device (batches of at most that many sequences use 16-warp CTAs)
 cudaError_t bf_mfe_fill_grid(const BfBatchDev &b, int sms, int *grid);
 cudaError_t bf_pf_fill_grid(const BfBatchDev &b, int sms, int *grid);
+// f5_out / f5_in (B x (stride + 4) ints): the 16-warp fill variants run the exterior recursion themselves (bf_mfe_fill_does_ext)
 cudaError_t bf_launch_mfe_fill(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *work_counter,
-                               cudaStream_t st);
+                               cudaStream_t st, int *f5_out = nullptr);
+bool bf_mfe_fill_does_ext(int nmax, int B);
 cudaError_t bf_launch_trace(const BfParams *dP, const BfBatchDev &b, const int *ctri, const int *ftri, int *out_mfe, char *out_ss,
-                            int ss_stride, cudaStream_t st);
+                            int ss_stride, cudaStream_t st, const int *f5_in = nullptr);
 // qmseq: optional per-sequence qm/qm1 storage (2 x bf_tri_slot doubles per sequence) for the outside pass
 cudaError_t bf_launch_pf_fill(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *qmws, double *qmseq, const int *mfe_for_scale,
                               double *lnscale, int sms, int *work_counter, cudaStream_t st, double *out5 = nullptr);
