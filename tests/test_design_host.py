@@ -237,3 +237,69 @@ def test_homodimer_moves_keep_the_strands_in_step():
         m = su.propose_mutation(cur2, nts2, o, inp2)
         a, b = m.split("&")
         assert len(a) == len(b) == 8 and set(m) <= set("ACGU&")
+
+
+class _FakeLoop:
+    """stands in for design.DesignLoop (no GPU): a loop whose jobs get solved after a given number of global steps"""
+    made = []
+
+    def __init__(self, inputs, sim_options, seed=0, init_seqs=None):
+        self.inputs, self.J, self.R = list(inputs), len(inputs), sim_options.replicas
+        self.stride = max(len(i.sec_struct) for i in inputs)
+        self.active = np.ones(self.J, np.uint8)
+        self.steps = 0
+        self.pending = 0
+        self.calls = []
+        self.solve_at = [len(i.sec_struct) // 10 for i in inputs]     # longer targets take more global steps
+        _FakeLoop.made.append(self)
+
+    def run(self, n):
+        self.calls.append(int(n))
+        self.pending += int(n)
+
+    def busy(self):
+        return False
+
+    def _flush(self):
+        self.steps += self.pending
+        self.pending = 0
+
+    def jobs(self):
+        self._flush()
+        step = np.array([s if self.steps >= s else -1 for s in self.solve_at], np.int32)
+        rec = np.zeros((self.J, 12))
+        rec[:, 8] = (step < 0)
+        return {"sequence": ["A" * len(i.sec_struct) for i in self.inputs], "mfe_ss": [i.sec_struct for i in self.inputs], "rec": rec,
+                "solved_step": step, "n_solved": np.zeros(self.J, np.uint32)}
+
+    def set_active(self, mask):
+        self.active = np.array(mask, np.uint8)
+
+    def close(self):
+        pass
+
+
+def test_design_batch_scheduling_without_a_gpu(monkeypatch):
+    """every length bucket is advanced on its own, solved jobs are retired, step limits and stop_when_solved are honoured"""
+    from desirna_b200 import design
+    _FakeLoop.made = []
+    monkeypatch.setattr(design, "DesignLoop", _FakeLoop)
+    inputs = [sio.make_input("j%d" % k, "(" * 4 + "." * n + ")" * 4) for k, n in enumerate([12, 22, 52, 92, 192, 292])]
+    o = design.DesignOptions(replicas=4, RE_attempt=10)
+    results, info = design.design_batch(inputs, o, global_steps=1000, seed=1)
+    assert info["solved"] == 6 and all(r["solved"] for r in results)
+    assert [r["name"] for r in results] == ["j%d" % k for k in range(6)]
+    assert len(_FakeLoop.made) == len(info["buckets"]) >= 4                  # one loop per length bucket
+    for loop in _FakeLoop.made:
+        assert not loop.active.any()                                       # every job retired once solved
+        assert loop.steps >= max(loop.solve_at) and loop.steps <= max(loop.solve_at) + 64
+        assert loop.calls[0] == 1 and max(loop.calls) <= 64                  # first batch is one step, later ones sized from the pace
+    # a step limit stops unsolved loops; stop_when_solved=False keeps solved jobs running to the limit
+    _FakeLoop.made = []
+    results, info = design.design_batch(inputs, o, global_steps=5, seed=1, stop_when_solved=False)
+    assert all(loop.steps == 5 for loop in _FakeLoop.made) and info["global_steps"] == 5
+    assert [r["solved"] for r in results] == [True, True, False, False, False, False]
+    # a time limit of zero: only the start sequences are read
+    _FakeLoop.made = []
+    results, info = design.design_batch(inputs, o, time_limit=0.0, seed=1)
+    assert all(loop.steps == 0 for loop in _FakeLoop.made) and info["solved"] == 0
