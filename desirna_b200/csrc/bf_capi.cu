@@ -609,9 +609,9 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   DCU(h->w.create(), "create design workspace");
   BfDesignDev &D = h->D;
   D.J = J; D.R = R; D.stride = S;
-  char *tgt; short *d_tpt; uint8_t *allowed; int *len, *d_len_a; unsigned short *d_avail; int *d_navail; double *temps, *tm_prob;
+  char *tgt; short *d_tpt; uint8_t *allowed, *d_same; int *len, *d_len_a; unsigned short *d_avail; int *d_navail; double *temps, *tm_prob;
   DCU(h->alloc(&tgt, (size_t)J * S), "cudaMalloc(design)"); DCU(h->alloc(&d_tpt, (size_t)J * S), "cudaMalloc(design)");
-  DCU(h->alloc(&allowed, (size_t)J * S), "cudaMalloc(design)"); DCU(h->alloc(&len, J), "cudaMalloc(design)"); DCU(h->alloc(&d_len_a, J), "cudaMalloc(design)");
+  DCU(h->alloc(&allowed, (size_t)J * S), "cudaMalloc(design)"); DCU(h->alloc(&len, J), "cudaMalloc(design)"); DCU(h->alloc(&d_len_a, J), "cudaMalloc(design)"); DCU(h->alloc(&d_same, J), "cudaMalloc(design)");
   DCU(h->alloc(&d_avail, (size_t)J * S), "cudaMalloc(design)"); DCU(h->alloc(&d_navail, J), "cudaMalloc(design)");
   DCU(h->alloc(&temps, R), "cudaMalloc(design)"); DCU(h->alloc(&tm_prob, R), "cudaMalloc(design)");
   DCU(h->alloc(&D.job_rng, J), "cudaMalloc(design)");
@@ -642,7 +642,7 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   C.oligo = c->oligo;
   if (two && (h->want & BF_WANT_DEFECT)) return bail(cudaErrorInvalidValue, "bf_design_create: the Edef term needs single-strand jobs");
   h->re_attempt = c->re_attempt;
-  D.tgt = tgt; D.tpt = d_tpt; D.allowed = allowed; D.len = len; D.len_a = d_len_a; D.avail = d_avail; D.n_avail = d_navail; D.temps = temps; D.tm_prob = tm_prob;
+  D.tgt = tgt; D.tpt = d_tpt; D.allowed = allowed; D.len = len; D.len_a = d_len_a; D.same_halves = d_same; D.avail = d_avail; D.n_avail = d_navail; D.temps = temps; D.tm_prob = tm_prob;
   D.rowmap = h->d_rowmap;
   // uploads
   std::vector<unsigned long long> rng(G), jrng(J);
@@ -656,6 +656,14 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   std::vector<int> sstep(J, -1);
   DCU(cudaMemcpy(tgt, c->target, (size_t)J * S, cudaMemcpyHostToDevice), "H2D design"); DCU(cudaMemcpy(d_tpt, tpt.data(), tpt.size() * sizeof(short), cudaMemcpyHostToDevice), "H2D design");
   DCU(cudaMemcpy(allowed, c->allowed, (size_t)J * S, cudaMemcpyHostToDevice), "H2D design"); DCU(cudaMemcpy(len, c->len, J * sizeof(int), cudaMemcpyHostToDevice), "H2D design"); DCU(cudaMemcpy(d_len_a, len_a.data(), J * sizeof(int), cudaMemcpyHostToDevice), "H2D design");
+  {
+    std::vector<uint8_t> same(J, 0);
+    for (int j = 0; j < J; j++) {
+      const int a = len_a[j], n = c->len[j];
+      same[j] = a > 0 && n == 2 * a && std::memcmp(c->target + (size_t)j * S, c->target + (size_t)j * S + a, a) == 0;
+    }
+    DCU(cudaMemcpy(d_same, same.data(), J, cudaMemcpyHostToDevice), "H2D design");
+  }
   DCU(cudaMemcpy(d_avail, avail.data(), avail.size() * sizeof(unsigned short), cudaMemcpyHostToDevice), "H2D design");
   DCU(cudaMemcpy(d_navail, n_avail.data(), J * sizeof(int), cudaMemcpyHostToDevice), "H2D design");
   DCU(cudaMemcpy(temps, c->temps, R * sizeof(double), cudaMemcpyHostToDevice), "H2D design"); DCU(cudaMemcpy(tm_prob, c->tm_prob, R * sizeof(double), cudaMemcpyHostToDevice), "H2D design");

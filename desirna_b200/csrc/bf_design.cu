@@ -192,6 +192,24 @@ __global__ void __launch_bounds__(kWPB * 32) bf_k_design_propose(BfDesignDev D, 
       if (m2) mut[partner] = code_letter(pick_letter(m2, C.acgu != 0, C, rng));
     }
     D.rng[g] = rng;
+    // homodimer designs keep the two strands identical (sequence_utils.py:1102-1128)
+    const int A = D.len_a[job];
+    if (C.oligo == 2 && A > 0 && n == 2 * A) {
+      if (D.same_halves[job]) {   // identical target halves: the strand that changed is copied over the other
+        bool da = false, db = false;
+        for (int k = 0; k < A; k++) { da |= mut[k] != cur[k]; db |= mut[A + k] != cur[A + k]; }
+        if (da) { for (int k = 0; k < A; k++) mut[A + k] = mut[k]; }
+        else if (db) { for (int k = 0; k < A; k++) mut[k] = mut[A + k]; }
+      } else if (partner >= 0) {  // different halves: the two letters of an inter-strand pair are mirrored onto the other strand
+        const int lo = min(pos, partner), hi = max(pos, partner);
+        if (lo < A && hi >= A) {
+          const int in_a = lo, in_b = hi - A;
+          const char ca = mut[A + in_b], cb = mut[in_a];
+          mut[in_b] = ca;
+          mut[A + in_a] = cb;
+        }
+      }
+    }
   }
 }
 
@@ -253,14 +271,14 @@ __global__ void __launch_bounds__(kWPB * 32) bf_k_design_accept(BfDesignDev D, B
         case kTermEdef: total += rec[kRecEdef] * wgt; break;
       }
     }
-    if (two && C.oligo == 1) {
+    if (two && C.oligo >= 1) {
       // equilibrium dimer fraction at 1 mM from FcAB - FA - FB (dimer_multichain_energy.py:36-63), float32 API values first
       const double kT = 0.001987204259 * (273.15 + 37);
       const double dF = (double)(float)D.o_pf[(size_t)row * 5 + 2] - (double)(float)D.o_pf[(size_t)row * 5 + 0] - (double)(float)D.o_pf[(size_t)row * 5 + 1];
       const double rhs = 1e-3 / 55.14 * exp(-dF / kT);
       const double frac = 1 - (sqrt(1 + 4 * rhs) - 1) / (2 * rhs);
       rec[kRecOligoFraction] = frac;
-      rec[kRecOligoBonus] = -kT * log(frac);
+      rec[kRecOligoBonus] = (C.oligo == 2 && D.same_halves[job]) ? -kT * log(1 - frac) : -kT * log(frac);
       total += rec[kRecOligoBonus];
     }
     rec[kRecScore] = total;

@@ -22,7 +22,9 @@ struct BfDesignCfg {
   int point_mutations;   // -tm on/off
   int acgu;              // -acgu on: paired letters drawn with nt_weight
   double nt_weight[4];   // A C G U
-  int oligo;             // 1: two-strand jobs add -kT ln(dimer fraction) (energy_scores.py:421-430, dimer_multichain_energy.py:36-63)
+  int oligo;             // two-strand jobs: 1 heterodimer, adds -kT ln(dimer fraction); 2 homodimer, strands kept identical and
+                         // -kT ln(dimer fraction) (different target halves) or -kT ln(1 - fraction) (identical halves)
+                         // (energy_scores.py:120-125,421-441, dimer_multichain_energy.py:36-76, sequence_utils.py:1102-1128)
 };
 
 struct BfDesignDev {
@@ -33,6 +35,7 @@ struct BfDesignDev {
   const uint8_t *allowed;        // J x stride   letters_allowed, bit 0..3 = A C G U  (sequence_utils.py:454-525)
   const int *len;                // J            nucleotides (both strands, no '&')
   const int *len_a;              // J            length of strand A, 0 = single strand ('&' sits after it in the reference's strings)
+  const uint8_t *same_halves;    // J            1: the two halves of the target are the same string (homodimer designs)
   const unsigned short *avail;   // J x stride   positions with more than one allowed letter (sequence_utils.py:1026-1029)
   const int *n_avail;            // J
   unsigned long long *job_rng;   // J            stream of the neighbour swaps

@@ -39,7 +39,7 @@ class DesignOptions:
         self.nt_percentages = nt_percentages or {"A": 15, "C": 30, "G": 30, "U": 15}
         self.diff_start_replicas = diff_start_replicas
         self.L = 504.12
-        self.oligo_state, self.pks, self.subopt, self.motifs = oligo_state, "off", "off", None   # "none" | "heterodimer"
+        self.oligo_state, self.pks, self.subopt, self.motifs = oligo_state, "off", "off", None   # "none" | "heterodimer" | "homodimer"
         self.rep_temps_shelfs = seq_utils.get_rep_temps(self)
 
 
@@ -94,8 +94,10 @@ class DesignLoop:
         for inp in self.inputs:
             if set(inp.sec_struct) - set(".()&") or inp.sec_struct.count("&") > 1:
                 raise ValueError("the device design loop takes targets made of . ( ), one strand or 'A&B': %r" % (inp.name,))
-            if "&" in inp.sec_struct and sim_options.oligo_state != "heterodimer":
-                raise ValueError("two-strand targets need oligo_state='heterodimer' (homodimer designs run on the lock-step path)")
+            if "&" in inp.sec_struct and sim_options.oligo_state not in ("heterodimer", "homodimer"):
+                raise ValueError("two-strand targets need oligo_state='heterodimer' or 'homodimer'")
+            if sim_options.oligo_state == "homodimer" and len(set(map(len, inp.sec_struct.split("&")))) != 1:
+                raise ValueError("homodimer targets need two strands of equal length: %r" % (inp.name,))
         # the reference's strings carry the '&'; the engine's do not: len_a remembers where it sat
         self.len_a = np.array([i.sec_struct.index("&") if "&" in i.sec_struct else 0 for i in self.inputs], np.int32)
         self.lens = np.array([len(i.sec_struct.replace("&", "")) for i in self.inputs], np.int32)
@@ -119,7 +121,7 @@ class DesignLoop:
                       np.array(sim_options.rep_temps_shelfs, np.float64), np.array(seq_utils.targeted_move_probabilities(sim_options), np.float64)]
         cfg.n_jobs, cfg.replicas, cfg.stride = self.J, self.R, self.stride
         cfg.target, cfg.len, cfg.len_a, cfg.allowed, cfg.init_seq, cfg.temps, cfg.tm_prob = (a.ctypes.data for a in self._keep)
-        cfg.oligo = int(sim_options.oligo_state == "heterodimer")
+        cfg.oligo = {"heterodimer": 1, "homodimer": 2}.get(sim_options.oligo_state, 0)
         cfg.n_terms = len(terms)
         for k, (t, w) in enumerate(terms):
             cfg.term[k], cfg.weight[k] = t, w

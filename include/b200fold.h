@@ -112,7 +112,7 @@ int bf_debug_copy_table(int which, int32_t n_seq, void *host, size_t host_bytes,
 /* ---------------------------------------------------------------------------------------------------------
  * Device-resident Replica-Exchange Monte-Carlo design loop: many design problems ("jobs") x replicas advance
  * in lock step with sequences, scores, temperature shelves and random streams resident in HBM.  Replaces,
- * for targets made of . ( ), one strand or two (heterodimer):
+ * for targets made of . ( ), one strand or two (heterodimer, homodimer):
  *   remc.mutate_sequence_re / single_replica_design / mc_delta      utils/replica_exchange_monte_carlo.py:26-110,176-271
  *   remc.replica_exchange / replica_exchange_attempt                utils/replica_exchange_monte_carlo.py:80-173
  *   seq_utils.mutate_sequence / get_mutation_position / expand_cases  utils/sequence_utils.py:926-1136
@@ -136,7 +136,8 @@ typedef struct {
   int32_t re_attempt;      /* Monte-Carlo sub-steps per global step (-e) */
   int32_t acgu;            /* -acgu on: paired letters drawn with nt_weight */
   double nt_weight[4];     /* A C G U */
-  int32_t oligo;           /* 1: heterodimer design, adds -kT ln(dimer fraction)   energy_scores.py:421-430 */
+  int32_t oligo;           /* two-strand jobs: 1 heterodimer (-kT ln(dimer fraction)), 2 homodimer (strands kept identical;
+                              -kT ln(fraction) or, for identical target halves, -kT ln(1 - fraction))   energy_scores.py:120-125,421-441 */
   uint64_t seed;
 } bf_design_t;
 

@@ -291,3 +291,62 @@ def test_trajectory_and_result_files(engine, tmp_path):
         assert solved == any(d["mcc"] == 0.0 for d in data)
         assert best[0]["mcc"] == min(d["mcc"] for d in data)
         assert (tmp_path / ("run%d_traj.csv" % k)).read_text().count("\n") == len(data) + 1
+
+
+HOMO_DIFF = ("((((....((((.....&))))....)))).....", "NNNNNNNNNNNNNNNNN&NNNNNNNNNNNNNNNNN")    # example_files/inputs/Homodimer_design_input.txt
+HOMO_SAME = ("((((....))))..&((((....))))..", "NNNNNNNNNNNNNN&NNNNNNNNNNNNNN")
+
+
+@pytest.mark.parametrize("case", [HOMO_DIFF, HOMO_SAME])
+def test_homodimer_jobs_on_the_device(engine, case):
+    """-d on (utils/sequence_utils.py:1102-1128, utils/energy_scores.py:120-125): mirrored moves in distribution against the host
+    mirror, score records (incl. the dimer / monomer fraction term) against the host scoring"""
+    from desirna_b200 import design
+    from desirna_b200.utils import energy_scores as es
+    from desirna_b200.utils import sequence_utils as su
+    from desirna_b200.utils import stats_inputs_outputs as sio
+    inp = sio.make_input("homodimer", *case)
+    half = len(case[0].split("&")[0])
+    o = design.DesignOptions(replicas=4, RE_attempt=15, oligo_state="homodimer", tm_max=0.8, tm_min=0.3)
+    random.seed(3)
+    start = "GGGGAAAACCCCAAGGU"[:half]
+    start = start + "A" * (half - len(start))
+    loop = design.DesignLoop([inp], o, seed=5, init_seqs=[start + "&" + start] * 4)
+    cur_ss = loop.replicas()["mfe_ss"][0]
+    N = 4000
+    dev = Counter()
+    for _ in range(N):
+        dev[loop.propose_only()[0]] += 1
+    nts = su.get_nt_list(inp)
+    cur = SimpleNamespace(sequence=start + "&" + start, mfe_ss=cur_ss, temp_shelf=o.rep_temps_shelfs[0])
+    host = Counter(su.propose_mutation(cur, nts, o, inp) for _ in range(N))
+    same = case[0].split("&")[0] == case[0].split("&")[1]
+    for m in dev:
+        a, b = m.split("&")
+        # identical target halves: the strands stay identical; different halves: only the two letters of a pair are mirrored,
+        # an unpaired position may differ between the strands -- in the reference as here
+        assert a == b or not same, m
+    assert set(dev) <= set(host) | {k for k in dev if dev[k] < 5}
+
+    def where(counter):
+        out = Counter()
+        for m, c in counter.items():
+            out[tuple(i for i in range(len(m)) if m[i] != cur.sequence[i])] += c
+        return out
+
+    hw, dw = where(host), where(dev)
+    tv = 0.5 * sum(abs(hw[k] - dw[k]) for k in set(hw) | set(dw)) / N
+    assert tv < 0.07, tv
+    # a few global steps, then the records against the host scoring of the same sequences
+    loop.run(3)
+    rep = loop.replicas()
+    ref = es.score_sequences(rep["sequence"], inp, o)
+    for g, (s, h) in enumerate(zip(rep["sequence"], ref)):
+        rec = dict(zip(design.REC_FIELDS, rep["rec"][g]))
+        a, b = s.split("&")
+        assert (a == b or not same) and rep["mfe_ss"][g] == h.mfe_ss
+        assert rec["edesired"] == h.edesired and abs(rec["Epf"] - h.Epf) <= 4e-6
+        assert rec["oligo_fraction"] == pytest.approx(h.oligo_fraction, rel=1e-6)
+        assert rec["oligomer_bonus"] == pytest.approx(h.oligomer_bonus, abs=1e-6)
+        assert rec["scoring_function"] == pytest.approx(h.scoring_function, abs=1e-5)
+    loop.close()
