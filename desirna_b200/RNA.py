@@ -26,17 +26,6 @@ import numpy as np
 
 from . import engine as _eng
 
-_backend = _eng  # tests may install a checker backend with the same score_batch() signature
-
-
-def set_backend(backend):
-    global _backend
-    _backend = backend
-
-
-def get_backend():
-    return _backend
-
 
 def f32(x):
     """round to C float, widen back to double (what SWIG hands to Python)"""
@@ -51,7 +40,7 @@ cvar = _Cvar()
 
 
 def params_load(path):
-    _backend.params_load(path)
+    _eng.params_load(path)
     return 1
 
 
@@ -81,7 +70,7 @@ class fold_compound:
         targets: optional list (per compound) of lists of dot-bracket strings for eval_structure."""
         if not compounds:
             return
-        E = _backend
+        E = _eng
         w = want if want is not None else (E.WANT_MFE | E.WANT_SS | E.WANT_PF)
         seqs = [c.sequence for c in compounds]
         tg = None
@@ -100,24 +89,43 @@ class fold_compound:
                 for t, db in enumerate(targets[k]):
                     c._cache[("eval", db.replace("&", ""))] = int(out["eval_dcal"][k, t])
 
+    @staticmethod
+    def prefetch_constrained(compounds):
+        """One engine call for the constrained MFE folds (hc_add_from_db 'x' masks) of many compounds: the refolds of one
+        round of the pseudoknot overlay (sequence_utils.py:1181-1216) across all mutants of a Monte-Carlo sub-step."""
+        todo = [c for c in compounds if c._nopair is not None and ("mfe", bytes(c._nopair)) not in c._cache]
+        if not todo:
+            return
+        E = _eng
+        stride = max(c.length for c in todo)
+        mask = np.zeros((len(todo), stride), np.uint8)
+        for k, c in enumerate(todo):
+            mask[k, :c.length] = c._nopair
+        out = E.score_batch([c.sequence for c in todo], None, nopair=mask, want=E.WANT_MFE | E.WANT_SS)
+        for k, c in enumerate(todo):
+            c._cache[("mfe", bytes(c._nopair))] = (out["mfe_ss"][k], int(out["mfe_dcal"][k]))
+
     # ---- single-object API ---------------------------------------------------------------------
     def _run(self, want, targets=None):
         mask = None
         if self._nopair is not None:
             mask = np.asarray(self._nopair, np.uint8)[None, :]
-        return _backend.score_batch([self.sequence], targets, nopair=mask, want=want)
+        return _eng.score_batch([self.sequence], targets, nopair=mask, want=want)
 
     def _mfe(self):
         key = "mfe" if self._nopair is None else ("mfe", bytes(self._nopair))
         if key not in self._cache:
-            E = _backend
+            E = _eng
             out = self._run(E.WANT_MFE | E.WANT_SS)
             self._cache[key] = (out["mfe_ss"][0], int(out["mfe_dcal"][0]))
         return self._cache[key]
 
     def _pf(self):
         if "pf" not in self._cache:
-            out = self._run(_backend.WANT_PF)
+            if self._nopair is not None and any(self._nopair):
+                # the partition-function kernels ignore hard constraints; DesiRNA always calls pf() before hc_add_from_db
+                raise RuntimeError("fold_compound.pf() after hc_add_from_db(): constrained partition functions are not supported")
+            out = self._run(_eng.WANT_PF)
             self._cache["pf"] = [float(x) for x in out["pf"][0]]
         return self._cache["pf"]
 
@@ -143,7 +151,7 @@ class fold_compound:
         db = structure.replace("&", "")
         key = ("eval", db)
         if key not in self._cache:
-            out = self._run(_backend.WANT_EVAL, targets=[[db]])
+            out = self._run(_eng.WANT_EVAL, targets=[[db]])
             self._cache[key] = int(out["eval_dcal"][0, 0])
         return f32(self._cache[key] / 100.0)
 
@@ -162,7 +170,7 @@ class fold_compound:
 
     def bpp(self):
         if "bpp" not in self._cache:
-            E = _backend
+            E = _eng
             out = self._run(E.WANT_MFE | E.WANT_PF | E.WANT_BPP)
             self._cache["bpp"] = out["bpp"][0]
             self._cache["pf"] = [float(x) for x in out["pf"][0]]
@@ -173,7 +181,7 @@ class fold_compound:
         db = structure.replace("&", "")
         key = ("defect", db)
         if key not in self._cache:
-            E = _backend
+            E = _eng
             out = self._run(E.WANT_MFE | E.WANT_PF | E.WANT_DEFECT, targets=[[db]])
             self._cache[key] = float(out["defect"][0])
         return self._cache[key]
@@ -184,7 +192,16 @@ class fold_compound:
         if "&" in self.sequence:
             raise NotImplementedError("subopt_cb on two-strand compounds is not part of the accelerated path")
         nopair = np.asarray(self._nopair, np.uint8) if self._nopair is not None and any(self._nopair) else None
-        found, _ = _backend.subopt(self.sequence, int(delta), nopair)
+        # the walk stops at max_out structures in search order, not energy order: a truncated band is not a band.  Grow the
+        # buffer until the whole band fits (ViennaRNA enumerates it completely, whatever its size).
+        cap = 4096
+        while True:
+            found, truncated = _eng.subopt(self.sequence, int(delta), nopair, max_out=cap)
+            if not truncated:
+                break
+            if cap >= (1 << 22):
+                raise RuntimeError("subopt_cb: more than %d structures within %d dcal/mol of the MFE" % (cap, int(delta)))
+            cap *= 8
         for structure, e in found:
             cb(structure, f32(e / 100.0), data)
         cb(None, 0.0, data)

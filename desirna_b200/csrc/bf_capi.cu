@@ -564,7 +564,9 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   if (!g.inited) return fail(BF_ERR_NOT_INIT, "bf_init has not been called");
   if (!g.have_params) return fail(BF_ERR_NOT_INIT, "no energy parameters loaded");
   if (!c || !handle) return fail(BF_ERR_ARG, "null argument");
-  if (c->n_jobs <= 0 || c->replicas <= 0 || c->stride <= 0 || c->stride > 4000) return fail(BF_ERR_ARG, "bf_design_create: bad shape");
+  if (c->n_jobs <= 0 || c->replicas <= 0 || c->stride <= 0 || c->stride > 2000) return fail(BF_ERR_ARG, "bf_design_create: bad shape (stride must be in 1..2000)");
+  for (int k = 0; k < c->n_terms && k < 8; k++)
+    if (c->term[k] < 0 || c->term[k] > kTermEdef) return fail(BF_ERR_ARG, "bf_design_create: unknown scoring term");
   if (!c->target || !c->len || !c->allowed || !c->init_seq || !c->temps || !c->tm_prob) return fail(BF_ERR_ARG, "bf_design_create: null buffer");
   if (c->n_terms <= 0 || c->n_terms > 8 || c->re_attempt <= 0) return fail(BF_ERR_ARG, "bf_design_create: bad scoring terms / re_attempt");
   const int J = c->n_jobs, R = c->replicas, S = c->stride;
@@ -640,7 +642,7 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   C.metropolis_L = c->metropolis_L; C.point_mutations = c->point_mutations; C.acgu = c->acgu;
   for (int k = 0; k < 4; k++) C.nt_weight[k] = c->nt_weight[k];
   C.oligo = c->oligo;
-  if (two && (h->want & BF_WANT_DEFECT)) return bail(cudaErrorInvalidValue, "bf_design_create: the Edef term needs single-strand jobs");
+  if (two && (h->want & BF_WANT_DEFECT)) { h->destroy(); delete h; return fail(BF_ERR_ARG, "bf_design_create: the Edef term needs single-strand jobs"); }
   h->re_attempt = c->re_attempt;
   D.tgt = tgt; D.tpt = d_tpt; D.allowed = allowed; D.len = len; D.len_a = d_len_a; D.same_halves = d_same; D.avail = d_avail; D.n_avail = d_navail; D.temps = temps; D.tm_prob = tm_prob;
   D.rowmap = h->d_rowmap;

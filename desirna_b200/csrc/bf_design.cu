@@ -207,6 +207,12 @@ __global__ void __launch_bounds__(kWPB * 32) bf_k_design_propose(BfDesignDev D, 
           const char ca = mut[A + in_b], cb = mut[in_a];
           mut[in_b] = ca;
           mut[A + in_a] = cb;
+        } else if (hi < A) {   // both letters inside strand A: mirrored onto strand B (deliberate; see the host mirror's propose_mutation)
+          mut[A + lo] = mut[lo];
+          mut[A + hi] = mut[hi];
+        } else {
+          mut[lo - A] = mut[lo];
+          mut[hi - A] = mut[hi];
         }
       }
     }

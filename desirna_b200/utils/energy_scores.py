@@ -43,6 +43,33 @@ def get_pk_struct(seq, ss_nopk, fc):
     return ss_pk
 
 
+def get_pk_structs(structures, compounds):
+    """get_pk_struct for all mutants of a sub-step at once: every round is ONE engine call (the constrained refolds of the
+    sequences whose previous round still found pairs).  Same result, sequence by sequence, as get_pk_struct."""
+    ss_pk = list(structures)
+    live = list(range(len(ss_pk)))
+    for opn, cls in _PK_BRACKETS:
+        if not live:
+            break
+        for k in live:
+            compounds[k].hc_add_from_db("".join("." if ch == "." else "x" for ch in ss_pk[k]))
+        RNA.fold_compound.prefetch_constrained([compounds[k] for k in live])
+        still = []
+        for k in live:
+            mfe_structure, _ = compounds[k].mfe()
+            chars = list(ss_pk[k])
+            for i, ch in enumerate(mfe_structure):
+                if ch == "(":
+                    chars[i] = opn
+                elif ch == ")":
+                    chars[i] = cls
+            ss_pk[k] = "".join(chars)
+            if "(" in mfe_structure:
+                still.append(k)
+        live = still
+    return ss_pk
+
+
 def get_mfe_e_ss(seq, sim_options):
     """(Epf, MFE structure, fold compound) -- energy_scores.py:128-159.  Single chain: ensemble free energy from
     fc.pf(), structure from fc.mfe() (+ pseudoknot overlay when sim_options.pks == "on"); two chains: structure from
@@ -141,18 +168,18 @@ def score_sequences(seqs, input_file, sim_options):
     targets = [t.replace("&", "") for t in targets]
     RNA.fold_compound.prefetch(compounds, [targets] * len(seqs))
     dimer = sim_options.oligo_state in {"homodimer", "heterodimer"}
-    out = []
+    folded = []
     for seq, fc in zip(seqs, compounds):
         if dimer:
             a = len(seq.split("&")[0])
             sd = fc.mfe_dimer()[0]
-            energy, structure = fc.pf_dimer()[-1], sd[:a] + "&" + sd[a:]
+            folded.append((fc.pf_dimer()[-1], sd[:a] + "&" + sd[a:]))
         else:
-            energy, structure = fc.pf()[1], fc.mfe()[0]
-            if sim_options.pks == "on":
-                structure = get_pk_struct(seq, structure, fc)
-        out.append(_score_with_compound(seq, input_file, sim_options, energy, structure, fc))
-    return out
+            folded.append((fc.pf()[1], fc.mfe()[0]))
+    structures = [f[1] for f in folded]
+    if not dimer and sim_options.pks == "on":
+        structures = get_pk_structs(structures, compounds)
+    return [_score_with_compound(seq, input_file, sim_options, f[0], ss, fc) for seq, f, ss, fc in zip(seqs, folded, structures, compounds)]
 
 
 class ScoreSeq:

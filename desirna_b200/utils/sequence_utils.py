@@ -254,8 +254,17 @@ def propose_mutation(sequence_obj, nt_list, sim_options, input_file):
     if half_a != half_b:
         if partner is not None:
             lo, hi = sorted((pos, partner))
-            in_a, in_b = lo, hi - len(old_a) - 1        # the reference reads the pair as (strand A, strand B)
-            new_a, new_b = (new_a[:in_b] + new_b[in_b] + new_a[in_b + 1:], new_b[:in_a] + new_a[in_a] + new_b[in_a + 1:])
+            A = len(old_a)
+            if lo < A < hi:
+                in_a, in_b = lo, hi - A - 1        # the reference reads the pair as (strand A, strand B)
+                new_a, new_b = (new_a[:in_b] + new_b[in_b] + new_a[in_b + 1:], new_b[:in_a] + new_a[in_a] + new_b[in_a + 1:])
+            elif hi < A:
+                # Both letters inside strand A.  The reference's index arithmetic goes negative here (Python wrap-around, strings
+                # of the wrong length for a pair ending at A-1); the deliberate choice, on host and device alike: the two new
+                # letters are mirrored onto the same positions of strand B, which is what keeps the strands identical.
+                new_b = "".join(new_a[k] if k in (lo, hi) else ch for k, ch in enumerate(new_b))
+            else:
+                new_a = "".join(new_b[k] if k in (lo - A - 1, hi - A - 1) else ch for k, ch in enumerate(new_a))
         return new_a + "&" + new_b
     if new_a != old_a:
         return new_a + "&" + new_a

@@ -36,9 +36,13 @@ class InputFile:
 
 def make_input(name, sec_struct, seq_restr=None):
     """InputFile with the derived fields DesiRNA.py fills before the loop starts (DesiRNA.py:274-284)."""
-    inp = InputFile(name, sec_struct, seq_restr if seq_restr is not None else "N" * len(sec_struct))
+    if seq_restr is None:
+        seq_restr = "".join("&" if ch == "&" else "N" for ch in sec_struct)
+    inp = InputFile(name, sec_struct, seq_restr)
     if len(inp.seq_restr) != len(inp.sec_struct):
         raise ValueError("Secondary structure and sequence restraints are of different length. Check input file.")
+    if [i for i, ch in enumerate(inp.seq_restr) if ch == "&"] != [i for i, ch in enumerate(inp.sec_struct) if ch == "&"]:
+        raise ValueError("Strand breaks ('&') of the sequence restraints and of the secondary structure differ. Check input file.")
     inp.pairs = seq_utils.check_dot_bracket(inp.sec_struct)
     inp.set_target_pairs_tupl()
     return inp

@@ -1,5 +1,8 @@
 import os
+import re
 import sys
+
+import numpy as np
 
 import pytest
 
@@ -30,6 +33,37 @@ def engine():
     eng.params_builtin(1999)
     return eng
 
+
+def synthetic_t2004_shaped_par(path):
+    """The vendored Turner-1999 file reshaped the way ViennaRNA's rna_turner2004.par differs from it IN STRUCTURE: non-empty
+    Triloops and Hexaloops sections, a negative MLintern with a large MLclosing, ninio 60, mismatch_interior_1n and
+    mismatch_interior_23 tables that differ from mismatch_interior, smaller dangles.  Values are synthetic (the real file is not
+    in the reference tree, DesiRNA.py:455-456 uses ViennaRNA's built-ins): the point is that every table and code path the 2004
+    set touches and the 1999 set does not is exercised identically by the engine and by the oracle."""
+    rng = np.random.default_rng(2004)
+    out, section = [], None
+    for line in open(PAR1999).read().split("\n"):
+        if line.startswith("# "):
+            section = line[2:].strip()
+            out.append(line)
+            if section == "Triloops":
+                out += ["CAACG 680 2370", "GUUAC 690 1080", "GAAAC 150 -400", "UGAAA 90 0"]
+            if section == "Hexaloops":
+                out += ["ACAGUACU 280 -1680", "ACAGUGAU 360 -1140", "ACAGUGCU 290 -1280", "ACAGUGUU 180 -1540", "GAAAAAAC 120 0"]
+            continue
+        if section == "ML_params" and line.strip():
+            line = "0 0 930 3000 -90 -220"
+        elif section == "NINIO" and line.strip():
+            line = "60 320 300"
+        elif section == "Misc" and line.strip():
+            line = "410 360 50 370 107.856000 0"
+        elif section in ("mismatch_interior_1n", "mismatch_interior_23", "dangle5", "dangle3") and line.strip() and not line.lstrip().startswith("/*"):
+            toks = line.split()
+            if all(re.fullmatch(r"-?\d+|INF", t) for t in toks):
+                line = " ".join(t if t == "INF" else str(int(t) + int(rng.integers(-3, 4)) * 10) for t in toks)
+        out.append(line)
+    with open(path, "w") as f:
+        f.write("\n".join(out))
 
 def load_golden(tag):
     import json

@@ -1,12 +1,26 @@
 """TEST INFRASTRUCTURE: an engine-shaped checker backend built on the CPU oracle.
 
-desirna_b200.RNA.set_backend(OracleBackend(...)) lets the CPU test-suite exercise the host-side mirror
+oracle_backend.install(OracleBackend(...)) swaps the module attribute desirna_b200.RNA._eng (the product has no backend
+switch of its own) so that the CPU test-suite can exercise the host-side mirror
 (score arithmetic, similarity scores, pseudoknot overlay, batching, replica loop) without a GPU, and gives
 the GPU tests a second implementation of the same score_batch() contract to compare with.  Never imported
 by the product package."""
 import numpy as np
 
 from oracle.pyoracle import Oracle
+
+
+def current():
+    from desirna_b200 import RNA
+    return RNA._eng
+
+
+def install(backend):
+    """test seam: replace the engine module the RNA shim calls; returns the previous one"""
+    from desirna_b200 import RNA
+    old = RNA._eng
+    RNA._eng = backend
+    return old
 
 
 class OracleBackend:

@@ -237,6 +237,24 @@ def test_homodimer_moves_keep_the_strands_in_step():
         m = su.propose_mutation(cur2, nts2, o, inp2)
         a, b = m.split("&")
         assert len(a) == len(b) == 8 and set(m) <= set("ACGU&")
+    # different halves with a helix INSIDE each strand: the reference's index arithmetic wraps around there; here the two new
+    # letters are mirrored onto the other strand (documented choice, same on the device): strands of the right length, the
+    # mutated pair identical in both strands
+    inp3 = sio.make_input("homo3", "((((....))))..((((&))))..((((....))))", "NNNNNNNNNNNNNNNNNN&NNNNNNNNNNNNNNNNNN")
+    nts3 = su.get_nt_list(inp3)
+    s3 = "GGGGAAAACCCCAAGGGG"
+    cur3 = SimpleNamespace(sequence=s3 + "&" + s3, mfe_ss=inp3.sec_struct, temp_shelf=o.rep_temps_shelfs[1])
+    intra = 0
+    for _ in range(400):
+        m = su.propose_mutation(cur3, nts3, o, inp3)
+        a, b = m.split("&")
+        assert len(a) == len(b) == 18 and set(m) <= set("ACGU&")
+        da = [k for k in range(18) if a[k] != s3[k]]
+        db = [k for k in range(18) if b[k] != s3[k]]
+        if any(k in (0, 1, 2, 3, 8, 9, 10, 11) for k in da) or any(k in (6, 7, 8, 9, 14, 15, 16, 17) for k in db):   # a pair inside one strand
+            intra += 1
+            assert da == db and all(a[k] == b[k] for k in da), m
+    assert intra > 50
 
 
 class _FakeLoop:

@@ -295,9 +295,10 @@ def test_trajectory_and_result_files(engine, tmp_path):
 
 HOMO_DIFF = ("((((....((((.....&))))....)))).....", "NNNNNNNNNNNNNNNNN&NNNNNNNNNNNNNNNNN")    # example_files/inputs/Homodimer_design_input.txt
 HOMO_SAME = ("((((....))))..&((((....))))..", "NNNNNNNNNNNNNN&NNNNNNNNNNNNNN")
+HOMO_INTRA = ("((((....))))..((((&))))..((((....))))", "NNNNNNNNNNNNNNNNNN&NNNNNNNNNNNNNNNNNN")    # helices inside each strand, halves differ
 
 
-@pytest.mark.parametrize("case", [HOMO_DIFF, HOMO_SAME])
+@pytest.mark.parametrize("case", [HOMO_DIFF, HOMO_SAME, HOMO_INTRA])
 def test_homodimer_jobs_on_the_device(engine, case):
     """-d on (utils/sequence_utils.py:1102-1128, utils/energy_scores.py:120-125): mirrored moves in distribution against the host
     mirror, score records (incl. the dimer / monomer fraction term) against the host scoring"""

@@ -7,6 +7,8 @@ check is exhaustive enumeration under the validated loop model (oracle) for shor
 import numpy as np
 import pytest
 
+import oracle_backend
+
 pytestmark = pytest.mark.gpu
 
 
@@ -59,7 +61,7 @@ def test_reference_helper_through_the_shim(engine, oracle):
     import struct
     from desirna_b200 import RNA
     from desirna_b200.utils import energy_scores as es
-    RNA.set_backend(engine)
+    oracle_backend.install(engine)
     s = "GGGAAAUCCCGCGAAAGC"
     fc = RNA.fold_compound(s)
     ss2, e2 = es.get_first_suboptimal_structure_and_energy(s, fc, 1)
@@ -67,3 +69,30 @@ def test_reference_helper_through_the_shim(engine, oracle):
     band = oracle.enumerate_band(s, mfe + 5000)
     assert e2 == struct.unpack("f", struct.pack("f", band[1][0] / 100.0))[0]
     assert oracle.eval(s, ss2) == band[1][0]
+
+
+def test_subopt_cb_is_complete_when_the_band_overflows_the_first_buffer(engine):
+    """The host walk stops at max_out structures in SEARCH order; the shim must not hand a truncated band to
+    get_first_suboptimal_structure_and_energy (the k-th best of a truncated band is not the k-th best).  A flat landscape:
+    grow delta until 4096 structures no longer hold the band, then the shim's callback count must equal the full band."""
+    from desirna_b200 import RNA
+    oracle_backend.install(engine)
+    rng = np.random.default_rng(4321)
+    s = "".join("ACGU"[x] for x in rng.integers(0, 4, 160))
+    delta = 100
+    while True:
+        part, trunc = engine.subopt(s, delta, max_out=4096)
+        if trunc:
+            break
+        delta += 100
+        assert delta < 3000
+    full, trunc_full = engine.subopt(s, delta, max_out=1 << 18)
+    assert not trunc_full and len(full) > 4096
+    got = []
+    RNA.fold_compound(s).subopt_cb(delta, lambda ss, e, data: got.append((ss, e)), None)
+    assert got[-1][0] is None
+    got = got[:-1]
+    assert len(got) == len(full) and len({g[0] for g in got}) == len(got)
+    mfe = full[0][1]
+    assert min(e for _, e in full) == mfe and max(e for _, e in full) <= mfe + delta
+    assert sorted(e for _, e in full)[:10] == [e for _, e in full[:10]]

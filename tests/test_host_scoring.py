@@ -5,6 +5,8 @@ import types
 
 import pytest
 
+import oracle_backend
+
 from conftest import PAR1999, load_golden
 
 
@@ -12,11 +14,11 @@ from conftest import PAR1999, load_golden
 def rna_on_oracle(oracle):
     from desirna_b200 import RNA
     from oracle_backend import OracleBackend
-    old = RNA.get_backend()
+    old = oracle_backend.current()
     be = OracleBackend(PAR1999)
-    RNA.set_backend(be)
+    oracle_backend.install(be)
     yield be
-    RNA.set_backend(old)
+    oracle_backend.install(old)
 
 
 def options(**kw):

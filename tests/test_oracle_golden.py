@@ -123,3 +123,46 @@ def test_relaxation_counts_match_closed_form(oracle):
     # bases can pair too (another factor 6/16).  Split-point terms agree up to the range conventions.
     assert abs(tot[0] - bench.P_PAIR * r_int) / (bench.P_PAIR * r_int) < 0.15
     assert abs((tot[1] + tot[2] + tot[3]) - (r_mfe - r_int)) / (r_mfe - r_int) < 0.3
+
+
+def test_synthetic_t2004_shaped_par_both_loaders_and_enumeration(tmp_path):
+    """Turner 2004 is not in the reference tree (DesiRNA.py:455-456 relies on ViennaRNA's built-ins).  What CAN be pinned without
+    it: the code paths only a 2004-shaped table set reaches (tabulated tri- and hexaloops, MLintern < 0, mismatch_interior_1n /
+    _23 different from mismatch_interior) -- the product's loader against the oracle's on every table, and the oracle's DP
+    (MFE, inside, outside) against exhaustive enumeration through its independent eval path."""
+    import itertools
+    from conftest import synthetic_t2004_shaped_par
+    from desirna_b200 import engine
+    from oracle.pyoracle import Oracle
+    p = str(tmp_path / "syn2004.par")
+    synthetic_t2004_shaped_par(p)
+    O = Oracle(p)
+    try:
+        engine.params_load(p)   # host-side parse works without a GPU
+        g = engine.params_get
+        assert (g("MLbase"), g("MLclosing"), g("MLintern"), g("ninio_m"), g("ninio_max")) == (0, 930, -90, 60, 300)
+        assert (g("n_tri"), g("n_tetra"), g("n_hexa")) == (4, 30, 5)
+        differs = 0
+        for name, dims in (("stack", (8, 8)), ("mmH", (8, 5, 5)), ("mmI", (8, 5, 5)), ("mm1nI", (8, 5, 5)), ("mm23I", (8, 5, 5)),
+                           ("mmM", (8, 5, 5)), ("mmE", (8, 5, 5)), ("dangle5", (8, 5)), ("dangle3", (8, 5)), ("hairpin", (31,)),
+                           ("bulge", (31,)), ("interior", (31,))):
+            for idx in itertools.product(*[range(1 if (d == 8 and len(dims) > 1) else 0, d) for d in dims]):
+                assert g(name, *idx) == O.get(name, *idx), (name, idx)
+                if name == "mm1nI" and g(name, *idx) != g("mmI", *idx):
+                    differs += 1
+        assert differs > 20
+    finally:
+        engine.params_builtin(1999)
+    rng = np.random.default_rng(2004)
+    seqs = ["GGGGGAAACCCCC", "GGGGCCAACGGCCCC", "GGGCACAGUGAUGCCC", "GGCGAAAAAACGCC", "GCGUUACGCAAAGCGAAAC"]
+    seqs += ["".join("ACGU"[x] for x in rng.integers(0, 4, n)) for n in (12, 15, 17, 18, 18)]
+    for s in seqs:
+        F, P, e1, e2 = O.enumerate(s, bpp=True)
+        pf, bpp = O.pf(s, bpp=True)
+        assert abs(pf[4] - F) < 1e-9 * max(1.0, abs(F)), s
+        assert np.abs(bpp - P).max() < 1e-9, s
+        e, ss = O.mfe(s)
+        assert e == e1 and O.eval(s, ss) == e, s
+    # the tabulated loops are really used: the triloop bonus of GAAAC (-400 total 150) beats the generic 3-loop
+    assert O.eval("GGGGGAAACCCCC", "(((((...)))))") == O.eval("GGGGGAUACCCCC", "(((((...)))))") - 570 + 150
+    assert O.mfe("GGGGGAAACCCCC")[1] == "(((((...)))))"

@@ -8,6 +8,8 @@ import types
 
 import pytest
 
+import oracle_backend
+
 from conftest import PAR1999, ROOT, load_golden
 
 TARGET = "((((((.((((((((....))))).)).).))))))"
@@ -46,7 +48,7 @@ def setup(R):
     from desirna_b200 import RNA
     from desirna_b200.utils import energy_scores as es
     from oracle_backend import OracleBackend
-    RNA.set_backend(OracleBackend(PAR1999))
+    oracle_backend.install(OracleBackend(PAR1999))
     opt = types.SimpleNamespace(oligo_state="none", pks="off", scoring_f=[("Ed-Epf", 1.0)], subopt="off", motifs={}, RE_attempt=6, L=504.12, replicas=R)
     inp = types.SimpleNamespace(sec_struct=TARGET, alt_sec_struct=None, alt_sec_structs=None)
     rows = load_golden("G1")[:R]
@@ -76,11 +78,11 @@ def reference_order(objs, opt, inp):
 def test_lockstep_equals_sequential():
     from desirna_b200 import RNA
     from desirna_b200.utils import replica_exchange_monte_carlo as remc
-    old = RNA.get_backend()
+    old = oracle_backend.current()
     try:
         opt, inp, objs = setup(5)
         want, wstats = reference_order(objs, opt, inp)
-        be = RNA.get_backend()
+        be = oracle_backend.current()
         calls0 = be.calls
         random.seed(2137)
         got, st = remc.mutate_sequence_re(objs, None, Stats(), opt, inp, mutate=toy_mutate)
@@ -90,12 +92,12 @@ def test_lockstep_equals_sequential():
         assert (st.acc_mc_step, st.acc_mc_better_e, st.rej_mc_step) == (wstats.acc_mc_step, wstats.acc_mc_better_e, wstats.rej_mc_step)
         assert st.step == opt.RE_attempt
     finally:
-        RNA.set_backend(old)
+        oracle_backend.install(old)
 
 
 def test_replica_exchange_swaps_neighbours():
     from desirna_b200.utils import replica_exchange_monte_carlo as remc
-    old = __import__("desirna_b200").RNA.get_backend()
+    old = oracle_backend.current()
     try:
         opt, inp, objs = setup(5)
         st = Stats(); st.global_step = 1          # odd step: pairs (0,1), (2,3)
@@ -107,7 +109,7 @@ def test_replica_exchange_swaps_neighbours():
         assert (out[0].temp_shelf, out[1].temp_shelf) == (t1, t0)
         assert st.acc_re_step + st.rej_re_step == 2
     finally:
-        __import__("desirna_b200").RNA.set_backend(old)
+        oracle_backend.install(old)
 
 
 WORKER = r'''
@@ -131,7 +133,7 @@ def test_two_ranks_gloo_match_single_process(tmp_path):
     import pickle
     from desirna_b200 import RNA
     from desirna_b200.utils import replica_exchange_monte_carlo as remc
-    old = RNA.get_backend()
+    old = oracle_backend.current()
     try:
         opt, inp, objs = setup(5)
         random.seed(2137)
@@ -139,7 +141,7 @@ def test_two_ranks_gloo_match_single_process(tmp_path):
         st.global_step = 1
         want, st = remc.replica_exchange(want, st, opt)
     finally:
-        RNA.set_backend(old)
+        oracle_backend.install(old)
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
     port = str(29500 + os.getpid() % 2000)
@@ -168,7 +170,7 @@ def test_lockstep_with_the_mirrored_move_generator():
     from desirna_b200.utils import replica_exchange_monte_carlo as remc
     from desirna_b200.utils import sequence_utils as su
     from desirna_b200.utils import stats_inputs_outputs as sio
-    old = RNA.get_backend()
+    old = oracle_backend.current()
     try:
         opt, _, objs = setup(4)
         inp = sio.make_input("t", TARGET)
@@ -188,4 +190,4 @@ def test_lockstep_with_the_mirrored_move_generator():
             for a, b in inp.pairs:
                 assert (o.sequence[a], o.sequence[b]) in {("A", "U"), ("U", "A"), ("G", "C"), ("C", "G"), ("G", "U"), ("U", "G")}
     finally:
-        RNA.set_backend(old)
+        oracle_backend.install(old)
