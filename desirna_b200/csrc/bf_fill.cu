@@ -1308,7 +1308,11 @@ int bf_fill_pf_mode(int nmax) {
   if (nmax < 1 || nmax > 2000) return 0;
   return pf_cfg(nmax).pl + 1;
 }
+// third-generation kernels (bf_fill3.cu) take every batch they cover, except the small batches of the 16-warp variants
+static bool use_fill3_mfe(int nmax, int B) { return !want_wide(B) && bf_fill3_mfe_ok(nmax); }
+
 size_t bf_mfe_ws_slot(int nmax, int B) {  // ints of per-CTA HBM workspace: [rings when they are not on chip][tile-major fML mirror when blocked]
+  if (use_fill3_mfe(nmax, B)) return bf_fill3_mfe_ws_slot(nmax);
   const FillCfg c = mfe_cfg(nmax, B);
   if (c.pl < 0) return 0;
   size_t o = 0;
@@ -1406,13 +1410,15 @@ static cudaError_t mfe_fill_dispatch(const BfParams *dP, const BfBatchDev &b, in
   return mfe_fill_pl<8>(c.pl, dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
 }
 cudaError_t bf_mfe_fill_grid(const BfBatchDev &b, int sms, int *grid) {
+  if (use_fill3_mfe(b.stride, b.B)) return bf_fill3_mfe_grid(b, sms, grid);
   return mfe_fill_dispatch(nullptr, b, nullptr, nullptr, nullptr, sms, grid, false, nullptr, nullptr);
 }
 // true: the fill kernel chosen for this batch also runs the exterior recursion and leaves f5 (B x (stride + 4) ints) for bf_k_trace
-bool bf_mfe_fill_does_ext(int nmax, int B) { return mfe_cfg(nmax, B).nw == 16; }
+bool bf_mfe_fill_does_ext(int nmax, int B) { return !use_fill3_mfe(nmax, B) && mfe_cfg(nmax, B).nw == 16; }
 
 cudaError_t bf_launch_mfe_fill(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *work_counter,
                                cudaStream_t st, int *f5_out) {
+  if (use_fill3_mfe(b.stride, b.B)) return bf_launch_mfe_fill3(dP, b, ctri, ftri, ws, sms, work_counter, st);
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
   g_f5_out = f5_out;

@@ -1,0 +1,635 @@
+// bf_fill3.cu -- third generation of the single-strand fill kernels (sm_100a): flat tap tables for the interior loops.
+//
+// Same recurrences, same diagonal-major tables in HBM and the same one-barrier-per-diagonal schedule as bf_fill.cu (the path behind
+// fc.mfe() / fc.pf(), utils/energy_scores.py:150-151 in the reference; recurrences SURVEY.md A.4-A.6).  What changed is how a
+// diagonal's work is dealt to the lanes, because the round-1 kernels spent 27 thread-instructions per candidate where the candidate
+// itself needs two (profiles/r01_s4_ncu_full.txt):
+//
+//  * Interior loops, the bulk of the work.  The decomposable candidates of a cell (i,j) on diagonal d are
+//        ring_kind[(d-2-s) mod 32][i+1+u1] + pen_kind(s,u1)              (u1 + u2 = s <= 30; 375 generic, 54 1xn, 58 bulge)
+//    i.e. the SAME 487 (row, column offset, penalty) "taps" for every cell, shifted by i.  One warp takes one pairable cell at a
+//    time and its LANES RUN OVER THE TAPS: every lane owns a fixed set of taps (18 "slots": 12 generic, 3 1xn, 3 bulge), keeps their
+//    ring offsets and penalties IN REGISTERS for the whole sequence, and a candidate costs exactly one LDS and one add-min
+//    (one LDS.64 and one DFMA in the partition function) with no address arithmetic, no penalty load and no idle lane; the warp's
+//    minimum / sum is one REDUX / five shuffles per cell.  Advancing to the next diagonal moves every tap one ring row down:
+//    two integer instructions per slot (add, wrap by unsigned min).
+//    - Taps are assigned to (slot, lane) on the host so that the 32 lanes of a slot hit 32 different banks: the bank of a tap is
+//      (u1 - s*c) mod 32 up to a per-cell constant, c = ring row stride mod 32 (mod 16 within each half-warp for the 8-byte
+//      partition-function rings).  The row stride is padded to a residue for which the greedy packing succeeds.
+//    - Slots are filled in order of loop size, and the short diagonals (d - 6 < 30) run only the leading slots they need.
+//    - Nothing is masked: the rings are reset to "no structure" (INF / 0) for every sequence and followed by one neutral row, so a
+//      tap that looks at a diagonal which does not exist yet reads a neutral element.
+//  * Per-cell constants (outer mismatch terms) are computed once per pairable cell when the diagonal's cell list is compacted
+//    (lanes = cells there) and travel in the list entry.
+//  * The fML / qm split keeps lanes = cells, all chunks of the diagonal in one thread so that the offset arithmetic (second-order
+//    increments of the packed-triangle offsets, no table look-up) is shared by up to four cells; the split points are dealt to
+//    the auxiliary warps, partial results meet in the combine step.
+//  * Warp specialisation inside a phase: warps [0, NWI) do the tap work; the other warps combine the previous diagonal, evaluate
+//    the nine non-decomposable interior candidates and the hairpin (lanes = cells), build the next cell list and do the split.
+//    All of it only reads diagonals <= d-2, so a phase still ends with a single barrier.
+#include "bf_kernels.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "bf_device.cuh"
+
+namespace {
+
+constexpr int kRing = 32;
+constexpr int kInfThr = BF_INF / 2;
+constexpr int kNSG = 12, kNS1 = 3, kNSB = 3, kNSlot = kNSG + kNS1 + kNSB + 1;   // + the slot of the nine special candidates
+
+__host__ __device__ __forceinline__ int tri_off(int n, int d) { return (d - 4) * n - (d * (d - 1) / 2 - 6); }
+__host__ __device__ __forceinline__ size_t tri_size(int n) { return n >= 5 ? (size_t)tri_off(n, n) : 0; }
+__device__ __forceinline__ int ptype_sp(const uint8_t *SP, int i, int j) { return bf_ptype_bases(SP[i], SP[j]); }
+
+// (u1, u2) of the nine non-decomposable interior candidates: stack, bulge-1 (2x), 1x1, 1x2, 2x1, 2x2, 2x3, 3x2
+__host__ __device__ __forceinline__ int special_u1(int k) { return (int)((0x322211100ull >> (4 * k)) & 15); }
+__host__ __device__ __forceinline__ int special_u2(int k) { return (int)((0x232121010ull >> (4 * k)) & 15); }
+
+// slots a diagonal needs, by its largest loop size smax = min(30, d - 6) (index smax + 1); stored behind the tap words
+struct TapMeta {
+  unsigned char ng[32], n1[32], nb[32];
+};
+
+// ---------------------------------------------------------------------------------------------
+// host: tap -> (slot, lane) assignment
+// ---------------------------------------------------------------------------------------------
+struct TapTable {
+  uint32_t tap[kNSlot][32];   // s | u1 << 8 | valid << 16
+  TapMeta meta;
+  bool ok = false;
+};
+
+// M = 32: 4-byte ring entries, one bank per entry; M = 16: 8-byte entries, conflicts counted within each half-warp
+TapTable build_taps(int c, int M) {
+  TapTable tt;
+  memset(&tt, 0, sizeof tt);
+  bool ok = true;
+  int first = 0;
+  for (int kind = 0; kind < 3; kind++) {
+    const int nslot = kind == 0 ? kNSG : kind == 1 ? kNS1 : kNSB;
+    std::vector<std::pair<int, int>> T;
+    if (kind == 0) { for (int s = 6; s <= 30; s++) for (int u1 = 2; u1 <= s - 2; u1++) T.push_back({s, u1}); }
+    else if (kind == 1) { for (int s = 4; s <= 30; s++) { T.push_back({s, 1}); T.push_back({s, s - 1}); } }
+    else { for (int s = 2; s <= 30; s++) { T.push_back({s, 0}); T.push_back({s, s}); } }
+    std::vector<std::vector<int>> lanes(nslot, std::vector<int>(32, -1));   // index into T
+    const int halves = M == 16 ? 2 : 1, per = 32 / halves;
+    std::vector<std::pair<int, int>> left;
+    for (int ti = 0; ti < (int)T.size(); ti++) {
+      const int b = (((T[ti].second - T[ti].first * c) % M) + M) % M;
+      bool placed = false;
+      for (int k = 0; k < nslot && !placed; k++)
+        for (int h = 0; h < halves && !placed; h++) {
+          int free_lane = -1;
+          bool clash = false;
+          for (int l = h * per; l < (h + 1) * per; l++) {
+            if (lanes[k][l] < 0) { if (free_lane < 0) free_lane = l; continue; }
+            const auto &o = T[lanes[k][l]];
+            if (((((o.second - o.first * c) % M) + M) % M) == b) clash = true;
+          }
+          if (!clash && free_lane >= 0) { lanes[k][free_lane] = ti; placed = true; }
+        }
+      if (!placed) left.push_back({ti, 0});
+    }
+    // what did not fit without a bank conflict goes wherever a lane is free (a two-way conflict on that slot)
+    for (auto &lf : left) {
+      bool placed = false;
+      for (int k = nslot - 1; k >= 0 && !placed; k--)
+        for (int l = 0; l < 32 && !placed; l++)
+          if (lanes[k][l] < 0) { lanes[k][l] = lf.first; placed = true; }
+      if (!placed) ok = false;
+    }
+    if (left.size() > 4) ok = false;
+    unsigned char *need = kind == 0 ? tt.meta.ng : kind == 1 ? tt.meta.n1 : tt.meta.nb;
+    for (int k = 0; k < nslot; k++) {
+      int mins = 99;
+      for (int l = 0; l < 32; l++) {
+        if (lanes[k][l] < 0) continue;
+        const auto &t = T[lanes[k][l]];
+        tt.tap[first + k][l] = (uint32_t)t.first | ((uint32_t)t.second << 8) | (1u << 16);
+        mins = std::min(mins, t.first);
+      }
+      for (int smax = -1; smax <= 30; smax++)
+        if (mins <= smax) need[smax + 1] = (unsigned char)(k + 1);   // slots 0..k are needed
+    }
+    first += nslot;
+  }
+  // last slot: the nine non-decomposable candidates read the bulge ring at (s, u1) = (u1 + u2, u1); the other lanes read a valid
+  // address and add the INF of the entry's padding
+  for (int l = 0; l < 32; l++) {
+    const int u1 = l < 9 ? special_u1(l) : 0, u2 = l < 9 ? special_u2(l) : 0;
+    tt.tap[kNSlot - 1][l] = (uint32_t)(u1 + u2) | ((uint32_t)u1 << 8) | (1u << 16);
+  }
+  tt.ok = ok;
+  return tt;
+}
+
+// smallest row stride >= want whose residue packs (cached per residue)
+struct TapCache {
+  TapTable t[2][32];
+  bool have[2][32] = {};
+  uint32_t *dev[2][32] = {};
+  std::mutex mu;
+};
+TapCache g_taps;
+
+const TapTable &taps_for(int rs, int M) {
+  const int w = M == 16 ? 1 : 0, c = rs % M;
+  if (!g_taps.have[w][c]) { g_taps.t[w][c] = build_taps(c, M); g_taps.have[w][c] = true; }
+  return g_taps.t[w][c];
+}
+int pick_rs(int nmax, int M) {
+  for (int rs = nmax + 2 > 40 ? nmax + 2 : 40;; rs++)   // column offsets reach 31: keep them inside one row
+    if (taps_for(rs, M).ok) return rs;
+}
+cudaError_t taps_device(int rs, int M, const uint32_t **out) {
+  const int w = M == 16 ? 1 : 0, c = rs % M;
+  std::lock_guard<std::mutex> lk(g_taps.mu);
+  const TapTable &t = taps_for(rs, M);
+  if (!g_taps.dev[w][c]) {
+    // device image: the tap words, then the slots-needed table (TapMeta)
+    cudaError_t e = cudaMalloc(&g_taps.dev[w][c], sizeof t.tap + sizeof t.meta);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpy(g_taps.dev[w][c], t.tap, sizeof t.tap, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpy(reinterpret_cast<unsigned char *>(g_taps.dev[w][c]) + sizeof t.tap, &t.meta, sizeof t.meta, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+  }
+  *out = g_taps.dev[w][c];
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-cell constants: everything that depends on the sequence but not on the DP tables.  A pre-pass (all warps, lanes = cells,
+// no barrier between diagonals) writes one entry per PAIRABLE cell, compacted per diagonal, into the CTA's HBM workspace (L2-
+// resident); the diagonal loop then contains no energy-table look-up at all.
+//   word 0: i      1: mismatchI(outer pair)      2: mismatch1nI(outer pair)     3: hairpin energy
+//        4: MLclosing + MLstem(closing pair seen from inside)
+//        5: mismatchI(as inner pair)   6: mismatch1nI(as inner pair)   7: terminalAU(pair)   8: MLstem(stem in a multiloop), INF at
+//           the sequence ends -- words 5..8 are what lanes 0..3 add to c(i,j) for the three ring rows and the fML candidate
+//    9..17: the nine non-decomposable interior candidates (stack, bulge-1, 1x1, 1x2, 2x1, 2x2, 2x3, 3x2): loop energy minus
+//           terminalAU(inner pair) -- lanes 0..8 add them to nine more taps on the bulge ring      18, 19: INF (the idle lanes)
+// ---------------------------------------------------------------------------------------------
+constexpr int kEntWords = 20;
+constexpr bool kPrepassInPhases = false;
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory plan of the MFE fill
+// ---------------------------------------------------------------------------------------------
+struct Mfe3Plan {
+  size_t o_S, o_SP, o_np, o_ring, o_dml, o_fm, o_stg, o_tmpe, o_ps, o_cl, o_pp, total;
+};
+__host__ __device__ inline Mfe3Plan mfe3_plan(int nmax, int rs, int nw, int nwa, bool fms) {
+  Mfe3Plan p;
+  size_t o = 0;
+  p.o_ring = o; o += ((size_t)3 * kRing * rs + rs) * sizeof(int);   // three rings + one neutral row
+  p.o_dml = o; o += (size_t)4 * rs * sizeof(int);
+  p.o_fm = o; o += fms ? (tri_size(nmax) + 4) * sizeof(int) : 0;
+  p.o_stg = o; o += (size_t)2 * 3 * rs * sizeof(int);               // newest ring row, staged by the tap warps (double-buffered)
+  p.o_tmpe = o; o += (size_t)2 * rs * sizeof(int);                  // c + MLstem of the newest diagonal
+  p.o_ps = o; o += (size_t)2 * nwa * rs * sizeof(int);
+  // per-sequence state exists twice: the auxiliary warps prepare the next sequence while the current one is folded
+  p.o_np = o; o += (size_t)2 * ((nmax + 4) / 4 * 4) * sizeof(unsigned short);
+  p.o_S = o; o += (size_t)2 * ((nmax + 2 + 15) / 16 * 16);
+  p.o_SP = o; o += (size_t)2 * ((nmax + 2 + 15) / 16 * 16);
+  // per tap warp: the entries of its cells of the current diagonal (copied from L2 one phase ahead)
+  o = (o + 15) / 16 * 16;
+  p.o_cl = o; o += (size_t)(rs + nw) * kEntWords * sizeof(int);
+  p.o_pp = o; o += (size_t)nwa * ((nmax + 7) / 8 * 8) * sizeof(unsigned short);   // pre-pass: pairable cells of one diagonal, per aux warp
+  p.total = (o + 15) / 16 * 16;
+  return p;
+}
+
+__device__ __forceinline__ int lds_s32(unsigned addr) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// =====================================================================================================
+//                                           MFE fill
+// =====================================================================================================
+// Phase d of the diagonal loop (one barrier per phase):
+//   tap warps [0, NWI):  every pairable cell of diagonal d -- 487 decomposable interior candidates + 9 special ones (taps), hairpin,
+//                        multiloop closing (split minima of diagonal d-2) -> c(i,j); written to the HBM table, to the staging row of
+//                        the rings and, with its multiloop-stem term, to TMPE
+//   aux warps [NWI, NW): diagonal d-1: staging row -> rings, fML (needs c of d-1, the split minima of d-1 and fML of d-2);
+//                        then their share of the split points of diagonal d
+// Ring row d must not be written while phase d still reads row d-32 (same slot): hence the staging row.
+template <int NW, int NWI, bool FMS>
+__global__ void __launch_bounds__(NW * 32, NW <= 8 ? 3 : 2) bf_k_mfe_fill3(const BfParams *__restrict__ P, BfBatchDev b, int *ctri, int *ftri, size_t tri_slot,
+                                                          int *ent_ws, size_t ent_slot, const uint32_t *__restrict__ taps, int RS,
+                                                          int *work_counter, int dbg) {
+  constexpr int NWA = NW - NWI;
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ int s_seq;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(BF_FULL, tid >> 5, 0);
+  const int nmax = b.stride;
+  const Mfe3Plan pl = mfe3_plan(nmax, RS, NW, NWA, FMS);
+  const int seq_pad = (nmax + 2 + 15) / 16 * 16, np_pad = (nmax + 4) / 4 * 4;
+  int *RG = reinterpret_cast<int *>(dyn + pl.o_ring);
+  int *CG = RG, *C1 = RG + kRing * RS, *CB = RG + 2 * kRing * RS;
+  int *DML = reinterpret_cast<int *>(dyn + pl.o_dml);
+  int *fms = reinterpret_cast<int *>(dyn + pl.o_fm);
+  int *STG = reinterpret_cast<int *>(dyn + pl.o_stg);
+  int *TMPE = reinterpret_cast<int *>(dyn + pl.o_tmpe);
+  int *PS = reinterpret_cast<int *>(dyn + pl.o_ps);
+  const BfSmallI &T = P->si;
+  const bool tapw = warp < NWI;
+  const unsigned char *meta = reinterpret_cast<const unsigned char *>(taps + kNSlot * 32);   // TapMeta: ng[32], n1[32], nb[32]
+  int *ent_base = ent_ws + (size_t)blockIdx.x * ent_slot;   // two halves: current and next sequence
+  const int tauE = T.TerminalAU;
+
+  // this lane's taps: penalties for the whole launch, ring offsets (bytes) re-based for every sequence
+  int pen[kNSlot], xk[kNSlot];
+#pragma unroll
+  for (int k = 0; k < kNSlot; k++) {
+    const uint32_t tp = tapw ? __ldg(taps + k * 32 + lane) : 0u;
+    const int s = tp & 255, u1 = (tp >> 8) & 255;
+    int v = BF_INF;
+    if (tp >> 16) {
+      if (k < kNSG) v = T.interior[s] + min(T.ninio_max, abs(s - 2 * u1) * T.ninio_m);
+      else if (k < kNSG + kNS1) v = T.interior[s] + min(T.ninio_max, (s - 2) * T.ninio_m);
+      else if (k < kNSG + kNS1 + kNSB) v = T.bulge[s];
+      else v = 0;   // special slot: the energy travels in the cell's entry
+    }
+    pen[k] = v;
+    xk[k] = 0;
+  }
+  const unsigned wrap = (unsigned)(kRing * RS);
+  const unsigned sCG = (unsigned)__cvta_generic_to_shared(CG);
+  const unsigned sFM = (unsigned)__cvta_generic_to_shared(fms);
+
+  // ---- per-sequence state, slot 0 / 1
+  auto load_seq = [&](int sq, int slot) -> int {   // all threads; returns the length (warp-uniform for the compiler)
+    const int n1 = __shfl_sync(BF_FULL, b.len[sq], 0);
+    uint8_t *S1 = dyn + pl.o_S + slot * seq_pad, *SP1 = dyn + pl.o_SP + slot * seq_pad;
+    const char *src = b.seq + (size_t)sq * b.stride;
+    const uint8_t *np = b.nopair ? b.nopair + (size_t)sq * b.stride : nullptr;
+    for (int k = tid; k <= n1 + 1; k += blockDim.x) {
+      const int code = (k >= 1 && k <= n1) ? bf_base_code(src[k - 1]) : 0;
+      S1[k] = (uint8_t)code;
+      SP1[k] = (uint8_t)((np && k >= 1 && k <= n1 && np[k - 1]) ? 0 : code);
+    }
+    return n1;
+  };
+  // pre-pass of one diagonal by one warp: per-cell constants (everything that depends on the sequence only) of its pairable cells,
+  // compacted, into the slot's half of the workspace; INF into the c table for the cells that cannot pair.  First the pairable
+  // cells are compacted (ballot), then the look-ups run with every lane busy.
+  auto prepass_diag = [&](int d, int slot, int n1, int *cgo, unsigned short *cl) {
+    const uint8_t *S1 = dyn + pl.o_S + slot * seq_pad, *SP1 = dyn + pl.o_SP + slot * seq_pad;
+    unsigned short *NP1 = reinterpret_cast<unsigned short *>(dyn + pl.o_np) + slot * np_pad;
+    int *ent1 = ent_base + (size_t)slot * (ent_slot / 2);
+    int count = 0;
+    const int od = tri_off(n1, d);
+    for (int base = 1; base <= n1 - d; base += 32) {
+      const int i = base + lane;
+      const bool in = i <= n1 - d;
+      const int t = in ? bf_ptype_bases(SP1[i], SP1[i + d]) : 0;
+      const unsigned mk = __ballot_sync(BF_FULL, t != 0);
+      if (in && !t) cgo[od + i - 1] = BF_INF;
+      if (t) cl[count + __popc(mk & ((1u << lane) - 1))] = (unsigned short)i;
+      count += __popc(mk);
+    }
+    if (lane == 0) NP1[d] = (unsigned short)count;
+    __syncwarp();
+    for (int c = lane; c < count; c += 32) {
+      const int i = cl[c], j = i + d;
+      const int t = bf_ptype_bases(SP1[i], SP1[j]);
+      const int si1 = S1[i + 1], sj1 = S1[j - 1], sim = S1[i - 1], sjp = S1[j + 1], tr = bf_rtype(t);
+      int4 *dst = reinterpret_cast<int4 *>(ent1 + (size_t)(od + c) * kEntWords);
+      dst[0] = make_int4(i, T.mmI[t][si1][sj1], T.mm1nI[t][si1][sj1], bf_e_hairpin(P, T, S1, i, j, t));
+      dst[1] = make_int4(T.MLclosing + bf_e_mlstem(T, tr, sj1, si1), T.mmI[tr][sjp][sim], T.mm1nI[tr][sjp][sim], t > 2 ? tauE : 0);
+      int w[12];
+      w[0] = (i > 1 && j < n1) ? bf_e_mlstem(T, t, sim, sjp) : BF_INF;
+#pragma unroll
+      for (int k = 0; k < 9; k++) {   // branch-free: the look-ups of a candidate do not wait for the previous candidate
+        const int u1 = special_u1(k), u2 = special_u2(k);
+        const bool ok = (j - 1 - u2) - (i + 1 + u1) > BF_TURN;
+        const int p = ok ? i + 1 + u1 : i + 1, q = ok ? j - 1 - u2 : j - 1;
+        const int t2 = ok ? bf_ptype_bases(SP1[p], SP1[q]) : 0;
+        const int e = bf_e_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S1[p - 1], S1[q + 1]);
+        w[1 + k] = t2 ? e - (t2 > 2 ? tauE : 0) : 0;   // no inner pair: the ring holds INF there
+      }
+      w[10] = w[11] = BF_INF;
+      dst[2] = make_int4(w[0], w[1], w[2], w[3]);
+      dst[3] = make_int4(w[4], w[5], w[6], w[7]);
+      dst[4] = make_int4(w[8], w[9], w[10], w[11]);
+    }
+    __syncwarp();
+  };
+
+  // ---- first sequence of this CTA: pre-pass by all warps
+  if (tid == 0) s_seq = atomicAdd(work_counter, 1);
+  __syncthreads();
+  int sq = s_seq;
+  if (sq >= b.B) return;
+  int cur = 0;
+  int n = load_seq(sq, 0);
+  __syncthreads();
+  // (all warps, before any tap list is in use: their scratch lists live in the tap warps' list area)
+  unsigned short *cl_all = reinterpret_cast<unsigned short *>(dyn + pl.o_cl) + (size_t)warp * ((nmax + 7) / 8 * 8);
+  unsigned short *cl_aux = reinterpret_cast<unsigned short *>(dyn + pl.o_pp) + (size_t)(warp >= NWI ? warp - NWI : 0) * ((nmax + 7) / 8 * 8);
+  for (int d = BF_TURN + 1 + warp; d <= n - 1; d += NW) prepass_diag(d, 0, n, ctri + (size_t)sq * tri_slot, cl_all);
+
+  for (;;) {
+    __syncthreads();   // the state of sequence sq (slot cur) is complete; nobody reads s_seq or the other slot any more
+    if (tid == 0) s_seq = atomicAdd(work_counter, 1);
+    for (int k = tid; k < 3 * kRing * RS + RS; k += blockDim.x) RG[k] = BF_INF;
+    for (int k = tid; k < 4 * RS; k += blockDim.x) DML[k] = BF_INF;
+    for (int k = tid; k < 6 * RS; k += blockDim.x) STG[k] = BF_INF;
+    for (int k = tid; k < 2 * RS; k += blockDim.x) TMPE[k] = BF_INF;
+    __syncthreads();
+    // the next sequence: its codes now, its pre-pass diagonal by diagonal on the auxiliary warps during the phases below
+    const int sqn = s_seq;
+    const bool have_next = sqn < b.B;
+    const int n1 = have_next ? load_seq(sqn, cur ^ 1) : 0;
+    int *cgo_next = ctri + (size_t)(have_next ? sqn : 0) * tri_slot;
+    int pd = BF_TURN + 1 + (warp - NWI);   // next pre-pass diagonal of this auxiliary warp
+    const unsigned short *NP = reinterpret_cast<const unsigned short *>(dyn + pl.o_np) + cur * np_pad;
+    const int *ent = ent_base + (size_t)cur * (ent_slot / 2);
+    int *cg_out = ctri + (size_t)sq * tri_slot;
+    int *fg_out = ftri + (size_t)sq * tri_slot;
+    int *FM = FMS ? fms : fg_out;
+    if (tapw) {
+#pragma unroll
+      for (int k = 0; k < kNSlot; k++) {
+        const uint32_t tp = __ldg(taps + k * 32 + lane);
+        const int s = tp & 255, u1 = (tp >> 8) & 255;
+        // bytes from the generic ring's origin: ring of the slot's kind, row of diagonal d-2-s for d = TURN+1, column offset 1+u1
+        xk[k] = 4 * ((k < kNSG ? 0 : k < kNSG + kNS1 ? 1 : 2) * kRing * RS + ((BF_TURN + 1 - 2 - s) & (kRing - 1)) * RS + 1 + u1);
+      }
+    }
+    __syncthreads();
+    // tap warp: asynchronous copy (LDGSTS) of the entries of its cells (c = warp, warp + NWI, ...) of diagonal dn into its list
+    int *wl = reinterpret_cast<int *>(dyn + pl.o_cl) + (size_t)warp * ((RS + NWI - 1) / NWI + 1) * kEntWords;
+    auto stage = [&](int dn) {
+      const int mine = (NP[dn] - warp + NWI - 1) / NWI;
+      const char *src = reinterpret_cast<const char *>(ent + ((size_t)tri_off(n, dn) + warp) * kEntWords);
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(wl);
+      for (int idx = lane; idx < mine * (kEntWords / 4); idx += 32) {
+        const int m = idx / (kEntWords / 4), q = idx - m * (kEntWords / 4);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)(m * kEntWords * 4 + q * 16)),
+                     "l"(src + (size_t)m * NWI * kEntWords * 4 + q * 16)
+                     : "memory");
+      }
+    };
+    if (tapw && n - 1 >= BF_TURN + 1 && !(dbg & 1)) stage(BF_TURN + 1);
+
+    for (int d = BF_TURN + 1; d <= n; d++) {
+      const int buf = d & 1;
+      if (tapw) {
+        // ------------------------------------------------------------ tap warps: c(i,j) of every pairable cell of diagonal d
+        if (d <= n - 1 && !(dbg & 1)) {
+          const int np = NP[d];
+          const int od = tri_off(n, d);
+          const unsigned sdml = (unsigned)__cvta_generic_to_shared(DML + ((d - 2) & 3) * RS + 1);
+          // lanes 0..2 write the staged ring row (generic, 1xn, bulge variant), lane 3 the fML candidate: lane's target array
+          const unsigned stail = (unsigned)__cvta_generic_to_shared(lane < 3 ? STG + (buf * 3 + lane) * RS : TMPE + buf * RS);
+          const int smax = min(BF_MAXLOOP, d - 6);
+          const int mi = smax + 1 < 0 ? 0 : smax + 1;
+          const int ng = __ldg(meta + mi), n1 = __ldg(meta + 32 + mi), nb = __ldg(meta + 64 + mi);
+          const int lsp = 9 + min(lane, 9), ltl = 5 + min(lane, 3);
+          auto cells = [&](auto cg_, auto c1_, auto cb_) {
+            constexpr int G = decltype(cg_)::value, O = decltype(c1_)::value, Bn = decltype(cb_)::value;
+            // the warp's entries were copied from L2 into its private list while the previous phase finished
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            const int *p = wl;
+            for (int c = warp; c < np; c += NWI, p += kEntWords) {
+              const int4 ea = *reinterpret_cast<const int4 *>(p);   // i, mismatchI, mismatch1nI, hairpin
+              const int ic = ea.x, mlc = p[4], tau = p[7], esp = p[lsp], etl = p[ltl];
+              // the cell index is the same in every lane: taken through REDUX it lands in a uniform register, and a tap load
+              // becomes LDS [R + UR] -- the lane's byte offset in a register, the cell's ring address uniform
+              const unsigned i4 = 4u * (unsigned)__reduce_min_sync(BF_FULL, ic);
+              const unsigned ug = sCG + i4;
+              int ag = BF_INF, a1 = BF_INF, ab = BF_INF;
+#pragma unroll
+              for (int k = 0; k < G; k++) ag = min(ag, lds_s32(ug + xk[k]) + pen[k]);
+#pragma unroll
+              for (int k = 0; k < O; k++) a1 = min(a1, lds_s32(ug + xk[kNSG + k]) + pen[kNSG + k]);
+#pragma unroll
+              for (int k = 0; k < Bn; k++) ab = min(ab, lds_s32(ug + xk[kNSG + kNS1 + k]) + pen[kNSG + kNS1 + k]);
+              const int vs = lds_s32(ug + xk[kNSlot - 1]) + esp;   // special candidates (lanes 0..8; the others add INF)
+              int tot = min(min(ag + ea.y, a1 + ea.z), min(ab + tau, vs));
+              tot = __reduce_min_sync(BF_FULL, tot);
+              tot = min(tot, ea.w);                                  // hairpin
+              const int dm = lds_s32(sdml + i4);                     // split minimum of (i+1, j-1)
+              if (dm < kInfThr) tot = min(tot, dm + mlc);            // multiloop closed by (i,j)
+              const bool fin = tot < kInfThr;
+              const int v = (fin && etl < kInfThr) ? tot + etl : BF_INF;
+              if (lane < 4) asm volatile("st.shared.s32 [%0], %1;" ::"r"(stail + i4), "r"(v) : "memory");
+              if (lane == 0) cg_out[od + (int)(i4 >> 2) - 1] = fin ? tot : BF_INF;
+            }
+          };
+          using std::integral_constant;
+          if (ng <= 2 && n1 <= 1 && nb <= 1) cells(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 1>());
+          else if (ng <= 5 && n1 <= 2 && nb <= 2) cells(integral_constant<int, 5>(), integral_constant<int, 2>(), integral_constant<int, 2>());
+          else if (ng <= 8) cells(integral_constant<int, 8>(), integral_constant<int, kNS1>(), integral_constant<int, kNSB>());
+          else cells(integral_constant<int, kNSG>(), integral_constant<int, kNS1>(), integral_constant<int, kNSB>());
+          __syncwarp();
+          if (d + 1 <= n - 1) stage(d + 1);
+        }
+        // every tap moves one ring row down for the next diagonal
+#pragma unroll
+        for (int k = 0; k < kNSlot; k++) {
+          const int kind = k < kNSG ? 0 : k < kNSG + kNS1 ? 1 : 2;
+          const unsigned x = (unsigned)xk[k] + 4u * (unsigned)RS;
+          xk[k] = (int)(x >= 4u * wrap * (unsigned)(kind + 1) ? x - 4u * wrap : x);
+        }
+      } else {
+        const int a = warp - NWI;   // auxiliary warp index
+        // ------------------------------------------------------------ diagonal d-1: staging row -> rings, fML
+        if (d > BF_TURN + 1 && !(dbg & 8)) {
+          const int dd = d - 1, ncell = n - dd, pb = dd & 1;
+          int *stg = STG + pb * 3 * RS, *tmpe = TMPE + pb * RS;
+          const int *ps = PS + pb * NWA * RS;
+          const int row = (dd & (kRing - 1)) * RS;
+          const int o0 = tri_off(n, dd), om = dd > BF_TURN + 1 ? tri_off(n, dd - 1) : 0;
+          for (int cell = a * 32 + lane; cell < ncell; cell += NWA * 32) {
+            const int i = cell + 1;
+            int sp = BF_INF;
+#pragma unroll
+            for (int w = 0; w < NWA; w++) sp = min(sp, ps[w * RS + cell]);
+            if (sp >= kInfThr) sp = BF_INF;
+            const int eg = stg[i], e1 = stg[RS + i], eb = stg[2 * RS + i], te = tmpe[i];
+            stg[i] = BF_INF; stg[RS + i] = BF_INF; stg[2 * RS + i] = BF_INF; tmpe[i] = BF_INF;   // only pairable cells are written
+            CG[row + i] = eg; C1[row + i] = e1; CB[row + i] = eb;
+            int m = min(sp, te);
+            if (dd > BF_TURN + 1) m = min(m, min(FM[om + i], FM[om + i - 1]) + T.MLbase);
+            if (m >= kInfThr) m = BF_INF;
+            fg_out[o0 + i - 1] = m;
+            if (FMS) fms[o0 + i - 1] = m;
+            DML[(dd & 3) * RS + i] = sp;
+          }
+        }
+        if (d <= n - 1) {
+          const int ncell = n - d;
+          // ------------------------------------------------------------ fML split: this warp's share of the split points, every cell
+          if (!(dbg & 2)) {
+            int *ps = PS + (buf * NWA + a) * RS;
+            constexpr int Q = NWA;
+            // operands of split point k: fML(i, i+k-1) at off(k-1) + cell, fML(i+k, j) at off(d-k) + k + cell.  The offsets are
+            // warp-uniform and advance by second-order increments (off(x+Q) - off(x) = Q(n-x) - Q(Q-1)/2): they live in uniform
+            // registers, a load is LDS [lane's cell offset + uniform].
+            for (int c0 = 0; c0 < ncell; c0 += 128) {
+              int ii[4], acc[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++) { ii[u] = 4 * min(c0 + 32 * u + lane, ncell - 1); acc[u] = BF_INF; }   // byte offset of the lane's cell
+              const bool many = c0 + 64 < ncell;   // warp-uniform: more than two chunks left
+              int k = 5 + a;
+              if (k <= d - 4) {
+                // running byte addresses of the two operands of every chunk; both advance by the same (uniform) first differences
+                const int oL = 4 * tri_off(n, k - 1), oR = 4 * (tri_off(n, d - k) + k);
+                int dL = 4 * (Q * (n - k + 1) - Q * (Q - 1) / 2), dR = 4 * (-Q * (n - d + k + Q) + Q * (Q - 1) / 2 + Q);
+                if (FMS) {
+                  unsigned pL[4], pR[4];
+#pragma unroll
+                  for (int u = 0; u < 4; u++) { pL[u] = sFM + (unsigned)(oL + ii[u]); pR[u] = sFM + (unsigned)(oR + ii[u]); }
+                  if (many) {
+#pragma unroll 2
+                    for (; k <= d - 4; k += Q) {
+#pragma unroll
+                      for (int u = 0; u < 4; u++) { acc[u] = min(acc[u], lds_s32(pL[u]) + lds_s32(pR[u])); pL[u] += dL; pR[u] += dR; }
+                      dL -= 4 * Q * Q; dR -= 4 * Q * Q;
+                    }
+                  } else {
+#pragma unroll 4
+                    for (; k <= d - 4; k += Q) {
+#pragma unroll
+                      for (int u = 0; u < 2; u++) { acc[u] = min(acc[u], lds_s32(pL[u]) + lds_s32(pR[u])); pL[u] += dL; pR[u] += dR; }
+                      dL -= 4 * Q * Q; dR -= 4 * Q * Q;
+                    }
+                  }
+                } else {
+                  const char *pL[4], *pR[4];
+#pragma unroll
+                  for (int u = 0; u < 4; u++) { pL[u] = reinterpret_cast<const char *>(FM) + oL + ii[u]; pR[u] = reinterpret_cast<const char *>(FM) + oR + ii[u]; }
+                  const int nu = many ? 4 : 2;
+                  for (; k <= d - 4; k += Q) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                      if (u < nu) {
+                        acc[u] = min(acc[u], *reinterpret_cast<const int *>(pL[u]) + *reinterpret_cast<const int *>(pR[u]));
+                        pL[u] += dL; pR[u] += dR;
+                      }
+                    dL -= 4 * Q * Q; dR -= 4 * Q * Q;
+                  }
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                const int cell = c0 + 32 * u + lane;
+                if (cell < ncell) ps[cell] = acc[u];
+              }
+            }
+          }
+        }
+        // ------------------------------------------------------------ one diagonal of the NEXT sequence's pre-pass
+        // (measured: two auxiliary warps cannot hide it -- 780 instructions per 32 pairable cells, 3.07 against 2.57 ms per 4096
+        // folds at L = 100 -- so by default all warps do it between two sequences, below)
+        if (kPrepassInPhases && have_next && pd <= n1 - 1) {
+          prepass_diag(pd, cur ^ 1, n1, cgo_next, cl_aux);
+          pd += NWA;
+        }
+      }
+      __syncthreads();
+    }
+    if (!have_next) break;
+    // what the auxiliary warps did not reach (a next sequence much longer than this one): all warps
+    for (int d = BF_TURN + 1 + (kPrepassInPhases ? NWA * (n - BF_TURN > 0 ? n - BF_TURN : 0) : 0) + warp; d <= n1 - 1; d += NW)
+      prepass_diag(d, cur ^ 1, n1, cgo_next, cl_all);
+    sq = sqn;
+    n = n1;
+    cur ^= 1;
+  }
+}
+
+constexpr size_t kSmemBudget = 232448 - 1024 - 256;
+
+int env_int(const char *name, int dflt) {
+  const char *v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+struct Mfe3Cfg { bool ok; int rs; bool fms; size_t smem; int nw, nwi; };
+Mfe3Cfg mfe3_cfg(int nmax) {
+  Mfe3Cfg c;
+  c.ok = false;
+  if (nmax < 1 || env_int("BF_FILL3", 1) == 0 || env_int("BF_FILL3_MFE", 1) == 0) return c;
+  c.rs = pick_rs(nmax, 32);
+  c.nw = env_int("BF_FILL3_NW", 8);
+  c.nwi = env_int("BF_FILL3_NWI", c.nw == 8 ? 6 : c.nw / 2);
+  const int NWA = c.nw - c.nwi;
+  // fML table on chip while three CTAs still share an SM; otherwise it is read through L1 / L2
+  const size_t with = mfe3_plan(nmax, c.rs, c.nw, NWA, true).total, without = mfe3_plan(nmax, c.rs, c.nw, NWA, false).total;
+  const int fm_env = env_int("BF_FILL3_FMS", -1);
+  c.fms = fm_env >= 0 ? fm_env != 0 : (with + 1024 + 64) * 3 <= 228 * 1024;   // 228 KB per SM, 1 KB reserved per CTA
+  if (c.fms && with > kSmemBudget) c.fms = false;
+  c.smem = c.fms ? with : without;
+  c.ok = c.smem <= kSmemBudget && nmax <= env_int("BF_FILL3_MAXN", 2000);
+  return c;
+}
+
+}  // namespace
+
+bool bf_fill3_mfe_ok(int nmax) { return mfe3_cfg(nmax).ok; }
+size_t bf_fill3_mfe_ws_slot(int nmax) { return 2 * ((tri_size(nmax) * kEntWords + 7) / 8 * 8); }   // ints per CTA: entries of every cell, two sequences
+
+template <int NW, int NWI, bool FMS>
+static cudaError_t mfe3_launch(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, const Mfe3Cfg &c, int sms, int *counter,
+                               cudaStream_t st, int *grid_out) {
+  auto kern = bf_k_mfe_fill3<NW, NWI, FMS>;
+  static int occ_cache[4096];   // per stride: CTAs per SM (0 = not asked yet); the attribute is set once per instance
+  static bool attr_set = false;
+  cudaError_t e;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  int occ_tmp = 0;
+  int &occ = b.stride < 4096 ? occ_cache[b.stride] : occ_tmp;
+  if (occ == 0) {
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, c.smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorInvalidConfiguration;
+  }
+  const int grid = b.B < sms * occ ? b.B : sms * occ;
+  if (grid_out) { *grid_out = grid; return cudaSuccess; }
+  const uint32_t *taps = nullptr;
+  e = taps_device(c.rs, 32, &taps);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, NW * 32, c.smem, st>>>(dP, b, ctri, ftri, bf_tri_slot(b.stride), ws, bf_fill3_mfe_ws_slot(b.stride), taps, c.rs, counter,
+                                      env_int("BF_FILL3_DBG", 0));
+  return cudaGetLastError();
+}
+
+static cudaError_t mfe3_dispatch(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *work_counter,
+                                 cudaStream_t st, int *grid_out) {
+  const Mfe3Cfg c = mfe3_cfg(b.stride);
+  if (!c.ok) return cudaErrorInvalidValue;
+#define BF_GO(NW_, NWI_)                                                                                          \
+  if (c.nw == NW_ && c.nwi == NWI_)                                                                                \
+    return c.fms ? mfe3_launch<NW_, NWI_, true>(dP, b, ctri, ftri, ws, c, sms, work_counter, st, grid_out)         \
+                 : mfe3_launch<NW_, NWI_, false>(dP, b, ctri, ftri, ws, c, sms, work_counter, st, grid_out)
+  BF_GO(8, 4); BF_GO(8, 5); BF_GO(8, 6); BF_GO(12, 8); BF_GO(12, 9);
+#undef BF_GO
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t bf_fill3_mfe_grid(const BfBatchDev &b, int sms, int *grid) {
+  return mfe3_dispatch(nullptr, b, nullptr, nullptr, nullptr, sms, nullptr, nullptr, grid);
+}
+
+cudaError_t bf_launch_mfe_fill3(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *work_counter,
+                                cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  return mfe3_dispatch(dP, b, ctri, ftri, ws, sms, work_counter, st, nullptr);
+}

@@ -44,6 +44,13 @@ bool bf_pf_fill_does_ext(int nmax, int B);
 cudaError_t bf_launch_pf_ext(const BfParams *dP, const BfBatchDev &b, const double *qbtri, const double *lnscale, double *out5,
                              cudaStream_t st);
 
+// ---- third-generation fill kernels (bf_fill3.cu): flat tap tables, rings always on chip
+bool bf_fill3_mfe_ok(int nmax);
+size_t bf_fill3_mfe_ws_slot(int nmax);   // ints of per-CTA HBM workspace (per-cell constants of one sequence)
+cudaError_t bf_fill3_mfe_grid(const BfBatchDev &b, int sms, int *grid);
+cudaError_t bf_launch_mfe_fill3(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *work_counter,
+                                cudaStream_t st);
+
 // ---- tile-wavefront fill path (bf_tile.cu): same tables in HBM as the diagonal-major path, 4x4 tiles by tile-diagonal
 int bf_tile_mfe_ok(int nmax);        // 1 if the tile MFE fill covers this length
 size_t bf_mfe_tile_ws_slot(int nmax);  // ints of per-CTA HBM workspace (tile-major fML when it is not on chip)
