@@ -1310,6 +1310,7 @@ int bf_fill_pf_mode(int nmax) {
 }
 // third-generation kernels (bf_fill3.cu) take every batch they cover, except the small batches of the 16-warp variants
 static bool use_fill3_mfe(int nmax, int B) { return !want_wide(B) && bf_fill3_mfe_ok(nmax); }
+static bool use_fill3_pf(int nmax, int B) { return !want_wide(B) && bf_fill3_pf_ok(nmax); }
 
 size_t bf_mfe_ws_slot(int nmax, int B) {  // ints of per-CTA HBM workspace: [rings when they are not on chip][tile-major fML mirror when blocked]
   if (use_fill3_mfe(nmax, B)) return bf_fill3_mfe_ws_slot(nmax);
@@ -1331,6 +1332,7 @@ static bool pf_half(int nmax, const FillCfg &c) {
          pf_plan(nmax, 8, 0, true).total <= 113 * 1024;
 }
 size_t bf_pf_ws_slot(int nmax, int B) {  // doubles of per-CTA HBM workspace: [tables that are not on chip][blocked split: qm/qm1 mirrors, sums]
+  if (use_fill3_pf(nmax, B)) return bf_fill3_pf_ws_slot(nmax);
   const FillCfg c = pf_cfg(nmax, B);
   if (c.pl < 0) return 0;
   size_t o = pf_ws_doubles(nmax, c.pl);
@@ -1500,14 +1502,16 @@ static cudaError_t pf_fill_dispatch(const BfParams *dP, const BfBatchDev &b, dou
 
 // grid size the fill will use (the caller sizes the per-CTA workspace with it)
 cudaError_t bf_pf_fill_grid(const BfBatchDev &b, int sms, int *grid) {
+  if (use_fill3_pf(b.stride, b.B)) return bf_fill3_pf_grid(b, sms, grid);
   return pf_fill_dispatch(nullptr, b, nullptr, nullptr, nullptr, nullptr, nullptr, sms, grid, false, nullptr, nullptr);
 }
 
 // true: the fill kernel chosen for this batch also runs the exterior recursion and writes out5 (no bf_launch_pf_ext needed)
-bool bf_pf_fill_does_ext(int nmax, int B) { return pf_cfg(nmax, B).nw == 16; }
+bool bf_pf_fill_does_ext(int nmax, int B) { return !use_fill3_pf(nmax, B) && pf_cfg(nmax, B).nw == 16; }
 
 cudaError_t bf_launch_pf_fill(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *qmws, double *qmseq, const int *mfe_for_scale,
                               double *lnscale, int sms, int *work_counter, cudaStream_t st, double *out5) {
+  if (use_fill3_pf(b.stride, b.B)) return bf_launch_pf_fill3(dP, b, qbtri, qmws, qmseq, mfe_for_scale, lnscale, sms, work_counter, st);
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
   g_pf_out5 = out5;

@@ -550,6 +550,360 @@ __global__ void __launch_bounds__(NW * 32, NW <= 8 ? 3 : 2) bf_k_mfe_fill3(const
   }
 }
 
+// =====================================================================================================
+//                                   partition function (inside) fill
+// =====================================================================================================
+// Same organisation as bf_k_mfe_fill3 with sums of Boltzmann weights (fp64) in place of minima:
+//   qb(i,j)  = hairpin + sum over the taps (ring value x weight) + qms(i+1,j-1) x closing            -- tap warps, phase d
+//   qm1(i,j) = qm1(i,j-1) bu + qb(i,j) xMLstem;  au(i,j) = bu (qm1(i+1,j) + au(i+1,j));  qm = qms + au + qm1   -- aux warps, phase d+1
+//   qms(i,j) = sum_k qm(i,i+k-1) qm1(i+k,j)                                                         -- aux warps, phase d
+// Tap weights carry the per-sequence scale (pf_scale^-(s+2)), so they are rebuilt for every sequence; a tap costs one LDS.64 and
+// one DFMA, the warp's sum five shuffle steps.  Entry of a pairable cell: 20 doubles
+//   0: i (int)   1: xmismatchI(outer)   2: xmismatch1nI(outer)   3: hairpin weight x scale   4: xMLclosing x xMLstem(closing)
+//   5: xmismatchI(inner role)   6: xmismatch1nI(inner role)   7: xterminalAU(pair)   8: xMLstem(stem), 0 at the sequence ends
+//   9..17: weights of the nine non-decomposable interior candidates / xterminalAU(inner pair)     18, 19: 0
+constexpr int kEntD = 20;
+
+struct Pf3Plan {
+  size_t o_S, o_np, o_ring, o_qms, o_au, o_qm, o_qm1, o_stg, o_tmpq, o_ps, o_scl, o_cl, o_pp, total;
+};
+__host__ __device__ inline Pf3Plan pf3_plan(int nmax, int rs, int nw, int nwa, bool qms) {
+  Pf3Plan p;
+  size_t o = 0;
+  p.o_ring = o; o += ((size_t)3 * kRing * rs + rs) * sizeof(double);
+  p.o_qms = o; o += (size_t)4 * rs * sizeof(double);
+  p.o_au = o; o += (size_t)2 * rs * sizeof(double);
+  p.o_qm = o; o += qms ? (tri_size(nmax) + 4) * sizeof(double) : 0;
+  p.o_qm1 = o; o += qms ? (tri_size(nmax) + 4) * sizeof(double) : 0;
+  p.o_stg = o; o += (size_t)2 * 3 * rs * sizeof(double);
+  p.o_tmpq = o; o += (size_t)2 * rs * sizeof(double);
+  p.o_ps = o; o += (size_t)2 * nwa * rs * sizeof(double);
+  p.o_scl = o; o += (size_t)(nmax + 8 > 40 ? nmax + 8 : 40) * sizeof(double);   // the tap weights need scale^k up to k = 32
+  o = (o + 15) / 16 * 16;   // LDGSTS copies 16 bytes at a time
+  p.o_cl = o; o += (size_t)(rs + nw) * kEntD * sizeof(double);
+  p.o_np = o; o += (size_t)((nmax + 4) / 4 * 4) * sizeof(unsigned short);
+  p.o_pp = o; o += (size_t)nw * ((nmax + 7) / 8 * 8) * sizeof(unsigned short);
+  p.o_S = o; o += (nmax + 2 + 15) / 16 * 16;
+  p.total = (o + 15) / 16 * 16;
+  return p;
+}
+
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+
+template <int NW, int NWI, bool QMSM>
+__global__ void __launch_bounds__(NW * 32, NW <= 8 ? 2 : 1) bf_k_pf_fill3(const BfParams *__restrict__ P, BfBatchDev b, double *qbtri, size_t tri_slot,
+                                                                          double *ws, size_t ws_slot, double *qm_perseq,
+                                                                          const int *__restrict__ mfe_for_scale, double *lnscale_out,
+                                                                          const uint32_t *__restrict__ taps, int RS, int *work_counter, int dbg) {
+  constexpr int NWA = NW - NWI;
+  extern __shared__ __align__(16) unsigned char dyn[];
+  __shared__ int s_seq;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(BF_FULL, tid >> 5, 0);
+  const int nmax = b.stride;
+  const Pf3Plan pl = pf3_plan(nmax, RS, NW, NWA, QMSM);
+  uint8_t *S = dyn + pl.o_S;
+  unsigned short *NP = reinterpret_cast<unsigned short *>(dyn + pl.o_np);
+  double *RG = reinterpret_cast<double *>(dyn + pl.o_ring);
+  double *QG = RG, *Q1 = RG + kRing * RS, *QBB = RG + 2 * kRing * RS;
+  double *QMS = reinterpret_cast<double *>(dyn + pl.o_qms);
+  double *AU = reinterpret_cast<double *>(dyn + pl.o_au);
+  double *STG = reinterpret_cast<double *>(dyn + pl.o_stg);
+  double *TMPQ = reinterpret_cast<double *>(dyn + pl.o_tmpq);
+  double *PS = reinterpret_cast<double *>(dyn + pl.o_ps);
+  double *scl = reinterpret_cast<double *>(dyn + pl.o_scl);
+  const BfSmallD &T = P->sd;
+  const bool tapw = warp < NWI;
+  const unsigned char *meta = reinterpret_cast<const unsigned char *>(taps + kNSlot * 32);
+  // per-CTA HBM workspace: [entries of every cell][qm, qm1 when they are not on chip]
+  double *ent = ws + (size_t)blockIdx.x * ws_slot;
+  const size_t tri_pad = (tri_size(nmax) + 7) / 8 * 8;
+  double *QM = QMSM ? reinterpret_cast<double *>(dyn + pl.o_qm) : ent + tri_pad * kEntD;
+  double *QM1 = QMSM ? reinterpret_cast<double *>(dyn + pl.o_qm1) : QM + tri_pad;
+  const double xtau = T.x_TerminalAU, inv_tau = 1.0 / xtau;
+
+  double wk[kNSlot - 1];
+  int xk[kNSlot];
+  const unsigned wrap = (unsigned)(kRing * RS);
+  const unsigned sQG = (unsigned)__cvta_generic_to_shared(QG);
+  const unsigned sQM = (unsigned)__cvta_generic_to_shared(QM), sQM1 = (unsigned)__cvta_generic_to_shared(QM1);
+
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_seq = atomicAdd(work_counter, 1);
+    __syncthreads();
+    const int sq = s_seq;
+    if (sq >= b.B) break;
+    const int n = __shfl_sync(BF_FULL, b.len[sq], 0);
+    {
+      const char *src = b.seq + (size_t)sq * b.stride;
+      for (int k = tid; k <= n + 1; k += blockDim.x) S[k] = (uint8_t)((k >= 1 && k <= n) ? bf_base_code(src[k - 1]) : 0);
+    }
+    // per-nucleotide scale (ViennaRNA exp_params_rescale, sfact 1.07; default estimate -185 cal/mol/nt)
+    double lns = 185.0 / T.kT;
+    if (mfe_for_scale && n > 0) {
+      const double m = (double)mfe_for_scale[sq] * 10.0;
+      if (m < 0.0) lns = -1.07 * m / T.kT / (double)n;
+      if (lns < 185.0 / T.kT * 0.25) lns = 185.0 / T.kT * 0.25;
+    }
+    for (int k = tid; k <= (n + 2 > 34 ? n + 2 : 34); k += blockDim.x) scl[k] = exp(-lns * k);
+    if (tid == 0 && lnscale_out) lnscale_out[sq] = lns;
+    const double bu1 = exp(log(T.x_MLbase) - lns);
+    const double xclose = T.x_MLclosing * exp(-2.0 * lns);
+    for (int k = tid; k < 3 * kRing * RS + RS; k += blockDim.x) RG[k] = 0.0;
+    for (int k = tid; k < 4 * RS; k += blockDim.x) QMS[k] = 0.0;
+    for (int k = tid; k < 2 * RS; k += blockDim.x) { AU[k] = 0.0; TMPQ[k] = 0.0; }
+    for (int k = tid; k < 6 * RS; k += blockDim.x) STG[k] = 0.0;
+    double *qb_out = qbtri + (size_t)sq * tri_slot;
+    double *qmg = qm_perseq ? qm_perseq + (size_t)sq * 2 * tri_slot : nullptr;   // the outside pass wants qm / qm1 of every sequence
+    __syncthreads();
+    if (tapw) {
+#pragma unroll
+      for (int k = 0; k < kNSlot; k++) {
+        const uint32_t tp = __ldg(taps + k * 32 + lane);
+        const int s = tp & 255, u1 = (tp >> 8) & 255;
+        xk[k] = 8 * ((k < kNSG ? 0 : k < kNSG + kNS1 ? 1 : 2) * kRing * RS + ((BF_TURN + 1 - 2 - s) & (kRing - 1)) * RS + 1 + u1);
+        if (k < kNSlot - 1) {
+          double v = 0.0;
+          if (tp >> 16) {
+            if (k < kNSG) v = T.x_interior[s] * T.x_ninio[abs(s - 2 * u1)] * scl[s + 2];
+            else if (k < kNSG + kNS1) v = T.x_interior[s] * T.x_ninio[s - 2] * scl[s + 2];
+            else v = T.x_bulge[s] * scl[s + 2];
+          }
+          wk[k] = v;
+        }
+      }
+    }
+    // ------------------------------------------------------------ pre-pass: per-cell constants of every diagonal
+    {
+      unsigned short *cl = reinterpret_cast<unsigned short *>(dyn + pl.o_pp) + (size_t)warp * ((nmax + 7) / 8 * 8);
+      for (int d = BF_TURN + 1 + warp; d <= n - 1 && !(dbg & 4); d += NW) {
+        int count = 0;
+        const int od = tri_off(n, d);
+        for (int base = 1; base <= n - d; base += 32) {
+          const int i = base + lane;
+          const bool in = i <= n - d;
+          const int t = in ? bf_ptype_bases(S[i], S[i + d]) : 0;
+          const unsigned mk = __ballot_sync(BF_FULL, t != 0);
+          if (in && !t) qb_out[od + i - 1] = 0.0;
+          if (t) cl[count + __popc(mk & ((1u << lane) - 1))] = (unsigned short)i;
+          count += __popc(mk);
+        }
+        if (lane == 0) NP[d] = (unsigned short)count;
+        __syncwarp();
+        for (int c = lane; c < count; c += 32) {
+          const int i = cl[c], j = i + d;
+          const int t = bf_ptype_bases(S[i], S[j]);
+          const int si1 = S[i + 1], sj1 = S[j - 1], sim = S[i - 1], sjp = S[j + 1], tr = bf_rtype(t);
+          double2 *dst = reinterpret_cast<double2 *>(ent + (size_t)(od + c) * kEntD);
+          dst[0] = make_double2(__longlong_as_double((long long)i), T.x_mmI[t][si1][sj1]);
+          dst[1] = make_double2(T.x_mm1nI[t][si1][sj1], bf_x_hairpin(P, T, S, i, j, t) * scl[d + 1]);
+          dst[2] = make_double2(xclose * bf_x_mlstem(T, tr, sj1, si1), T.x_mmI[tr][sjp][sim]);
+          dst[3] = make_double2(T.x_mm1nI[tr][sjp][sim], t > 2 ? xtau : 1.0);
+          double w[12];
+          w[0] = (i > 1 && j < n) ? bf_x_mlstem(T, t, sim, sjp) : 0.0;
+#pragma unroll
+          for (int k = 0; k < 9; k++) {
+            const int u1 = special_u1(k), u2 = special_u2(k);
+            const bool ok = (j - 1 - u2) - (i + 1 + u1) > BF_TURN;
+            const int p = ok ? i + 1 + u1 : i + 1, q = ok ? j - 1 - u2 : j - 1;
+            const int t2 = ok ? bf_ptype_bases(S[p], S[q]) : 0;
+            const double e = bf_x_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]) * scl[u1 + u2 + 2];
+            w[1 + k] = t2 ? (t2 > 2 ? e * inv_tau : e) : 0.0;   // the bulge ring carries xterminalAU of the inner pair
+          }
+          w[10] = w[11] = 0.0;
+#pragma unroll
+          for (int q2 = 0; q2 < 6; q2++) dst[4 + q2] = make_double2(w[2 * q2], w[2 * q2 + 1]);
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    // tap warp: asynchronous copy (LDGSTS) of the entries of its cells (c = warp, warp + NWI, ...) of diagonal dn into its list
+    double *wl = reinterpret_cast<double *>(dyn + pl.o_cl) + (size_t)warp * ((RS + NWI - 1) / NWI + 1) * kEntD;
+    auto stage = [&](int dn) {
+      const int mine = ((int)NP[dn] - warp + NWI - 1) / NWI;
+      const char *src = reinterpret_cast<const char *>(ent + ((size_t)tri_off(n, dn) + warp) * kEntD);
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(wl);
+      constexpr int CH = kEntD * 8 / 16;
+      for (int idx = lane; idx < mine * CH; idx += 32) {
+        const int m = idx / CH, q = idx - m * CH;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + (unsigned)(m * kEntD * 8 + q * 16)),
+                     "l"(src + (size_t)m * NWI * kEntD * 8 + q * 16)
+                     : "memory");
+      }
+    };
+    if (tapw && n - 1 >= BF_TURN + 1 && !(dbg & 1)) stage(BF_TURN + 1);
+
+    for (int d = BF_TURN + 1; d <= n; d++) {
+      const int buf = d & 1;
+      if (tapw) {
+        // ------------------------------------------------------------ tap warps: qb(i,j) of every pairable cell of diagonal d
+        if (d <= n - 1 && !(dbg & 1)) {
+          const int np = NP[d];
+          const int od = tri_off(n, d);
+          const unsigned sqms = (unsigned)__cvta_generic_to_shared(QMS + ((d - 2) & 3) * RS + 1);
+          // lanes 0..2 write the staged ring row (generic, 1xn, bulge variant), lane 3 qb x xMLstem: lane's target array
+          const unsigned stail = (unsigned)__cvta_generic_to_shared(lane < 3 ? STG + (buf * 3 + lane) * RS : TMPQ + buf * RS);
+          const int smax = min(BF_MAXLOOP, d - 6);
+          const int mi = smax + 1 < 0 ? 0 : smax + 1;
+          const int ng = __ldg(meta + mi), n1 = __ldg(meta + 32 + mi), nb = __ldg(meta + 64 + mi);
+          const int lsp = 9 + min(lane, 9), ltl = 5 + min(lane, 3);
+          auto cells = [&](auto cg_, auto c1_, auto cb_) {
+            constexpr int G = decltype(cg_)::value, O = decltype(c1_)::value, Bn = decltype(cb_)::value;
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            const double *p = wl;
+            double2 e01n = *reinterpret_cast<const double2 *>(p);   // the next cell's index and first field: one cell ahead
+            for (int c = warp; c < np; c += NWI, p += kEntD) {
+              const double2 e01 = e01n, e23 = *reinterpret_cast<const double2 *>(p + 2);
+              const double mlc = p[4], xt = p[7], esp = p[lsp], etl = p[ltl];
+              e01n = *reinterpret_cast<const double2 *>(p + kEntD);   // (the list has one spare entry)
+              // every lane holds the same cell index; the addresses are formed per lane (no detour through a uniform register:
+              // with 8-byte taps the compiler adds per lane anyway)
+              const unsigned i8 = 8u * (unsigned)(int)__double_as_longlong(e01.x);
+              const unsigned ug = sQG + i8;
+              double ag0 = 0.0, ag1 = 0.0, a1 = 0.0, ab = 0.0;
+#pragma unroll
+              for (int k = 0; k < G; k++) {
+                if (k & 1) ag1 = fma(lds_f64(ug + xk[k]), wk[k], ag1);
+                else ag0 = fma(lds_f64(ug + xk[k]), wk[k], ag0);
+              }
+#pragma unroll
+              for (int k = 0; k < O; k++) a1 = fma(lds_f64(ug + xk[kNSG + k]), wk[kNSG + k], a1);
+#pragma unroll
+              for (int k = 0; k < Bn; k++) ab = fma(lds_f64(ug + xk[kNSG + kNS1 + k]), wk[kNSG + kNS1 + k], ab);
+              double tot = fma(lds_f64(ug + xk[kNSlot - 1]), esp, (ag0 + ag1) * e01.y);   // special candidates (lanes 0..8)
+              tot = fma(a1, e23.x, fma(ab, xt, tot));
+              tot = bf_warp_sum(tot);
+              const double qb = tot + e23.y + lds_f64(sqms + i8) * mlc;   // + hairpin + multiloop closed by (i,j)
+              if (lane < 4) asm volatile("st.shared.f64 [%0], %1;" ::"r"(stail + i8), "d"(qb * etl) : "memory");
+              if (lane == 0) qb_out[od + (int)(i8 >> 3) - 1] = qb;
+            }
+          };
+          using std::integral_constant;
+          if (ng <= 2 && n1 <= 1 && nb <= 1) cells(integral_constant<int, 2>(), integral_constant<int, 1>(), integral_constant<int, 1>());
+          else if (ng <= 5 && n1 <= 2 && nb <= 2) cells(integral_constant<int, 5>(), integral_constant<int, 2>(), integral_constant<int, 2>());
+          else if (ng <= 8) cells(integral_constant<int, 8>(), integral_constant<int, kNS1>(), integral_constant<int, kNSB>());
+          else cells(integral_constant<int, kNSG>(), integral_constant<int, kNS1>(), integral_constant<int, kNSB>());
+          __syncwarp();
+          if (d + 1 <= n - 1) stage(d + 1);
+        }
+        // every tap moves one ring row down for the next diagonal
+#pragma unroll
+        for (int k = 0; k < kNSlot; k++) {
+          const int kind = k < kNSG ? 0 : k < kNSG + kNS1 ? 1 : 2;
+          const unsigned x = (unsigned)xk[k] + 8u * (unsigned)RS;
+          xk[k] = (int)(x >= 8u * wrap * (unsigned)(kind + 1) ? x - 8u * wrap : x);
+        }
+      } else {
+        const int a = warp - NWI;
+        // ------------------------------------------------------------ diagonal d-1: staging row -> rings, qm1, au, qm
+        if (d > BF_TURN + 1 && !(dbg & 8)) {
+          const int dd = d - 1, ncell = n - dd, pb = dd & 1;
+          double *stg = STG + pb * 3 * RS, *tmpq = TMPQ + pb * RS;
+          const double *ps = PS + pb * NWA * RS;
+          const int row = (dd & (kRing - 1)) * RS;
+          const int o0 = tri_off(n, dd), om = dd > BF_TURN + 1 ? tri_off(n, dd - 1) : 0;
+          for (int cell = a * 32 + lane; cell < ncell; cell += NWA * 32) {
+            const int i = cell + 1;
+            double qms = 0.0;
+#pragma unroll
+            for (int w = 0; w < NWA; w++) qms += ps[w * RS + cell];
+            const double g = stg[i], g1 = stg[RS + i], gb = stg[2 * RS + i], tq = tmpq[i];
+            stg[i] = 0.0; stg[RS + i] = 0.0; stg[2 * RS + i] = 0.0; tmpq[i] = 0.0;   // only pairable cells are written
+            QG[row + i] = g; Q1[row + i] = g1; QBB[row + i] = gb;
+            double qm1 = tq, au = 0.0;
+            if (dd > BF_TURN + 1) {
+              qm1 = fma(QM1[om + i - 1], bu1, tq);                                   // (i, j-1) plus one unpaired base
+              au = bu1 * (QM1[om + i] + AU[((dd - 1) & 1) * RS + i + 1]);            // stems starting right of i
+            }
+            const double qm = qms + au + qm1;
+            QM[o0 + i - 1] = qm;
+            QM1[o0 + i - 1] = qm1;
+            if (qmg) { qmg[o0 + i - 1] = qm; qmg[tri_slot + o0 + i - 1] = qm1; }
+            QMS[(dd & 3) * RS + i] = qms;
+            AU[(dd & 1) * RS + i] = au;
+          }
+        }
+        if (d <= n - 1 && !(dbg & 2)) {
+          const int ncell = n - d;
+          // ------------------------------------------------------------ qm split: this warp's share of the split points, every cell
+          double *ps = PS + (buf * NWA + a) * RS;
+          constexpr int Q = NWA;
+          for (int c0 = 0; c0 < ncell; c0 += 128) {
+            int ii[4];
+            double acc[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { ii[u] = 8 * min(c0 + 32 * u + lane, ncell - 1); acc[u] = 0.0; }
+            const bool many = c0 + 64 < ncell;
+            int k = 5 + a;
+            if (k <= d - 4) {
+              const int oL = 8 * tri_off(n, k - 1), oR = 8 * (tri_off(n, d - k) + k);
+              int dL = 8 * (Q * (n - k + 1) - Q * (Q - 1) / 2), dR = 8 * (-Q * (n - d + k + Q) + Q * (Q - 1) / 2 + Q);
+              if (QMSM) {
+                unsigned pL[4], pR[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { pL[u] = sQM + (unsigned)(oL + ii[u]); pR[u] = sQM1 + (unsigned)(oR + ii[u]); }
+                if (many) {
+#pragma unroll 2
+                  for (; k <= d - 4; k += Q) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { acc[u] = fma(lds_f64(pL[u]), lds_f64(pR[u]), acc[u]); pL[u] += dL; pR[u] += dR; }
+                    dL -= 8 * Q * Q; dR -= 8 * Q * Q;
+                  }
+                } else {
+#pragma unroll 4
+                  for (; k <= d - 4; k += Q) {
+#pragma unroll
+                    for (int u = 0; u < 2; u++) { acc[u] = fma(lds_f64(pL[u]), lds_f64(pR[u]), acc[u]); pL[u] += dL; pR[u] += dR; }
+                    dL -= 8 * Q * Q; dR -= 8 * Q * Q;
+                  }
+                }
+              } else {
+                const char *pL[4], *pR[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) { pL[u] = reinterpret_cast<const char *>(QM) + oL + ii[u]; pR[u] = reinterpret_cast<const char *>(QM1) + oR + ii[u]; }
+                if (many) {
+#pragma unroll 2
+                  for (; k <= d - 4; k += Q) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                      acc[u] = fma(*reinterpret_cast<const double *>(pL[u]), *reinterpret_cast<const double *>(pR[u]), acc[u]);
+                      pL[u] += dL; pR[u] += dR;
+                    }
+                    dL -= 8 * Q * Q; dR -= 8 * Q * Q;
+                  }
+                } else {
+#pragma unroll 4
+                  for (; k <= d - 4; k += Q) {
+#pragma unroll
+                    for (int u = 0; u < 2; u++) {
+                      acc[u] = fma(*reinterpret_cast<const double *>(pL[u]), *reinterpret_cast<const double *>(pR[u]), acc[u]);
+                      pL[u] += dL; pR[u] += dR;
+                    }
+                    dL -= 8 * Q * Q; dR -= 8 * Q * Q;
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const int cell = c0 + 32 * u + lane;
+              if (cell < ncell) ps[cell] = acc[u];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
 constexpr size_t kSmemBudget = 232448 - 1024 - 256;
 
 int env_int(const char *name, int dflt) {
@@ -566,13 +920,15 @@ Mfe3Cfg mfe3_cfg(int nmax) {
   c.nw = env_int("BF_FILL3_NW", 8);
   c.nwi = env_int("BF_FILL3_NWI", c.nw == 8 ? 6 : c.nw / 2);
   const int NWA = c.nw - c.nwi;
-  // fML table on chip while three CTAs still share an SM; otherwise it is read through L1 / L2
+  // The fML table has to be on chip: with two auxiliary warps per CTA the split cannot hide L2 latency (measured: L = 120 7.8 ms
+  // per 4096 folds against 5.96 ms of the round-1 kernel, L = 200 33 against 16).  Three CTAs per SM up to ~105 nt, two up to
+  // ~150 nt; longer sequences stay on the round-1 kernels (bf_fill.cu).
   const size_t with = mfe3_plan(nmax, c.rs, c.nw, NWA, true).total, without = mfe3_plan(nmax, c.rs, c.nw, NWA, false).total;
   const int fm_env = env_int("BF_FILL3_FMS", -1);
-  c.fms = fm_env >= 0 ? fm_env != 0 : (with + 1024 + 64) * 3 <= 228 * 1024;   // 228 KB per SM, 1 KB reserved per CTA
-  if (c.fms && with > kSmemBudget) c.fms = false;
+  c.fms = fm_env >= 0 ? fm_env != 0 : true;
   c.smem = c.fms ? with : without;
-  c.ok = c.smem <= kSmemBudget && nmax <= env_int("BF_FILL3_MAXN", 2000);
+  const size_t cap = fm_env >= 0 ? kSmemBudget : (size_t)env_int("BF_FILL3_MFE_KB", 112) * 1024;
+  c.ok = c.smem <= cap && c.smem <= kSmemBudget && nmax <= env_int("BF_FILL3_MAXN", 2000);
   return c;
 }
 
@@ -632,4 +988,88 @@ cudaError_t bf_launch_mfe_fill3(const BfParams *dP, const BfBatchDev &b, int *ct
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
   return mfe3_dispatch(dP, b, ctri, ftri, ws, sms, work_counter, st, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------------- partition function, host side
+namespace {
+struct Pf3Cfg { bool ok; int rs; bool qms; size_t smem; int nw, nwi; };
+Pf3Cfg pf3_cfg(int nmax) {
+  Pf3Cfg c;
+  c.ok = false;
+  if (nmax < 1 || env_int("BF_FILL3", 1) == 0 || env_int("BF_FILL3_PF", 1) == 0) return c;
+  c.rs = pick_rs(nmax, 16);
+  // two CTAs of 8 warps per SM while that fits (qm / qm1 through L2); else one CTA of 16 warps with as much on chip as fits
+  const int nw_env = env_int("BF_FILL3_PF_NW", 0);
+  const size_t two_ctas = (228 * 1024) / 2 - 1024 - 64;
+  c.nw = nw_env ? nw_env : (pf3_plan(nmax, c.rs, 8, 2, false).total <= two_ctas ? 8 : 16);
+  c.nwi = env_int("BF_FILL3_PF_NWI", c.nw == 8 ? 6 : c.nw == 16 ? 12 : c.nw * 3 / 4);
+  const int nwa = c.nw - c.nwi;
+  const size_t with = pf3_plan(nmax, c.rs, c.nw, nwa, true).total, without = pf3_plan(nmax, c.rs, c.nw, nwa, false).total;
+  const int q_env = env_int("BF_FILL3_PF_QMS", -1);
+  c.qms = q_env >= 0 ? q_env != 0 : (c.nw >= 16 && with <= kSmemBudget);
+  if (c.qms && with > kSmemBudget) c.qms = false;
+  c.smem = c.qms ? with : without;
+  // measured against the round-1 kernel (profiles/r02_sweep_len.txt): ahead up to 150 nt, level beyond
+  c.ok = c.smem <= kSmemBudget && nmax <= env_int("BF_FILL3_PF_MAXN", 150);
+  return c;
+}
+}  // namespace
+
+bool bf_fill3_pf_ok(int nmax) { return pf3_cfg(nmax).ok; }
+size_t bf_fill3_pf_ws_slot(int nmax) {   // doubles per CTA: entries of every cell, qm and qm1
+  const size_t tri_pad = (tri_size(nmax) + 7) / 8 * 8;
+  return tri_pad * kEntD + 2 * tri_pad;
+}
+
+template <int NW, int NWI, bool QMSM>
+static cudaError_t pf3_launch(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale,
+                              double *lnscale, const Pf3Cfg &c, int sms, int *counter, cudaStream_t st, int *grid_out) {
+  auto kern = bf_k_pf_fill3<NW, NWI, QMSM>;
+  static int occ_cache[4096];
+  static bool attr_set = false;
+  cudaError_t e;
+  if (!attr_set) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  int occ_tmp = 0;
+  int &occ = b.stride < 4096 ? occ_cache[b.stride] : occ_tmp;
+  if (occ == 0) {
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, c.smem);
+    if (e != cudaSuccess) return e;
+    if (occ < 1) return cudaErrorInvalidConfiguration;
+  }
+  const int grid = b.B < sms * occ ? b.B : sms * occ;
+  if (grid_out) { *grid_out = grid; return cudaSuccess; }
+  const uint32_t *taps = nullptr;
+  e = taps_device(c.rs, 16, &taps);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, NW * 32, c.smem, st>>>(dP, b, qbtri, bf_tri_slot(b.stride), ws, bf_fill3_pf_ws_slot(b.stride), qmseq, mfe_for_scale, lnscale,
+                                      taps, c.rs, counter, env_int("BF_FILL3_DBG", 0));
+  return cudaGetLastError();
+}
+
+static cudaError_t pf3_dispatch(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale,
+                                double *lnscale, int sms, int *counter, cudaStream_t st, int *grid_out) {
+  const Pf3Cfg c = pf3_cfg(b.stride);
+  if (!c.ok) return cudaErrorInvalidValue;
+#define BF_GO(NW_, NWI_)                                                                                                              \
+  if (c.nw == NW_ && c.nwi == NWI_)                                                                                                    \
+    return c.qms ? pf3_launch<NW_, NWI_, true>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, c, sms, counter, st, grid_out)         \
+                 : pf3_launch<NW_, NWI_, false>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, c, sms, counter, st, grid_out)
+  BF_GO(8, 6); BF_GO(8, 5); BF_GO(16, 12); BF_GO(16, 10); BF_GO(16, 13); BF_GO(16, 14); BF_GO(12, 9);
+#undef BF_GO
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t bf_fill3_pf_grid(const BfBatchDev &b, int sms, int *grid) {
+  return pf3_dispatch(nullptr, b, nullptr, nullptr, nullptr, nullptr, nullptr, sms, nullptr, nullptr, grid);
+}
+
+cudaError_t bf_launch_pf_fill3(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale,
+                               double *lnscale, int sms, int *work_counter, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  return pf3_dispatch(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, work_counter, st, nullptr);
 }

@@ -51,6 +51,12 @@ cudaError_t bf_fill3_mfe_grid(const BfBatchDev &b, int sms, int *grid);
 cudaError_t bf_launch_mfe_fill3(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *work_counter,
                                 cudaStream_t st);
 
+bool bf_fill3_pf_ok(int nmax);
+size_t bf_fill3_pf_ws_slot(int nmax);    // doubles of per-CTA HBM workspace
+cudaError_t bf_fill3_pf_grid(const BfBatchDev &b, int sms, int *grid);
+cudaError_t bf_launch_pf_fill3(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale,
+                               double *lnscale, int sms, int *work_counter, cudaStream_t st);
+
 // ---- tile-wavefront fill path (bf_tile.cu): same tables in HBM as the diagonal-major path, 4x4 tiles by tile-diagonal
 int bf_tile_mfe_ok(int nmax);        // 1 if the tile MFE fill covers this length
 size_t bf_mfe_tile_ws_slot(int nmax);  // ints of per-CTA HBM workspace (tile-major fML when it is not on chip)

@@ -203,3 +203,51 @@ def test_synthetic_t2004_shaped_parameters(engine, t2004_shaped):
         pf, bpp = O.pf(s, bpp=True)
         n = len(s)
         assert np.abs(o2["bpp"][k][:n, :n] - bpp).max() < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------ third-generation fill kernels
+def test_fill3_ragged_batch_vs_oracle(engine, oracle, monkeypatch):
+    """bf_fill3.cu takes batches of more than one sequence per SM (the sweep): a ragged batch (lengths 1..110 in one stride,
+    consecutive sequences of very different length on the same CTA) with hard constraints on a third of the rows."""
+    rng = np.random.default_rng(303)
+    lens = list(rng.integers(1, 111, 300)) + [1, 2, 3, 4, 5, 6, 110, 110, 7, 110]
+    seqs = ["".join("ACGU"[x] for x in rng.integers(0, 4, int(L))) for L in lens]
+    stride = max(lens)
+    mask = np.zeros((len(seqs), stride), np.uint8)
+    for k in range(0, len(seqs), 3):
+        mask[k, :lens[k]] = rng.random(lens[k]) < 0.25
+    out = engine.score_batch(seqs, nopair=mask, want=engine.WANT_MFE | engine.WANT_SS | engine.WANT_PF)
+    for k, s in enumerate(seqs):
+        e, ss = oracle.mfe(s, nopair=mask[k, :len(s)] if k % 3 == 0 else None)
+        assert out["mfe_dcal"][k] == e and out["mfe_ss"][k] == ss, (k, len(s))
+        f = oracle.pf(s)[4]
+        assert close(out["pf"][k, 4], f), (k, len(s))
+
+
+@pytest.mark.parametrize("L", [60, 100, 128, 150])
+def test_fill3_equals_round1_kernels(engine, monkeypatch, L):
+    """the two generations of fill kernels on the same batch: identical integers, ensemble energies to 1e-12"""
+    seqs = rand_seqs(808 + L, 200, L)
+    want = engine.WANT_MFE | engine.WANT_SS | engine.WANT_PF
+    monkeypatch.setenv("BF_FILL3", "1")
+    new = engine.score_batch(seqs, want=want)
+    tc = engine.debug_table(0, len(seqs)).copy()
+    tf = engine.debug_table(1, len(seqs)).copy()
+    monkeypatch.setenv("BF_FILL3", "0")
+    old = engine.score_batch(seqs, want=want)
+    assert (new["mfe_dcal"] == old["mfe_dcal"]).all() and new["mfe_ss"] == old["mfe_ss"]
+    assert np.allclose(new["pf"][:, 4], old["pf"][:, 4], rtol=1e-12, atol=0)
+    # the DP tables the backtrack and the suboptimal walk read: same c and fML, cell by cell
+    assert (engine.debug_table(0, len(seqs)) == tc).all()
+    assert (engine.debug_table(1, len(seqs)) == tf).all()
+
+
+def test_fill3_outside_pass_uses_its_tables(engine, oracle, monkeypatch):
+    """base-pair probabilities on top of the third-generation inside pass (qb, qm, qm1 per sequence): B > SM count"""
+    seqs = rand_seqs(909, 160, 70)
+    mfe, ss, epf, ed = oracle.fold_batch(seqs, nthreads=8)
+    out = engine.score_batch(seqs, [[s] for s in ss], want=engine.WANT_BPP | engine.WANT_DEFECT)
+    for k in range(0, 160, 9):
+        pf, bpp = oracle.pf(seqs[k], bpp=True)
+        assert np.abs(out["bpp"][k][:70, :70] - bpp).max() < 1e-9
+        assert abs(out["defect"][k] - oracle.ensemble_defect(bpp, ss[k])) < 1e-9
