@@ -594,7 +594,9 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
   return v;
 }
 
-template <int NW, int NWI, bool QMSM>
+// PAIR: a tap warp works on two cells at a time (twice the loads in flight, one shared butterfly: lanes 0..15 end up with the
+// first cell's sum, lanes 16..31 with the second's); costs ~40 registers, used by the configurations that can afford them
+template <int NW, int NWI, bool QMSM, bool PAIR = false>
 __global__ void __launch_bounds__(NW * 32, NW <= 8 ? 2 : 1) bf_k_pf_fill3(const BfParams *__restrict__ P, BfBatchDev b, double *qbtri, size_t tri_slot,
                                                                           double *ws, size_t ws_slot, double *qm_perseq,
                                                                           const int *__restrict__ mfe_for_scale, double *lnscale_out,
@@ -748,15 +750,55 @@ __global__ void __launch_bounds__(NW * 32, NW <= 8 ? 2 : 1) bf_k_pf_fill3(const 
           const int od = tri_off(n, d);
           const unsigned sqms = (unsigned)__cvta_generic_to_shared(QMS + ((d - 2) & 3) * RS + 1);
           // lanes 0..2 write the staged ring row (generic, 1xn, bulge variant), lane 3 qb x xMLstem: lane's target array
-          const unsigned stail = (unsigned)__cvta_generic_to_shared(lane < 3 ? STG + (buf * 3 + lane) * RS : TMPQ + buf * RS);
+          const int ltail = PAIR ? (lane & 15) : lane;
+          const unsigned stail = (unsigned)__cvta_generic_to_shared(ltail < 3 ? STG + (buf * 3 + ltail) * RS : TMPQ + buf * RS);
           const int smax = min(BF_MAXLOOP, d - 6);
           const int mi = smax + 1 < 0 ? 0 : smax + 1;
           const int ng = __ldg(meta + mi), n1 = __ldg(meta + 32 + mi), nb = __ldg(meta + 64 + mi);
-          const int lsp = 9 + min(lane, 9), ltl = 5 + min(lane, 3);
+          const int lsp = 9 + min(lane, 9), ltl = 5 + min(lane & (PAIR ? 15 : 31), 3);
           auto cells = [&](auto cg_, auto c1_, auto cb_) {
             constexpr int G = decltype(cg_)::value, O = decltype(c1_)::value, Bn = decltype(cb_)::value;
             asm volatile("cp.async.wait_all;" ::: "memory");
             __syncwarp();
+            if (PAIR) {
+              const bool hi = lane >= 16;
+              const double *p = wl;
+              for (int c = warp; c < np; c += 2 * NWI, p += 2 * kEntD) {
+                const bool hasB = c + NWI < np;
+                const double *pA = p, *pB = hasB ? p + kEntD : p;   // no second cell: the first once more, its stores dropped
+                const double2 a01 = *reinterpret_cast<const double2 *>(pA), b01 = *reinterpret_cast<const double2 *>(pB);
+                const double x1A = pA[2], xtA = pA[7], espA = pA[lsp], x1B = pB[2], xtB = pB[7], espB = pB[lsp];
+                const unsigned iA = 8u * (unsigned)(int)__double_as_longlong(a01.x), iB = 8u * (unsigned)(int)__double_as_longlong(b01.x);
+                const unsigned uA = sQG + iA, uB = sQG + iB;
+                double gA = 0.0, gB = 0.0, oA = 0.0, oB = 0.0, bA = 0.0, bB = 0.0;
+#pragma unroll
+                for (int k = 0; k < G; k++) { gA = fma(lds_f64(uA + xk[k]), wk[k], gA); gB = fma(lds_f64(uB + xk[k]), wk[k], gB); }
+#pragma unroll
+                for (int k = 0; k < O; k++) {
+                  oA = fma(lds_f64(uA + xk[kNSG + k]), wk[kNSG + k], oA);
+                  oB = fma(lds_f64(uB + xk[kNSG + k]), wk[kNSG + k], oB);
+                }
+#pragma unroll
+                for (int k = 0; k < Bn; k++) {
+                  bA = fma(lds_f64(uA + xk[kNSG + kNS1 + k]), wk[kNSG + kNS1 + k], bA);
+                  bB = fma(lds_f64(uB + xk[kNSG + kNS1 + k]), wk[kNSG + kNS1 + k], bB);
+                }
+                double tA = fma(lds_f64(uA + xk[kNSlot - 1]), espA, gA * a01.y), tB = fma(lds_f64(uB + xk[kNSlot - 1]), espB, gB * b01.y);
+                tA = fma(oA, x1A, fma(bA, xtA, tA));
+                tB = fma(oB, x1B, fma(bB, xtB, tB));
+                // one butterfly for both cells
+                double keep = hi ? tB : tA;
+                keep += __shfl_xor_sync(BF_FULL, hi ? tA : tB, 16);
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(BF_FULL, keep, o);
+                const double *pm = hi ? pB : pA;
+                const unsigned im = hi ? iB : iA;
+                const double qb = keep + pm[3] + lds_f64(sqms + im) * pm[4];   // + hairpin + multiloop closed by (i,j)
+                if ((lane & 15) < 4 && (!hi || hasB)) asm volatile("st.shared.f64 [%0], %1;" ::"r"(stail + im), "d"(qb * pm[ltl]) : "memory");
+                if ((lane & 15) == 0 && (!hi || hasB)) qb_out[od + (int)(im >> 3) - 1] = qb;
+              }
+              return;
+            }
             const double *p = wl;
             double2 e01n = *reinterpret_cast<const double2 *>(p);   // the next cell's index and first field: one cell ahead
             for (int c = warp; c < np; c += NWI, p += kEntD) {
@@ -998,15 +1040,17 @@ Pf3Cfg pf3_cfg(int nmax) {
   c.ok = false;
   if (nmax < 1 || env_int("BF_FILL3", 1) == 0 || env_int("BF_FILL3_PF", 1) == 0) return c;
   c.rs = pick_rs(nmax, 16);
-  // two CTAs of 8 warps per SM while that fits (qm / qm1 through L2); else one CTA of 16 warps with as much on chip as fits
+  // One CTA of 16 warps (12 tap + 4 auxiliary) per SM with qm / qm1 on chip while they fit (~105 nt), through L2 beyond.  Measured
+  // at L = 100 (4096 folds): 16 warps on chip 5.01 ms, 12 warps with paired cells 5.13, two CTAs of 8 warps (qm / qm1 in L2) 5.14;
+  // at L = 120 / 150 the 16-warp CTA is ahead of the 8-warp pair by 20 / 30 % (profiles/r02_sweep_len.txt).
   const int nw_env = env_int("BF_FILL3_PF_NW", 0);
-  const size_t two_ctas = (228 * 1024) / 2 - 1024 - 64;
-  c.nw = nw_env ? nw_env : (pf3_plan(nmax, c.rs, 8, 2, false).total <= two_ctas ? 8 : 16);
-  c.nwi = env_int("BF_FILL3_PF_NWI", c.nw == 8 ? 6 : c.nw == 16 ? 12 : c.nw * 3 / 4);
-  const int nwa = c.nw - c.nwi;
-  const size_t with = pf3_plan(nmax, c.rs, c.nw, nwa, true).total, without = pf3_plan(nmax, c.rs, c.nw, nwa, false).total;
+  c.nw = nw_env ? nw_env : 16;
+  const int nwr = c.nw % 100;   // (100 + warps: the paired variant)
+  c.nwi = env_int("BF_FILL3_PF_NWI", nwr == 8 ? 6 : nwr == 16 ? 12 : nwr * 3 / 4);
+  const int nwa = nwr - c.nwi;
+  const size_t with = pf3_plan(nmax, c.rs, nwr, nwa, true).total, without = pf3_plan(nmax, c.rs, nwr, nwa, false).total;
   const int q_env = env_int("BF_FILL3_PF_QMS", -1);
-  c.qms = q_env >= 0 ? q_env != 0 : (c.nw >= 16 && with <= kSmemBudget);
+  c.qms = q_env >= 0 ? q_env != 0 : (nwr >= 12 && with <= kSmemBudget);
   if (c.qms && with > kSmemBudget) c.qms = false;
   c.smem = c.qms ? with : without;
   // measured against the round-1 kernel (profiles/r02_sweep_len.txt): ahead up to 150 nt, level beyond
@@ -1021,10 +1065,10 @@ size_t bf_fill3_pf_ws_slot(int nmax) {   // doubles per CTA: entries of every ce
   return tri_pad * kEntD + 2 * tri_pad;
 }
 
-template <int NW, int NWI, bool QMSM>
+template <int NW, int NWI, bool QMSM, bool PAIR = false>
 static cudaError_t pf3_launch(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale,
                               double *lnscale, const Pf3Cfg &c, int sms, int *counter, cudaStream_t st, int *grid_out) {
-  auto kern = bf_k_pf_fill3<NW, NWI, QMSM>;
+  auto kern = bf_k_pf_fill3<NW, NWI, QMSM, PAIR>;
   static int occ_cache[4096];
   static bool attr_set = false;
   cudaError_t e;
@@ -1058,8 +1102,15 @@ static cudaError_t pf3_dispatch(const BfParams *dP, const BfBatchDev &b, double 
   if (c.nw == NW_ && c.nwi == NWI_)                                                                                                    \
     return c.qms ? pf3_launch<NW_, NWI_, true>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, c, sms, counter, st, grid_out)         \
                  : pf3_launch<NW_, NWI_, false>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, c, sms, counter, st, grid_out)
-  BF_GO(8, 6); BF_GO(8, 5); BF_GO(16, 12); BF_GO(16, 10); BF_GO(16, 13); BF_GO(16, 14); BF_GO(12, 9);
+  BF_GO(8, 6); BF_GO(16, 12); BF_GO(16, 10); BF_GO(12, 9);
 #undef BF_GO
+  // 12 warps, one CTA per SM: 170 registers per thread -- tap warps take their cells in pairs
+#define BF_GO2(NW_, NWI_)                                                                                                                   \
+  if (c.nw == NW_ + 100 && c.nwi == NWI_)                                                                                                    \
+    return c.qms ? pf3_launch<NW_, NWI_, true, true>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, c, sms, counter, st, grid_out)         \
+                 : pf3_launch<NW_, NWI_, false, true>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, c, sms, counter, st, grid_out)
+  BF_GO2(12, 8); BF_GO2(12, 9); BF_GO2(12, 10);
+#undef BF_GO2
   return cudaErrorInvalidValue;
 }
 
