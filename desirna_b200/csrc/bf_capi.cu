@@ -117,7 +117,8 @@ int validate(const bf_batch_t *b, const bf_result_t *r) {
 // scale_override (device, B ints, dcal/mol): energies that set the partition function's per-nucleotide scale instead of this
 // call's own MFE.  The result does not depend on the scale beyond rounding, and without that dependency the partition function
 // runs on the workspace's second stream beside the MFE fill -- worth it when both grids fit the GPU together (small batches).
-int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t st, const int *scale_override = nullptr) {
+int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two, cudaStream_t st, const int *scale_override = nullptr,
+               bool timing = true) {
   if (b->B == 0) return BF_OK;
   BfBatchDev db;
   db.B = b->B; db.stride = b->stride; db.seq = b->seq; db.len = b->len; db.cut = b->cut; db.nopair = b->nopair;
@@ -131,7 +132,7 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
   if (b->want & (BF_WANT_MFE | BF_WANT_SS)) {
     int *out_mfe = r->mfe_dcal;
     if (!out_mfe) { CU(w.d_mfe_scratch.reserve((size_t)b->B * sizeof(int)), "cudaMalloc(mfe scratch)"); out_mfe = (int *)w.d_mfe_scratch.p; }
-    cudaEventRecord(w.ev[0], st);
+    if (timing) cudaEventRecord(w.ev[0], st);
     if (fill_mfe) {
       const size_t slot = bf_tri_slot(b->stride) * sizeof(int);
       CU(w.tri_c.reserve((size_t)b->B * slot), "cudaMalloc(c table)");
@@ -174,8 +175,8 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
                        (b->want & BF_WANT_SS) ? r->mfe_ss : nullptr, b->stride + 1, st), "launch bf_k_mfe");
       g.launches++;
     }
-    cudaEventRecord(w.ev[1], st);
-    w.ran[0] = true;
+    if (timing) cudaEventRecord(w.ev[1], st);
+    w.ran[0] = timing;
     mfe_for_scale = out_mfe;
   }
   const bool want_out = (b->want & (BF_WANT_BPP | BF_WANT_DEFECT)) != 0;
@@ -189,7 +190,7 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
     cudaStream_t sp = beside ? w.st2 : st;
     if (beside) CU(cudaStreamWaitEvent(sp, w.ev_fork, 0), "fork");
     const int *scale_src = beside ? scale_override : (b->nopair ? nullptr : mfe_for_scale);
-    cudaEventRecord(w.ev[2], sp);
+    if (timing) cudaEventRecord(w.ev[2], sp);
     if (fill_pf) {
       const size_t slot = bf_tri_slot(b->stride) * sizeof(double);
       CU(w.tri_qb.reserve((size_t)b->B * slot), "cudaMalloc(qb table)");
@@ -230,14 +231,14 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
       CU(bf_launch_pf(g.dP, dbp, two, (double *)w.ws_pf.p, wstride, grid, w.d_counters + 1, scale_src, r->pf, st), "launch bf_k_pf");
       g.launches++;
     }
-    cudaEventRecord(w.ev[3], sp);
+    if (timing) cudaEventRecord(w.ev[3], sp);
     if (beside) { CU(cudaEventRecord(w.ev_join, sp), "join"); CU(cudaStreamWaitEvent(st, w.ev_join, 0), "join"); }
-    w.ran[1] = true;
+    w.ran[1] = timing;
   }
   if (b->want & BF_WANT_EVAL) {
-    cudaEventRecord(w.ev[4], st);
+    if (timing) cudaEventRecord(w.ev[4], st);
     CU(bf_launch_eval(g.dP, db, b->targets, b->n_targets, b->stride, r->eval_dcal, st), "launch bf_k_eval");
-    cudaEventRecord(w.ev[5], st);
+    if (timing) cudaEventRecord(w.ev[5], st);
     w.ran[2] = true;
     g.launches++;
   }
@@ -506,6 +507,11 @@ struct DesignLoop {
   bool overlap = true;  // BF_DESIGN_OVERLAP=0: always fold MFE, then PF
   int overlap_x2 = 16;  // BF_DESIGN_OVERLAP_X: batch size up to which the two fills run side by side, in units of half the SM count
                         // (measured: pays at every size tried, 0.76 -> 0.42 ms per sub-step at 64 x 104 nt, 15.5 -> 14.4 ms at 296 x 400 nt)
+  // one global step (re_attempt sub-steps, neighbour swaps) as a CUDA graph: one launch instead of ~8 per sub-step
+  bool use_graph = false;         // BF_DESIGN_GRAPH=1
+  cudaGraphExec_t gexec = nullptr;
+  int graph_B = -1;
+  int64_t graph_nodes = 0;
   std::vector<void *> allocs;
   std::vector<uint8_t> active;
   uint8_t *d_active = nullptr;
@@ -520,6 +526,8 @@ struct DesignLoop {
   }
   void destroy() {
     if (st) cudaStreamSynchronize(st);
+    if (gexec) cudaGraphExecDestroy(gexec);
+    gexec = nullptr;
     for (void *q : allocs) cudaFree(q);
     allocs.clear();
     w.destroy();
@@ -554,7 +562,21 @@ int design_score(DesignLoop *h, bool init = false) {
   r.mfe_dcal = h->D.o_mfe; r.mfe_ss = h->D.o_ss; r.pf = h->D.o_pf; r.eval_dcal = h->D.o_eval; r.defect = h->D.o_defect;
   // small batches: partition function beside the MFE fill, scaled by the parent sequence's MFE (kept per replica)
   const bool beside = !init && !h->two && h->overlap && h->B * 2 <= g.sm_count * h->overlap_x2 && !(h->want & BF_WANT_DEFECT);
-  return run_device(h->w, &b, &r, h->two, h->st, beside ? h->D.row_scale : nullptr);
+  return run_device(h->w, &b, &r, h->two, h->st, beside ? h->D.row_scale : nullptr, false);
+}
+
+// the launches of one global step; gstep < 0: inside a graph capture (the kernels read the step number from device memory)
+int design_enqueue_global_step(DesignLoop *h, int gstep, int64_t *launches) {
+  for (int k = 0; k < h->re_attempt && h->B > 0; k++) {
+    CU(bf_launch_design_propose(h->D, h->C, h->B, false, h->st), "launch bf_k_design_propose");
+    int rc = design_score(h);
+    if (rc) return rc;
+    CU(bf_launch_design_accept(h->D, h->C, h->B, false, gstep, h->st), "launch bf_k_design_accept");
+    *launches += 2;
+  }
+  CU(bf_launch_design_exchange(h->D, h->C, h->d_active, gstep, h->st), "launch bf_k_design_exchange");
+  *launches += 2;
+  return BF_OK;
 }
 }  // namespace
 
@@ -603,6 +625,10 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   h->two = two;
   { const char *ov = getenv("BF_DESIGN_OVERLAP"); h->overlap = !(ov && ov[0] == '0'); }
   { const char *ox = getenv("BF_DESIGN_OVERLAP_X"); h->overlap_x2 = (ox && atoi(ox) > 0) ? atoi(ox) : 16; }
+  // measured (bench.py design_loop, profiles/r02_design_graph.txt): one loop alone gains 2-6 % per sub-step (36 nt x 10: 0.111 ->
+  // 0.104 ms, 104 nt x 64: 0.402 -> 0.396 ms) -- the sub-step is a chain of short kernels, not launch-bound -- while seven loops
+  // advancing side by side lose 16 % (their graphs overlap less than their plain launches): opt-in
+  { const char *gr = getenv("BF_DESIGN_GRAPH"); h->use_graph = gr && gr[0] == '1'; }
   std::memset(&h->D, 0, sizeof h->D);
   std::memset(&h->C, 0, sizeof h->C);
   auto bail = [&](cudaError_t e, const char *what) { h->destroy(); delete h; return cuda_fail(e, what); };
@@ -621,6 +647,7 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   DCU(h->alloc(&D.best_rec, (size_t)J * kDesignRec), "cudaMalloc(design)");
   DCU(h->alloc(&D.solved_step, J), "cudaMalloc(design)"); DCU(h->alloc(&D.n_solved, J), "cudaMalloc(design)");
   DCU(h->alloc(&D.re_counts, (size_t)J * 3), "cudaMalloc(design)");
+  DCU(h->alloc(&D.gstep_dev, 1), "cudaMalloc(design)");
   DCU(h->alloc(&D.cur_seq, G * S), "cudaMalloc(design)"); DCU(h->alloc(&D.cur_ss, G * (S + 1)), "cudaMalloc(design)");
   DCU(h->alloc(&D.rec, G * kDesignRec), "cudaMalloc(design)"); DCU(h->alloc(&D.shelf, G), "cudaMalloc(design)");
   DCU(h->alloc(&D.rng, G), "cudaMalloc(design)"); DCU(h->alloc(&D.counts, G * 3), "cudaMalloc(design)");
@@ -695,15 +722,34 @@ int bf_design_run(void *handle, int32_t global_steps) {
   if (!h || global_steps < 0) return fail(BF_ERR_ARG, "bf_design_run: bad argument");
   for (int s = 0; s < global_steps; s++) {
     h->gstep++;
-    for (int k = 0; k < h->re_attempt && h->B > 0; k++) {
-      CU(bf_launch_design_propose(h->D, h->C, h->B, false, h->st), "launch bf_k_design_propose");
-      int rc = design_score(h);
+    if (h->use_graph && h->B > 0) {
+      if (!h->gexec || h->graph_B != h->B) {
+        // (re-)capture: the set of active rows changed, or first use.  Buffers were sized by the uncaptured scoring pass of
+        // bf_design_create; the kernels take the global-step number from device memory.
+        if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        int64_t nodes = 0;
+        const int64_t before = g.launches;   // the fold pipeline counts its kernels as it enqueues them: during capture nothing runs
+        CU(cudaStreamBeginCapture(h->st, cudaStreamCaptureModeRelaxed), "cudaStreamBeginCapture");
+        int rc = design_enqueue_global_step(h, -1, &nodes);
+        cudaError_t ce = cudaStreamEndCapture(h->st, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+        ce = cudaGraphInstantiate(&h->gexec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { h->gexec = nullptr; return cuda_fail(ce, "cudaGraphInstantiate"); }
+        h->graph_B = h->B;
+        h->graph_nodes = nodes + (g.launches - before);   // kernels per launch of the graph
+        g.launches = before;
+      }
+      CU(cudaGraphLaunch(h->gexec, h->st), "cudaGraphLaunch");
+      g.launches += h->graph_nodes;
+    } else {
+      int64_t n = 0;
+      int rc = design_enqueue_global_step(h, h->gstep, &n);
       if (rc) return rc;
-      CU(bf_launch_design_accept(h->D, h->C, h->B, false, h->gstep, h->st), "launch bf_k_design_accept");
-      g.launches += 2;
+      g.launches += n;
     }
-    CU(bf_launch_design_exchange(h->D, h->C, h->d_active, h->gstep, h->st), "launch bf_k_design_exchange");
-    g.launches++;
   }
   return BF_OK;
 }

@@ -1044,7 +1044,7 @@ Pf3Cfg pf3_cfg(int nmax) {
   // at L = 100 (4096 folds): 16 warps on chip 5.01 ms, 12 warps with paired cells 5.13, two CTAs of 8 warps (qm / qm1 in L2) 5.14;
   // at L = 120 / 150 the 16-warp CTA is ahead of the 8-warp pair by 20 / 30 % (profiles/r02_sweep_len.txt).
   const int nw_env = env_int("BF_FILL3_PF_NW", 0);
-  c.nw = nw_env ? nw_env : 16;
+  c.nw = nw_env ? nw_env : 116;   // 16 warps, cells in pairs (4.90 against 5.01 ms)
   const int nwr = c.nw % 100;   // (100 + warps: the paired variant)
   c.nwi = env_int("BF_FILL3_PF_NWI", nwr == 8 ? 6 : nwr == 16 ? 12 : nwr * 3 / 4);
   const int nwa = nwr - c.nwi;
@@ -1109,7 +1109,7 @@ static cudaError_t pf3_dispatch(const BfParams *dP, const BfBatchDev &b, double 
   if (c.nw == NW_ + 100 && c.nwi == NWI_)                                                                                                    \
     return c.qms ? pf3_launch<NW_, NWI_, true, true>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, c, sms, counter, st, grid_out)         \
                  : pf3_launch<NW_, NWI_, false, true>(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, c, sms, counter, st, grid_out)
-  BF_GO2(12, 8); BF_GO2(12, 9); BF_GO2(12, 10);
+  BF_GO2(12, 8); BF_GO2(12, 9); BF_GO2(12, 10); BF_GO2(16, 12); BF_GO2(16, 10);
 #undef BF_GO2
   return cudaErrorInvalidValue;
 }
