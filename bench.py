@@ -97,28 +97,87 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------- reference arm (CPU oracle port)
-def cpu_sample(L, budget_s, threads):
-    """Time the oracle (MFE+backtrack, PF inside, eval) on a bounded sample of the L-workload."""
+def vienna_available():
+    """BASELINE.md comparator A: DesiRNA's own ViennaRNA path, if the GPU host happens to have the module"""
+    try:
+        import RNA  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
+def _vienna_one(seq):
+    import RNA
+    md = RNA.md()
+    md.compute_bpp = 0
+    fc = RNA.fold_compound(seq, md)
+    fc.pf()
+    ss, _ = fc.mfe()
+    return fc.eval_structure(ss)
+
+
+def cpu_sample(L, budget_s, threads, fast=True):
+    """Time the CPU arm (MFE + backtrack, PF inside, eval) on a bounded sample of the L-workload.
+    fast: the tuned port (orc_mfe_fast / orc_pf_fast, bit-identical to the oracle, ~5x faster); else the clarity-first oracle.
+    With ViennaRNA importable the sample runs get_mfe_e_ss's call sequence over a process pool instead (kind "reference")."""
     from oracle.pyoracle import Oracle, build
     build()
     O = Oracle(os.path.join(ROOT, "desirna_b200", "params", "turner1999_37C.par"))
-    per_fold = 2.6e-8 * L ** 3 + 1.3e-6 * L ** 2  # rough single-thread seconds, only used to size the sample
-    n = int(max(threads, min(4096, budget_s * threads / per_fold)))
+    per_fold = (2.6e-8 * L ** 3 + 1.3e-6 * L ** 2) / (5.0 if fast else 1.0)  # rough single-thread seconds, only used to size the sample
+    n = int(max(threads, min(65536, budget_s * threads / per_fold)))
     n = max(threads, (n // threads) * threads)
     seqs = to_strings(synth(L, n, rank=7))
+    if fast and vienna_available():
+        import multiprocessing as mp
+        with mp.Pool(threads) as pool:
+            pool.map(_vienna_one, seqs[:threads])
+            t0 = time.perf_counter()
+            pool.map(_vienna_one, seqs, chunksize=max(1, n // (4 * threads)))
+            dt = time.perf_counter() - t0
+        return n / dt, n, dt
     t0 = time.perf_counter()
-    O.fold_batch(seqs, nthreads=threads)
+    O.fold_batch(seqs, nthreads=threads, fast=fast)
     dt = time.perf_counter() - t0
     return n / dt, n, dt
 
 
+def cpu_kind():
+    return "reference" if vienna_available() else "port"
+
+
+def cpu_desc(threads):
+    if vienna_available():
+        return f"ViennaRNA (import RNA): fc.pf(), fc.mfe(), fc.eval_structure() per sequence, multiprocessing.Pool({threads})"
+    phys = physical_cores()
+    return (f"oracle/orc_fold.c tuned arm (orc_mfe_fast / orc_pf_fast: bit-identical to the oracle, decomposed interior loops, AVX2) on {threads} threads"
+            f" ({phys} physical cores); ViennaRNA 2.6.4 is not installable offline")
+
+
+def physical_cores():
+    try:
+        cores = set()
+        phys = core = None
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("physical id"):
+                phys = line.split(":")[1].strip()
+            elif line.startswith("core id"):
+                core = line.split(":")[1].strip()
+            elif not line.strip():
+                if phys is not None and core is not None:
+                    cores.add((phys, core))
+                phys = core = None
+        return len(cores) or None
+    except Exception:
+        return None
+
+
 def run_reference(args):
+    """The CPU arm on all host threads: the tuned port (or ViennaRNA when importable), each step a bounded sample of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     L = args.L
-    # warm-up + K timed steps, each a bounded sample
     vals = []
     budget = max(1.0, min(20.0, 60.0 / max(1, args.steps)))
     for _ in range(min(args.warmup, 1)):
@@ -133,14 +192,20 @@ def run_reference(args):
     if not args.no_sweep:
         for l in SWEEP:
             by[str(l)] = value if l == L else cpu_sample(l, 8.0, threads)[0]
+    # the clarity-first oracle on the same workload, and the cost of one counted relaxation on one core
+    slow = cpu_sample(L, 4.0, threads, fast=False)[0]
+    r_mfe, r_pf = relaxations(L)
+    ns_per_relax = 1e9 * threads / value / (r_mfe + r_pf)
     line = {
         "impl": "reference", "metric": "MFE+PF folds/sec", "value": value, "unit": "folds/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
         "config": {"workload": f"synthetic batched fold sweep: random sequences x L={L}, MFE+backtrack+PF+eval, Turner 1999", "L": L,
                    "sample_per_step": n_used, "params": "turner1999"},
-        "cpu_baseline": {"value": value, "unit": "folds/s", "cores": threads, "kind": "port",
-                         "sample": f"{n_used} random sequences of L={L} per step, oracle/orc_fold.c on {threads} threads (ViennaRNA 2.6.4 not installable offline)"},
+        "cpu_baseline": {"value": value, "unit": "folds/s", "cores": threads, "physical_cores": physical_cores(), "kind": cpu_kind(),
+                         "sample": f"{n_used} random sequences of L={L} per step; " + cpu_desc(threads),
+                         "oracle_port_value": slow, "ns_per_relaxation_per_thread": ns_per_relax,
+                         "relaxations_per_fold": r_mfe + r_pf},
         "e2e": {"value": value, "unit": "folds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "by_length": by,
     }
@@ -269,7 +334,7 @@ def run_ours(args):
         for l in SWEEP:
             if l == L:
                 continue
-            m = measure(l, B, max(2, min(args.steps, 3)), 3)
+            m = measure(l, B, 10 if l == 400 else max(2, min(args.steps, 3)), 3)   # L = 400 is the second headline length: 10 steps
             by[str(l)] = world * B * len(m["ms"]) / (m["total_ms"] * 1e-3)
             kern[str(l)] = m["kernel_ms"]; checks[str(l)] = m["ok"]
             del m
@@ -374,8 +439,12 @@ def run_ours(args):
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
         v, n, dt = cpu_sample(L, 12.0, threads)
-        cpu = {"value": v, "unit": "folds/s", "cores": threads, "kind": "port",
-               "sample": f"{n} random sequences of L={L} ({dt:.1f} s), oracle/orc_fold.c on {threads} threads; ViennaRNA 2.6.4 is not installable offline"}
+        v400 = cpu_sample(400, 8.0, threads)[0] if L != 400 else v
+        slow = cpu_sample(L, 4.0, threads, fast=False)[0]
+        r_all = sum(relaxations(L))
+        cpu = {"value": v, "unit": "folds/s", "cores": threads, "physical_cores": physical_cores(), "kind": cpu_kind(),
+               "sample": f"{n} random sequences of L={L} ({dt:.1f} s); " + cpu_desc(threads),
+               "value_L400": v400, "oracle_port_value": slow, "ns_per_relaxation_per_thread": 1e9 * threads / v / r_all}
     line = {
         "metric": "MFE+PF folds/sec", "value": value, "unit": "folds/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": main["total_ms"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

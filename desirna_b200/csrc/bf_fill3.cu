@@ -221,7 +221,7 @@ __device__ __forceinline__ int lds_s32(unsigned addr) {
 //                        then their share of the split points of diagonal d
 // Ring row d must not be written while phase d still reads row d-32 (same slot): hence the staging row.
 template <int NW, int NWI, bool FMS>
-__global__ void __launch_bounds__(NW * 32, NW <= 8 ? 3 : 2) bf_k_mfe_fill3(const BfParams *__restrict__ P, BfBatchDev b, int *ctri, int *ftri, size_t tri_slot,
+__global__ void __launch_bounds__(NW * 32, NW <= 8 ? 3 : NW <= 12 ? 2 : 1) bf_k_mfe_fill3(const BfParams *__restrict__ P, BfBatchDev b, int *ctri, int *ftri, size_t tri_slot,
                                                           int *ent_ws, size_t ent_slot, const uint32_t *__restrict__ taps, int RS,
                                                           int *work_counter, int dbg) {
   constexpr int NWA = NW - NWI;
@@ -1016,7 +1016,7 @@ static cudaError_t mfe3_dispatch(const BfParams *dP, const BfBatchDev &b, int *c
   if (c.nw == NW_ && c.nwi == NWI_)                                                                                \
     return c.fms ? mfe3_launch<NW_, NWI_, true>(dP, b, ctri, ftri, ws, c, sms, work_counter, st, grid_out)         \
                  : mfe3_launch<NW_, NWI_, false>(dP, b, ctri, ftri, ws, c, sms, work_counter, st, grid_out)
-  BF_GO(8, 4); BF_GO(8, 5); BF_GO(8, 6); BF_GO(12, 8); BF_GO(12, 9);
+  BF_GO(8, 4); BF_GO(8, 5); BF_GO(8, 6); BF_GO(12, 9); BF_GO(16, 12);
 #undef BF_GO
   return cudaErrorInvalidValue;
 }

@@ -47,6 +47,12 @@ def lib():
         L.orc_fold_batch.restype = C.c_int
         L.orc_fold_batch.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_fold_batch_fast.restype = C.c_int
+        L.orc_fold_batch_fast.argtypes = L.orc_fold_batch.argtypes
+        L.orc_mfe_fast.restype = C.c_int
+        L.orc_mfe_fast.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p]
+        L.orc_pf_fast.restype = C.c_double
+        L.orc_pf_fast.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         _lib = L
     return _lib
 
@@ -120,14 +126,22 @@ class Oracle:
         raw = ss.raw
         return sorted((int(en[k]), raw[k * (n + 1): k * (n + 1) + n].decode()) for k in range(cnt))
 
-    def fold_batch(self, seqs, targets=None, nthreads=1):
-        """seqs: list of equal-length strings -> (mfe[int32], ss[list], epf[f64], ed[int32])"""
+    def mfe_fast(self, seq):
+        out = C.create_string_buffer(len(seq) + 1)
+        e = lib().orc_mfe_fast(self.P, seq.encode(), len(seq), out)
+        return e, out.value.decode()
+
+    def pf_fast(self, seq):
+        return lib().orc_pf_fast(self.P, seq.encode(), len(seq))
+
+    def fold_batch(self, seqs, targets=None, nthreads=1, fast=False):
+        """seqs: list of equal-length strings -> (mfe[int32], ss[list], epf[f64], ed[int32]); fast: the tuned CPU arm"""
         import numpy as np
         B, n = len(seqs), len(seqs[0])
         mfe = np.zeros(B, np.int32); ed = np.zeros(B, np.int32); epf = np.zeros(B, np.float64)
         ss = C.create_string_buffer(B * (n + 1))
         tg = "".join(targets).encode() if targets is not None else None
-        lib().orc_fold_batch(self.P, "".join(seqs).encode(), tg, B, n, nthreads,
+        (lib().orc_fold_batch_fast if fast else lib().orc_fold_batch)(self.P, "".join(seqs).encode(), tg, B, n, nthreads,
                              mfe.ctypes.data, C.addressof(ss), epf.ctypes.data, ed.ctypes.data)
         raw = ss.raw
         return mfe, [raw[b * (n + 1): b * (n + 1) + n].decode() for b in range(B)], epf, ed

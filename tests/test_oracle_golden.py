@@ -166,3 +166,20 @@ def test_synthetic_t2004_shaped_par_both_loaders_and_enumeration(tmp_path):
     # the tabulated loops are really used: the triloop bonus of GAAAC (-400 total 150) beats the generic 3-loop
     assert O.eval("GGGGGAAACCCCC", "(((((...)))))") == O.eval("GGGGGAUACCCCC", "(((((...)))))") - 570 + 150
     assert O.mfe("GGGGGAAACCCCC")[1] == "(((((...)))))"
+
+
+def test_tuned_cpu_arm_equals_the_oracle(oracle):
+    """bench.py's CPU arm (orc_mfe_fast / orc_pf_fast: decomposed, vectorisable loops) against the clarity-first oracle it is
+    timed in place of: MFE energy and structure bit for bit, ensemble free energy to rounding -- random sequences 5..200 nt,
+    the golden sequences, and the batch entry point."""
+    rng = np.random.default_rng(77)
+    seqs = ["".join("ACGU"[x] for x in rng.integers(0, 4, int(L))) for L in list(rng.integers(5, 120, 60)) + [150, 200]]
+    seqs += [r["sequence"] for r in load_golden("G1")[:40]] + ["GGGGAAAACCCC", "A", "GC", "ACGUA", "G" * 15 + "AAAA" + "C" * 15]
+    for s in seqs:
+        assert oracle.mfe_fast(s) == oracle.mfe(s), s
+        f, g = oracle.pf(s)[4], oracle.pf_fast(s)
+        assert abs(f - g) <= 1e-11 * max(1.0, abs(f)), s
+    same = ["".join("ACGU"[x] for x in row) for row in rng.integers(0, 4, (24, 80))]
+    a = oracle.fold_batch(same, nthreads=4)
+    b = oracle.fold_batch(same, nthreads=4, fast=True)
+    assert (a[0] == b[0]).all() and a[1] == b[1] and np.abs(a[2] - b[2]).max() < 1e-10 and (a[3] == b[3]).all()
