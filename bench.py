@@ -464,6 +464,74 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_remc(args):
+    """`--workload remc`: BASELINE.json config 3's shape through the lock-step replica loop of
+    desirna_b200.utils.replica_exchange_monte_carlo (the reference's utils/replica_exchange_monte_carlo.py:233-271 re-plumbed):
+    R = 64 replicas of one target, replica r on rank r mod G, every Monte-Carlo sub-step one engine call per rank for its R/G
+    mutants, ONE all-gather of the packed replica records per global step (NCCL), neighbour swaps recomputed on every rank.
+    Value = Monte-Carlo sub-steps of all replicas per second (R x RE_attempt x global steps / time), max time over ranks."""
+    import random
+    import torch
+    import torch.distributed as dist
+    from desirna_b200 import design, engine as eng
+    from desirna_b200.utils import replica_exchange_monte_carlo as remc
+    from desirna_b200.utils import sequence_utils as su
+    from desirna_b200.utils import stats_inputs_outputs as sio
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    eng.init(local)
+    eng.params_builtin(1999)
+    rows = [json.loads(x) for x in open(os.path.join(ROOT, "tests", "golden", "E1.jsonl"))]
+    targets = {"L104": next(r for r in rows if len(r["target"]) == 104), "L400": next(r for r in rows if len(r["target"]) == 400)}
+    R, att = 64, args.re_attempt
+    out = {}
+    for tag, row in targets.items():
+        random.seed(1234)                       # same start state and parent stream on every rank
+        o = design.DesignOptions(replicas=R, RE_attempt=att)
+        inp = sio.make_input(row["file"], row["target"])
+        nts = su.get_nt_list(inp)
+        objs = su.generate_initial_list(nts, inp, o)
+        st = sio.Stats()
+        def gstep(objs, st):
+            objs, st = remc.mutate_sequence_re(objs, nts, st, o, inp, mutate=su.mutate_sequence)
+            st.global_step += 1
+            return remc.replica_exchange(objs, st, o)
+        for _ in range(args.warmup):
+            objs, st = gstep(objs, st)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            objs, st = gstep(objs, st)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        dt = float(dt.item())
+        same = [x.sequence for x in objs]
+        if world > 1:   # every rank must hold the same replica list after the all-gather + swaps
+            gathered = [None] * world
+            dist.all_gather_object(gathered, same)
+            assert all(g == gathered[0] for g in gathered), "ranks disagree on the replica state"
+        out[tag] = {"global_steps_per_s": args.steps / dt, "substeps_per_s": R * att * args.steps / dt, "ms_per_global_step": 1e3 * dt / args.steps,
+                    "best_distance": min(sum(a != b for a, b in zip(x.mfe_ss, row["target"])) for x in objs)}
+    if rank == 0:
+        print(json.dumps({"metric": "REMC Monte-Carlo sub-steps/sec (R=64 replicas sharded r mod G, lock-step host loop, one all-gather per global step)",
+                          "value": out["L104"]["substeps_per_s"], "unit": "sub-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "higher_is_better": True, "scaling": "strong", "data": "Eterna100-V1 targets of 104 and 400 nt (tests/golden/E1.jsonl)",
+                          "config": {"workload": "remc", "replicas": R, "re_attempt": att, "scoring": "Ed-Epf:1.0", "params": "turner1999"},
+                          "by_target": out,
+                          "limiter": "per sub-step one engine call for R/G mutants: single-sequence latency of the fill kernels + Python move generator; the all-gather moves R x ~(2 L + 150) bytes once per global step"}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def bench_design_loop():
     """Sub-step cost of the replica-exchange design loop (bf_design_*: propose -> MFE + backtrack -> PF -> eval -> accept,
     all on the device).  (a) the shape of BASELINE.json's config 3 on one target: 64 replicas of one median-length Eterna
@@ -534,6 +602,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--L", type=int, default=100)
     ap.add_argument("--B", type=int, default=4096)
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "remc"])
+    ap.add_argument("--re-attempt", type=int, default=10, dest="re_attempt")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--peaks", action="store_true", help="measure INT32/FP64/smem chip peaks and write profiles/chip_peaks.json")
@@ -549,6 +619,8 @@ def main():
         return
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "remc":
+        run_remc(args)
     else:
         run_ours(args)
 

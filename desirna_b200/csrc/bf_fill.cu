@@ -1309,10 +1309,14 @@ int bf_fill_pf_mode(int nmax) {
   return pf_cfg(nmax).pl + 1;
 }
 // third-generation kernels (bf_fill3.cu) take every batch they cover, except the small batches of the 16-warp variants
-static bool use_fill3_mfe(int nmax, int B) { return !want_wide(B) && bf_fill3_mfe_ok(nmax); }
-static bool use_fill3_pf(int nmax, int B) { return !want_wide(B) && bf_fill3_pf_ok(nmax); }
+// cluster-per-sequence kernels (bf_cluster.cu): small batches of long sequences (rule in bf_cluster.cu; BF_CL=0/1 overrides)
+static bool use_cl_mfe(int nmax, int B) { return B > 0 && bf_cl_mfe_use(nmax, B); }
+static bool use_fill3_mfe(int nmax, int B) { return !use_cl_mfe(nmax, B) && !want_wide(B) && bf_fill3_mfe_ok(nmax); }
+static bool use_cl_pf(int nmax, int B) { return B > 0 && bf_cl_pf_use(nmax, B); }
+static bool use_fill3_pf(int nmax, int B) { return !use_cl_pf(nmax, B) && !want_wide(B) && bf_fill3_pf_ok(nmax); }
 
 size_t bf_mfe_ws_slot(int nmax, int B) {  // ints of per-CTA HBM workspace: [rings when they are not on chip][tile-major fML mirror when blocked]
+  if (use_cl_mfe(nmax, B)) return bf_cl_mfe_ws_slot(nmax, B);
   if (use_fill3_mfe(nmax, B)) return bf_fill3_mfe_ws_slot(nmax);
   const FillCfg c = mfe_cfg(nmax, B);
   if (c.pl < 0) return 0;
@@ -1332,6 +1336,7 @@ static bool pf_half(int nmax, const FillCfg &c) {
          pf_plan(nmax, 8, 0, true).total <= 113 * 1024;
 }
 size_t bf_pf_ws_slot(int nmax, int B) {  // doubles of per-CTA HBM workspace: [tables that are not on chip][blocked split: qm/qm1 mirrors, sums]
+  if (use_cl_pf(nmax, B)) return bf_cl_pf_ws_slot(nmax, B);
   if (use_fill3_pf(nmax, B)) return bf_fill3_pf_ws_slot(nmax);
   const FillCfg c = pf_cfg(nmax, B);
   if (c.pl < 0) return 0;
@@ -1412,14 +1417,16 @@ static cudaError_t mfe_fill_dispatch(const BfParams *dP, const BfBatchDev &b, in
   return mfe_fill_pl<8>(c.pl, dP, b, ctri, ftri, ws, sms, grid_out, launch, counter, st);
 }
 cudaError_t bf_mfe_fill_grid(const BfBatchDev &b, int sms, int *grid) {
+  if (use_cl_mfe(b.stride, b.B)) return bf_cl_mfe_grid(b, sms, grid);
   if (use_fill3_mfe(b.stride, b.B)) return bf_fill3_mfe_grid(b, sms, grid);
   return mfe_fill_dispatch(nullptr, b, nullptr, nullptr, nullptr, sms, grid, false, nullptr, nullptr);
 }
 // true: the fill kernel chosen for this batch also runs the exterior recursion and leaves f5 (B x (stride + 4) ints) for bf_k_trace
-bool bf_mfe_fill_does_ext(int nmax, int B) { return !use_fill3_mfe(nmax, B) && mfe_cfg(nmax, B).nw == 16; }
+bool bf_mfe_fill_does_ext(int nmax, int B) { return !use_cl_mfe(nmax, B) && !use_fill3_mfe(nmax, B) && mfe_cfg(nmax, B).nw == 16; }
 
 cudaError_t bf_launch_mfe_fill(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *work_counter,
                                cudaStream_t st, int *f5_out) {
+  if (use_cl_mfe(b.stride, b.B)) return bf_launch_mfe_cl(dP, b, ctri, ftri, ws, sms, work_counter, st);
   if (use_fill3_mfe(b.stride, b.B)) return bf_launch_mfe_fill3(dP, b, ctri, ftri, ws, sms, work_counter, st);
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
@@ -1502,15 +1509,17 @@ static cudaError_t pf_fill_dispatch(const BfParams *dP, const BfBatchDev &b, dou
 
 // grid size the fill will use (the caller sizes the per-CTA workspace with it)
 cudaError_t bf_pf_fill_grid(const BfBatchDev &b, int sms, int *grid) {
+  if (use_cl_pf(b.stride, b.B)) return bf_cl_pf_grid(b, sms, grid);
   if (use_fill3_pf(b.stride, b.B)) return bf_fill3_pf_grid(b, sms, grid);
   return pf_fill_dispatch(nullptr, b, nullptr, nullptr, nullptr, nullptr, nullptr, sms, grid, false, nullptr, nullptr);
 }
 
 // true: the fill kernel chosen for this batch also runs the exterior recursion and writes out5 (no bf_launch_pf_ext needed)
-bool bf_pf_fill_does_ext(int nmax, int B) { return !use_fill3_pf(nmax, B) && pf_cfg(nmax, B).nw == 16; }
+bool bf_pf_fill_does_ext(int nmax, int B) { return !use_cl_pf(nmax, B) && !use_fill3_pf(nmax, B) && pf_cfg(nmax, B).nw == 16; }
 
 cudaError_t bf_launch_pf_fill(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *qmws, double *qmseq, const int *mfe_for_scale,
                               double *lnscale, int sms, int *work_counter, cudaStream_t st, double *out5) {
+  if (use_cl_pf(b.stride, b.B)) return bf_launch_pf_cl(dP, b, qbtri, qmws, qmseq, mfe_for_scale, lnscale, sms, work_counter, st);
   if (use_fill3_pf(b.stride, b.B)) return bf_launch_pf_fill3(dP, b, qbtri, qmws, qmseq, mfe_for_scale, lnscale, sms, work_counter, st);
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;

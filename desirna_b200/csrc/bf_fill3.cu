@@ -36,132 +36,10 @@
 
 #include "bf_device.cuh"
 
+#include "bf_taps.cuh"
+
 namespace {
 
-constexpr int kRing = 32;
-constexpr int kInfThr = BF_INF / 2;
-constexpr int kNSG = 12, kNS1 = 3, kNSB = 3, kNSlot = kNSG + kNS1 + kNSB + 1;   // + the slot of the nine special candidates
-
-__host__ __device__ __forceinline__ int tri_off(int n, int d) { return (d - 4) * n - (d * (d - 1) / 2 - 6); }
-__host__ __device__ __forceinline__ size_t tri_size(int n) { return n >= 5 ? (size_t)tri_off(n, n) : 0; }
-__device__ __forceinline__ int ptype_sp(const uint8_t *SP, int i, int j) { return bf_ptype_bases(SP[i], SP[j]); }
-
-// (u1, u2) of the nine non-decomposable interior candidates: stack, bulge-1 (2x), 1x1, 1x2, 2x1, 2x2, 2x3, 3x2
-__host__ __device__ __forceinline__ int special_u1(int k) { return (int)((0x322211100ull >> (4 * k)) & 15); }
-__host__ __device__ __forceinline__ int special_u2(int k) { return (int)((0x232121010ull >> (4 * k)) & 15); }
-
-// slots a diagonal needs, by its largest loop size smax = min(30, d - 6) (index smax + 1); stored behind the tap words
-struct TapMeta {
-  unsigned char ng[32], n1[32], nb[32];
-};
-
-// ---------------------------------------------------------------------------------------------
-// host: tap -> (slot, lane) assignment
-// ---------------------------------------------------------------------------------------------
-struct TapTable {
-  uint32_t tap[kNSlot][32];   // s | u1 << 8 | valid << 16
-  TapMeta meta;
-  bool ok = false;
-};
-
-// M = 32: 4-byte ring entries, one bank per entry; M = 16: 8-byte entries, conflicts counted within each half-warp
-TapTable build_taps(int c, int M) {
-  TapTable tt;
-  memset(&tt, 0, sizeof tt);
-  bool ok = true;
-  int first = 0;
-  for (int kind = 0; kind < 3; kind++) {
-    const int nslot = kind == 0 ? kNSG : kind == 1 ? kNS1 : kNSB;
-    std::vector<std::pair<int, int>> T;
-    if (kind == 0) { for (int s = 6; s <= 30; s++) for (int u1 = 2; u1 <= s - 2; u1++) T.push_back({s, u1}); }
-    else if (kind == 1) { for (int s = 4; s <= 30; s++) { T.push_back({s, 1}); T.push_back({s, s - 1}); } }
-    else { for (int s = 2; s <= 30; s++) { T.push_back({s, 0}); T.push_back({s, s}); } }
-    std::vector<std::vector<int>> lanes(nslot, std::vector<int>(32, -1));   // index into T
-    const int halves = M == 16 ? 2 : 1, per = 32 / halves;
-    std::vector<std::pair<int, int>> left;
-    for (int ti = 0; ti < (int)T.size(); ti++) {
-      const int b = (((T[ti].second - T[ti].first * c) % M) + M) % M;
-      bool placed = false;
-      for (int k = 0; k < nslot && !placed; k++)
-        for (int h = 0; h < halves && !placed; h++) {
-          int free_lane = -1;
-          bool clash = false;
-          for (int l = h * per; l < (h + 1) * per; l++) {
-            if (lanes[k][l] < 0) { if (free_lane < 0) free_lane = l; continue; }
-            const auto &o = T[lanes[k][l]];
-            if (((((o.second - o.first * c) % M) + M) % M) == b) clash = true;
-          }
-          if (!clash && free_lane >= 0) { lanes[k][free_lane] = ti; placed = true; }
-        }
-      if (!placed) left.push_back({ti, 0});
-    }
-    // what did not fit without a bank conflict goes wherever a lane is free (a two-way conflict on that slot)
-    for (auto &lf : left) {
-      bool placed = false;
-      for (int k = nslot - 1; k >= 0 && !placed; k--)
-        for (int l = 0; l < 32 && !placed; l++)
-          if (lanes[k][l] < 0) { lanes[k][l] = lf.first; placed = true; }
-      if (!placed) ok = false;
-    }
-    if (left.size() > 4) ok = false;
-    unsigned char *need = kind == 0 ? tt.meta.ng : kind == 1 ? tt.meta.n1 : tt.meta.nb;
-    for (int k = 0; k < nslot; k++) {
-      int mins = 99;
-      for (int l = 0; l < 32; l++) {
-        if (lanes[k][l] < 0) continue;
-        const auto &t = T[lanes[k][l]];
-        tt.tap[first + k][l] = (uint32_t)t.first | ((uint32_t)t.second << 8) | (1u << 16);
-        mins = std::min(mins, t.first);
-      }
-      for (int smax = -1; smax <= 30; smax++)
-        if (mins <= smax) need[smax + 1] = (unsigned char)(k + 1);   // slots 0..k are needed
-    }
-    first += nslot;
-  }
-  // last slot: the nine non-decomposable candidates read the bulge ring at (s, u1) = (u1 + u2, u1); the other lanes read a valid
-  // address and add the INF of the entry's padding
-  for (int l = 0; l < 32; l++) {
-    const int u1 = l < 9 ? special_u1(l) : 0, u2 = l < 9 ? special_u2(l) : 0;
-    tt.tap[kNSlot - 1][l] = (uint32_t)(u1 + u2) | ((uint32_t)u1 << 8) | (1u << 16);
-  }
-  tt.ok = ok;
-  return tt;
-}
-
-// smallest row stride >= want whose residue packs (cached per residue)
-struct TapCache {
-  TapTable t[2][32];
-  bool have[2][32] = {};
-  uint32_t *dev[2][32] = {};
-  std::mutex mu;
-};
-TapCache g_taps;
-
-const TapTable &taps_for(int rs, int M) {
-  const int w = M == 16 ? 1 : 0, c = rs % M;
-  if (!g_taps.have[w][c]) { g_taps.t[w][c] = build_taps(c, M); g_taps.have[w][c] = true; }
-  return g_taps.t[w][c];
-}
-int pick_rs(int nmax, int M) {
-  for (int rs = nmax + 2 > 40 ? nmax + 2 : 40;; rs++)   // column offsets reach 31: keep them inside one row
-    if (taps_for(rs, M).ok) return rs;
-}
-cudaError_t taps_device(int rs, int M, const uint32_t **out) {
-  const int w = M == 16 ? 1 : 0, c = rs % M;
-  std::lock_guard<std::mutex> lk(g_taps.mu);
-  const TapTable &t = taps_for(rs, M);
-  if (!g_taps.dev[w][c]) {
-    // device image: the tap words, then the slots-needed table (TapMeta)
-    cudaError_t e = cudaMalloc(&g_taps.dev[w][c], sizeof t.tap + sizeof t.meta);
-    if (e != cudaSuccess) return e;
-    e = cudaMemcpy(g_taps.dev[w][c], t.tap, sizeof t.tap, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) return e;
-    e = cudaMemcpy(reinterpret_cast<unsigned char *>(g_taps.dev[w][c]) + sizeof t.tap, &t.meta, sizeof t.meta, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) return e;
-  }
-  *out = g_taps.dev[w][c];
-  return cudaSuccess;
-}
 
 // ---------------------------------------------------------------------------------------------
 // per-cell constants: everything that depends on the sequence but not on the DP tables.  A pre-pass (all warps, lanes = cells,
@@ -198,7 +76,7 @@ __host__ __device__ inline Mfe3Plan mfe3_plan(int nmax, int rs, int nw, int nwa,
   p.o_SP = o; o += (size_t)2 * ((nmax + 2 + 15) / 16 * 16);
   // per tap warp: the entries of its cells of the current diagonal (copied from L2 one phase ahead)
   o = (o + 15) / 16 * 16;
-  p.o_cl = o; o += (size_t)(rs + nw) * kEntWords * sizeof(int);
+  p.o_cl = o; o += (size_t)(rs + 2 * nw + 2) * kEntWords * sizeof(int);   // NWI lists of ceil(rs / NWI) + 1 entries each
   p.o_pp = o; o += (size_t)nwa * ((nmax + 7) / 8 * 8) * sizeof(unsigned short);   // pre-pass: pairable cells of one diagonal, per aux warp
   p.total = (o + 15) / 16 * 16;
   return p;
@@ -580,7 +458,7 @@ __host__ __device__ inline Pf3Plan pf3_plan(int nmax, int rs, int nw, int nwa, b
   p.o_ps = o; o += (size_t)2 * nwa * rs * sizeof(double);
   p.o_scl = o; o += (size_t)(nmax + 8 > 40 ? nmax + 8 : 40) * sizeof(double);   // the tap weights need scale^k up to k = 32
   o = (o + 15) / 16 * 16;   // LDGSTS copies 16 bytes at a time
-  p.o_cl = o; o += (size_t)(rs + nw) * kEntD * sizeof(double);
+  p.o_cl = o; o += (size_t)(rs + 2 * nw + 2) * kEntD * sizeof(double);   // NWI lists of ceil(rs / NWI) + 1 entries each
   p.o_np = o; o += (size_t)((nmax + 4) / 4 * 4) * sizeof(unsigned short);
   p.o_pp = o; o += (size_t)nw * ((nmax + 7) / 8 * 8) * sizeof(unsigned short);
   p.o_S = o; o += (nmax + 2 + 15) / 16 * 16;

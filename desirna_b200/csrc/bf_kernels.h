@@ -57,6 +57,20 @@ cudaError_t bf_fill3_pf_grid(const BfBatchDev &b, int sms, int *grid);
 cudaError_t bf_launch_pf_fill3(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale,
                                double *lnscale, int sms, int *work_counter, cudaStream_t st);
 
+// ---- cluster-per-sequence fill kernels (bf_cluster.cu): tables partitioned over the shared memories of a thread-block cluster
+bool bf_cl_mfe_use(int nmax, int B);           // does the cluster kernel take this batch (default rule, BF_CL=0/1 override)
+int bf_cl_mfe_csize(int nmax, int B);          // cluster size it would use (0: length not covered)
+size_t bf_cl_mfe_ws_slot(int nmax, int B);     // ints of HBM workspace per cluster
+cudaError_t bf_cl_mfe_grid(const BfBatchDev &b, int sms, int *nclusters);
+cudaError_t bf_launch_mfe_cl(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *work_counter,
+                             cudaStream_t st);
+bool bf_cl_pf_use(int nmax, int B);
+int bf_cl_pf_csize(int nmax, int B);
+size_t bf_cl_pf_ws_slot(int nmax, int B);      // doubles of HBM workspace per cluster
+cudaError_t bf_cl_pf_grid(const BfBatchDev &b, int sms, int *nclusters);
+cudaError_t bf_launch_pf_cl(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale,
+                            double *lnscale, int sms, int *work_counter, cudaStream_t st);
+
 // ---- tile-wavefront fill path (bf_tile.cu): same tables in HBM as the diagonal-major path, 4x4 tiles by tile-diagonal
 int bf_tile_mfe_ok(int nmax);        // 1 if the tile MFE fill covers this length
 size_t bf_mfe_tile_ws_slot(int nmax);  // ints of per-CTA HBM workspace (tile-major fML when it is not on chip)
