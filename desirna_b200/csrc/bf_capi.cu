@@ -113,6 +113,13 @@ int validate(const bf_batch_t *b, const bf_result_t *r) {
   return BF_OK;
 }
 
+// exterior recursions by one CTA per sequence instead of one warp per sequence: batches that leave SMs idle (BF_EXT_WIDE=0/1 overrides)
+bool wide_ext(int B, int stride) {
+  const char *v = getenv("BF_EXT_WIDE");
+  if (v && *v) return atoi(v) != 0 && bf_ext_wide_ok(stride);
+  return B <= 2 * g.sm_count && bf_ext_wide_ok(stride);
+}
+
 // all pointers are device pointers
 // scale_override (device, B ints, dcal/mol): energies that set the partition function's per-nucleotide scale instead of this
 // call's own MFE.  The result does not depend on the scale beyond rounding, and without that dependency the partition function
@@ -160,6 +167,12 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
         }
         CU(bf_launch_mfe_fill(g.dP, db, (int *)w.tri_c.p, (int *)w.tri_f.p, (int *)w.ws_ring.p, g.sm_count, w.d_counters + 0, st, f5),
            "launch bf_k_mfe_fill");
+        if (!f5 && wide_ext(b->B, b->stride)) {   // few sequences: the exterior recursion by one CTA per sequence (bf_ext.cu)
+          CU(w.f5buf.reserve((size_t)b->B * (b->stride + 4) * sizeof(int)), "cudaMalloc(f5)");
+          f5 = (int *)w.f5buf.p;
+          CU(bf_launch_f5_wide(g.dP, db, (const int *)w.tri_c.p, f5, st), "launch bf_k_f5_wide");
+          g.launches++;
+        }
       }
       CU(bf_launch_trace(g.dP, db, (const int *)w.tri_c.p, (const int *)w.tri_f.p, out_mfe, (b->want & BF_WANT_SS) ? r->mfe_ss : nullptr,
                          b->stride + 1, st, f5), "launch bf_k_trace");
@@ -208,7 +221,10 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
                            w.d_counters + 1, sp, r->pf), "launch bf_k_pf_fill");
       g.launches++;
       if (!bf_pf_fill_does_ext(b->stride, b->B)) {
-        CU(bf_launch_pf_ext(g.dP, dbp, (const double *)w.tri_qb.p, (const double *)w.d_lnscale.p, r->pf, sp), "launch bf_k_pf_ext");
+        if (wide_ext(b->B, b->stride))
+          CU(bf_launch_q5_wide(g.dP, dbp, (const double *)w.tri_qb.p, (const double *)w.d_lnscale.p, r->pf, sp), "launch bf_k_q5_wide");
+        else
+          CU(bf_launch_pf_ext(g.dP, dbp, (const double *)w.tri_qb.p, (const double *)w.d_lnscale.p, r->pf, sp), "launch bf_k_pf_ext");
         g.launches++;
       }
       if (want_out) {

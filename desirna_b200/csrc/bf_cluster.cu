@@ -898,11 +898,13 @@ const ClSlots &cl_slots(ClSlots &s, K kern) {
   return s;
 }
 
-// Measured on one B200 (scripts/cl_sweep.py, profiles/r02_cluster_sweep.txt): a cluster folds one sequence in ~2.7 us per diagonal
-// almost independently of its size, the single-CTA kernels need 3 us (150 nt) to 8 us (MFE) / 17 us (PF) per diagonal at 400 nt.
-// So the cluster kernels take a batch when it fits in few rounds of the clusters in flight: rounds allowed by length.
-int mfe_rounds_allowed(int nmax) { return nmax < 160 ? 0 : nmax < 230 ? 1 : nmax < 330 ? 2 : 3; }
-int pf_rounds_allowed(int nmax) { return nmax < 140 ? 0 : nmax < 190 ? 1 : nmax < 330 ? 2 : 3; }
+// Measured on one B200 (scripts/cl_sweep.py, profiles/r02_cluster_sweep.txt; fill + exterior recursion + backtrack per call): a
+// cluster folds one sequence in ~2.7 us per diagonal almost independently of its size -- 0.41 / 0.57 / 0.74 / 0.9 / 1.3 ms at
+// 150 / 200 / 250 / 300 / 400 nt -- where the single-CTA kernels need 0.59 / 1.03 / 1.87 / 2.6 / 4.3 ms (MFE) and 0.77 / 1.38 / 2.6 /
+// 3.7 / 7.2 ms (PF) however few sequences there are.  So the cluster kernels take a batch when it fits in few ROUNDS of the
+// clusters in flight: rounds allowed by length.
+int mfe_rounds_allowed(int nmax) { return nmax < 130 ? 0 : nmax < 230 ? 1 : nmax < 330 ? 2 : 3; }
+int pf_rounds_allowed(int nmax) { return nmax < 130 ? 0 : nmax < 180 ? 1 : nmax < 230 ? 2 : nmax < 350 ? 3 : 5; }
 
 struct ClCfg { bool ok, dflt; int slots; ClGeom g; MfeClPlan pl; };
 ClCfg mfe_cl_cfg(int nmax, int B) {

@@ -71,6 +71,11 @@ cudaError_t bf_cl_pf_grid(const BfBatchDev &b, int sms, int *nclusters);
 cudaError_t bf_launch_pf_cl(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale,
                             double *lnscale, int sms, int *work_counter, cudaStream_t st);
 
+// ---- exterior recursions for small batches (bf_ext.cu): one CTA per sequence
+bool bf_ext_wide_ok(int nmax);
+cudaError_t bf_launch_f5_wide(const BfParams *dP, const BfBatchDev &b, const int *ctri, int *f5_out, cudaStream_t st);   // f5_out: B x (stride + 4)
+cudaError_t bf_launch_q5_wide(const BfParams *dP, const BfBatchDev &b, const double *qbtri, const double *lnscale, double *out5, cudaStream_t st);
+
 // ---- tile-wavefront fill path (bf_tile.cu): same tables in HBM as the diagonal-major path, 4x4 tiles by tile-diagonal
 int bf_tile_mfe_ok(int nmax);        // 1 if the tile MFE fill covers this length
 size_t bf_mfe_tile_ws_slot(int nmax);  // ints of per-CTA HBM workspace (tile-major fML when it is not on chip)
