@@ -572,6 +572,27 @@ def bench_design_loop():
     loop.close()
     out["heterodimer_17_18nt_64_replicas"] = {"ms_per_substep": dt / 200 * 1e3, "sequences_scored_per_s": 64 * 200 / dt,
                                               "reference_example_run": "933 score calls/s on 10 processes (example_files/outputs/RNA_RNA_complex*/*_stats)"}
+    # (e) what the reference does per run: ONE target, its default 10 replicas -- here the longest Eterna V1 targets.  A sub-step
+    # scores 10 sequences: the cluster-per-sequence kernels (csrc/bf_cluster.cu, a thread-block cluster per sequence) against the
+    # single-CTA kernels (BF_CL=0 BF_EXT_WIDE=0)
+    for L in (200, 400):
+        one_long = min(rows, key=lambda r: (abs(len(r["target"]) - L), r["file"]))
+        res = {"target": one_long["file"], "L": len(one_long["target"])}
+        for tag, env in (("cluster_kernels", {}), ("single_cta_kernels", {"BF_CL": "0", "BF_EXT_WIDE": "0"})):
+            os.environ.update(env)
+            try:
+                o = design.DesignOptions(replicas=10, RE_attempt=20)
+                loop = design.DesignLoop([sio.make_input(one_long["file"], one_long["target"])], o, seed=5)
+                loop.run(1); loop.sync()
+                t0 = time.perf_counter()
+                loop.run(2); loop.sync()
+                dt = time.perf_counter() - t0
+                loop.close()
+                res[tag] = {"ms_per_substep": dt / 40 * 1e3, "sequences_scored_per_s": 10 * 40 / dt}
+            finally:
+                for k in env:
+                    os.environ.pop(k, None)
+        out["one_target_%dnt_10_replicas" % L] = res
     o = design.DesignOptions(replicas=10, RE_attempt=100)
     inputs = [sio.make_input(r["file"], r["target"]) for r in rows]
     groups = design.bucket_jobs([len(i.sec_struct) for i in inputs])

@@ -71,7 +71,6 @@ struct Engine {
   BfParams *hP = nullptr;  // host image
   BfParams *dP = nullptr;  // device image
   Workspace w;             // tables and workspaces of the bf_score_batch* entry points
-  int fill_kind = 0;                              // BF_FILL=tile: tile-wavefront fill kernels (bf_tile.cu); diag: bf_fill.cu
   bool force_generic = false;                     // BF_FORCE_GENERIC=1: route single strands through the generic kernels too
   // staging for the host-buffer entry point
   DevBuf d_seq, d_len, d_cut, d_nopair, d_targets, d_mfe, d_ss, d_pf, d_eval, d_defect, d_bpp;
@@ -145,34 +144,23 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
       CU(w.tri_c.reserve((size_t)b->B * slot), "cudaMalloc(c table)");
       CU(w.tri_f.reserve((size_t)b->B * slot), "cudaMalloc(fML table)");
       int *f5 = nullptr;
-      if (g.fill_kind == 1 && bf_tile_mfe_ok(b->stride)) {
-        const size_t wsi = bf_mfe_tile_ws_slot(b->stride) * sizeof(int);
-        if (wsi) {
-          int grid = 0;
-          CU(bf_mfe_tile_grid(db, g.sm_count, &grid), "size bf_k_mfe_tile");
-          CU(w.ws_ring.reserve((size_t)grid * wsi), "cudaMalloc(tile workspace)");
-        }
-        CU(bf_launch_mfe_tile(g.dP, db, (int *)w.tri_c.p, (int *)w.tri_f.p, (int *)w.ws_ring.p, g.sm_count, w.d_counters + 0, st),
-           "launch bf_k_mfe_tile");
-      } else {
-        const size_t wsi = bf_mfe_ws_slot(b->stride, b->B) * sizeof(int);
-        if (wsi) {
-          int grid = 0;
-          CU(bf_mfe_fill_grid(db, g.sm_count, &grid), "size bf_k_mfe_fill");
-          CU(w.ws_ring.reserve((size_t)grid * wsi), "cudaMalloc(ring workspace)");
-        }
-        if (bf_mfe_fill_does_ext(b->stride, b->B)) {
-          CU(w.f5buf.reserve((size_t)b->B * (b->stride + 4) * sizeof(int)), "cudaMalloc(f5)");
-          f5 = (int *)w.f5buf.p;
-        }
-        CU(bf_launch_mfe_fill(g.dP, db, (int *)w.tri_c.p, (int *)w.tri_f.p, (int *)w.ws_ring.p, g.sm_count, w.d_counters + 0, st, f5),
-           "launch bf_k_mfe_fill");
-        if (!f5 && wide_ext(b->B, b->stride)) {   // few sequences: the exterior recursion by one CTA per sequence (bf_ext.cu)
-          CU(w.f5buf.reserve((size_t)b->B * (b->stride + 4) * sizeof(int)), "cudaMalloc(f5)");
-          f5 = (int *)w.f5buf.p;
-          CU(bf_launch_f5_wide(g.dP, db, (const int *)w.tri_c.p, f5, st), "launch bf_k_f5_wide");
-          g.launches++;
-        }
+      const size_t wsi = bf_mfe_ws_slot(b->stride, b->B) * sizeof(int);
+      if (wsi) {
+        int grid = 0;
+        CU(bf_mfe_fill_grid(db, g.sm_count, &grid), "size bf_k_mfe_fill");
+        CU(w.ws_ring.reserve((size_t)grid * wsi), "cudaMalloc(ring workspace)");
+      }
+      if (bf_mfe_fill_does_ext(b->stride, b->B)) {
+        CU(w.f5buf.reserve((size_t)b->B * (b->stride + 4) * sizeof(int)), "cudaMalloc(f5)");
+        f5 = (int *)w.f5buf.p;
+      }
+      CU(bf_launch_mfe_fill(g.dP, db, (int *)w.tri_c.p, (int *)w.tri_f.p, (int *)w.ws_ring.p, g.sm_count, w.d_counters + 0, st, f5),
+         "launch bf_k_mfe_fill");
+      if (!f5 && wide_ext(b->B, b->stride)) {   // few sequences: the exterior recursion by one CTA per sequence (bf_ext.cu)
+        CU(w.f5buf.reserve((size_t)b->B * (b->stride + 4) * sizeof(int)), "cudaMalloc(f5)");
+        f5 = (int *)w.f5buf.p;
+        CU(bf_launch_f5_wide(g.dP, db, (const int *)w.tri_c.p, f5, st), "launch bf_k_f5_wide");
+        g.launches++;
       }
       CU(bf_launch_trace(g.dP, db, (const int *)w.tri_c.p, (const int *)w.tri_f.p, out_mfe, (b->want & BF_WANT_SS) ? r->mfe_ss : nullptr,
                          b->stride + 1, st, f5), "launch bf_k_trace");
@@ -285,7 +273,6 @@ int bf_init(int device) {
   if (prop.major < 10) return fail(BF_ERR_CUDA, std::string("built for sm_100a, found ") + prop.name);
   g.device = device;
   { const char *fg = getenv("BF_FORCE_GENERIC"); g.force_generic = fg && fg[0] == '1'; }
-  { const char *fk = getenv("BF_FILL"); g.fill_kind = (fk && !strcmp(fk, "tile")) ? 1 : 0; }
   g.sm_count = prop.multiProcessorCount;
   bf_fill_set_sms(g.sm_count);
   CU(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking), "cudaStreamCreate");
@@ -484,9 +471,19 @@ int bf_last_kernel_ms(double out[3]) {
 }
 
 int bf_set_option(const char *key, int value) {
-  if (!key) return fail(BF_ERR_ARG, "null option key");
-  if (!strcmp(key, "fill")) { g.fill_kind = value ? 1 : 0; return BF_OK; }
-  return fail(BF_ERR_ARG, std::string("unknown option: ") + key);
+  // Kernel variants are chosen per call from BF_* environment variables (bf_fill.cu, bf_fill3.cu, bf_cluster.cu, this file); this
+  // sets one of them from the host program: key "cl" -> BF_CL, "cl_c" -> BF_CL_C, "ext_wide" -> BF_EXT_WIDE, "wide" -> BF_WIDE, ...
+  // A negative value removes the variable (back to the default rule).
+  if (!key || !*key) return fail(BF_ERR_ARG, "null option key");
+  std::string name = "BF_";
+  for (const char *p = key; *p; p++) {
+    const char ch = *p;
+    if (!((ch >= 'a' && ch <= 'z') || (ch >= 'A' && ch <= 'Z') || (ch >= '0' && ch <= '9') || ch == '_')) return fail(BF_ERR_ARG, std::string("bad option key: ") + key);
+    name += (char)((ch >= 'a' && ch <= 'z') ? ch - 'a' + 'A' : ch);
+  }
+  if (value < 0) unsetenv(name.c_str());
+  else setenv(name.c_str(), std::to_string(value).c_str(), 1);
+  return BF_OK;
 }
 
 int bf_debug_copy_table(int which, int32_t n_seq, void *host, size_t host_bytes, size_t *slot_entries) {

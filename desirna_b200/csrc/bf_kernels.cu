@@ -14,6 +14,8 @@
 // Recurrences: SURVEY.md A.4 (fill), A.5 (backtrack order), A.6 (inside), A.7 (two strands), A.8 (eval).
 #include "bf_kernels.h"
 
+#include <cstdlib>
+
 #include "bf_device.cuh"
 
 namespace {
@@ -50,7 +52,8 @@ __device__ __forceinline__ void load_sequence(const BfBatchDev &b, int s, uint8_
 // =====================================================================================================
 template <bool TWO>
 __global__ void __launch_bounds__(BF_THREADS) bf_k_mfe(const BfParams *__restrict__ P, BfBatchDev b, int *ws, size_t ws_slot_ints,
-                                                       int wstride, int *work_counter, int *out_mfe, char *out_ss, int ss_stride) {
+                                                       int wstride, int *work_counter, int *out_mfe, char *out_ss, int ss_stride,
+                                                       unsigned tables_smem_off) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ BfSmallI T;
   __shared__ uint8_t cu1[BF_NCAND], cu2[BF_NCAND];
@@ -70,7 +73,8 @@ __global__ void __launch_bounds__(BF_THREADS) bf_k_mfe(const BfParams *__restric
   int *fcB = fcA + (nmax + 4);
   BfSector *stk = reinterpret_cast<BfSector *>(fcB + (nmax + 4));
 
-  int *c = ws + (size_t)blockIdx.x * ws_slot_ints;
+  // short sequences: the three tables live in shared memory behind the per-sequence arrays (offset passed by the host), else in HBM
+  int *c = tables_smem_off ? reinterpret_cast<int *>(dyn + tables_smem_off) : ws + (size_t)blockIdx.x * ws_slot_ints;
   int *fml = c + (size_t)W * W;
   int *fmlT = fml + (size_t)W * W;
 #define C_(i, j) c[(i) * W + (j)]
@@ -404,7 +408,8 @@ __global__ void __launch_bounds__(BF_THREADS) bf_k_mfe(const BfParams *__restric
 // =====================================================================================================
 template <bool TWO>
 __global__ void __launch_bounds__(BF_THREADS) bf_k_pf(const BfParams *__restrict__ P, BfBatchDev b, double *ws, size_t ws_slot_dbl,
-                                                      int wstride, int *work_counter, const int *mfe_for_scale, double *out5) {
+                                                      int wstride, int *work_counter, const int *mfe_for_scale, double *out5,
+                                                      unsigned tables_smem_off) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ BfSmallD T;
   __shared__ uint8_t cu1[BF_NCAND], cu2[BF_NCAND];
@@ -424,7 +429,7 @@ __global__ void __launch_bounds__(BF_THREADS) bf_k_pf(const BfParams *__restrict
   uint8_t *S = reinterpret_cast<uint8_t *>(qB + (nmax + 4));
   uint8_t *SP = S + align_up(nmax + 2, 16);
 
-  double *qb = ws + (size_t)blockIdx.x * ws_slot_dbl;
+  double *qb = tables_smem_off ? reinterpret_cast<double *>(dyn + tables_smem_off) : ws + (size_t)blockIdx.x * ws_slot_dbl;
   double *qm = qb + (size_t)W * W;
   double *qm1T = qm + (size_t)W * W;  // qm1T[j][i] = qm1[i][j]
 #define QB_(i, j) qb[(i) * W + (j)]
@@ -722,16 +727,34 @@ static size_t pf_smem(int wstride) {
   size_t nmax = wstride - 2;
   return 5 * (nmax + 4) * sizeof(double) + 2 * ((nmax + 2 + 15) / 16 * 16);
 }
+// The generic kernels (two strands; any length the fill path does not cover) keep three W x W tables per CTA.  Short sequences --
+// the reference's two-strand examples are 17 & 18 nt -- fit in shared memory next to the per-sequence arrays, which takes the L2
+// round trip out of every table access (BF_GEN_SMEM=0: always HBM).  Capped so that at least two CTAs share an SM.
+static size_t gen_tables_cap() {
+  const char *v = getenv("BF_GEN_SMEM");
+  if (v && *v && atoi(v) == 0) return 0;
+  return (size_t)100 * 1024;
+}
+static unsigned mfe_tables_off(int wstride) {   // 0: tables in HBM
+  const size_t base = (mfe_smem(wstride) + 15) / 16 * 16;
+  return base + bf_mfe_slot_ints(wstride) * sizeof(int) <= gen_tables_cap() ? (unsigned)base : 0u;
+}
+static unsigned pf_tables_off(int wstride) {
+  const size_t base = (pf_smem(wstride) + 15) / 16 * 16;
+  return base + bf_pf_slot_doubles(wstride) * sizeof(double) <= gen_tables_cap() ? (unsigned)base : 0u;
+}
+static size_t mfe_smem_total(int wstride) { const unsigned o = mfe_tables_off(wstride); return o ? o + bf_mfe_slot_ints(wstride) * sizeof(int) : mfe_smem(wstride); }
+static size_t pf_smem_total(int wstride) { const unsigned o = pf_tables_off(wstride); return o ? o + bf_pf_slot_doubles(wstride) * sizeof(double) : pf_smem(wstride); }
 static size_t eval_smem(int stride) { return 2 * (stride + 4) * sizeof(short) + 2 * ((stride + 2 + 15) / 16 * 16); }
 
 cudaError_t bf_launch_mfe(const BfParams *dP, const BfBatchDev &b, bool two, int *ws, int wstride, int grid, int *work_counter,
                           int *out_mfe, char *out_ss, int ss_stride, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
-  size_t sm = mfe_smem(wstride);
+  size_t sm = mfe_smem_total(wstride);
   auto kern = two ? bf_k_mfe<true> : bf_k_mfe<false>;
   if (sm > 48 * 1024) { e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; }
-  kern<<<grid, BF_THREADS, sm, st>>>(dP, b, ws, bf_mfe_slot_ints(wstride), wstride, work_counter, out_mfe, out_ss, ss_stride);
+  kern<<<grid, BF_THREADS, sm, st>>>(dP, b, ws, bf_mfe_slot_ints(wstride), wstride, work_counter, out_mfe, out_ss, ss_stride, mfe_tables_off(wstride));
   return cudaGetLastError();
 }
 
@@ -739,10 +762,10 @@ cudaError_t bf_launch_pf(const BfParams *dP, const BfBatchDev &b, bool two, doub
                          const int *mfe_for_scale, double *out5, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
-  size_t sm = pf_smem(wstride);
+  size_t sm = pf_smem_total(wstride);
   auto kern = two ? bf_k_pf<true> : bf_k_pf<false>;
   if (sm > 48 * 1024) { e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; }
-  kern<<<grid, BF_THREADS, sm, st>>>(dP, b, ws, bf_pf_slot_doubles(wstride), wstride, work_counter, mfe_for_scale, out5);
+  kern<<<grid, BF_THREADS, sm, st>>>(dP, b, ws, bf_pf_slot_doubles(wstride), wstride, work_counter, mfe_for_scale, out5, pf_tables_off(wstride));
   return cudaGetLastError();
 }
 
@@ -758,12 +781,14 @@ cudaError_t bf_launch_eval(const BfParams *dP, const BfBatchDev &b, const char *
 int bf_occupancy_mfe(bool two, int wstride) {
   int nb = 0;
   auto kern = two ? bf_k_mfe<true> : bf_k_mfe<false>;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, BF_THREADS, mfe_smem(wstride)) != cudaSuccess) return 1;
+  if (mfe_smem_total(wstride) > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mfe_smem_total(wstride));
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, BF_THREADS, mfe_smem_total(wstride)) != cudaSuccess) return 1;
   return nb < 1 ? 1 : nb;
 }
 int bf_occupancy_pf(bool two, int wstride) {
   int nb = 0;
   auto kern = two ? bf_k_pf<true> : bf_k_pf<false>;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, BF_THREADS, pf_smem(wstride)) != cudaSuccess) return 1;
+  if (pf_smem_total(wstride) > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_smem_total(wstride));
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, BF_THREADS, pf_smem_total(wstride)) != cudaSuccess) return 1;
   return nb < 1 ? 1 : nb;
 }

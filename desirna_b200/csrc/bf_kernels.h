@@ -76,13 +76,6 @@ bool bf_ext_wide_ok(int nmax);
 cudaError_t bf_launch_f5_wide(const BfParams *dP, const BfBatchDev &b, const int *ctri, int *f5_out, cudaStream_t st);   // f5_out: B x (stride + 4)
 cudaError_t bf_launch_q5_wide(const BfParams *dP, const BfBatchDev &b, const double *qbtri, const double *lnscale, double *out5, cudaStream_t st);
 
-// ---- tile-wavefront fill path (bf_tile.cu): same tables in HBM as the diagonal-major path, 4x4 tiles by tile-diagonal
-int bf_tile_mfe_ok(int nmax);        // 1 if the tile MFE fill covers this length
-size_t bf_mfe_tile_ws_slot(int nmax);  // ints of per-CTA HBM workspace (tile-major fML when it is not on chip)
-cudaError_t bf_mfe_tile_grid(const BfBatchDev &b, int sms, int *grid);
-cudaError_t bf_launch_mfe_tile(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *work_counter,
-                               cudaStream_t st);
-
 // ---- outside pass: base-pair probabilities and ensemble defect (bf_outside.cu)
 size_t bf_out_ws_slot(int nmax);   // doubles of per-CTA HBM workspace
 cudaError_t bf_out_grid(const BfBatchDev &b, int sms, int *grid);

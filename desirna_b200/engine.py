@@ -139,7 +139,8 @@ def subopt(seq, delta_dcal, nopair=None, max_out=4096):
 
 
 def set_option(key, value):
-    """Tuning / test hook (bf_set_option): e.g. set_option("fill", 1) selects the tile-wavefront fill kernels."""
+    """Tuning / test hook (bf_set_option): sets the engine's BF_<KEY> variable, e.g. set_option("cl", 0) switches the
+    cluster-per-sequence fill kernels off, set_option("cl", -1) restores the default rule."""
     ensure_ready()
     _check(lib().bf_set_option(key.encode(), int(value)))
 

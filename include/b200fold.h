@@ -101,7 +101,10 @@ int bf_microbench(double out[3]);
 int64_t bf_kernel_launches(void);
 /* SM count of the device in use */
 int bf_sm_count(void);
-/* Tuning / test hook.  key "fill": 0 = diagonal-major fill kernels (bf_fill.cu), 1 = tile-wavefront fill kernels (bf_tile.cu). */
+/* Tuning / test hook.  Kernel variants are chosen per call by default rules that BF_* environment variables override; this sets
+ * the variable BF_<KEY> from the host program (value < 0: remove it).  E.g. "cl" 0 / 1: never / always use the cluster-per-sequence
+ * fill kernels where they cover the length, "cl_c" 4 | 8 | 16: their cluster size, "ext_wide" 0 / 1: exterior recursions by one warp /
+ * one CTA per sequence, "wide" 0: no 16-warp variants for small batches. */
 int bf_set_option(const char *key, int value);
 /* Test hook: copy one engine-internal DP table of the most recent call to host memory.
  * which: 0 = c (int32), 1 = fML (int32), 2 = qb (double); layout: per sequence a packed, diagonal-major triangle of
