@@ -50,8 +50,8 @@ __device__ __forceinline__ void load_sequence(const BfBatchDev &b, int s, uint8_
 // =====================================================================================================
 //                                               MFE
 // =====================================================================================================
-template <bool TWO>
-__global__ void __launch_bounds__(BF_THREADS) bf_k_mfe(const BfParams *__restrict__ P, BfBatchDev b, int *ws, size_t ws_slot_ints,
+template <bool TWO, int NWG>
+__global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict__ P, BfBatchDev b, int *ws, size_t ws_slot_ints,
                                                        int wstride, int *work_counter, int *out_mfe, char *out_ss, int ss_stride,
                                                        unsigned tables_smem_off) {
   extern __shared__ __align__(16) unsigned char dyn[];
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(BF_THREADS) bf_k_mfe(const BfParams *__restric
         }
         __syncthreads();
       }
-      for (int i = 1 + warp; i + d <= n; i += BF_WARPS) {
+      for (int i = 1 + warp; i + d <= n; i += NWG) {
         const int j = i + d;
         const int t = bf_ptype<TWO>(X, i, j);
         int e = BF_INF;
@@ -406,8 +406,8 @@ __global__ void __launch_bounds__(BF_THREADS) bf_k_mfe(const BfParams *__restric
 // =====================================================================================================
 //                                     partition function (inside)
 // =====================================================================================================
-template <bool TWO>
-__global__ void __launch_bounds__(BF_THREADS) bf_k_pf(const BfParams *__restrict__ P, BfBatchDev b, double *ws, size_t ws_slot_dbl,
+template <bool TWO, int NWG>
+__global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__ P, BfBatchDev b, double *ws, size_t ws_slot_dbl,
                                                       int wstride, int *work_counter, const int *mfe_for_scale, double *out5,
                                                       unsigned tables_smem_off) {
   extern __shared__ __align__(16) unsigned char dyn[];
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(BF_THREADS) bf_k_pf(const BfParams *__restrict
         }
         __syncthreads();
       }
-      for (int i = 1 + warp; i + d <= n; i += BF_WARPS) {
+      for (int i = 1 + warp; i + d <= n; i += NWG) {
         const int j = i + d;
         const int t = bf_ptype<TWO>(X, i, j);
         double qbij = 0.0;
@@ -730,6 +730,12 @@ static size_t pf_smem(int wstride) {
 // The generic kernels (two strands; any length the fill path does not cover) keep three W x W tables per CTA.  Short sequences --
 // the reference's two-strand examples are 17 & 18 nt -- fit in shared memory next to the per-sequence arrays, which takes the L2
 // round trip out of every table access (BF_GEN_SMEM=0: always HBM).  Capped so that at least two CTAs share an SM.
+static bool gen_wide(int B) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const char *v = getenv("BF_WIDE");
+  return B > 0 && B <= sms && !(v && *v && atoi(v) == 0);
+}
 static size_t gen_tables_cap() {
   const char *v = getenv("BF_GEN_SMEM");
   if (v && *v && atoi(v) == 0) return 0;
@@ -752,9 +758,11 @@ cudaError_t bf_launch_mfe(const BfParams *dP, const BfBatchDev &b, bool two, int
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
   size_t sm = mfe_smem_total(wstride);
-  auto kern = two ? bf_k_mfe<true> : bf_k_mfe<false>;
+  // a warp per cell: with few sequences (a CTA owns its SM) 16 warps per CTA halve the rounds per diagonal
+  const bool wide = gen_wide(b.B);
+  auto kern = two ? (wide ? bf_k_mfe<true, 16> : bf_k_mfe<true, BF_WARPS>) : (wide ? bf_k_mfe<false, 16> : bf_k_mfe<false, BF_WARPS>);
   if (sm > 48 * 1024) { e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; }
-  kern<<<grid, BF_THREADS, sm, st>>>(dP, b, ws, bf_mfe_slot_ints(wstride), wstride, work_counter, out_mfe, out_ss, ss_stride, mfe_tables_off(wstride));
+  kern<<<grid, (wide ? 16 : BF_WARPS) * 32, sm, st>>>(dP, b, ws, bf_mfe_slot_ints(wstride), wstride, work_counter, out_mfe, out_ss, ss_stride, mfe_tables_off(wstride));
   return cudaGetLastError();
 }
 
@@ -763,9 +771,10 @@ cudaError_t bf_launch_pf(const BfParams *dP, const BfBatchDev &b, bool two, doub
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
   size_t sm = pf_smem_total(wstride);
-  auto kern = two ? bf_k_pf<true> : bf_k_pf<false>;
+  const bool wide = gen_wide(b.B);
+  auto kern = two ? (wide ? bf_k_pf<true, 16> : bf_k_pf<true, BF_WARPS>) : (wide ? bf_k_pf<false, 16> : bf_k_pf<false, BF_WARPS>);
   if (sm > 48 * 1024) { e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; }
-  kern<<<grid, BF_THREADS, sm, st>>>(dP, b, ws, bf_pf_slot_doubles(wstride), wstride, work_counter, mfe_for_scale, out5, pf_tables_off(wstride));
+  kern<<<grid, (wide ? 16 : BF_WARPS) * 32, sm, st>>>(dP, b, ws, bf_pf_slot_doubles(wstride), wstride, work_counter, mfe_for_scale, out5, pf_tables_off(wstride));
   return cudaGetLastError();
 }
 
@@ -780,14 +789,14 @@ cudaError_t bf_launch_eval(const BfParams *dP, const BfBatchDev &b, const char *
 
 int bf_occupancy_mfe(bool two, int wstride) {
   int nb = 0;
-  auto kern = two ? bf_k_mfe<true> : bf_k_mfe<false>;
+  auto kern = two ? bf_k_mfe<true, BF_WARPS> : bf_k_mfe<false, BF_WARPS>;
   if (mfe_smem_total(wstride) > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mfe_smem_total(wstride));
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, BF_THREADS, mfe_smem_total(wstride)) != cudaSuccess) return 1;
   return nb < 1 ? 1 : nb;
 }
 int bf_occupancy_pf(bool two, int wstride) {
   int nb = 0;
-  auto kern = two ? bf_k_pf<true> : bf_k_pf<false>;
+  auto kern = two ? bf_k_pf<true, BF_WARPS> : bf_k_pf<false, BF_WARPS>;
   if (pf_smem_total(wstride) > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_smem_total(wstride));
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, BF_THREADS, pf_smem_total(wstride)) != cudaSuccess) return 1;
   return nb < 1 ? 1 : nb;
