@@ -361,6 +361,28 @@ def run_ours(args):
         dist.all_reduce(tD, op=dist.ReduceOp.MAX)
     with_defect = {"value": world * B * nD / (float(tD.item()) * 1e-3), "unit": "folds/s", "ms_per_step": float(tD.item()) / nD,
                    "defect_in_0_1": bool(((dfc >= -1e-9) & (dfc <= 1.0 + 1e-9)).all().item()), "defect_mean": float(dfc.mean().item())}
+    # the same column at the second headline length (BASELINE config 5's Edef scoring is quoted on long targets): 1024 sequences of 400 nt
+    if not args.no_sweep and L != 400:
+        B4 = min(B, 1024)
+        _c4, b4 = make(400, B4)
+        d4 = torch.zeros(B4, dtype=torch.float64, device=dev)
+        def stepD4():
+            eng.score_batch_device(b4["seq"], b4["lens"], WANTD, targets=b4["targets"], mfe=b4["mfe"], ss=b4["ss"], pf=b4["pf"], ev=b4["ev"],
+                                   stream=stream, defect=d4)
+        for _ in range(2):
+            stepD4()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(3):
+            stepD4()
+        f1.record(); f1.synchronize()
+        t4 = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+        with_defect["L400"] = {"value": world * B4 * 3 / (float(t4.item()) * 1e-3), "unit": "folds/s", "B_per_gpu": B4, "ms_per_step": float(t4.item()) / 3,
+                               "defect_in_0_1": bool(((d4 >= -1e-9) & (d4 <= 1.0 + 1e-9)).all().item())}
+        del b4, d4
 
     # ---- the path's caller: Monte-Carlo sub-steps of the device-resident replica-exchange design loop (N=1 only)
     design_blk = bench_design_loop() if world == 1 else None
@@ -375,7 +397,11 @@ def run_ours(args):
     if os.path.exists(pk_path):
         try:
             cp = json.load(open(pk_path))
-            peaks.update(int32_tops=cp["int32_ops_per_s"] / 1e12, fp64_tflops=cp["fp64_flops_per_s"] / 1e12, smem_tbs=cp["smem_bytes_per_s"] / 1e12, chip_src="measured (profiles/chip_peaks.json)")
+            # shared memory: the microbenchmark's best-of-5 (38.2 TB/s) sits 2.6 % above 128 B/clk x 148 SMs x 1965 MHz = 37.2 TB/s, i.e.
+            # within its timing error of the architectural ceiling -- the ceiling is what is reported
+            smem_nominal = 128.0 * 148 * 1965e6 / 1e12
+            peaks.update(int32_tops=cp["int32_ops_per_s"] / 1e12, fp64_tflops=cp["fp64_flops_per_s"] / 1e12,
+                         smem_tbs=min(cp["smem_bytes_per_s"] / 1e12, smem_nominal), chip_src="measured (profiles/chip_peaks.json; shared memory capped at 128 B/clk/SM)")
         except Exception:
             pass
     r_mfe, r_pf = relaxations(L)
@@ -397,6 +423,10 @@ def run_ours(args):
         if key in tr:
             roof["traffic"] = tr[key]["dram_bytes"]
             roof["traffic_src"] = tr[key]["src"]
+        # executed thread-instructions per relaxation of both fill kernels at both headline lengths, from the same committed captures
+        roof["thread_inst_per_relaxation"] = {k: {"value": v["thread_inst_per_relaxation"], "kernel": v.get("kernel"), "issue_active_pct": v.get("issue_active_pct")}
+                                              for k, v in tr.items() if "thread_inst_per_relaxation" in v}
+        roof["thread_inst_src"] = "profiles/ncu_traffic.json (smsp__inst_executed.sum x smsp__thread_inst_executed_per_inst_executed.ratio / (folds x closed-form relaxations))"
     except Exception:
         pass
     roof["kernel_ms"] = dict(zip(names, main["kernel_ms"]))

@@ -922,7 +922,9 @@ Pf3Cfg pf3_cfg(int nmax) {
   // at L = 100 (4096 folds): 16 warps on chip 5.01 ms, 12 warps with paired cells 5.13, two CTAs of 8 warps (qm / qm1 in L2) 5.14;
   // at L = 120 / 150 the 16-warp CTA is ahead of the 8-warp pair by 20 / 30 % (profiles/r02_sweep_len.txt).
   const int nw_env = env_int("BF_FILL3_PF_NW", 0);
-  c.nw = nw_env ? nw_env : 116;   // 16 warps, cells in pairs (4.90 against 5.01 ms)
+  // 16 warps with cells in pairs from 90 nt (L = 100: 4.90 ms per 4096 folds against 5.14 for two 8-warp CTAs); below, two or three
+  // 8-warp CTAs per SM are ahead (L = 30 / 50 / 75: 0.60 / 1.26 / 2.79 ms against 0.88 / 1.71 / 3.13; scripts/sweep_pfnw.sh)
+  c.nw = nw_env ? nw_env : (nmax < 90 ? 8 : 116);
   const int nwr = c.nw % 100;   // (100 + warps: the paired variant)
   c.nwi = env_int("BF_FILL3_PF_NWI", nwr == 8 ? 6 : nwr == 16 ? 12 : nwr * 3 / 4);
   const int nwa = nwr - c.nwi;

@@ -18,3 +18,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'bf_
    python bench.py --steps 1 --warmup 3 --no-sweep --no-cpu --L $2 --B 592 > gpurun_out/${tag}_ncu_full$2.log 2>&1; echo "ncu full L=$2 rc=$?"
 fi
 head -c 3500 gpurun_out/${tag}_bench.json; echo; head -c 1500 gpurun_out/${tag}_bench_reference.json
+# cluster-per-sequence kernels: ncu --set full on a small batch of 400-nt sequences (8 sequences: one round of clusters)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'bf_k_(mfe|pf)_cl|bf_k_(f5|q5)_wide' -s 8 -c 4 -f -o gpurun_out/${tag}_prof_cl \
+   python scripts/cl_time.py both 400 8 > gpurun_out/${tag}_ncu_cl.log 2>&1; echo "ncu cluster rc=$?"
