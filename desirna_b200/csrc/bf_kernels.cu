@@ -72,11 +72,22 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
   int *fcA = f5 + (nmax + 4);
   int *fcB = fcA + (nmax + 4);
   BfSector *stk = reinterpret_cast<BfSector *>(fcB + (nmax + 4));
+  // per-cell arrays of the diagonal in work (index = i)
+  int *cT = reinterpret_cast<int *>(stk + (2 * nmax + 16));
+  int *cE0 = cT + (nmax + 4), *cMMO = cE0 + (nmax + 4), *cMM1O = cMMO + (nmax + 4), *cMLC = cMM1O + (nmax + 4);
+  int *cEC = cMLC + (nmax + 4), *cMS = cEC + (nmax + 4), *cLIST = cMS + (nmax + 4);
+  __shared__ int s_np;
+  if (tid == 0) s_np = 0;
 
   // short sequences: the three tables live in shared memory behind the per-sequence arrays (offset passed by the host), else in HBM
   int *c = tables_smem_off ? reinterpret_cast<int *>(dyn + tables_smem_off) : ws + (size_t)blockIdx.x * ws_slot_ints;
   int *fml = c + (size_t)W * W;
   int *fmlT = fml + (size_t)W * W;
+  // c with the inner-pair term of a decomposable interior loop folded in (generic: + mismatchI, 1xn: + mismatch1nI, bulge: + terminalAU)
+  int *cG = fmlT + (size_t)W * W, *c1 = cG + (size_t)W * W, *cB = c1 + (size_t)W * W;
+#define CG_(i, j) cG[(i) * W + (j)]
+#define C1_(i, j) c1[(i) * W + (j)]
+#define CB_(i, j) cB[(i) * W + (j)]
 #define C_(i, j) c[(i) * W + (j)]
 #define M_(i, j) fml[(i) * W + (j)]
 #define MT_(j, i) fmlT[(j) * W + (i)]
@@ -94,7 +105,7 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
     const int d0 = TWO ? 1 : BF_TURN + 1;
     for (int k = tid; k < d0 * (n + 1); k += blockDim.x) {
       int d = k / (n + 1), i = k % (n + 1) + 1, j = i + d;
-      if (j <= n + 1 && i <= n) { M_(i, j) = BF_INF; MT_(j, i) = BF_INF; C_(i, j) = BF_INF; }
+      if (j <= n + 1 && i <= n) { M_(i, j) = BF_INF; MT_(j, i) = BF_INF; C_(i, j) = BF_INF; CG_(i, j) = BF_INF; C1_(i, j) = BF_INF; CB_(i, j) = BF_INF; }
     }
     for (int k = tid; k <= n + 2; k += blockDim.x) { fcA[k] = 0; fcB[k] = 0; }
     __syncthreads();
@@ -134,34 +145,63 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
         }
         __syncthreads();
       }
-      for (int i = 1 + warp; i + d <= n; i += NWG) {
+      // Three stages per diagonal.  A (lanes = cells): everything of a cell that depends on the sequence only -- pair type, the hairpin
+      // or nick-loop term, the closing pair's terms -- and the list of pairable cells.  B (a warp per item): interior-loop candidates
+      // (all but nine shapes decomposed: one table value + a size penalty + a term of the closing pair, as in bf_fill3.cu) and the
+      // multiloop-closing split of every pairable cell; the fML split of every cell.  C (lanes = cells): c, fML and the three variants.
+      const int ncell = n - d;
+      for (int i = 1 + tid; i <= ncell; i += blockDim.x) {
         const int j = i + d;
         const int t = bf_ptype<TWO>(X, i, j);
-        int e = BF_INF;
+        cT[i] = t;
         if (t) {
           const int si1 = S[i + 1], sj1 = S[j - 1];
-          if (lane == 0) {
-            if (TWO && i < cp && j >= cp) {
-              int a, bb; bf_nick_nb(X, i, j, &a, &bb);
-              e = bf_e_ext(T, bf_rtype(t), a, bb) + fcA[i + 1] + fcB[j - 1];
-            } else {
-              e = bf_e_hairpin(P, T, S, i, j, t);
-            }
+          int e0;
+          if (TWO && i < cp && j >= cp) {
+            int a, bb; bf_nick_nb(X, i, j, &a, &bb);
+            e0 = bf_e_ext(T, bf_rtype(t), a, bb) + fcA[i + 1] + fcB[j - 1];
+          } else {
+            e0 = bf_e_hairpin(P, T, S, i, j, t);
           }
-          // interior loops: lanes split the (u1,u2) candidates
-          for (int k = lane; k < BF_NCAND; k += 32) {
-            const int u1 = cu1[k], u2 = cu2[k];
+          cE0[i] = e0; cMMO[i] = T.mmI[t][si1][sj1]; cMM1O[i] = T.mm1nI[t][si1][sj1];
+          cMLC[i] = (!TWO || (bf_same<TWO>(X, i, i + 1) && bf_same<TWO>(X, j - 1, j))) ? T.MLclosing + bf_e_mlstem(T, bf_rtype(t), sj1, si1) : BF_INF;
+          cLIST[atomicAdd(&s_np, 1)] = i;
+        }
+      }
+      __syncthreads();
+      const int np = s_np;
+      for (int it = warp; it < np + ncell; it += NWG) {
+        if (it < np) {
+          const int i = cLIST[it], j = i + d, t = cT[i];
+          const int si1 = S[i + 1], sj1 = S[j - 1];
+          const int mmO = cMMO[i], mm1O = cMM1O[i], tauO = t > 2 ? T.TerminalAU : 0, mlc = cMLC[i];
+          int e = BF_INF;
+          const int smx = min(BF_MAXLOOP, d - 3), kmax = smx >= 0 ? (smx + 1) * (smx + 2) / 2 : 0;   // candidates are ordered by size
+          for (int k = lane; k < kmax; k += 32) {
+            const int u1 = cu1[k], u2 = cu2[k], sz = u1 + u2;
             const int p = i + 1 + u1, q = j - 1 - u2;
             if (q <= p) continue;
             if (TWO && (!bf_same<TWO>(X, i, p) || !bf_same<TWO>(X, q, j))) continue;
-            const int t2 = bf_ptype<TWO>(X, p, q);
-            if (!t2) continue;
-            const int cc = C_(p, q);
-            if (cc >= BF_INF) continue;
-            e = min(e, cc + bf_e_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]));
+            const bool special = sz <= 1 || (u1 == 1 && u2 == 1) || (sz == 3 && u1 >= 1 && u2 >= 1) || (u1 == 2 && u2 == 2) ||
+                                 (sz == 5 && (u1 == 2 || u1 == 3));
+            if (special) {
+              const int t2 = bf_ptype<TWO>(X, p, q);
+              if (!t2) continue;
+              const int cc = C_(p, q);
+              if (cc >= BF_INF) continue;
+              e = min(e, cc + bf_e_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]));
+            } else if (u1 == 0 || u2 == 0) {
+              const int cc = CB_(p, q);
+              if (cc < BF_INF) e = min(e, cc + T.bulge[sz] + tauO);
+            } else if (u1 == 1 || u2 == 1) {
+              const int cc = C1_(p, q);
+              if (cc < BF_INF) e = min(e, cc + T.interior[sz] + min(T.ninio_max, (sz - 2) * T.ninio_m) + mm1O);
+            } else {
+              const int cc = CG_(p, q);
+              if (cc < BF_INF) e = min(e, cc + T.interior[sz] + min(T.ninio_max, abs(u1 - u2) * T.ninio_m) + mmO);
+            }
           }
-          // multiloop closed by (i,j)
-          if (!TWO || (bf_same<TWO>(X, i, i + 1) && bf_same<TWO>(X, j - 1, j))) {
+          if (mlc < BF_INF) {   // multiloop closed by (i,j)
             int dec = BF_INF;
             const int *rowL = &M_(i + 1, 0);
             const int *rowR = &MT_(j - 1, 0);
@@ -170,13 +210,13 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
               if (TWO && !bf_same<TWO>(X, u - 1, u)) continue;
               dec = min(dec, rowL[u - 1] + rowR[u]);
             }
-            if (dec < BF_INF) e = min(e, dec + T.MLclosing + bf_e_mlstem(T, bf_rtype(t), sj1, si1));
+            if (dec < BF_INF) e = min(e, dec + mlc);
           }
-          e = min(bf_warp_min(e), BF_INF);
-        }
-        // fML(i,j)
-        int m = BF_INF;
-        {
+          e = bf_warp_min(e);
+          if (lane == 0) cEC[i] = min(min(e, cE0[i]), BF_INF);
+        } else {
+          const int i = it - np + 1, j = i + d;
+          int m = BF_INF;
           const int *rowL = &M_(i, 0);
           const int *rowR = &MT_(j, 0);
           const int ulo = TWO ? i + 1 : i + 1 + BF_TURN + 1, uhi = TWO ? j : j - 1 - BF_TURN;
@@ -184,16 +224,29 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
             if (TWO && !bf_same<TWO>(X, u - 1, u)) continue;
             m = min(m, rowL[u - 1] + rowR[u]);
           }
-          if (lane == 0) {
-            if (e < BF_INF && i > 1 && j < n && bf_same<TWO>(X, i - 1, i) && bf_same<TWO>(X, j, j + 1))
-              m = min(m, e + bf_e_mlstem(T, t, S[i - 1], S[j + 1]));
-            if (bf_same<TWO>(X, i, i + 1)) m = min(m, M_(i + 1, j) + T.MLbase);
-            if (bf_same<TWO>(X, j - 1, j)) m = min(m, M_(i, j - 1) + T.MLbase);
-          }
-          m = min(bf_warp_min(m), BF_INF);
+          m = bf_warp_min(m);
+          if (lane == 0) cMS[i] = m;
         }
-        if (lane == 0) { C_(i, j) = e; M_(i, j) = m; MT_(j, i) = m; }
       }
+      __syncthreads();
+      for (int i = 1 + tid; i <= ncell; i += blockDim.x) {
+        const int j = i + d, t = cT[i];
+        const int e = t ? cEC[i] : BF_INF;
+        int m = cMS[i];
+        if (e < BF_INF && i > 1 && j < n && bf_same<TWO>(X, i - 1, i) && bf_same<TWO>(X, j, j + 1))
+          m = min(m, e + bf_e_mlstem(T, t, S[i - 1], S[j + 1]));
+        if (bf_same<TWO>(X, i, i + 1)) m = min(m, M_(i + 1, j) + T.MLbase);
+        if (bf_same<TWO>(X, j - 1, j)) m = min(m, M_(i, j - 1) + T.MLbase);
+        m = min(m, BF_INF);
+        C_(i, j) = e; M_(i, j) = m; MT_(j, i) = m;
+        if (e < BF_INF) {
+          const int tr = bf_rtype(t), a = S[j + 1], bb = S[i - 1];
+          CG_(i, j) = e + T.mmI[tr][a][bb]; C1_(i, j) = e + T.mm1nI[tr][a][bb]; CB_(i, j) = e + (t > 2 ? T.TerminalAU : 0);
+        } else {
+          CG_(i, j) = BF_INF; C1_(i, j) = BF_INF; CB_(i, j) = BF_INF;
+        }
+      }
+      if (tid == 0) s_np = 0;
       __syncthreads();
     }
 
@@ -426,12 +479,22 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
   double *q5 = bu + (nmax + 4);
   double *qA = q5 + (nmax + 4);
   double *qB = qA + (nmax + 4);
-  uint8_t *S = reinterpret_cast<uint8_t *>(qB + (nmax + 4));
+  // per-cell arrays of the diagonal in work (index = i)
+  double *cB0 = qB + (nmax + 4), *cXMMO = cB0 + (nmax + 4), *cXMM1O = cXMMO + (nmax + 4), *cXMLC = cXMM1O + (nmax + 4);
+  double *cQBr = cXMLC + (nmax + 4), *cQS = cQBr + (nmax + 4);
+  int *cT = reinterpret_cast<int *>(cQS + (nmax + 4)), *cLIST = cT + (nmax + 4);
+  uint8_t *S = reinterpret_cast<uint8_t *>(cLIST + (nmax + 4));
   uint8_t *SP = S + align_up(nmax + 2, 16);
+  __shared__ int s_np;
+  if (tid == 0) s_np = 0;
 
   double *qb = tables_smem_off ? reinterpret_cast<double *>(dyn + tables_smem_off) : ws + (size_t)blockIdx.x * ws_slot_dbl;
   double *qm = qb + (size_t)W * W;
   double *qm1T = qm + (size_t)W * W;  // qm1T[j][i] = qm1[i][j]
+  double *qG = qm1T + (size_t)W * W, *q1 = qG + (size_t)W * W, *qBB = q1 + (size_t)W * W;   // qb x inner-pair factor (see bf_k_mfe)
+#define QG_(i, j) qG[(i) * W + (j)]
+#define Q1_(i, j) q1[(i) * W + (j)]
+#define QBB_(i, j) qBB[(i) * W + (j)]
 #define QB_(i, j) qb[(i) * W + (j)]
 #define QM_(i, j) qm[(i) * W + (j)]
 #define QM1T_(j, i) qm1T[(j) * W + (i)]
@@ -462,7 +525,7 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
     const int d0 = TWO ? 1 : BF_TURN + 1;
     for (int k = tid; k < d0 * (n + 1); k += blockDim.x) {
       int d = k / (n + 1), i = k % (n + 1) + 1, j = i + d;
-      if (j <= n + 1 && i <= n) { QB_(i, j) = 0.0; QM_(i, j) = 0.0; QM1T_(j, i) = 0.0; }
+      if (j <= n + 1 && i <= n) { QB_(i, j) = 0.0; QM_(i, j) = 0.0; QM1T_(j, i) = 0.0; QG_(i, j) = 0.0; Q1_(i, j) = 0.0; QBB_(i, j) = 0.0; }
     }
     for (int k = tid; k <= n + 2; k += blockDim.x) { qA[k] = 0.0; qB[k] = 0.0; }
     __syncthreads();
@@ -496,31 +559,55 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
         }
         __syncthreads();
       }
-      for (int i = 1 + warp; i + d <= n; i += NWG) {
+      // the three stages of bf_k_mfe, with sums of Boltzmann weights
+      const int ncell = n - d;
+      for (int i = 1 + tid; i <= ncell; i += blockDim.x) {
         const int j = i + d;
         const int t = bf_ptype<TWO>(X, i, j);
-        double qbij = 0.0;
+        cT[i] = t;
         if (t) {
           const int si1 = S[i + 1], sj1 = S[j - 1];
-          double acc = 0.0;
-          if (lane == 0) {
-            if (TWO && i < cp && j >= cp) {
-              int a, bb; bf_nick_nb(X, i, j, &a, &bb);
-              acc = bf_x_ext(T, bf_rtype(t), a, bb) * qA[i + 1] * qB[j - 1] * scl[2];
-            } else {
-              acc = bf_x_hairpin(P, T, S, i, j, t) * scl[d + 1];
-            }
+          double b0;
+          if (TWO && i < cp && j >= cp) {
+            int a, bb; bf_nick_nb(X, i, j, &a, &bb);
+            b0 = bf_x_ext(T, bf_rtype(t), a, bb) * qA[i + 1] * qB[j - 1] * scl[2];
+          } else {
+            b0 = bf_x_hairpin(P, T, S, i, j, t) * scl[d + 1];
           }
-          for (int k = lane; k < BF_NCAND; k += 32) {
-            const int u1 = cu1[k], u2 = cu2[k];
+          cB0[i] = b0; cXMMO[i] = T.x_mmI[t][si1][sj1]; cXMM1O[i] = T.x_mm1nI[t][si1][sj1];
+          cXMLC[i] = (!TWO || (bf_same<TWO>(X, i, i + 1) && bf_same<TWO>(X, j - 1, j))) ? T.x_MLclosing * bf_x_mlstem(T, bf_rtype(t), sj1, si1) * scl[2] : 0.0;
+          cLIST[atomicAdd(&s_np, 1)] = i;
+        }
+      }
+      __syncthreads();
+      const int np = s_np;
+      for (int it = warp; it < np + ncell; it += NWG) {
+        if (it < np) {
+          const int i = cLIST[it], j = i + d, t = cT[i];
+          const int si1 = S[i + 1], sj1 = S[j - 1];
+          const double xmmO = cXMMO[i], xmm1O = cXMM1O[i], xtauO = t > 2 ? T.x_TerminalAU : 1.0, xmlc = cXMLC[i];
+          double acc = 0.0;
+          const int smx = min(BF_MAXLOOP, d - 3), kmax = smx >= 0 ? (smx + 1) * (smx + 2) / 2 : 0;   // candidates are ordered by size
+          for (int k = lane; k < kmax; k += 32) {
+            const int u1 = cu1[k], u2 = cu2[k], sz = u1 + u2;
             const int p = i + 1 + u1, q = j - 1 - u2;
             if (q <= p) continue;
             if (TWO && (!bf_same<TWO>(X, i, p) || !bf_same<TWO>(X, q, j))) continue;
-            const int t2 = bf_ptype<TWO>(X, p, q);
-            if (!t2) continue;
-            acc += QB_(p, q) * bf_x_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]) * scl[u1 + u2 + 2];
+            const bool special = sz <= 1 || (u1 == 1 && u2 == 1) || (sz == 3 && u1 >= 1 && u2 >= 1) || (u1 == 2 && u2 == 2) ||
+                                 (sz == 5 && (u1 == 2 || u1 == 3));
+            if (special) {
+              const int t2 = bf_ptype<TWO>(X, p, q);
+              if (!t2) continue;
+              acc += QB_(p, q) * bf_x_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]) * scl[sz + 2];
+            } else if (u1 == 0 || u2 == 0) {
+              acc += QBB_(p, q) * (T.x_bulge[sz] * xtauO * scl[sz + 2]);
+            } else if (u1 == 1 || u2 == 1) {
+              acc += Q1_(p, q) * (T.x_interior[sz] * T.x_ninio[sz - 2] * xmm1O * scl[sz + 2]);
+            } else {
+              acc += QG_(p, q) * (T.x_interior[sz] * T.x_ninio[abs(u1 - u2)] * xmmO * scl[sz + 2]);
+            }
           }
-          if (!TWO || (bf_same<TWO>(X, i, i + 1) && bf_same<TWO>(X, j - 1, j))) {
+          if (xmlc != 0.0) {
             double dec = 0.0;
             const double *rowL = &QM_(i + 1, 0);
             const double *rowR = &QM1T_(j - 1, 0);
@@ -529,20 +616,14 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
               if (TWO && !bf_same<TWO>(X, u - 1, u)) continue;
               dec += rowL[u - 1] * rowR[u];
             }
-            acc += dec * (T.x_MLclosing * bf_x_mlstem(T, bf_rtype(t), sj1, si1) * scl[2]);
+            acc += dec * xmlc;
           }
-          qbij = bf_warp_sum(acc);
-        }
-        // qm1[i][j]: exactly one stem, starting at i, unpaired tail up to j
-        double qm1ij = 0.0;
-        if (lane == 0) {
-          if (bf_same<TWO>(X, j - 1, j)) qm1ij = QM1T_(j - 1, i) * bu[1];
-          if (t && i > 1 && j < n && bf_same<TWO>(X, i - 1, i) && bf_same<TWO>(X, j, j + 1)) qm1ij += qbij * bf_x_mlstem(T, t, S[i - 1], S[j + 1]);
-        }
-        qm1ij = __shfl_sync(BF_FULL, qm1ij, 0);
-        // qm[i][j] = sum_u (bu[u-i] + qm[i][u-1]) * qm1[u][j]   (u = i contributes qm1[i][j] itself)
-        double qmij = 0.0;
-        {
+          acc = bf_warp_sum(acc);
+          if (lane == 0) cQBr[i] = acc + cB0[i];
+        } else {
+          // qm[i][j] - qm1[i][j] = sum_u (bu[u-i] + qm[i][u-1]) * qm1[u][j]
+          const int i = it - np + 1, j = i + d;
+          double sum = 0.0;
           const double *rowL = &QM_(i, 0);
           const double *rowR = &QM1T_(j, 0);
           const int uhi = TWO ? j : j - BF_TURN - 1;
@@ -550,12 +631,29 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
             double left = 0.0;
             if (!TWO || bf_same<TWO>(X, i, u)) left = bu[u - i];
             if (!TWO || bf_same<TWO>(X, u - 1, u)) left += rowL[u - 1];
-            qmij += left * rowR[u];
+            sum += left * rowR[u];
           }
-          qmij = bf_warp_sum(qmij) + qm1ij;
+          sum = bf_warp_sum(sum);
+          if (lane == 0) cQS[i] = sum;
         }
-        if (lane == 0) { QB_(i, j) = qbij; QM_(i, j) = qmij; QM1T_(j, i) = qm1ij; }
       }
+      __syncthreads();
+      for (int i = 1 + tid; i <= ncell; i += blockDim.x) {
+        const int j = i + d, t = cT[i];
+        const double qbij = t ? cQBr[i] : 0.0;
+        // qm1[i][j]: exactly one stem, starting at i, unpaired tail up to j
+        double qm1ij = 0.0;
+        if (bf_same<TWO>(X, j - 1, j)) qm1ij = QM1T_(j - 1, i) * bu[1];
+        if (t && i > 1 && j < n && bf_same<TWO>(X, i - 1, i) && bf_same<TWO>(X, j, j + 1)) qm1ij += qbij * bf_x_mlstem(T, t, S[i - 1], S[j + 1]);
+        QB_(i, j) = qbij; QM_(i, j) = cQS[i] + qm1ij; QM1T_(j, i) = qm1ij;
+        if (t) {
+          const int tr = bf_rtype(t), a = S[j + 1], bb = S[i - 1];
+          QG_(i, j) = qbij * T.x_mmI[tr][a][bb]; Q1_(i, j) = qbij * T.x_mm1nI[tr][a][bb]; QBB_(i, j) = qbij * (t > 2 ? T.x_TerminalAU : 1.0);
+        } else {
+          QG_(i, j) = 0.0; Q1_(i, j) = 0.0; QBB_(i, j) = 0.0;
+        }
+      }
+      if (tid == 0) s_np = 0;
       __syncthreads();
     }
 
@@ -707,8 +805,9 @@ cudaError_t bf_upload_constants() {
   if (g_cand_uploaded) return cudaSuccess;
   uint8_t u1[BF_NCAND], u2[BF_NCAND];
   int k = 0;
-  for (int a = 0; a <= BF_MAXLOOP; a++)
-    for (int c = 0; a + c <= BF_MAXLOOP; c++) { u1[k] = (uint8_t)a; u2[k] = (uint8_t)c; k++; }
+  // ordered by loop size u1 + u2: a cell of span d only has candidates up to size d - 3, i.e. the first (d-2)(d-1)/2 entries
+  for (int sz = 0; sz <= BF_MAXLOOP; sz++)
+    for (int a = 0; a <= sz; a++) { u1[k] = (uint8_t)a; u2[k] = (uint8_t)(sz - a); k++; }
   cudaError_t e = cudaMemcpyToSymbol(c_cand_u1, u1, sizeof u1);
   if (e != cudaSuccess) return e;
   e = cudaMemcpyToSymbol(c_cand_u2, u2, sizeof u2);
@@ -716,16 +815,16 @@ cudaError_t bf_upload_constants() {
   return e;
 }
 
-size_t bf_mfe_slot_ints(int wstride) { return (size_t)3 * wstride * wstride; }
-size_t bf_pf_slot_doubles(int wstride) { return (size_t)3 * wstride * wstride; }
+size_t bf_mfe_slot_ints(int wstride) { return (size_t)6 * wstride * wstride; }      // c, fML, fML^T + the three inner-term variants of c
+size_t bf_pf_slot_doubles(int wstride) { return (size_t)6 * wstride * wstride; }   // qb, qm, qm1^T + the three variants of qb
 
 static size_t mfe_smem(int wstride) {
   size_t nmax = wstride - 2;
-  return 2 * ((nmax + 2 + 15) / 16 * 16) + 3 * (nmax + 4) * sizeof(int) + (2 * nmax + 16) * sizeof(BfSector);
+  return 2 * ((nmax + 2 + 15) / 16 * 16) + (3 + 8) * (nmax + 4) * sizeof(int) + (2 * nmax + 16) * sizeof(BfSector);
 }
 static size_t pf_smem(int wstride) {
   size_t nmax = wstride - 2;
-  return 5 * (nmax + 4) * sizeof(double) + 2 * ((nmax + 2 + 15) / 16 * 16);
+  return (5 + 6) * (nmax + 4) * sizeof(double) + 2 * (nmax + 4) * sizeof(int) + 2 * ((nmax + 2 + 15) / 16 * 16);
 }
 // The generic kernels (two strands; any length the fill path does not cover) keep three W x W tables per CTA.  Short sequences --
 // the reference's two-strand examples are 17 & 18 nt -- fit in shared memory next to the per-sequence arrays, which takes the L2
