@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(NW * 32, NW <= 8 ? 3 : NW <= 12 ? 2 : 1) bf_k_
         const uint32_t tp = __ldg(taps + k * 32 + lane);
         const int s = tp & 255, u1 = (tp >> 8) & 255;
         // bytes from the generic ring's origin: ring of the slot's kind, row of diagonal d-2-s for d = TURN+1, column offset 1+u1
-        xk[k] = 4 * ((k < kNSG ? 0 : k < kNSG + kNS1 ? 1 : 2) * kRing * RS + ((BF_TURN + 1 - 2 - s) & (kRing - 1)) * RS + 1 + u1);
+        xk[k] = 4 * (((BF_TURN + 1 - 2 - s) & (kRing - 1)) * RS + 1 + u1);   // relative to the origin of the slot's ring variant
       }
     }
     __syncthreads();
@@ -285,15 +285,15 @@ __global__ void __launch_bounds__(NW * 32, NW <= 8 ? 3 : NW <= 12 ? 2 : 1) bf_k_
               // the cell index is the same in every lane: taken through REDUX it lands in a uniform register, and a tap load
               // becomes LDS [R + UR] -- the lane's byte offset in a register, the cell's ring address uniform
               const unsigned i4 = 4u * (unsigned)__reduce_min_sync(BF_FULL, ic);
-              const unsigned ug = sCG + i4;
+              const unsigned ug = sCG + i4, u1n = ug + 4u * wrap, ubg = ug + 8u * wrap;   // generic, 1xn, bulge ring
               int ag = BF_INF, a1 = BF_INF, ab = BF_INF;
 #pragma unroll
               for (int k = 0; k < G; k++) ag = min(ag, lds_s32(ug + xk[k]) + pen[k]);
 #pragma unroll
-              for (int k = 0; k < O; k++) a1 = min(a1, lds_s32(ug + xk[kNSG + k]) + pen[kNSG + k]);
+              for (int k = 0; k < O; k++) a1 = min(a1, lds_s32(u1n + xk[kNSG + k]) + pen[kNSG + k]);
 #pragma unroll
-              for (int k = 0; k < Bn; k++) ab = min(ab, lds_s32(ug + xk[kNSG + kNS1 + k]) + pen[kNSG + kNS1 + k]);
-              const int vs = lds_s32(ug + xk[kNSlot - 1]) + esp;   // special candidates (lanes 0..8; the others add INF)
+              for (int k = 0; k < Bn; k++) ab = min(ab, lds_s32(ubg + xk[kNSG + kNS1 + k]) + pen[kNSG + kNS1 + k]);
+              const int vs = lds_s32(ubg + xk[kNSlot - 1]) + esp;   // special candidates (lanes 0..8; the others add INF)
               int tot = min(min(ag + ea.y, a1 + ea.z), min(ab + tau, vs));
               tot = __reduce_min_sync(BF_FULL, tot);
               tot = min(tot, ea.w);                                  // hairpin
@@ -315,10 +315,9 @@ __global__ void __launch_bounds__(NW * 32, NW <= 8 ? 3 : NW <= 12 ? 2 : 1) bf_k_
         }
         // every tap moves one ring row down for the next diagonal
 #pragma unroll
-        for (int k = 0; k < kNSlot; k++) {
-          const int kind = k < kNSG ? 0 : k < kNSG + kNS1 ? 1 : 2;
+        for (int k = 0; k < kNSlot; k++) {   // add, wrap by unsigned min
           const unsigned x = (unsigned)xk[k] + 4u * (unsigned)RS;
-          xk[k] = (int)(x >= 4u * wrap * (unsigned)(kind + 1) ? x - 4u * wrap : x);
+          xk[k] = (int)min(x, x - 4u * wrap);
         }
       } else {
         const int a = warp - NWI;   // auxiliary warp index
@@ -546,7 +545,7 @@ __global__ void __launch_bounds__(NW * 32, NW <= 8 ? 2 : 1) bf_k_pf_fill3(const 
       for (int k = 0; k < kNSlot; k++) {
         const uint32_t tp = __ldg(taps + k * 32 + lane);
         const int s = tp & 255, u1 = (tp >> 8) & 255;
-        xk[k] = 8 * ((k < kNSG ? 0 : k < kNSG + kNS1 ? 1 : 2) * kRing * RS + ((BF_TURN + 1 - 2 - s) & (kRing - 1)) * RS + 1 + u1);
+        xk[k] = 8 * (((BF_TURN + 1 - 2 - s) & (kRing - 1)) * RS + 1 + u1);   // relative to the origin of the slot's ring variant
         if (k < kNSlot - 1) {
           double v = 0.0;
           if (tp >> 16) {
@@ -647,21 +646,21 @@ __global__ void __launch_bounds__(NW * 32, NW <= 8 ? 2 : 1) bf_k_pf_fill3(const 
                 const double2 a01 = *reinterpret_cast<const double2 *>(pA), b01 = *reinterpret_cast<const double2 *>(pB);
                 const double x1A = pA[2], xtA = pA[7], espA = pA[lsp], x1B = pB[2], xtB = pB[7], espB = pB[lsp];
                 const unsigned iA = 8u * (unsigned)(int)__double_as_longlong(a01.x), iB = 8u * (unsigned)(int)__double_as_longlong(b01.x);
-                const unsigned uA = sQG + iA, uB = sQG + iB;
+                const unsigned uA = sQG + iA, uB = sQG + iB, u1A = uA + 8u * wrap, u1B = uB + 8u * wrap, ubA = uA + 16u * wrap, ubB = uB + 16u * wrap;
                 double gA = 0.0, gB = 0.0, oA = 0.0, oB = 0.0, bA = 0.0, bB = 0.0;
 #pragma unroll
                 for (int k = 0; k < G; k++) { gA = fma(lds_f64(uA + xk[k]), wk[k], gA); gB = fma(lds_f64(uB + xk[k]), wk[k], gB); }
 #pragma unroll
                 for (int k = 0; k < O; k++) {
-                  oA = fma(lds_f64(uA + xk[kNSG + k]), wk[kNSG + k], oA);
-                  oB = fma(lds_f64(uB + xk[kNSG + k]), wk[kNSG + k], oB);
+                  oA = fma(lds_f64(u1A + xk[kNSG + k]), wk[kNSG + k], oA);
+                  oB = fma(lds_f64(u1B + xk[kNSG + k]), wk[kNSG + k], oB);
                 }
 #pragma unroll
                 for (int k = 0; k < Bn; k++) {
-                  bA = fma(lds_f64(uA + xk[kNSG + kNS1 + k]), wk[kNSG + kNS1 + k], bA);
-                  bB = fma(lds_f64(uB + xk[kNSG + kNS1 + k]), wk[kNSG + kNS1 + k], bB);
+                  bA = fma(lds_f64(ubA + xk[kNSG + kNS1 + k]), wk[kNSG + kNS1 + k], bA);
+                  bB = fma(lds_f64(ubB + xk[kNSG + kNS1 + k]), wk[kNSG + kNS1 + k], bB);
                 }
-                double tA = fma(lds_f64(uA + xk[kNSlot - 1]), espA, gA * a01.y), tB = fma(lds_f64(uB + xk[kNSlot - 1]), espB, gB * b01.y);
+                double tA = fma(lds_f64(ubA + xk[kNSlot - 1]), espA, gA * a01.y), tB = fma(lds_f64(ubB + xk[kNSlot - 1]), espB, gB * b01.y);
                 tA = fma(oA, x1A, fma(bA, xtA, tA));
                 tB = fma(oB, x1B, fma(bB, xtB, tB));
                 // one butterfly for both cells
@@ -686,7 +685,7 @@ __global__ void __launch_bounds__(NW * 32, NW <= 8 ? 2 : 1) bf_k_pf_fill3(const 
               // every lane holds the same cell index; the addresses are formed per lane (no detour through a uniform register:
               // with 8-byte taps the compiler adds per lane anyway)
               const unsigned i8 = 8u * (unsigned)(int)__double_as_longlong(e01.x);
-              const unsigned ug = sQG + i8;
+              const unsigned ug = sQG + i8, u1n = ug + 8u * wrap, ubg = ug + 16u * wrap;
               double ag0 = 0.0, ag1 = 0.0, a1 = 0.0, ab = 0.0;
 #pragma unroll
               for (int k = 0; k < G; k++) {
@@ -694,10 +693,10 @@ __global__ void __launch_bounds__(NW * 32, NW <= 8 ? 2 : 1) bf_k_pf_fill3(const 
                 else ag0 = fma(lds_f64(ug + xk[k]), wk[k], ag0);
               }
 #pragma unroll
-              for (int k = 0; k < O; k++) a1 = fma(lds_f64(ug + xk[kNSG + k]), wk[kNSG + k], a1);
+              for (int k = 0; k < O; k++) a1 = fma(lds_f64(u1n + xk[kNSG + k]), wk[kNSG + k], a1);
 #pragma unroll
-              for (int k = 0; k < Bn; k++) ab = fma(lds_f64(ug + xk[kNSG + kNS1 + k]), wk[kNSG + kNS1 + k], ab);
-              double tot = fma(lds_f64(ug + xk[kNSlot - 1]), esp, (ag0 + ag1) * e01.y);   // special candidates (lanes 0..8)
+              for (int k = 0; k < Bn; k++) ab = fma(lds_f64(ubg + xk[kNSG + kNS1 + k]), wk[kNSG + kNS1 + k], ab);
+              double tot = fma(lds_f64(ubg + xk[kNSlot - 1]), esp, (ag0 + ag1) * e01.y);   // special candidates (lanes 0..8)
               tot = fma(a1, e23.x, fma(ab, xt, tot));
               tot = bf_warp_sum(tot);
               const double qb = tot + e23.y + lds_f64(sqms + i8) * mlc;   // + hairpin + multiloop closed by (i,j)
@@ -715,10 +714,9 @@ __global__ void __launch_bounds__(NW * 32, NW <= 8 ? 2 : 1) bf_k_pf_fill3(const 
         }
         // every tap moves one ring row down for the next diagonal
 #pragma unroll
-        for (int k = 0; k < kNSlot; k++) {
-          const int kind = k < kNSG ? 0 : k < kNSG + kNS1 ? 1 : 2;
+        for (int k = 0; k < kNSlot; k++) {   // add, wrap by unsigned min
           const unsigned x = (unsigned)xk[k] + 8u * (unsigned)RS;
-          xk[k] = (int)(x >= 8u * wrap * (unsigned)(kind + 1) ? x - 8u * wrap : x);
+          xk[k] = (int)min(x, x - 8u * wrap);
         }
       } else {
         const int a = warp - NWI;
