@@ -568,7 +568,7 @@ int design_rows(DesignLoop *h) {
 int design_score(DesignLoop *h, bool init = false) {
   bf_batch_t b;
   std::memset(&b, 0, sizeof b);
-  b.B = h->B; b.stride = h->D.stride; b.seq = h->D.mut_seq; b.len = h->D.row_len; b.targets = h->D.row_tgt; b.n_targets = 1; b.want = h->want;
+  b.B = h->B; b.stride = h->D.stride; b.seq = h->D.mut_seq; b.len = h->D.row_len; b.targets = h->D.row_tgt; b.n_targets = h->D.T; b.want = h->want;
   b.cut = h->two ? h->D.row_cut : nullptr;
   bf_result_t r;
   std::memset(&r, 0, sizeof r);
@@ -634,6 +634,25 @@ int bf_design_create(const bf_design_t *c, void **handle) {
     if (!stk.empty()) return fail(BF_ERR_ARG, "bf_design_create: unbalanced target");
   }
   if (!two && (bf_fill_mfe_mode(S) == 0 || bf_fill_pf_mode(S) == 0)) return fail(BF_ERR_UNAVAILABLE, "bf_design_create: stride outside the fill path");
+  // optional scenario terms: alternative structures, motifs
+  const int max_alt = c->alt_targets ? c->max_alt : 0;
+  if (max_alt < 0 || max_alt > 16 || (max_alt > 0 && !c->n_alt)) return fail(BF_ERR_ARG, "bf_design_create: alternative structures: max_alt outside 0..16 or n_alt missing");
+  for (int j = 0; j < J && max_alt > 0; j++) {
+    if (c->n_alt[j] < 0 || c->n_alt[j] > max_alt) return fail(BF_ERR_ARG, "bf_design_create: n_alt outside 0..max_alt");
+    for (int a = 0; a < c->n_alt[j]; a++) {
+      int depth = 0;
+      for (int i = 0; i < c->len[j]; i++) {
+        const char ch = c->alt_targets[((size_t)j * max_alt + a) * S + i];
+        if (ch == '(') depth++;
+        else if (ch == ')') { if (--depth < 0) break; }
+        else if (ch != '.') return fail(BF_ERR_ARG, "bf_design_create: alternative structures may contain only . ( )");
+      }
+      if (depth != 0) return fail(BF_ERR_ARG, "bf_design_create: unbalanced alternative structure");
+    }
+  }
+  if (c->n_motifs < 0 || c->n_motifs > 8 || (c->n_motifs > 0 && (!c->motif_mask || !c->motif_len || !c->motif_bonus))) return fail(BF_ERR_ARG, "bf_design_create: at most 8 motifs, with masks, lengths and bonuses");
+  for (int m = 0; m < c->n_motifs; m++)
+    if (c->motif_len[m] < 1 || c->motif_len[m] > 32) return fail(BF_ERR_ARG, "bf_design_create: motif length outside 1..32");
   DesignLoop *h = new DesignLoop;
   h->two = two;
   { const char *ov = getenv("BF_DESIGN_OVERLAP"); h->overlap = !(ov && ov[0] == '0'); }
@@ -667,9 +686,17 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   DCU(h->alloc(&h->d_rowmap, G), "cudaMalloc(design)"); DCU(h->alloc(&h->d_active, J), "cudaMalloc(design)");
   DCU(h->alloc(&D.mut_seq, G * S), "cudaMalloc(design)"); DCU(h->alloc(&D.row_len, G), "cudaMalloc(design)"); DCU(h->alloc(&D.row_cut, G), "cudaMalloc(design)");
   DCU(h->alloc(&D.row_scale, G), "cudaMalloc(design)"); DCU(h->alloc(&D.cur_mfe, G), "cudaMalloc(design)");
-  DCU(h->alloc(&D.row_tgt, G * S), "cudaMalloc(design)"); DCU(h->alloc(&D.o_mfe, G), "cudaMalloc(design)");
+  D.max_alt = max_alt; D.T = 1 + max_alt;
+  if (max_alt > 0) {
+    char *d_alt; int *d_nalt;
+    DCU(h->alloc(&d_alt, (size_t)J * max_alt * S), "cudaMalloc(design)"); DCU(h->alloc(&d_nalt, J), "cudaMalloc(design)");
+    DCU(cudaMemcpy(d_alt, c->alt_targets, (size_t)J * max_alt * S, cudaMemcpyHostToDevice), "H2D design");
+    DCU(cudaMemcpy(d_nalt, c->n_alt, J * sizeof(int), cudaMemcpyHostToDevice), "H2D design");
+    D.alt = d_alt; D.n_alt = d_nalt;
+  }
+  DCU(h->alloc(&D.row_tgt, G * D.T * S), "cudaMalloc(design)"); DCU(h->alloc(&D.o_mfe, G), "cudaMalloc(design)");
   DCU(h->alloc(&D.o_ss, G * (S + 1)), "cudaMalloc(design)"); DCU(h->alloc(&D.o_pf, G * 5), "cudaMalloc(design)");
-  DCU(h->alloc(&D.o_eval, G), "cudaMalloc(design)");
+  DCU(h->alloc(&D.o_eval, G * D.T), "cudaMalloc(design)");
   h->want = BF_WANT_MFE | BF_WANT_SS | BF_WANT_PF | BF_WANT_EVAL;
   BfDesignCfg &C = h->C;
   C.n_terms = c->n_terms;
@@ -682,6 +709,11 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   C.metropolis_L = c->metropolis_L; C.point_mutations = c->point_mutations; C.acgu = c->acgu;
   for (int k = 0; k < 4; k++) C.nt_weight[k] = c->nt_weight[k];
   C.oligo = c->oligo;
+  C.n_motifs = c->n_motifs;
+  for (int m = 0; m < c->n_motifs; m++) {
+    C.motif_len[m] = c->motif_len[m]; C.motif_bonus[m] = c->motif_bonus[m];
+    for (int k = 0; k < 32; k++) C.motif_mask[m][k] = k < c->motif_len[m] ? c->motif_mask[(size_t)m * 32 + k] : 0;
+  }
   if (two && (h->want & BF_WANT_DEFECT)) { h->destroy(); delete h; return fail(BF_ERR_ARG, "bf_design_create: the Edef term needs single-strand jobs"); }
   h->re_attempt = c->re_attempt;
   D.tgt = tgt; D.tpt = d_tpt; D.allowed = allowed; D.len = len; D.len_a = d_len_a; D.same_halves = d_same; D.avail = d_avail; D.n_avail = d_navail; D.temps = temps; D.tm_prob = tm_prob;

@@ -103,7 +103,10 @@ __global__ void bf_k_design_gather(BfDesignDev D, int B) {
   if (row >= B) return;
   const int job = D.rowmap[row] / D.R;
   if (lane == 0) { D.row_len[row] = D.len[job]; D.row_cut[row] = D.len_a[job] > 0 ? D.len_a[job] + 1 : 0; }
-  for (int k = lane; k < D.stride; k += 32) D.row_tgt[(size_t)row * D.stride + k] = D.tgt[(size_t)job * D.stride + k];
+  for (int t = 0; t < D.T; t++) {
+    const char *src = (t >= 1 && t - 1 < D.n_alt[job]) ? D.alt + ((size_t)job * D.max_alt + (t - 1)) * D.stride : D.tgt + (size_t)job * D.stride;
+    for (int k = lane; k < D.stride; k += 32) D.row_tgt[((size_t)row * D.T + t) * D.stride + k] = src[k];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ propose
@@ -247,6 +250,23 @@ __global__ void __launch_bounds__(kWPB * 32) bf_k_design_accept(BfDesignDev D, B
   }
   const bool two = D.len_a[job] > 0;
   if (two) tp += 2;   // '&' becomes the always-matching pair "Ee" for the similarity scores (energy_scores.py:79)
+  // -motifs: does the motif occur in the mutant (lanes over the start positions; a window may not span the '&' of two strands)
+  unsigned motif_hit = 0;
+  if (C.n_motifs > 0) {
+    const char *mut = D.mut_seq + (size_t)row * S;
+    const int la = D.len_a[job];
+    for (int m = 0; m < C.n_motifs; m++) {
+      const int ml = C.motif_len[m];
+      bool found = false;
+      for (int p0 = 0; p0 + ml <= n && !found; p0 += 32) {
+        const int p = p0 + lane;
+        bool hit = p + ml <= n && !(la > 0 && p < la && p + ml > la);
+        for (int k = 0; k < ml && hit; k++) hit = (C.motif_mask[m][k] >> letter_code(mut[p + k])) & 1;
+        found = __any_sync(BF_FULL, hit);
+      }
+      if (found) motif_hit |= 1u << m;
+    }
+  }
   int ok = 0;
   double rec[kDesignRec];
   if (lane == 0) {
@@ -259,12 +279,12 @@ __global__ void __launch_bounds__(kWPB * 32) bf_k_design_accept(BfDesignDev D, B
     const double mcc = rint(num / (den + 0.00001) * 1000.0) / 1000.0;
     const double recall = rint((double)tp / ((double)(tp + fn) + 0.001) * 1000.0) / 1000.0;
     const double precision = rint((double)tp / ((double)(tp + fp) + 0.001) * 1000.0) / 1000.0;
-    const double Ed = (double)(float)((double)D.o_eval[row] / 100.0);
+    const double Ed = (double)(float)((double)D.o_eval[(size_t)row * D.T] / 100.0);
     const double Epf = (double)(float)D.o_pf[(size_t)row * 5 + (two ? 3 : 4)];   // two strands: FAB (energy_scores.py:157)
     const double MFE = (double)(float)((double)D.o_mfe[row] / 100.0);
     rec[kRecEd] = Ed; rec[kRecEpf] = Epf; rec[kRecMcc] = 1.0 - mcc; rec[kRecPrecision] = 1.0 - precision; rec[kRecRecall] = 1.0 - recall;
     rec[kRecMFE] = MFE; rec[kRecEdef] = D.o_defect ? D.o_defect[row] : 0.0; rec[kRecDist] = (double)(fp + fn); rec[kRecStep] = (double)gstep;
-    rec[kRecOligoFraction] = 0.0; rec[kRecOligoBonus] = 0.0;
+    rec[kRecOligoFraction] = 0.0; rec[kRecOligoBonus] = 0.0; rec[kRecEd2] = 0.0; rec[kRecMotif] = 0.0;
     double total = 0.0;
     for (int k = 0; k < C.n_terms; k++) {
       const double wgt = C.weight[k];
@@ -278,6 +298,12 @@ __global__ void __launch_bounds__(kWPB * 32) bf_k_design_accept(BfDesignDev D, B
         case kTermEdef: total += rec[kRecEdef] * wgt; break;
       }
     }
+    if (D.n_alt && D.n_alt[job] > 0) {   // alternative structures: mean of their (float32) energies minus Epf (energy_scores.py:98-102)
+      double sum = 0.0;
+      for (int k = 0; k < D.n_alt[job]; k++) sum += (double)(float)((double)D.o_eval[(size_t)row * D.T + 1 + k] / 100.0);
+      rec[kRecEd2] = sum / D.n_alt[job];
+      total += rec[kRecEd2] - Epf;
+    }
     if (two && C.oligo >= 1) {
       // equilibrium dimer fraction at 1 mM from FcAB - FA - FB (dimer_multichain_energy.py:36-63), float32 API values first
       const double kT = 0.001987204259 * (273.15 + 37);
@@ -288,6 +314,9 @@ __global__ void __launch_bounds__(kWPB * 32) bf_k_design_accept(BfDesignDev D, B
       rec[kRecOligoBonus] = (C.oligo == 2 && D.same_halves[job]) ? -kT * log(1 - frac) : -kT * log(frac);
       total += rec[kRecOligoBonus];
     }
+    for (int m = 0; m < C.n_motifs; m++)
+      if (motif_hit >> m & 1u) rec[kRecMotif] += C.motif_bonus[m];
+    total += rec[kRecMotif];   // (after the oligomer terms, as in score_sequence)
     rec[kRecScore] = total;
     if (init) ok = 1;
     else {

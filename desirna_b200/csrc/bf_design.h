@@ -8,9 +8,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-constexpr int kDesignRec = 12;   // doubles per replica record
+constexpr int kDesignRec = 14;   // doubles per replica record
 // record slots (names of the reference's ScoreSeq fields, utils/energy_scores.py:176-195)
-enum { kRecScore = 0, kRecEd = 1, kRecEpf = 2, kRecMcc = 3, kRecPrecision = 4, kRecRecall = 5, kRecMFE = 6, kRecEdef = 7, kRecDist = 8, kRecStep = 9, kRecOligoFraction = 10, kRecOligoBonus = 11 };
+enum { kRecScore = 0, kRecEd = 1, kRecEpf = 2, kRecMcc = 3, kRecPrecision = 4, kRecRecall = 5, kRecMFE = 6, kRecEdef = 7, kRecDist = 8, kRecStep = 9, kRecOligoFraction = 10, kRecOligoBonus = 11, kRecEd2 = 12, kRecMotif = 13 };
 // scoring terms (-sf), in the order of ScoreSeq.get_scoring_function (utils/energy_scores.py:376-398)
 enum { kTermEdEpf = 0, kTermMcc = 1, kTermSlnEpf = 2, kTermEdMfe = 3, kTermPrecision = 4, kTermRecall = 5, kTermEdef = 6 };
 
@@ -25,6 +25,10 @@ struct BfDesignCfg {
   int oligo;             // two-strand jobs: 1 heterodimer, adds -kT ln(dimer fraction); 2 homodimer, strands kept identical and
                          // -kT ln(dimer fraction) (different target halves) or -kT ln(1 - fraction) (identical halves)
                          // (energy_scores.py:120-125,421-441, dimer_multichain_energy.py:36-76, sequence_utils.py:1102-1128)
+  int n_motifs;          // -motifs: IUPAC motifs, bonus added when the motif occurs in the sequence (sequence_utils.py:1231-1256)
+  int motif_len[8];
+  double motif_bonus[8];
+  unsigned char motif_mask[8][32];
 };
 
 struct BfDesignDev {
@@ -36,6 +40,9 @@ struct BfDesignDev {
   const int *len;                // J            nucleotides (both strands, no '&')
   const int *len_a;              // J            length of strand A, 0 = single strand ('&' sits after it in the reference's strings)
   const uint8_t *same_halves;    // J            1: the two halves of the target are the same string (homodimer designs)
+  const char *alt;               // J x max_alt x stride   alternative structures (energy_scores.py:98-102), or null
+  const int *n_alt;              // J
+  int max_alt, T;                // T = 1 + max_alt targets per batch row
   const unsigned short *avail;   // J x stride   positions with more than one allowed letter (sequence_utils.py:1026-1029)
   const int *n_avail;            // J
   unsigned long long *job_rng;   // J            stream of the neighbour swaps
@@ -61,11 +68,11 @@ struct BfDesignDev {
   int *row_len;                  // B
   int *row_cut;                  // B            1-based first nucleotide of strand B, 0 = single strand (bf_batch_t.cut)
   int *row_scale;                // B            cur_mfe of the row's replica (written by bf_k_design_propose)
-  char *row_tgt;                 // B x stride
+  char *row_tgt;                 // B x T x stride   target, then the alternative structures (rows beyond n_alt repeat the target)
   int *o_mfe;                    // B
   char *o_ss;                    // B x (stride+1)
   double *o_pf;                  // B x 5
-  int *o_eval;                   // B
+  int *o_eval;                   // B x T
   double *o_defect;              // B (only with the Edef term)
 };
 

@@ -11,6 +11,7 @@ Host work per poll: read the per-job best records, retire solved jobs (`-sws on`
 """
 import ctypes as C
 import random
+import re
 import time
 
 import numpy as np
@@ -20,7 +21,7 @@ from .utils import sequence_utils as seq_utils
 
 TERM_ID = {"Ed-Epf": 0, "1-MCC": 1, "sln_Epf": 2, "Ed-MFE": 3, "1-precision": 4, "1-recall": 5, "Edef": 6}
 REC_FIELDS = ("scoring_function", "edesired", "Epf", "mcc", "precision", "recall", "MFE", "ensemble_defect", "distance", "global_step",
-              "oligo_fraction", "oligomer_bonus")
+              "oligo_fraction", "oligomer_bonus", "edesired2", "motif_bonus")
 REC = len(REC_FIELDS)
 
 
@@ -28,7 +29,8 @@ class DesignOptions:
     """The fields of DesiRNA.py's DesignOptions (:520-633) the loop reads, with the CLI defaults (:92-139)."""
 
     def __init__(self, replicas=10, RE_attempt=100, T_min=10.0, T_max=150.0, scoring_f=(("Ed-Epf", 1.0),), point_mutations="on",
-                 tm_max=0.7, tm_min=0.0, acgu_percentages="off", nt_percentages=None, diff_start_replicas="one", oligo_state="none"):
+                 tm_max=0.7, tm_min=0.0, acgu_percentages="off", nt_percentages=None, diff_start_replicas="one", oligo_state="none",
+                 motifs=None):
         self.replicas = replicas
         self.RE_attempt = RE_attempt
         self.T_min, self.T_max = T_min, T_max
@@ -39,7 +41,9 @@ class DesignOptions:
         self.nt_percentages = nt_percentages or {"A": 15, "C": 30, "G": 30, "U": 15}
         self.diff_start_replicas = diff_start_replicas
         self.L = 504.12
-        self.oligo_state, self.pks, self.subopt, self.motifs = oligo_state, "off", "off", None   # "none" | "heterodimer" | "homodimer"
+        self.oligo_state, self.pks, self.subopt = oligo_state, "off", "off"   # "none" | "heterodimer" | "homodimer"
+        # -motifs "KEY,bonus,KEY,bonus": IUPAC motif -> (compiled regex, bonus) as DesiRNA.py:212-224 builds it
+        self.motifs = {k: (re.compile("".join("[%s]" % seq_utils.IUPAC.get(ch, ch) for ch in k)), float(v)) for k, v in (motifs or {}).items()} or None
         self.rep_temps_shelfs = seq_utils.get_rep_temps(self)
 
 
@@ -48,7 +52,8 @@ class bf_design_t(C.Structure):
                 ("len_a", C.c_void_p), ("allowed", C.c_void_p), ("init_seq", C.c_void_p), ("temps", C.c_void_p), ("tm_prob", C.c_void_p),
                 ("n_terms", C.c_int32), ("term", C.c_int32 * 8), ("weight", C.c_double * 8), ("metropolis_L", C.c_double),
                 ("point_mutations", C.c_int32), ("re_attempt", C.c_int32), ("acgu", C.c_int32), ("nt_weight", C.c_double * 4),
-                ("oligo", C.c_int32), ("seed", C.c_uint64)]
+                ("oligo", C.c_int32), ("seed", C.c_uint64), ("alt_targets", C.c_void_p), ("n_alt", C.c_void_p), ("max_alt", C.c_int32),
+                ("n_motifs", C.c_int32), ("motif_mask", C.c_void_p), ("motif_len", C.c_void_p), ("motif_bonus", C.c_void_p)]
 
 
 def _bind():
@@ -132,6 +137,32 @@ class DesignLoop:
         for k, l in enumerate("ACGU"):
             cfg.nt_weight[k] = float(sim_options.nt_percentages[l])
         cfg.seed = seed
+        # alternative structures (scored as mean(eval) - Epf, energy_scores.py:98-102; the move generator keeps to the main target)
+        alts = [list(i.alt_sec_structs) if i.alt_sec_struct is not None else [] for i in self.inputs]
+        if any(alts):
+            for inp, al in zip(self.inputs, alts):
+                if any(set(a) - set(".()") or len(a) != len(inp.sec_struct) for a in al):
+                    raise ValueError("alternative structures must be made of . ( ) and as long as the target: %r" % (inp.name,))
+            max_alt = max(len(a) for a in alts)
+            buf = np.full((self.J, max_alt, self.stride), ord("."), np.uint8)
+            for j, al in enumerate(alts):
+                for k, a in enumerate(al):
+                    buf[j, k, :len(a)] = np.frombuffer(a.encode("ascii"), np.uint8)
+            n_alt = np.array([len(a) for a in alts], np.int32)
+            self._keep += [buf, n_alt]
+            cfg.alt_targets, cfg.n_alt, cfg.max_alt = buf.ctypes.data, n_alt.ctypes.data, max_alt
+        if sim_options.motifs:
+            keys = list(sim_options.motifs)
+            if len(keys) > 8 or any(len(k) > 32 or set(k) - set(seq_utils.IUPAC) - set("ACGU") for k in keys):
+                raise ValueError("the device loop takes up to 8 IUPAC motifs of up to 32 letters")
+            mm = np.zeros((len(keys), 32), np.uint8)
+            for m, k in enumerate(keys):
+                for p, ch in enumerate(k):
+                    mm[m, p] = sum(1 << "ACGU".index(x) for x in seq_utils.IUPAC.get(ch, ch))
+            ml = np.array([len(k) for k in keys], np.int32)
+            mb = np.array([sim_options.motifs[k][1] for k in keys], np.float64)
+            self._keep += [mm, ml, mb]
+            cfg.n_motifs, cfg.motif_mask, cfg.motif_len, cfg.motif_bonus = len(keys), mm.ctypes.data, ml.ctypes.data, mb.ctypes.data
         self.h = C.c_void_p()
         engine._check(self.lib.bf_design_create(C.byref(cfg), C.byref(self.h)))
         self.active = np.ones(self.J, np.uint8)
@@ -199,7 +230,10 @@ class DesignLoop:
                        "sln_Epf": (v["Epf"] + 0.3759 * n + 5.7534) / 10 if any(f == "sln_Epf" for f, _ in sim_options.scoring_f) else 0,
                        "MFE": v["MFE"] if any(f == "Ed-MFE" for f, _ in sim_options.scoring_f) else 0,
                        "edesired_minus_MFE": v["edesired"] - v["MFE"] if any(f == "Ed-MFE" for f, _ in sim_options.scoring_f) else 0,
-                       "recall": v["recall"], "precision": v["precision"], "edesired2": 0, "edesired2_minus_Epf": 0}
+                       "recall": v["recall"], "precision": v["precision"]}
+                has_alt = self.inputs[j].alt_sec_struct is not None
+                row["edesired2"] = v["edesired2"] if has_alt else 0
+                row["edesired2_minus_Epf"] = v["edesired2"] - v["Epf"] if has_alt else 0
                 if any(f == "Edef" for f, _ in sim_options.scoring_f):
                     row["ensemble_defect"] = v["ensemble_defect"]
                 if self.len_a[j] > 0:

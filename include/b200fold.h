@@ -142,11 +142,20 @@ typedef struct {
   int32_t oligo;           /* two-strand jobs: 1 heterodimer (-kT ln(dimer fraction)), 2 homodimer (strands kept identical;
                               -kT ln(fraction) or, for identical target halves, -kT ln(1 - fraction))   energy_scores.py:120-125,421-441 */
   uint64_t seed;
+  /* optional scenario terms (all zero = absent) */
+  const char *alt_targets;   /* n_jobs x max_alt x stride: alternative structures (input_file.alt_sec_structs), only . ( );
+                                adds mean(eval(alt)) - Epf to the scoring function                    energy_scores.py:98-102 */
+  const int32_t *n_alt;      /* n_jobs: alternative structures of each job, 0..max_alt */
+  int32_t max_alt;
+  int32_t n_motifs;          /* -motifs: up to 8 IUPAC motifs of up to 32 letters, bonus added when the motif occurs   sequence_utils.py:1231-1256 */
+  const uint8_t *motif_mask; /* n_motifs x 32: letters allowed at each motif position (A=1 C=2 G=4 U=8), 0 beyond its length */
+  const int32_t *motif_len;  /* n_motifs */
+  const double *motif_bonus; /* n_motifs */
 } bf_design_t;
 
-enum { BF_DESIGN_REC = 12 }; /* doubles per record: scoring_function, edesired, Epf, 1-mcc, 1-precision, 1-recall, MFE,
+enum { BF_DESIGN_REC = 14 }; /* doubles per record: scoring_function, edesired, Epf, 1-mcc, 1-precision, 1-recall, MFE,
                                 ensemble_defect, positions whose partner differs from the target's (0 = solved), global step,
-                                oligo_fraction, oligomer_bonus */
+                                oligo_fraction, oligomer_bonus, edesired2 (mean energy of the alternative structures), motif bonus */
 
 /* Allocates the loop on the engine's GPU, scores the start sequences (global step 0). */
 int bf_design_create(const bf_design_t *cfg, void **handle);

@@ -285,7 +285,8 @@ class _FakeLoop:
     def jobs(self):
         self._flush()
         step = np.array([s if self.steps >= s else -1 for s in self.solve_at], np.int32)
-        rec = np.zeros((self.J, 12))
+        from desirna_b200.design import REC
+        rec = np.zeros((self.J, REC))
         rec[:, 8] = (step < 0)
         return {"sequence": ["A" * len(i.sec_struct) for i in self.inputs], "mfe_ss": [i.sec_struct for i in self.inputs], "rec": rec,
                 "solved_step": step, "n_solved": np.zeros(self.J, np.uint32)}

@@ -12,6 +12,11 @@ from conftest import load_golden
 
 pytestmark = pytest.mark.gpu
 
+
+def f32(x):
+    import struct
+    return struct.unpack("f", struct.pack("f", x))[0]
+
 PAIR_OK = {("A", "U"), ("U", "A"), ("G", "C"), ("C", "G"), ("G", "U"), ("U", "G")}
 
 
@@ -74,6 +79,66 @@ def test_records_match_host_scoring_and_invariants_hold(engine, monkeypatch, sco
         assert (jobs["rec"][j][8], jobs["rec"][j][0]) <= cur_key
         if jobs["solved_step"][j] >= 0:
             assert jobs["mfe_ss"][j] == inp.sec_struct and jobs["rec"][j][8] == 0
+    loop.close()
+
+
+def test_device_records_against_the_oracle(engine, oracle):
+    """test_records_match_host_scoring... compares the device loop with the host mirror of score_sequence, and that mirror folds
+    through the same CUDA kernels -- it checks the loop's bookkeeping, not the folds.  Here the records of a few global steps are
+    checked against the CPU oracle instead: MFE structure and energy, energy of the target (Ed), ensemble energy (Epf)."""
+    from desirna_b200 import design
+    inputs = small_inputs(limit=5)
+    o = design.DesignOptions(replicas=5, RE_attempt=10, scoring_f=[("Ed-MFE", 0.5), ("Ed-Epf", 0.5)])
+    random.seed(11)
+    loop = design.DesignLoop(inputs, o, seed=3)
+    loop.run(3)
+    rep = loop.replicas()
+    R = loop.R
+    for j, inp in enumerate(inputs):
+        for r in range(R):
+            g = j * R + r
+            s = rep["sequence"][g]
+            rec = dict(zip(design.REC_FIELDS, rep["rec"][g]))
+            e, ss = oracle.mfe(s)
+            assert rep["mfe_ss"][g] == ss and rec["MFE"] == f32(e / 100.0), (inp.name, s)
+            assert rec["edesired"] == f32(oracle.eval(s, inp.sec_struct) / 100.0), (inp.name, s)
+            assert abs(rec["Epf"] - oracle.pf(s)[4]) <= 1e-5 * max(1.0, abs(rec["Epf"])), (inp.name, s)   # float32-rounded API value
+    loop.close()
+
+
+def test_alternative_structures_and_motifs_on_the_device(engine):
+    """the reference's Alternative-structures example (example_files/inputs/Alternative_structures_design_input.txt: one target, two
+    alternative structures, scored as mean(eval(alt)) - Epf, utils/energy_scores.py:98-102) next to a plain target, both with two
+    IUPAC motifs (-motifs, utils/sequence_utils.py:1231-1256): device records against the host mirror of score_sequence"""
+    from desirna_b200 import design
+    from desirna_b200.utils import energy_scores as es
+    from desirna_b200.utils import stats_inputs_outputs as sio
+    alt = sio.make_input("Alt_Struct_Example", "((((((.((((((((....))))).)).).))))))")
+    alt.add_alt_sec_struct(["(((((((((((((....)))..)).)).).))))).", "(((((((((((((....)))))...)).).)))))."])
+    plain = sio.make_input("plain", "((((....))))....((((...)))).")
+    inputs = [alt, plain]
+    o = design.DesignOptions(replicas=6, RE_attempt=12, scoring_f=[("Ed-Epf", 0.7), ("1-MCC", 0.3)], motifs={"GNRA": -3.5, "UUCG": 2.0})
+    random.seed(21)
+    loop = design.DesignLoop(inputs, o, seed=9)
+    loop.run(3)
+    rep = loop.replicas()
+    R = loop.R
+    seen_motif = 0
+    for j, inp in enumerate(inputs):
+        seqs = rep["sequence"][j * R:(j + 1) * R]
+        ref = es.score_sequences(seqs, inp, o)
+        for r, (s, h) in enumerate(zip(seqs, ref)):
+            rec = dict(zip(design.REC_FIELDS, rep["rec"][j * R + r]))
+            assert rec["edesired"] == h.edesired and abs(rec["Epf"] - h.Epf) <= 4e-6
+            if inp is alt:
+                assert rec["edesired2"] == pytest.approx(h.edesired2, abs=1e-12)
+            else:
+                assert rec["edesired2"] == 0.0
+            want_motif = es.score_motifs(s, o)
+            assert rec["motif_bonus"] == want_motif, (s, rec["motif_bonus"], want_motif)
+            seen_motif += want_motif != 0
+            assert rec["scoring_function"] == pytest.approx(h.scoring_function, abs=1e-5)
+    assert seen_motif > 0   # (GNRA is common enough in 12 random-ish sequences)
     loop.close()
 
 
