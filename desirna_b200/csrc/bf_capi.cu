@@ -517,6 +517,7 @@ struct DesignLoop {
   int B = 0, gstep = 0, re_attempt = 0;
   uint32_t want = 0;
   bool two = false;   // some job has two strands: the loop folds with the two-strand kernels
+  bool pks = false;   // pseudoknot overlay: three constrained refolds after the MFE fold of every sub-step
   bool overlap = true;  // BF_DESIGN_OVERLAP=0: always fold MFE, then PF
   int overlap_x2 = 16;  // BF_DESIGN_OVERLAP_X: batch size up to which the two fills run side by side, in units of half the SM count
                         // (measured: pays at every size tried, 0.76 -> 0.42 ms per sub-step at 64 x 104 nt, 15.5 -> 14.4 ms at 296 x 400 nt)
@@ -575,7 +576,24 @@ int design_score(DesignLoop *h, bool init = false) {
   r.mfe_dcal = h->D.o_mfe; r.mfe_ss = h->D.o_ss; r.pf = h->D.o_pf; r.eval_dcal = h->D.o_eval; r.defect = h->D.o_defect;
   // small batches: partition function beside the MFE fill, scaled by the parent sequence's MFE (kept per replica)
   const bool beside = !init && !h->two && h->overlap && h->B * 2 <= g.sm_count * h->overlap_x2 && !(h->want & BF_WANT_DEFECT);
-  return run_device(h->w, &b, &r, h->two, h->st, beside ? h->D.row_scale : nullptr, false);
+  int rc = run_device(h->w, &b, &r, h->two, h->st, beside ? h->D.row_scale : nullptr, false);
+  if (rc || !h->pks) return rc;
+  // pseudoknot overlay (sequence_utils.py:1166-1228): forbid what is paired, fold again, paint the new pairs with the next bracket
+  // family; three rounds.  A round that finds no pair leaves the overlay and the mask as they are, so the rounds the reference
+  // skips are no-ops here; all rows go through all rounds.
+  bf_batch_t b2 = b;
+  b2.want = BF_WANT_MFE | BF_WANT_SS; b2.nopair = h->D.pk_nopair; b2.targets = nullptr; b2.n_targets = 0;
+  bf_result_t r2;
+  std::memset(&r2, 0, sizeof r2);
+  r2.mfe_dcal = h->D.o_mfe2; r2.mfe_ss = h->D.o_ss2;
+  for (int round = 0; round < 3; round++) {
+    CU(bf_launch_design_pk_mask(h->D, h->B, h->st), "launch bf_k_design_pk_mask");
+    rc = run_device(h->w, &b2, &r2, false, h->st, nullptr, false);
+    if (rc) return rc;
+    CU(bf_launch_design_pk_paint(h->D, h->B, round, h->st), "launch bf_k_design_pk_paint");
+    g.launches += 2;
+  }
+  return BF_OK;
 }
 
 // the launches of one global step; gstep < 0: inside a graph capture (the kernels read the step number from device memory)
@@ -619,20 +637,27 @@ int bf_design_create(const bf_design_t *c, void **handle) {
       len_a[j] = c->len_a[j];
       two = two || len_a[j] > 0;
     }
-    std::vector<int> stk;
+    // one stack per bracket family; the families beyond ( ) only with the pseudoknot overlay
+    std::vector<int> stk[4];
     for (int i = 0; i < n; i++) {
       const char ch = c->target[(size_t)j * S + i];
-      if (ch == '(') stk.push_back(i);
-      else if (ch == ')') {
-        if (stk.empty()) return fail(BF_ERR_ARG, "bf_design_create: unbalanced target");
-        tpt[(size_t)j * S + i] = (short)stk.back(); tpt[(size_t)j * S + stk.back()] = (short)i; stk.pop_back();
-      } else if (ch != '.') return fail(BF_ERR_ARG, "bf_design_create: targets may contain only . ( )");
+      const char *po = strchr("([<{", ch), *pc = strchr(")]>}", ch);
+      if (ch && po) {
+        if (po - "([<{" > 0 && !c->pks) return fail(BF_ERR_ARG, "bf_design_create: targets may contain only . ( ) (pseudoknot brackets need pks = 1)");
+        stk[po - "([<{"].push_back(i);
+      } else if (ch && pc) {
+        std::vector<int> &sk = stk[pc - ")]>}"];
+        if (sk.empty()) return fail(BF_ERR_ARG, "bf_design_create: unbalanced target");
+        tpt[(size_t)j * S + i] = (short)sk.back(); tpt[(size_t)j * S + sk.back()] = (short)i; sk.pop_back();
+      } else if (ch != '.') return fail(BF_ERR_ARG, "bf_design_create: targets may contain only . ( ) and, with pks = 1, [ ] < > { }");
       const uint8_t a = c->allowed[(size_t)j * S + i];
       if (a == 0 || a > 15) return fail(BF_ERR_ARG, "bf_design_create: allowed-letter mask outside 1..15");
       if (__builtin_popcount(a) > 1) avail[(size_t)j * S + n_avail[j]++] = (unsigned short)i;
     }
-    if (!stk.empty()) return fail(BF_ERR_ARG, "bf_design_create: unbalanced target");
+    for (auto &sk : stk)
+      if (!sk.empty()) return fail(BF_ERR_ARG, "bf_design_create: unbalanced target");
   }
+  if (c->pks && two) return fail(BF_ERR_ARG, "bf_design_create: the pseudoknot overlay needs single-strand jobs");
   if (!two && (bf_fill_mfe_mode(S) == 0 || bf_fill_pf_mode(S) == 0)) return fail(BF_ERR_UNAVAILABLE, "bf_design_create: stride outside the fill path");
   // optional scenario terms: alternative structures, motifs
   const int max_alt = c->alt_targets ? c->max_alt : 0;
@@ -655,6 +680,7 @@ int bf_design_create(const bf_design_t *c, void **handle) {
     if (c->motif_len[m] < 1 || c->motif_len[m] > 32) return fail(BF_ERR_ARG, "bf_design_create: motif length outside 1..32");
   DesignLoop *h = new DesignLoop;
   h->two = two;
+  h->pks = c->pks != 0;
   { const char *ov = getenv("BF_DESIGN_OVERLAP"); h->overlap = !(ov && ov[0] == '0'); }
   { const char *ox = getenv("BF_DESIGN_OVERLAP_X"); h->overlap_x2 = (ox && atoi(ox) > 0) ? atoi(ox) : 16; }
   // measured (bench.py design_loop, profiles/r02_design_graph.txt): one loop alone gains 2-6 % per sub-step (36 nt x 10: 0.111 ->
@@ -697,6 +723,7 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   DCU(h->alloc(&D.row_tgt, G * D.T * S), "cudaMalloc(design)"); DCU(h->alloc(&D.o_mfe, G), "cudaMalloc(design)");
   DCU(h->alloc(&D.o_ss, G * (S + 1)), "cudaMalloc(design)"); DCU(h->alloc(&D.o_pf, G * 5), "cudaMalloc(design)");
   DCU(h->alloc(&D.o_eval, G * D.T), "cudaMalloc(design)");
+  if (h->pks) { DCU(h->alloc(&D.pk_nopair, G * S), "cudaMalloc(design)"); DCU(h->alloc(&D.o_mfe2, G), "cudaMalloc(design)"); DCU(h->alloc(&D.o_ss2, G * (S + 1)), "cudaMalloc(design)"); }
   h->want = BF_WANT_MFE | BF_WANT_SS | BF_WANT_PF | BF_WANT_EVAL;
   BfDesignCfg &C = h->C;
   C.n_terms = c->n_terms;

@@ -58,11 +58,24 @@ __device__ int pick_letter(unsigned m, bool weighted, const BfDesignCfg &C, unsi
 // dot-bracket -> partner table (lane 0; balanced strings as produced by bf_k_trace); characters other than ( ) are unpaired
 __device__ void pair_table(const char *ss, int n, short *pt, short *stk) {
   int sp = 0;
+  bool other = false;
   for (int i = 0; i < n; i++) {
     const char ch = ss[i];
     pt[i] = -1;
     if (ch == '(') stk[sp++] = (short)i;
     else if (ch == ')' && sp > 0) { const int j = stk[--sp]; pt[i] = (short)j; pt[j] = (short)i; }
+    else if (ch != '.') other = true;
+  }
+  if (!other) return;
+  // pseudoknot overlay: one more pass per bracket family present (check_dot_bracket, sequence_utils.py:74-116)
+  for (int f = 0; f < 3; f++) {
+    const char opn = "[<{"[f], cls = "]>}"[f];
+    sp = 0;
+    for (int i = 0; i < n; i++) {
+      const char ch = ss[i];
+      if (ch == opn) stk[sp++] = (short)i;
+      else if (ch == cls && sp > 0) { const int j = stk[--sp]; pt[i] = (short)j; pt[j] = (short)i; }
+    }
   }
 }
 
@@ -106,6 +119,25 @@ __global__ void bf_k_design_gather(BfDesignDev D, int B) {
   for (int t = 0; t < D.T; t++) {
     const char *src = (t >= 1 && t - 1 < D.n_alt[job]) ? D.alt + ((size_t)job * D.max_alt + (t - 1)) * D.stride : D.tgt + (size_t)job * D.stride;
     for (int k = lane; k < D.stride; k += 32) D.row_tgt[((size_t)row * D.T + t) * D.stride + k] = src[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ pseudoknot overlay
+__global__ void bf_k_design_pk_mask(BfDesignDev D, int B) {
+  const int lane = threadIdx.x & 31, row = blockIdx.x * kWPB + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const char *ss = D.o_ss + (size_t)row * (D.stride + 1);
+  for (int k = lane; k < D.stride; k += 32) D.pk_nopair[(size_t)row * D.stride + k] = (k < D.row_len[row] && ss[k] != '.') ? 1 : 0;
+}
+__global__ void bf_k_design_pk_paint(BfDesignDev D, int B, int round) {
+  const int lane = threadIdx.x & 31, row = blockIdx.x * kWPB + (threadIdx.x >> 5);
+  if (row >= B) return;
+  char *ss = D.o_ss + (size_t)row * (D.stride + 1);
+  const char *s2 = D.o_ss2 + (size_t)row * (D.stride + 1);
+  const char opn = "[<{"[round], cls = "]>}"[round];
+  for (int k = lane; k < D.row_len[row]; k += 32) {
+    if (s2[k] == '(') ss[k] = opn;
+    else if (s2[k] == ')') ss[k] = cls;
   }
 }
 
@@ -401,6 +433,16 @@ __global__ void bf_k_design_exchange(BfDesignDev D, BfDesignCfg C, const uint8_t
 
 }  // namespace
 
+cudaError_t bf_launch_design_pk_mask(const BfDesignDev &D, int B, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  bf_k_design_pk_mask<<<(B + kWPB - 1) / kWPB, kWPB * 32, 0, st>>>(D, B);
+  return cudaGetLastError();
+}
+cudaError_t bf_launch_design_pk_paint(const BfDesignDev &D, int B, int round, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  bf_k_design_pk_paint<<<(B + kWPB - 1) / kWPB, kWPB * 32, 0, st>>>(D, B, round);
+  return cudaGetLastError();
+}
 cudaError_t bf_launch_design_gather(const BfDesignDev &D, int B, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
   bf_k_design_gather<<<(B + kWPB - 1) / kWPB, kWPB * 32, 0, st>>>(D, B);

@@ -74,9 +74,15 @@ struct BfDesignDev {
   double *o_pf;                  // B x 5
   int *o_eval;                   // B x T
   double *o_defect;              // B (only with the Edef term)
+  // pseudoknot overlay (sequence_utils.py:1166-1228): constrained refolds of the rows
+  uint8_t *pk_nopair;            // B x stride      positions already paired
+  int *o_mfe2;                   // B
+  char *o_ss2;                   // B x (stride+1)  structure of the constrained refold
 };
 
 cudaError_t bf_launch_design_gather(const BfDesignDev &D, int B, cudaStream_t st);
+cudaError_t bf_launch_design_pk_mask(const BfDesignDev &D, int B, cudaStream_t st);                 // pk_nopair from the overlay so far (o_ss)
+cudaError_t bf_launch_design_pk_paint(const BfDesignDev &D, int B, int round, cudaStream_t st);     // pairs of o_ss2 into o_ss as [] <> {}
 cudaError_t bf_launch_design_propose(const BfDesignDev &D, const BfDesignCfg &C, int B, bool copy_only, cudaStream_t st);
 cudaError_t bf_launch_design_accept(const BfDesignDev &D, const BfDesignCfg &C, int B, bool init, int gstep, cudaStream_t st);
 cudaError_t bf_launch_design_exchange(const BfDesignDev &D, const BfDesignCfg &C, const uint8_t *active, int gstep, cudaStream_t st);

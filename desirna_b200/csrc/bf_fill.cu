@@ -1221,7 +1221,7 @@ struct FillCfg { int nw, pl; };
 // what matters is the latency of ONE sequence, so a CTA gets 16 warps instead of 8 when every sequence still gets its own SM.
 static int g_fill_sms = 148;
 void bf_fill_set_sms(int sms) { if (sms > 0) g_fill_sms = sms; }
-static bool want_wide(int B) { return B > 0 && B <= g_fill_sms && env_int("BF_WIDE", 1) != 0; }
+static bool want_wide(int B) { const int w = env_int("BF_WIDE", 1); return B > 0 && (w == 2 || (B <= g_fill_sms && w != 0)); }   // 2: always (experiments)
 
 static bool mfe_fits(int nmax, int nw, int pl) { return mfe_plan(nmax, nw, pl).total <= kSmemBudget; }
 static bool pf_fits(int nmax, int nw, int pl) { return pf_plan(nmax, nw, pl).total <= kSmemBudget; }

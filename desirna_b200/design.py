@@ -30,7 +30,7 @@ class DesignOptions:
 
     def __init__(self, replicas=10, RE_attempt=100, T_min=10.0, T_max=150.0, scoring_f=(("Ed-Epf", 1.0),), point_mutations="on",
                  tm_max=0.7, tm_min=0.0, acgu_percentages="off", nt_percentages=None, diff_start_replicas="one", oligo_state="none",
-                 motifs=None):
+                 motifs=None, pks="off"):
         self.replicas = replicas
         self.RE_attempt = RE_attempt
         self.T_min, self.T_max = T_min, T_max
@@ -41,7 +41,7 @@ class DesignOptions:
         self.nt_percentages = nt_percentages or {"A": 15, "C": 30, "G": 30, "U": 15}
         self.diff_start_replicas = diff_start_replicas
         self.L = 504.12
-        self.oligo_state, self.pks, self.subopt = oligo_state, "off", "off"   # "none" | "heterodimer" | "homodimer"
+        self.oligo_state, self.pks, self.subopt = oligo_state, pks, "off"   # "none" | "heterodimer" | "homodimer"
         # -motifs "KEY,bonus,KEY,bonus": IUPAC motif -> (compiled regex, bonus) as DesiRNA.py:212-224 builds it
         self.motifs = {k: (re.compile("".join("[%s]" % seq_utils.IUPAC.get(ch, ch) for ch in k)), float(v)) for k, v in (motifs or {}).items()} or None
         self.rep_temps_shelfs = seq_utils.get_rep_temps(self)
@@ -53,7 +53,7 @@ class bf_design_t(C.Structure):
                 ("n_terms", C.c_int32), ("term", C.c_int32 * 8), ("weight", C.c_double * 8), ("metropolis_L", C.c_double),
                 ("point_mutations", C.c_int32), ("re_attempt", C.c_int32), ("acgu", C.c_int32), ("nt_weight", C.c_double * 4),
                 ("oligo", C.c_int32), ("seed", C.c_uint64), ("alt_targets", C.c_void_p), ("n_alt", C.c_void_p), ("max_alt", C.c_int32),
-                ("n_motifs", C.c_int32), ("motif_mask", C.c_void_p), ("motif_len", C.c_void_p), ("motif_bonus", C.c_void_p)]
+                ("n_motifs", C.c_int32), ("motif_mask", C.c_void_p), ("motif_len", C.c_void_p), ("motif_bonus", C.c_void_p), ("pks", C.c_int32)]
 
 
 def _bind():
@@ -97,8 +97,9 @@ class DesignLoop:
         self.inputs = list(inputs)
         self.J, self.R = len(self.inputs), sim_options.replicas
         for inp in self.inputs:
-            if set(inp.sec_struct) - set(".()&") or inp.sec_struct.count("&") > 1:
-                raise ValueError("the device design loop takes targets made of . ( ), one strand or 'A&B': %r" % (inp.name,))
+            pk_ok = sim_options.pks == "on" and "&" not in inp.sec_struct
+            if set(inp.sec_struct) - set(".()&" + ("[]<>{}" if pk_ok else "")) or inp.sec_struct.count("&") > 1:
+                raise ValueError("the device design loop takes targets made of . ( ), one strand or 'A&B' (with pks='on': also [ ] < > { }): %r" % (inp.name,))
             if "&" in inp.sec_struct and sim_options.oligo_state not in ("heterodimer", "homodimer"):
                 raise ValueError("two-strand targets need oligo_state='heterodimer' or 'homodimer'")
             if sim_options.oligo_state == "homodimer" and len(set(map(len, inp.sec_struct.split("&")))) != 1:
@@ -137,6 +138,7 @@ class DesignLoop:
         for k, l in enumerate("ACGU"):
             cfg.nt_weight[k] = float(sim_options.nt_percentages[l])
         cfg.seed = seed
+        cfg.pks = int(sim_options.pks == "on")
         # alternative structures (scored as mean(eval) - Epf, energy_scores.py:98-102; the move generator keeps to the main target)
         alts = [list(i.alt_sec_structs) if i.alt_sec_struct is not None else [] for i in self.inputs]
         if any(alts):

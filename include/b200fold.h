@@ -151,6 +151,9 @@ typedef struct {
   const uint8_t *motif_mask; /* n_motifs x 32: letters allowed at each motif position (A=1 C=2 G=4 U=8), 0 beyond its length */
   const int32_t *motif_len;  /* n_motifs */
   const double *motif_bonus; /* n_motifs */
+  int32_t pks;               /* 1: pseudoknot overlay (targets may use the bracket families () [] <> {}): after the MFE fold the
+                                paired positions are forbidden, the sequence is folded again and the new pairs painted with the next
+                                family, up to three rounds                                  sequence_utils.py:1166-1228 */
 } bf_design_t;
 
 enum { BF_DESIGN_REC = 14 }; /* doubles per record: scoring_function, edesired, Epf, 1-mcc, 1-precision, 1-recall, MFE,

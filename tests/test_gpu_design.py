@@ -142,6 +142,72 @@ def test_alternative_structures_and_motifs_on_the_device(engine):
     loop.close()
 
 
+def test_pseudoknot_overlay_on_the_device(engine):
+    """the reference's Pseudoknot example (example_files/inputs/Pseudoknot_design_input.txt): after the MFE fold of every mutant the
+    paired positions are forbidden, the sequence is folded again and the new pairs painted with the next bracket family
+    (utils/sequence_utils.py:1166-1228).  Device records and overlaid structures against the host mirror (pks = "on")."""
+    from desirna_b200 import design
+    from desirna_b200.utils import energy_scores as es
+    from desirna_b200.utils import stats_inputs_outputs as sio
+    inputs = [sio.make_input("Pseudoknot_Example", "((((((....[[[[..))))))......]]]]...."),
+              sio.make_input("two_knots", "..((((..[[[..))))..<<<..]]]...>>>.."),
+              sio.make_input("plain", "((((....))))....((((...)))).")]
+    o = design.DesignOptions(replicas=6, RE_attempt=12, scoring_f=[("Ed-Epf", 0.5), ("1-MCC", 0.5)], pks="on")
+    random.seed(33)
+    loop = design.DesignLoop(inputs, o, seed=13)
+    loop.run(3)
+    rep = loop.replicas()
+    R = loop.R
+    painted = 0
+    for j, inp in enumerate(inputs):
+        seqs = rep["sequence"][j * R:(j + 1) * R]
+        ref = es.score_sequences(seqs, inp, o)
+        for r, (s, h) in enumerate(zip(seqs, ref)):
+            g = j * R + r
+            rec = dict(zip(design.REC_FIELDS, rep["rec"][g]))
+            assert rep["mfe_ss"][g] == h.mfe_ss, (inp.name, s, rep["mfe_ss"][g], h.mfe_ss)
+            painted += "[" in h.mfe_ss
+            assert rec["edesired"] == h.edesired and abs(rec["Epf"] - h.Epf) <= 4e-6
+            assert rec["mcc"] == pytest.approx(h.mcc, abs=1e-12) and rec["precision"] == pytest.approx(h.precision, abs=1e-12)
+            assert rec["recall"] == pytest.approx(h.recall, abs=1e-12)
+            assert rec["scoring_function"] == pytest.approx(h.scoring_function, abs=1e-5)
+    assert painted > 0   # some replica did get a second layer of pairs
+    loop.close()
+
+
+def test_the_six_example_scenarios_run_through_design_batch(engine):
+    """every input of the reference's example_files/inputs (Standard, Seed sequence, Alternative structures, Pseudoknot, RNA-RNA
+    complex, Homodimer) is designed by the device-resident loop; every reported solution is folded again through the host mirror"""
+    from desirna_b200 import design
+    from desirna_b200.utils import energy_scores as es
+    from desirna_b200.utils import stats_inputs_outputs as sio
+    std = sio.make_input("Design", "((((((.((((((((....))))).)).).))))))")
+    seed = sio.make_input("Seed_Seq_Example", "((((((.((((((((....))))).)).).))))))")
+    seed.add_seed_seq("GCCCCGGCCCCCGGCGAAAGCCGGUGGAGGCGGGGC")
+    alt = sio.make_input("Alt_Struct_Example", "((((((.((((((((....))))).)).).))))))")
+    alt.add_alt_sec_struct(["(((((((((((((....)))..)).)).).))))).", "(((((((((((((....)))))...)).).)))))."])
+    pk = sio.make_input("Pseudoknot_Example", "((((((....[[[[..))))))......]]]]....")
+    het = sio.make_input("RNA-RNA Complex_Example", "(((.(((((....))..&(((....)))..))))))", "NNNNNNNNNNNNNNNNN&NNNNNNNNNNNNNNNNNN")
+    hom = sio.make_input("Homodimer_Example", "((((....((((.....&))))....)))).....", "NNNNNNNNNNNNNNNNN&NNNNNNNNNNNNNNNNN")
+    runs = [([std, seed, alt], design.DesignOptions(replicas=10, RE_attempt=20)),
+            ([pk], design.DesignOptions(replicas=10, RE_attempt=20, pks="on")),
+            ([het], design.DesignOptions(replicas=10, RE_attempt=20, oligo_state="heterodimer")),
+            ([hom], design.DesignOptions(replicas=10, RE_attempt=20, oligo_state="homodimer"))]
+    random.seed(2)
+    solved = 0
+    for inputs, o in runs:
+        res, info = design.design_batch(inputs, o, global_steps=30, seed=17)
+        assert len(res) == len(inputs) and info["jobs"] == len(inputs)
+        for inp, r in zip(inputs, res):
+            h = es.score_sequences([r["sequence"]], inp, o)[0]
+            assert h.mfe_ss == r["mfe_ss"], (inp.name, r["sequence"])
+            assert r["scoring_function"] == pytest.approx(h.scoring_function, abs=1e-5)
+            if r["solved"]:
+                solved += 1
+                assert h.mfe_ss == inp.sec_struct or sorted(map(tuple, sio.seq_utils.check_dot_bracket(h.mfe_ss))) == sorted(map(tuple, inp.pairs))
+    assert solved >= 4   # six 35-nt targets, 600 Monte-Carlo sub-steps x 10 replicas each
+
+
 def test_same_seed_same_trajectory(engine):
     from desirna_b200 import design
     inputs = small_inputs(limit=4)
