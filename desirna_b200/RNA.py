@@ -186,6 +186,16 @@ class fold_compound:
             self._cache[key] = float(out["defect"][0])
         return self._cache[key]
 
+    def second_best_energy(self):
+        """(MFE, energy of the second-best structure) in kcal/mol as C floats, or (MFE, None) when the sequence has a single
+        structure: bf_second_best, a 2-best DP on the unambiguous grammar -- the number DesiRNA reads off subopt_cb's enumeration
+        (energy_scores.py:453-488) without the enumeration.  Extension of the shim; ViennaRNA has no such call."""
+        if "&" in self.sequence:
+            raise NotImplementedError("second_best_energy on two-strand compounds is not part of the accelerated path")
+        nopair = np.asarray(self._nopair, np.uint8)[None, :] if self._nopair is not None and any(self._nopair) else None
+        e1, e2 = _eng.second_best([self.sequence], nopair)
+        return f32(int(e1[0]) / 100.0), (f32(int(e2[0]) / 100.0) if int(e2[0]) < 10000000 else None)
+
     def subopt_cb(self, delta, cb, data=None):
         """vrna_subopt_cb as DesiRNA calls it (energy_scores.py:465-474, uniq_ML = 1): cb(structure, energy, data) for every
         structure within `delta` dcal/mol of the MFE, then once more with structure None."""

@@ -418,6 +418,39 @@ int bf_score_batch(const bf_batch_t *b, bf_result_t *r) {
   return BF_OK;
 }
 
+int bf_second_best(const bf_batch_t *b, int32_t *e1_dcal, int32_t *e2_dcal) {
+  if (!g.inited) return fail(BF_ERR_NOT_INIT, "bf_init has not been called");
+  if (!g.have_params) return fail(BF_ERR_NOT_INIT, "no energy parameters loaded");
+  if (!b || !e1_dcal || !e2_dcal || b->B < 0 || b->stride <= 0 || (b->B && (!b->seq || !b->len))) return fail(BF_ERR_ARG, "bf_second_best: bad argument");
+  if (b->stride > 2000) return fail(BF_ERR_ARG, "bf_second_best: stride > 2000 not supported");
+  if (b->cut) for (int k = 0; k < b->B; k++) if (b->cut[k] > 0) return fail(BF_ERR_UNAVAILABLE, "bf_second_best: single-strand sequences only");
+  if (b->B == 0) return BF_OK;
+  cudaStream_t st = g.stream;
+  const size_t B = b->B, S = b->stride;
+  CU(g.d_seq.reserve(B * S), "cudaMalloc(seq)");
+  CU(g.d_len.reserve(B * sizeof(int)), "cudaMalloc(len)");
+  CU(g.d_mfe.reserve(2 * B * sizeof(int)), "cudaMalloc(second best)");
+  CU(cudaMemcpyAsync(g.d_seq.p, b->seq, B * S, cudaMemcpyHostToDevice, st), "H2D seq");
+  CU(cudaMemcpyAsync(g.d_len.p, b->len, B * sizeof(int), cudaMemcpyHostToDevice, st), "H2D len");
+  BfBatchDev db;
+  db.B = b->B; db.stride = b->stride; db.seq = (const char *)g.d_seq.p; db.len = (const int *)g.d_len.p; db.cut = nullptr; db.nopair = nullptr;
+  if (b->nopair) {
+    CU(g.d_nopair.reserve(B * S), "cudaMalloc(nopair)");
+    CU(cudaMemcpyAsync(g.d_nopair.p, b->nopair, B * S, cudaMemcpyHostToDevice, st), "H2D nopair");
+    db.nopair = (const uint8_t *)g.d_nopair.p;
+  }
+  const int wstride = b->stride + 2;
+  const int grid = std::min(b->B, 2 * g.sm_count);
+  CU(g.w.ws_mfe.reserve((size_t)grid * bf_twobest_slot(wstride) * sizeof(int2)), "cudaMalloc(second-best workspace)");
+  int *d_e = (int *)g.d_mfe.p;
+  CU(bf_launch_twobest(g.dP, db, (int2 *)g.w.ws_mfe.p, wstride, grid, g.w.d_counters + 0, d_e, d_e + B, st), "launch bf_k_mfe2");
+  g.launches++;
+  CU(cudaMemcpyAsync(e1_dcal, d_e, B * sizeof(int), cudaMemcpyDeviceToHost, st), "D2H e1");
+  CU(cudaMemcpyAsync(e2_dcal, d_e + B, B * sizeof(int), cudaMemcpyDeviceToHost, st), "D2H e2");
+  CU(cudaStreamSynchronize(st), "bf_second_best");
+  return BF_OK;
+}
+
 int bf_subopt(const char *seq, int32_t len, const uint8_t *nopair, int32_t delta_dcal, int32_t max_out, char *ss_out, int32_t *e_out,
               int32_t *n_out, int32_t *truncated) {
   if (!g.inited) return fail(BF_ERR_NOT_INIT, "bf_init has not been called");
@@ -577,7 +610,18 @@ int design_score(DesignLoop *h, bool init = false) {
   // small batches: partition function beside the MFE fill, scaled by the parent sequence's MFE (kept per replica)
   const bool beside = !init && !h->two && h->overlap && h->B * 2 <= g.sm_count * h->overlap_x2 && !(h->want & BF_WANT_DEFECT);
   int rc = run_device(h->w, &b, &r, h->two, h->st, beside ? h->D.row_scale : nullptr, false);
-  if (rc || !h->pks) return rc;
+  if (rc) return rc;
+  if (h->C.subopt) {
+    // negative design: (best, second best) energies of the rows that fold into their target (rare rows; the others are skipped)
+    CU(bf_launch_design_nd_flag(h->D, h->B, h->st), "launch bf_k_design_nd_flag");
+    BfBatchDev db;
+    db.B = h->B; db.stride = h->D.stride; db.seq = h->D.mut_seq; db.len = h->D.row_len; db.cut = nullptr; db.nopair = nullptr;
+    const int wstride = h->D.stride + 2, grid = std::min(h->B, g.sm_count);
+    CU(h->w.ws_mfe.reserve((size_t)grid * bf_twobest_slot(wstride) * sizeof(int2)), "cudaMalloc(second-best workspace)");
+    CU(bf_launch_twobest(g.dP, db, (int2 *)h->w.ws_mfe.p, wstride, grid, h->w.d_counters + 3, h->D.o_e1, h->D.o_e2, h->st, h->D.nd_flag), "launch bf_k_mfe2");
+    g.launches += 2;
+  }
+  if (!h->pks) return BF_OK;
   // pseudoknot overlay (sequence_utils.py:1166-1228): forbid what is paired, fold again, paint the new pairs with the next bracket
   // family; three rounds.  A round that finds no pair leaves the overlay and the mask as they are, so the rounds the reference
   // skips are no-ops here; all rows go through all rounds.
@@ -658,6 +702,7 @@ int bf_design_create(const bf_design_t *c, void **handle) {
       if (!sk.empty()) return fail(BF_ERR_ARG, "bf_design_create: unbalanced target");
   }
   if (c->pks && two) return fail(BF_ERR_ARG, "bf_design_create: the pseudoknot overlay needs single-strand jobs");
+  if (c->subopt && (two || c->pks)) return fail(BF_ERR_ARG, "bf_design_create: negative design (subopt) needs single-strand jobs without the pseudoknot overlay");
   if (!two && (bf_fill_mfe_mode(S) == 0 || bf_fill_pf_mode(S) == 0)) return fail(BF_ERR_UNAVAILABLE, "bf_design_create: stride outside the fill path");
   // optional scenario terms: alternative structures, motifs
   const int max_alt = c->alt_targets ? c->max_alt : 0;
@@ -723,6 +768,7 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   DCU(h->alloc(&D.row_tgt, G * D.T * S), "cudaMalloc(design)"); DCU(h->alloc(&D.o_mfe, G), "cudaMalloc(design)");
   DCU(h->alloc(&D.o_ss, G * (S + 1)), "cudaMalloc(design)"); DCU(h->alloc(&D.o_pf, G * 5), "cudaMalloc(design)");
   DCU(h->alloc(&D.o_eval, G * D.T), "cudaMalloc(design)");
+  if (c->subopt) { DCU(h->alloc(&D.nd_flag, G), "cudaMalloc(design)"); DCU(h->alloc(&D.o_e1, G), "cudaMalloc(design)"); DCU(h->alloc(&D.o_e2, G), "cudaMalloc(design)"); }
   if (h->pks) { DCU(h->alloc(&D.pk_nopair, G * S), "cudaMalloc(design)"); DCU(h->alloc(&D.o_mfe2, G), "cudaMalloc(design)"); DCU(h->alloc(&D.o_ss2, G * (S + 1)), "cudaMalloc(design)"); }
   h->want = BF_WANT_MFE | BF_WANT_SS | BF_WANT_PF | BF_WANT_EVAL;
   BfDesignCfg &C = h->C;
@@ -736,6 +782,7 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   C.metropolis_L = c->metropolis_L; C.point_mutations = c->point_mutations; C.acgu = c->acgu;
   for (int k = 0; k < 4; k++) C.nt_weight[k] = c->nt_weight[k];
   C.oligo = c->oligo;
+  C.subopt = c->subopt != 0;
   C.n_motifs = c->n_motifs;
   for (int m = 0; m < c->n_motifs; m++) {
     C.motif_len[m] = c->motif_len[m]; C.motif_bonus[m] = c->motif_bonus[m];

@@ -122,6 +122,23 @@ __global__ void bf_k_design_gather(BfDesignDev D, int B) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ negative design
+// which rows fold into their target (1 - MCC == 0 in the accept kernel): only those need the second-best structure
+__global__ void __launch_bounds__(kWPB * 32) bf_k_design_nd_flag(BfDesignDev D, int B) {
+  extern __shared__ __align__(16) unsigned char dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, row = blockIdx.x * kWPB + warp;
+  if (row >= B) return;
+  const int g = D.rowmap[row], job = g / D.R, n = D.len[job], S = D.stride;
+  WarpScratch w = scratch(dyn, S, warp);
+  if (lane == 0) pair_table(D.o_ss + (size_t)row * (S + 1), n, w.pt, w.stk);
+  __syncwarp();
+  const short *tpt = D.tpt + (size_t)job * S;
+  bool same = true;
+  for (int i = lane; i < n; i += 32) same = same && tpt[i] == w.pt[i];
+  same = __all_sync(BF_FULL, same);
+  if (lane == 0) D.nd_flag[row] = same ? 1 : 0;
+}
+
 // ------------------------------------------------------------------------------------------------ pseudoknot overlay
 __global__ void bf_k_design_pk_mask(BfDesignDev D, int B) {
   const int lane = threadIdx.x & 31, row = blockIdx.x * kWPB + (threadIdx.x >> 5);
@@ -316,7 +333,7 @@ __global__ void __launch_bounds__(kWPB * 32) bf_k_design_accept(BfDesignDev D, B
     const double MFE = (double)(float)((double)D.o_mfe[row] / 100.0);
     rec[kRecEd] = Ed; rec[kRecEpf] = Epf; rec[kRecMcc] = 1.0 - mcc; rec[kRecPrecision] = 1.0 - precision; rec[kRecRecall] = 1.0 - recall;
     rec[kRecMFE] = MFE; rec[kRecEdef] = D.o_defect ? D.o_defect[row] : 0.0; rec[kRecDist] = (double)(fp + fn); rec[kRecStep] = (double)gstep;
-    rec[kRecOligoFraction] = 0.0; rec[kRecOligoBonus] = 0.0; rec[kRecEd2] = 0.0; rec[kRecMotif] = 0.0;
+    rec[kRecOligoFraction] = 0.0; rec[kRecOligoBonus] = 0.0; rec[kRecEd2] = 0.0; rec[kRecMotif] = 0.0; rec[kRecSubopt] = 0.0;
     double total = 0.0;
     for (int k = 0; k < C.n_terms; k++) {
       const double wgt = C.weight[k];
@@ -335,6 +352,11 @@ __global__ void __launch_bounds__(kWPB * 32) bf_k_design_accept(BfDesignDev D, B
       for (int k = 0; k < D.n_alt[job]; k++) sum += (double)(float)((double)D.o_eval[(size_t)row * D.T + 1 + k] / 100.0);
       rec[kRecEd2] = sum / D.n_alt[job];
       total += rec[kRecEd2] - Epf;
+    }
+    if (C.subopt && D.nd_flag && D.nd_flag[row]) {   // -nd on: the mutant folds into the target; second-best structure within 49 kcal/mol, else 0
+      const int e1 = D.o_e1[row], e2 = D.o_e2[row];
+      rec[kRecSubopt] = (e2 < BF_INF && e2 - e1 <= 4900) ? (double)(float)((double)e2 / 100.0) : 0.0;
+      total -= rec[kRecSubopt] - Epf;
     }
     if (two && C.oligo >= 1) {
       // equilibrium dimer fraction at 1 mM from FcAB - FA - FB (dimer_multichain_energy.py:36-63), float32 API values first
@@ -433,6 +455,11 @@ __global__ void bf_k_design_exchange(BfDesignDev D, BfDesignCfg C, const uint8_t
 
 }  // namespace
 
+cudaError_t bf_launch_design_nd_flag(const BfDesignDev &D, int B, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  bf_k_design_nd_flag<<<(B + kWPB - 1) / kWPB, kWPB * 32, scratch_bytes(D.stride), st>>>(D, B);
+  return cudaGetLastError();
+}
 cudaError_t bf_launch_design_pk_mask(const BfDesignDev &D, int B, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
   bf_k_design_pk_mask<<<(B + kWPB - 1) / kWPB, kWPB * 32, 0, st>>>(D, B);

@@ -8,9 +8,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-constexpr int kDesignRec = 14;   // doubles per replica record
+constexpr int kDesignRec = 15;   // doubles per replica record
 // record slots (names of the reference's ScoreSeq fields, utils/energy_scores.py:176-195)
-enum { kRecScore = 0, kRecEd = 1, kRecEpf = 2, kRecMcc = 3, kRecPrecision = 4, kRecRecall = 5, kRecMFE = 6, kRecEdef = 7, kRecDist = 8, kRecStep = 9, kRecOligoFraction = 10, kRecOligoBonus = 11, kRecEd2 = 12, kRecMotif = 13 };
+enum { kRecScore = 0, kRecEd = 1, kRecEpf = 2, kRecMcc = 3, kRecPrecision = 4, kRecRecall = 5, kRecMFE = 6, kRecEdef = 7, kRecDist = 8, kRecStep = 9, kRecOligoFraction = 10, kRecOligoBonus = 11, kRecEd2 = 12, kRecMotif = 13, kRecSubopt = 14 };
 // scoring terms (-sf), in the order of ScoreSeq.get_scoring_function (utils/energy_scores.py:376-398)
 enum { kTermEdEpf = 0, kTermMcc = 1, kTermSlnEpf = 2, kTermEdMfe = 3, kTermPrecision = 4, kTermRecall = 5, kTermEdef = 6 };
 
@@ -25,6 +25,7 @@ struct BfDesignCfg {
   int oligo;             // two-strand jobs: 1 heterodimer, adds -kT ln(dimer fraction); 2 homodimer, strands kept identical and
                          // -kT ln(dimer fraction) (different target halves) or -kT ln(1 - fraction) (identical halves)
                          // (energy_scores.py:120-125,421-441, dimer_multichain_energy.py:36-76, sequence_utils.py:1102-1128)
+  int subopt;            // -nd on: Epf - E(second-best structure) for mutants that fold into the target (energy_scores.py:104-107)
   int n_motifs;          // -motifs: IUPAC motifs, bonus added when the motif occurs in the sequence (sequence_utils.py:1231-1256)
   int motif_len[8];
   double motif_bonus[8];
@@ -78,9 +79,13 @@ struct BfDesignDev {
   uint8_t *pk_nopair;            // B x stride      positions already paired
   int *o_mfe2;                   // B
   char *o_ss2;                   // B x (stride+1)  structure of the constrained refold
+  // negative design: rows whose structure equals the target, and their (best, second-best) energies from bf_k_mfe2
+  uint8_t *nd_flag;              // B
+  int *o_e1, *o_e2;              // B
 };
 
 cudaError_t bf_launch_design_gather(const BfDesignDev &D, int B, cudaStream_t st);
+cudaError_t bf_launch_design_nd_flag(const BfDesignDev &D, int B, cudaStream_t st);                 // nd_flag: does o_ss equal the target
 cudaError_t bf_launch_design_pk_mask(const BfDesignDev &D, int B, cudaStream_t st);                 // pk_nopair from the overlay so far (o_ss)
 cudaError_t bf_launch_design_pk_paint(const BfDesignDev &D, int B, int round, cudaStream_t st);     // pairs of o_ss2 into o_ss as [] <> {}
 cudaError_t bf_launch_design_propose(const BfDesignDev &D, const BfDesignCfg &C, int B, bool copy_only, cudaStream_t st);

@@ -71,6 +71,11 @@ cudaError_t bf_cl_pf_grid(const BfBatchDev &b, int sms, int *nclusters);
 cudaError_t bf_launch_pf_cl(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale,
                             double *lnscale, int sms, int *work_counter, cudaStream_t st);
 
+// ---- second-best structure energy by a 2-best DP on the unambiguous grammar (bf_twobest.cu)
+size_t bf_twobest_slot(int wstride);   // int2 entries of HBM workspace per CTA
+cudaError_t bf_launch_twobest(const BfParams *dP, const BfBatchDev &b, int2 *ws, int wstride, int grid, int *work_counter, int *out_e1, int *out_e2,
+                              cudaStream_t st, const uint8_t *only = nullptr);   // only: optional per-sequence flags, 0 = skip
+
 // ---- exterior recursions for small batches (bf_ext.cu): one CTA per sequence
 bool bf_ext_wide_ok(int nmax);
 cudaError_t bf_launch_f5_wide(const BfParams *dP, const BfBatchDev &b, const int *ctri, int *f5_out, cudaStream_t st);   // f5_out: B x (stride + 4)

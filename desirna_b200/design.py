@@ -21,7 +21,7 @@ from .utils import sequence_utils as seq_utils
 
 TERM_ID = {"Ed-Epf": 0, "1-MCC": 1, "sln_Epf": 2, "Ed-MFE": 3, "1-precision": 4, "1-recall": 5, "Edef": 6}
 REC_FIELDS = ("scoring_function", "edesired", "Epf", "mcc", "precision", "recall", "MFE", "ensemble_defect", "distance", "global_step",
-              "oligo_fraction", "oligomer_bonus", "edesired2", "motif_bonus")
+              "oligo_fraction", "oligomer_bonus", "edesired2", "motif_bonus", "subopt_e")
 REC = len(REC_FIELDS)
 
 
@@ -30,7 +30,7 @@ class DesignOptions:
 
     def __init__(self, replicas=10, RE_attempt=100, T_min=10.0, T_max=150.0, scoring_f=(("Ed-Epf", 1.0),), point_mutations="on",
                  tm_max=0.7, tm_min=0.0, acgu_percentages="off", nt_percentages=None, diff_start_replicas="one", oligo_state="none",
-                 motifs=None, pks="off"):
+                 motifs=None, pks="off", subopt="off"):
         self.replicas = replicas
         self.RE_attempt = RE_attempt
         self.T_min, self.T_max = T_min, T_max
@@ -41,7 +41,7 @@ class DesignOptions:
         self.nt_percentages = nt_percentages or {"A": 15, "C": 30, "G": 30, "U": 15}
         self.diff_start_replicas = diff_start_replicas
         self.L = 504.12
-        self.oligo_state, self.pks, self.subopt = oligo_state, pks, "off"   # "none" | "heterodimer" | "homodimer"
+        self.oligo_state, self.pks, self.subopt = oligo_state, pks, subopt   # "none" | "heterodimer" | "homodimer"
         # -motifs "KEY,bonus,KEY,bonus": IUPAC motif -> (compiled regex, bonus) as DesiRNA.py:212-224 builds it
         self.motifs = {k: (re.compile("".join("[%s]" % seq_utils.IUPAC.get(ch, ch) for ch in k)), float(v)) for k, v in (motifs or {}).items()} or None
         self.rep_temps_shelfs = seq_utils.get_rep_temps(self)
@@ -53,7 +53,7 @@ class bf_design_t(C.Structure):
                 ("n_terms", C.c_int32), ("term", C.c_int32 * 8), ("weight", C.c_double * 8), ("metropolis_L", C.c_double),
                 ("point_mutations", C.c_int32), ("re_attempt", C.c_int32), ("acgu", C.c_int32), ("nt_weight", C.c_double * 4),
                 ("oligo", C.c_int32), ("seed", C.c_uint64), ("alt_targets", C.c_void_p), ("n_alt", C.c_void_p), ("max_alt", C.c_int32),
-                ("n_motifs", C.c_int32), ("motif_mask", C.c_void_p), ("motif_len", C.c_void_p), ("motif_bonus", C.c_void_p), ("pks", C.c_int32)]
+                ("n_motifs", C.c_int32), ("motif_mask", C.c_void_p), ("motif_len", C.c_void_p), ("motif_bonus", C.c_void_p), ("pks", C.c_int32), ("subopt", C.c_int32)]
 
 
 def _bind():
@@ -139,6 +139,7 @@ class DesignLoop:
             cfg.nt_weight[k] = float(sim_options.nt_percentages[l])
         cfg.seed = seed
         cfg.pks = int(sim_options.pks == "on")
+        cfg.subopt = int(sim_options.subopt == "on")
         # alternative structures (scored as mean(eval) - Epf, energy_scores.py:98-102; the move generator keeps to the main target)
         alts = [list(i.alt_sec_structs) if i.alt_sec_struct is not None else [] for i in self.inputs]
         if any(alts):
@@ -228,7 +229,7 @@ class DesignLoop:
                 row = {"sequence": rep["sequence"][g], "scoring_function": v["scoring_function"], "replica_num": r + 1,
                        "temp_shelf": sim_options.rep_temps_shelfs[rep["shelf"][j, r]], "sim_step": sim_step,
                        "edesired_minus_Epf": v["edesired"] - v["Epf"], "Epf": v["Epf"], "edesired": v["edesired"], "mcc": v["mcc"], "mcc_alt": 0,
-                       "mfe_ss": rep["mfe_ss"][g], "subopt_e": 0, "esubopt_minus_Epf": 0,
+                       "mfe_ss": rep["mfe_ss"][g], "subopt_e": v["subopt_e"], "esubopt_minus_Epf": (v["subopt_e"] - v["Epf"]) if sim_options.subopt == "on" and v["mcc"] == 0 else 0,
                        "sln_Epf": (v["Epf"] + 0.3759 * n + 5.7534) / 10 if any(f == "sln_Epf" for f, _ in sim_options.scoring_f) else 0,
                        "MFE": v["MFE"] if any(f == "Ed-MFE" for f, _ in sim_options.scoring_f) else 0,
                        "edesired_minus_MFE": v["edesired"] - v["MFE"] if any(f == "Ed-MFE" for f, _ in sim_options.scoring_f) else 0,

@@ -54,6 +54,7 @@ def lib():
         L.bf_kernel_launches.restype = C.c_int64
         L.bf_last_kernel_ms.argtypes = [C.POINTER(C.c_double)]
         L.bf_microbench.argtypes = [C.POINTER(C.c_double)]
+        L.bf_second_best.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.bf_subopt.argtypes = [C.c_char_p, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                 C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.bf_set_option.argtypes = [C.c_char_p, C.c_int]
@@ -136,6 +137,27 @@ def subopt(seq, delta_dcal, nopair=None, max_out=4096):
     _check(lib().bf_subopt(s, n, mask.ctypes.data if mask is not None else None, int(delta_dcal), max_out, ss.ctypes.data, en.ctypes.data,
                            C.byref(cnt), C.byref(trunc)))
     return [(bytes(ss[k, :n]).decode("ascii"), int(en[k])) for k in range(cnt.value)], bool(trunc.value)
+
+
+def second_best(seqs, nopair=None):
+    """bf_second_best: (e1, e2) int32 arrays, dcal/mol -- energies of the best and the second-best structure of every sequence
+    (single strands); e2 >= 10000000 where a sequence has no second structure."""
+    ensure_ready()
+    buf, lens, cuts = pack([s.upper().replace("T", "U") for s in seqs])
+    if cuts.any():
+        raise EngineError(3, "second_best: single-strand sequences only")
+    b = bf_batch_t()
+    b.B, b.stride = len(seqs), buf.shape[1]
+    b.seq, b.len = buf.ctypes.data, lens.ctypes.data
+    keep = [buf, lens]
+    if nopair is not None:
+        nopair = np.ascontiguousarray(nopair, np.uint8)
+        assert nopair.shape == buf.shape
+        b.nopair = nopair.ctypes.data
+        keep.append(nopair)
+    e1, e2 = np.zeros(len(seqs), np.int32), np.zeros(len(seqs), np.int32)
+    _check(lib().bf_second_best(C.byref(b), e1.ctypes.data, e2.ctypes.data))
+    return e1, e2
 
 
 def set_option(key, value):

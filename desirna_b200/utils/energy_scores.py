@@ -121,7 +121,7 @@ def _score_with_compound(seq, input_file, sim_options, pf_energy, mfe_structure,
         s.get_scoring_function_w_alt_ss()
 
     if sim_options.subopt == "on" and s.mcc == 0:
-        s.get_subopt_e(get_first_suboptimal_structure_and_energy(seq, fold_comp, 1)[1])
+        s.get_subopt_e(get_first_suboptimal_energy(seq, fold_comp))
         s.get_esubopt_minus_Epf(s.Epf, s.subopt_e)
         s.get_scoring_function_w_subopt()
 
@@ -316,6 +316,19 @@ class ScoreSeq:
 
     def update_scoring_function_w_motifs(self, motif_bonus):
         self.scoring_function += motif_bonus
+
+
+def get_first_suboptimal_energy(sequence, a):
+    """get_first_suboptimal_structure_and_energy(sequence, a, 1)[1] without the enumeration: the reference widens the band from 1 to
+    49 kcal/mol until it holds two structures and takes the second of the sorted list -- i.e. the energy of the second-best
+    structure if it lies within 49 kcal/mol of the MFE, else 0 (utils/energy_scores.py:476-488).  Two-strand compounds fall back to
+    the enumeration (which the shim does not provide for them either)."""
+    if "&" in sequence or not hasattr(a, "second_best_energy"):
+        return get_first_suboptimal_structure_and_energy(sequence, a, 1)[1]
+    e1, e2 = a.second_best_energy()
+    if e2 is None or round((e2 - e1) * 100.0) > 4900:
+        return 0
+    return e2
 
 
 def get_first_suboptimal_structure_and_energy(sequence, a, number_of_suboptimals):

@@ -87,6 +87,11 @@ int bf_score_batch_device(const bf_batch_t *batch, bf_result_t *result, void *cu
  * sorted by energy.  The O(N^3) tables come from the GPU MFE fill; the output-sensitive walk over them runs on the host.
  * ss_out: max_out x (len+1) chars, e_out: max_out energies in dcal/mol, *n_out: structures written (<= max_out),
  * *truncated: 1 if the band holds more than max_out structures.  nopair: optional len bytes (hard constraint 'x'). */
+/* Energies (dcal/mol) of the best and of the second-best secondary structure of every sequence of the batch (seq, len, nopair,
+ * stride as in bf_score_batch; single strands), by one DP over (best, second best) pairs on the unambiguous grammar -- what
+ * get_first_suboptimal_structure_and_energy(seq, fc, 1)[1] reads off fc.subopt_cb's enumeration (utils/energy_scores.py:453-488,
+ * RNA.cvar.uniq_ML = 1).  e2 >= 10000000: there is no second structure.  Two structures of equal energy count twice (e2 == e1). */
+int bf_second_best(const bf_batch_t *batch, int32_t *e1_dcal, int32_t *e2_dcal);
 int bf_subopt(const char *seq, int32_t len, const uint8_t *nopair, int32_t delta_dcal, int32_t max_out, char *ss_out, int32_t *e_out,
               int32_t *n_out, int32_t *truncated);
 
@@ -154,11 +159,13 @@ typedef struct {
   int32_t pks;               /* 1: pseudoknot overlay (targets may use the bracket families () [] <> {}): after the MFE fold the
                                 paired positions are forbidden, the sequence is folded again and the new pairs painted with the next
                                 family, up to three rounds                                  sequence_utils.py:1166-1228 */
+  int32_t subopt;            /* 1: negative design (-nd on): a mutant that folds into its target also pays Epf - E(second-best
+                                structure), the latter from bf_second_best's DP                 energy_scores.py:104-107,453-488 */
 } bf_design_t;
 
-enum { BF_DESIGN_REC = 14 }; /* doubles per record: scoring_function, edesired, Epf, 1-mcc, 1-precision, 1-recall, MFE,
+enum { BF_DESIGN_REC = 15 }; /* doubles per record: scoring_function, edesired, Epf, 1-mcc, 1-precision, 1-recall, MFE,
                                 ensemble_defect, positions whose partner differs from the target's (0 = solved), global step,
-                                oligo_fraction, oligomer_bonus, edesired2 (mean energy of the alternative structures), motif bonus */
+                                oligo_fraction, oligomer_bonus, edesired2 (mean energy of the alternative structures), motif bonus, subopt_e */
 
 /* Allocates the loop on the engine's GPU, scores the start sequences (global step 0). */
 int bf_design_create(const bf_design_t *cfg, void **handle);

@@ -67,3 +67,15 @@ class OracleBackend:
         mfe = self.O.mfe(s)[0]
         band = self.O.enumerate_band(s, mfe + int(delta_dcal))
         return [(ss, e) for e, ss in band[:max_out]], len(band) > max_out
+
+    def second_best(self, seqs, nopair=None):
+        """brute force (short sequences only): same contract as engine.second_best"""
+        assert nopair is None
+        e1, e2 = np.zeros(len(seqs), np.int32), np.zeros(len(seqs), np.int32)
+        for k, seq in enumerate(seqs):
+            s = seq.upper().replace("T", "U")
+            assert len(s) <= 20
+            band = self.O.enumerate_band(s, 10 ** 6)
+            e1[k] = band[0][0]
+            e2[k] = band[1][0] if len(band) > 1 else 10000000
+        return e1, e2

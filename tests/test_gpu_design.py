@@ -208,6 +208,34 @@ def test_the_six_example_scenarios_run_through_design_batch(engine):
     assert solved >= 4   # six 35-nt targets, 600 Monte-Carlo sub-steps x 10 replicas each
 
 
+def test_negative_design_term_on_the_device(engine):
+    """-nd on (utils/energy_scores.py:104-107): a mutant that folds into its target also pays Epf - E(second-best structure); the
+    device loop gets that energy from the 2-best DP (csrc/bf_twobest.cu) for exactly those rows.  Records against the host mirror."""
+    from desirna_b200 import design
+    from desirna_b200.utils import energy_scores as es
+    from desirna_b200.utils import stats_inputs_outputs as sio
+    inputs = [sio.make_input("hp", "((((....))))"), sio.make_input("two", "((((....))))..(((....)))"), sio.make_input("std", "((((((.((((((((....))))).)).).))))))")]
+    o = design.DesignOptions(replicas=8, RE_attempt=25, scoring_f=[("Ed-Epf", 1.0)], subopt="on")
+    random.seed(41)
+    loop = design.DesignLoop(inputs, o, seed=19)
+    loop.run(6)
+    rep = loop.replicas()
+    R = loop.R
+    hits = 0
+    for j, inp in enumerate(inputs):
+        seqs = rep["sequence"][j * R:(j + 1) * R]
+        ref = es.score_sequences(seqs, inp, o)
+        for r, (s, h) in enumerate(zip(seqs, ref)):
+            rec = dict(zip(design.REC_FIELDS, rep["rec"][j * R + r]))
+            assert rep["mfe_ss"][j * R + r] == h.mfe_ss
+            assert rec["subopt_e"] == h.subopt_e, (inp.name, s, rec["subopt_e"], h.subopt_e)
+            assert (rec["subopt_e"] != 0) <= (h.mfe_ss == inp.sec_struct)
+            hits += h.mfe_ss == inp.sec_struct
+            assert rec["scoring_function"] == pytest.approx(h.scoring_function, abs=1e-5)
+    assert hits > 0   # some replica reached its target, i.e. the term was exercised
+    loop.close()
+
+
 def test_same_seed_same_trajectory(engine):
     from desirna_b200 import design
     inputs = small_inputs(limit=4)

@@ -96,3 +96,58 @@ def test_subopt_cb_is_complete_when_the_band_overflows_the_first_buffer(engine):
     mfe = full[0][1]
     assert min(e for _, e in full) == mfe and max(e for _, e in full) <= mfe + delta
     assert sorted(e for _, e in full)[:10] == [e for _, e in full[:10]]
+
+
+# ------------------------------------------------------------------------------------------------ second-best structure by a 2-best DP
+@pytest.mark.parametrize("seed", [4, 5])
+def test_second_best_equals_brute_force(engine, oracle, seed):
+    """bf_second_best (csrc/bf_twobest.cu: one DP over (best, second best) pairs on the unambiguous grammar) against exhaustive
+    enumeration of every structure of short sequences: e1 = the lowest energy, e2 = the second entry of the sorted list, ties
+    counted as two structures -- what get_first_suboptimal_structure_and_energy(seq, fc, 1)[1] reads off subopt_cb
+    (utils/energy_scores.py:453-488)."""
+    rng = np.random.default_rng(seed)
+    seqs = []
+    for n in [6, 8, 9, 10, 12, 13, 14, 15, 16, 17, 18, 19]:
+        for _ in range(3):
+            seqs.append(rand_seq(rng, n) if rng.random() < 0.5 else "GGG" + rand_seq(rng, n - 6) + "CCC")
+    seqs += ["AAAAAAAAAA", "GGGAAACCC", "GGGGAAAACCCC"]
+    e1, e2 = engine.second_best(seqs)
+    some = 0
+    for k, s in enumerate(seqs):
+        want = oracle.enumerate_band(s, 10 ** 6)          # every structure, sorted by energy
+        assert want[0][0] == e1[k] == oracle.mfe(s)[0], s
+        if len(want) >= 2:
+            assert want[1][0] == e2[k], (s, want[:3], int(e2[k]))
+            some += 1
+        else:
+            assert e2[k] >= 10000000, s
+    assert some > 30
+
+
+def test_second_best_long_sequences_and_constraints(engine):
+    """longer sequences: e1 is the MFE of the fill kernels, e2 the second energy of the band walk (bf_subopt); with hard constraints too"""
+    rng = np.random.default_rng(17)
+    seqs = [rand_seq(rng, n) for n in (40, 75, 120, 200)]
+    nopair = np.zeros((len(seqs), 200), np.uint8)
+    nopair[1, 10:30] = 1
+    nopair[3, ::7] = 1
+    e1, e2 = engine.second_best(seqs, nopair)
+    for k, s in enumerate(seqs):
+        mask = nopair[k, :len(s)] if nopair[k].any() else None
+        band, trunc = engine.subopt(s, int(e2[k] - e1[k]), mask, max_out=200000)
+        assert not trunc
+        en = sorted(e for _, e in band)
+        assert en[0] == e1[k] and en[1] == e2[k], (len(s), en[:3], int(e1[k]), int(e2[k]))
+
+
+def test_negative_design_term_uses_the_two_best_dp(engine, oracle):
+    """get_first_suboptimal_energy == get_first_suboptimal_structure_and_energy(...)[1] (the enumeration) on the shim"""
+    from desirna_b200 import RNA
+    from desirna_b200.utils import energy_scores as es
+    rng = np.random.default_rng(23)
+    for n in (20, 36, 60):
+        s = "GGGG" + rand_seq(rng, n - 8) + "CCCC"
+        fast = es.get_first_suboptimal_energy(s, RNA.fold_compound(s))
+        slow = es.get_first_suboptimal_structure_and_energy(s, RNA.fold_compound(s), 1)[1]
+        assert fast == slow, (s, fast, slow)
+    assert es.get_first_suboptimal_energy("A" * 20, RNA.fold_compound("A" * 20)) == 0   # a single structure: the reference returns 0
