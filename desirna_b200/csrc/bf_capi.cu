@@ -720,6 +720,11 @@ int bf_design_create(const bf_design_t *c, void **handle) {
       if (depth != 0) return fail(BF_ERR_ARG, "bf_design_create: unbalanced alternative structure");
     }
   }
+  if (c->move_partner)
+    for (int j = 0; j < J; j++)
+      for (int i = 0; i < c->len[j]; i++)
+        if (c->move_partner[(size_t)j * S + i] < -1 || c->move_partner[(size_t)j * S + i] >= c->len[j]) return fail(BF_ERR_ARG, "bf_design_create: move_partner outside the sequence");
+  if ((c->snake_id != nullptr) != (c->snake_letter != nullptr)) return fail(BF_ERR_ARG, "bf_design_create: snake_id and snake_letter go together");
   if (c->n_motifs < 0 || c->n_motifs > 8 || (c->n_motifs > 0 && (!c->motif_mask || !c->motif_len || !c->motif_bonus))) return fail(BF_ERR_ARG, "bf_design_create: at most 8 motifs, with masks, lengths and bonuses");
   for (int m = 0; m < c->n_motifs; m++)
     if (c->motif_len[m] < 1 || c->motif_len[m] > 32) return fail(BF_ERR_ARG, "bf_design_create: motif length outside 1..32");
@@ -757,6 +762,19 @@ int bf_design_create(const bf_design_t *c, void **handle) {
   DCU(h->alloc(&h->d_rowmap, G), "cudaMalloc(design)"); DCU(h->alloc(&h->d_active, J), "cudaMalloc(design)");
   DCU(h->alloc(&D.mut_seq, G * S), "cudaMalloc(design)"); DCU(h->alloc(&D.row_len, G), "cudaMalloc(design)"); DCU(h->alloc(&D.row_cut, G), "cudaMalloc(design)");
   DCU(h->alloc(&D.row_scale, G), "cudaMalloc(design)"); DCU(h->alloc(&D.cur_mfe, G), "cudaMalloc(design)");
+  if (c->move_partner) {
+    short *d_mpt;
+    DCU(h->alloc(&d_mpt, (size_t)J * S), "cudaMalloc(design)");
+    DCU(cudaMemcpy(d_mpt, c->move_partner, (size_t)J * S * sizeof(short), cudaMemcpyHostToDevice), "H2D design");
+    D.mpt = d_mpt;
+  }
+  if (c->snake_id && c->snake_letter) {
+    signed char *d_sid; char *d_sl;
+    DCU(h->alloc(&d_sid, (size_t)J * S), "cudaMalloc(design)"); DCU(h->alloc(&d_sl, (size_t)J * S * 4), "cudaMalloc(design)");
+    DCU(cudaMemcpy(d_sid, c->snake_id, (size_t)J * S, cudaMemcpyHostToDevice), "H2D design");
+    DCU(cudaMemcpy(d_sl, c->snake_letter, (size_t)J * S * 4, cudaMemcpyHostToDevice), "H2D design");
+    D.snake_id = d_sid; D.snake_letter = d_sl;
+  }
   D.max_alt = max_alt; D.T = 1 + max_alt;
   if (max_alt > 0) {
     char *d_alt; int *d_nalt;

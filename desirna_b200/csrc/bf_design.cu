@@ -228,8 +228,26 @@ __global__ void __launch_bounds__(kWPB * 32) bf_k_design_propose(BfDesignDev D, 
   if (lane == 0 && pos >= 0) {
     const int curl = letter_code(cur[pos]);
     const unsigned a1 = allowed[pos];
-    const int partner = tpt[pos];
-    if (partner < 0) {
+    const int partner = D.mpt ? D.mpt[(size_t)job * S + pos] : tpt[pos];
+    const int snake = D.snake_id ? D.snake_id[(size_t)job * S + pos] : -1;
+    if (snake >= 0) {
+      // a node of a conflict graph: the whole graph jumps to another of its colourings (sequence_utils.py:1085-1094)
+      const char *sl = D.snake_letter + ((size_t)job * S + pos) * 4;
+      int now = -1, nstates = 0;
+      for (int s = 0; s < 4; s++) {
+        if (sl[s]) nstates++;
+        if (now < 0 && sl[s] == cur[pos]) now = s;
+      }
+      const int others = nstates - (now >= 0 ? 1 : 0);
+      if (others > 0) {
+        int k = below(rng, others), pick = -1;
+        for (int s = 0; s < 4 && pick < 0; s++)
+          if (sl[s] && s != now && k-- == 0) pick = s;
+        const signed char *sid = D.snake_id + (size_t)job * S;
+        for (int x = 0; x < n; x++)
+          if (sid[x] == snake) mut[x] = D.snake_letter[((size_t)job * S + x) * 4 + pick];
+      }
+    } else if (partner < 0) {
       if (__popc(a1) > 1) {
         unsigned m = a1 & ~(1u << curl);
         if (!m) m = a1;

@@ -41,6 +41,9 @@ struct BfDesignDev {
   const int *len;                // J            nucleotides (both strands, no '&')
   const int *len_a;              // J            length of strand A, 0 = single strand ('&' sits after it in the reference's strings)
   const uint8_t *same_halves;    // J            1: the two halves of the target are the same string (homodimer designs)
+  const short *mpt;              // J x stride   partner for the move generator (Nucleotide.pairs_with), or null = tpt
+  const signed char *snake_id;   // J x stride   conflict graph of the position, -1 none; or null
+  const char *snake_letter;      // J x stride x 4   letter of the position in each colouring of its graph (0 = absent)
   const char *alt;               // J x max_alt x stride   alternative structures (energy_scores.py:98-102), or null
   const int *n_alt;              // J
   int max_alt, T;                // T = 1 + max_alt targets per batch row

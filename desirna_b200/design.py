@@ -53,7 +53,8 @@ class bf_design_t(C.Structure):
                 ("n_terms", C.c_int32), ("term", C.c_int32 * 8), ("weight", C.c_double * 8), ("metropolis_L", C.c_double),
                 ("point_mutations", C.c_int32), ("re_attempt", C.c_int32), ("acgu", C.c_int32), ("nt_weight", C.c_double * 4),
                 ("oligo", C.c_int32), ("seed", C.c_uint64), ("alt_targets", C.c_void_p), ("n_alt", C.c_void_p), ("max_alt", C.c_int32),
-                ("n_motifs", C.c_int32), ("motif_mask", C.c_void_p), ("motif_len", C.c_void_p), ("motif_bonus", C.c_void_p), ("pks", C.c_int32), ("subopt", C.c_int32)]
+                ("n_motifs", C.c_int32), ("motif_mask", C.c_void_p), ("motif_len", C.c_void_p), ("motif_bonus", C.c_void_p), ("pks", C.c_int32), ("move_partner", C.c_void_p), ("snake_id", C.c_void_p),
+                ("snake_letter", C.c_void_p), ("subopt", C.c_int32)]
 
 
 def _bind():
@@ -108,6 +109,9 @@ class DesignLoop:
         self.len_a = np.array([i.sec_struct.index("&") if "&" in i.sec_struct else 0 for i in self.inputs], np.int32)
         self.lens = np.array([len(i.sec_struct.replace("&", "")) for i in self.inputs], np.int32)
         self.stride = int(self.lens.max())
+        for inp in self.inputs:   # alternative structures: conflict graphs before the per-position restraints (DesiRNA.py:277-284)
+            if inp.alt_sec_struct is not None and "&" not in inp.sec_struct and inp.graphs is None and inp.excluded_alt_pairs is None:
+                seq_utils.attach_alternatives(inp)
         nt_lists = [seq_utils.get_nt_list(i) for i in self.inputs]
         allowed = np.full((self.J, self.stride), 15, np.uint8)
         for j, nts in enumerate(nt_lists):
@@ -143,6 +147,21 @@ class DesignLoop:
         # alternative structures (scored as mean(eval) - Epf, energy_scores.py:98-102; the move generator keeps to the main target)
         alts = [list(i.alt_sec_structs) if i.alt_sec_struct is not None else [] for i in self.inputs]
         if any(alts):
+            # the move generator's partners (the clash-free pairs of the alternatives are restraints too) and the conflict graphs
+            mp = np.full((self.J, self.stride), -1, np.int16)
+            sid = np.full((self.J, self.stride), -1, np.int8)
+            sl = np.zeros((self.J, self.stride, 4), np.uint8)
+            for j, nts in enumerate(nt_lists):
+                for nt in nts:
+                    if nt.pairs_with is not None:
+                        mp[j, nt.number] = nt.pairs_with
+                    if nt.snake:
+                        sid[j, nt.number] = nt.snake_number
+                        at = nt.snake_nts.index(nt.number)
+                        for k, st in enumerate(nt.snake_states):
+                            sl[j, nt.number, k] = ord(st[at])
+            self._keep += [mp, sid, sl]
+            cfg.move_partner, cfg.snake_id, cfg.snake_letter = mp.ctypes.data, sid.ctypes.data, sl.ctypes.data
             for inp, al in zip(self.inputs, alts):
                 if any(set(a) - set(".()") or len(a) != len(inp.sec_struct) for a in al):
                     raise ValueError("alternative structures must be made of . ( ) and as long as the target: %r" % (inp.name,))

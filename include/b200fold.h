@@ -159,6 +159,13 @@ typedef struct {
   int32_t pks;               /* 1: pseudoknot overlay (targets may use the bracket families () [] <> {}): after the MFE fold the
                                 paired positions are forbidden, the sequence is folded again and the new pairs painted with the next
                                 family, up to three rounds                                  sequence_utils.py:1166-1228 */
+  const int16_t *move_partner; /* n_jobs x stride or NULL: partner of each position FOR THE MOVE GENERATOR (Nucleotide.pairs_with,
+                                sequence_utils.py:486-505), -1 = none; NULL = the target's partner.  Differs from the target's with
+                                alternative structures: their clash-free pairs are pair restraints too */
+  const int8_t *snake_id;    /* n_jobs x stride or NULL: index of the conflict graph ("snake") a position belongs to, -1 = none
+                                sequence_utils.py:119-396 */
+  const char *snake_letter;  /* n_jobs x stride x 4: letter of the position in each colouring of its graph, 0 = colouring absent;
+                                a move on a graph node sets every node of the graph to another colouring   :1085-1094 */
   int32_t subopt;            /* 1: negative design (-nd on): a mutant that folds into its target also pays Epf - E(second-best
                                 structure), the latter from bf_second_best's DP                 energy_scores.py:104-107,453-488 */
 } bf_design_t;

@@ -322,3 +322,20 @@ def test_design_batch_scheduling_without_a_gpu(monkeypatch):
     _FakeLoop.made = []
     results, info = design.design_batch(inputs, o, time_limit=0.0, seed=1)
     assert all(loop.steps == 0 for loop in _FakeLoop.made) and info["solved"] == 0
+
+
+# ------------------------------------------------------------------------------------------------ alternative structures: snake graphs
+def test_snake_graphs_and_moves_match_the_reference_draw_for_draw():
+    """tests/golden/S1.json was produced by importing the reference's utils/sequence_utils.py (tests/golden/make_snake_golden.py):
+    conflict graphs and their colourings (order included: the first colouring is the start state), the pairs moved into the
+    ordinary restraints, per-position letters, start sequences and 2 x 150 consecutive moves from the same seeds.
+    The reference draws the partner letter of a pair move from an UNSORTED set of strings (utils/sequence_utils.py:1062-1070), so
+    its draws depend on the interpreter's string-hash seed: vectors and check both run under PYTHONHASHSEED=0 (a subprocess)."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, PYTHONHASHSEED="0")
+    out = subprocess.run([sys.executable, os.path.join(here, "snake_golden_check.py")], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "moves checked" in out.stdout and int(out.stdout.split("moves checked")[0].split()[-1]) >= 1500

@@ -289,6 +289,41 @@ def test_move_generator_matches_host_mirror_in_distribution(engine):
         assert tv_all < 0.15, (r, tv_all)
 
 
+def test_snake_moves_on_the_device_match_the_host_mirror(engine):
+    """alternative structures: positions in more than one pair across the target and the alternatives form conflict graphs whose
+    nodes change together from one Watson-Crick colouring to another (utils/sequence_utils.py:119-396, 1085-1094); the clash-free
+    pairs of the alternatives are pair restraints of the move generator too.  bf_k_design_propose against the host mirror (itself
+    pinned draw for draw to the reference, tests/golden/S1.json): same set of mutants, same distribution."""
+    from desirna_b200 import design
+    from desirna_b200.utils import sequence_utils as su
+    from desirna_b200.utils import stats_inputs_outputs as sio
+    inp = sio.make_input("switch", "((((((....))))))....((((....))))")
+    inp.add_alt_sec_struct(["....((((((....))))))((((....))))", "((((((....))))))....((((....))))"])
+    o = design.DesignOptions(replicas=3, RE_attempt=1, tm_max=0.8, tm_min=0.1)
+    random.seed(3)
+    loop = design.DesignLoop([inp], o, seed=5)
+    assert inp.graphs and loop.replicas()["sequence"][0] == loop.replicas()["sequence"][1]
+    start = loop.replicas()["sequence"][0]
+    cur_ss = loop.replicas()["mfe_ss"][0]
+    N = 6000
+    dev = [Counter() for _ in range(3)]
+    for _ in range(N):
+        for r, m in enumerate(loop.propose_only()):
+            dev[r][m] += 1
+    loop.close()
+    nts = su.get_nt_list(inp)
+    snake_nodes = {x for g in inp.graphs for x in g["numbers"]}
+    random.seed(2)
+    for r in range(3):
+        cur = SimpleNamespace(sequence=start, mfe_ss=cur_ss, temp_shelf=o.rep_temps_shelfs[r])
+        host = Counter(su.propose_mutation(cur, nts, o, inp) for _ in range(N))
+        assert set(dev[r]) <= set(host) | {k for k in dev[r] if dev[r][k] < 5}, "device proposes mutants the reference cannot"
+        jumps = lambda c: sum(v for m, v in c.items() if any(m[x] != start[x] for x in snake_nodes))
+        assert jumps(host) > 300 and abs(jumps(host) - jumps(dev[r])) < 0.05 * N          # whole-graph jumps are as frequent
+        tv_all = 0.5 * sum(abs(host[k] - dev[r][k]) for k in set(host) | set(dev[r])) / N
+        assert tv_all < 0.15, (r, tv_all)
+
+
 def test_design_batch_solves_short_eterna_targets(engine, oracle):
     from desirna_b200 import design
     inputs = small_inputs(max_len=40, limit=10)
