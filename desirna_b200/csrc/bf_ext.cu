@@ -50,28 +50,34 @@ __global__ void __launch_bounds__(NW * 32) bf_k_f5_wide(const BfParams *__restri
   }
   __syncthreads();
   const int *c = ctri + (size_t)sq * tri_slot;
-  // columns j0 .. j0+JB-1 into tile buffer bf: warp w takes the diagonals 4+w, 4+w+NW, ...; lane = column
-  auto fill = [&](int j0, int bf) {
+  // columns j0 .. j0+JB-1 into tile buffer bf: nw warps starting at w0 share the diagonals, lane = column; the table reads of
+  // eight diagonals are issued before any of them is used (the kernel is L2-latency-bound otherwise)
+  auto fill = [&](int j0, int bf, int w0, int nw) {
     int *tl = tile + bf * JB * TS;
     const int j = j0 + lane;
     const bool jin = lane < JB && j <= n;
     const int sj = jin ? SP[j] : 0, bb = (jin && j < n) ? S[j + 1] : -1;
     const int dmax = min(n - 1, j0 + JB - 2);
-#pragma unroll 4
-    for (int d = BF_TURN + 1 + warp; d <= dmax; d += NW) {
-      const int i = j - d;
-      if (jin && i >= 1) {
-        const int t = bf_ptype_bases(SP[i], sj);
-        int v = BF_INF;
-        if (t) {
-          const int cc = __ldg(c + tri_off(n, d) + i - 1);
-          if (cc < BF_INF) v = cc + bf_e_ext(T, t, (i > 1) ? S[i - 1] : -1, bb);
+    for (int d0 = BF_TURN + 1 + (warp - w0); d0 <= dmax; d0 += 8 * nw) {
+      int cc[8], tt[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int d = d0 + k * nw, i = j - d;
+        tt[k] = (jin && d <= dmax && i >= 1) ? bf_ptype_bases(SP[i], sj) : 0;
+        cc[k] = tt[k] ? __ldg(c + tri_off(n, d) + i - 1) : BF_INF;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int d = d0 + k * nw, i = j - d;
+        if (jin && d <= dmax && i >= 1) {
+          int v = BF_INF;
+          if (tt[k] && cc[k] < BF_INF) v = cc[k] + bf_e_ext(T, tt[k], (i > 1) ? S[i - 1] : -1, bb);
+          tl[lane * TS + i] = v;
         }
-        tl[lane * TS + i] = v;
       }
     }
   };
-  fill(1, 0);
+  fill(1, 0, 0, NW);
   __syncthreads();
   int bf = 0;
   for (int j0 = 1; j0 <= n; j0 += JB, bf ^= 1) {
@@ -89,25 +95,7 @@ __global__ void __launch_bounds__(NW * 32) bf_k_f5_wide(const BfParams *__restri
         __syncwarp();
       }
     } else if (j0 + JB <= n) {
-      // the other warps transpose the next columns meanwhile (NW-1 warps share the diagonals)
-      int *tl = tile + (bf ^ 1) * JB * TS;
-      const int j1 = j0 + JB, j = j1 + lane;
-      const bool jin = lane < JB && j <= n;
-      const int sj = jin ? SP[j] : 0, bb = (jin && j < n) ? S[j + 1] : -1;
-      const int dmax = min(n - 1, j1 + JB - 2);
-#pragma unroll 4
-      for (int d = BF_TURN + 1 + (warp - 1); d <= dmax; d += NW - 1) {
-        const int i = j - d;
-        if (jin && i >= 1) {
-          const int t = bf_ptype_bases(SP[i], sj);
-          int v = BF_INF;
-          if (t) {
-            const int cc = __ldg(c + tri_off(n, d) + i - 1);
-            if (cc < BF_INF) v = cc + bf_e_ext(T, t, (i > 1) ? S[i - 1] : -1, bb);
-          }
-          tl[lane * TS + i] = v;
-        }
-      }
+      fill(j0 + JB, bf ^ 1, 1, NW - 1);   // the other warps transpose the next columns meanwhile
     }
     __syncthreads();
   }
@@ -134,44 +122,31 @@ __global__ void __launch_bounds__(NW * 32) bf_k_q5_wide(const BfParams *__restri
   __syncthreads();
   const double lns = lnscale[sq], sc1 = exp(-lns);
   const double *qb = qbtri + (size_t)sq * tri_slot;
-  // lane = column (lanes >= JB idle); nw warps starting at w0 share the diagonals
-  auto fill = [&](int j0, int bf, int w0, int nw) {
-    double *tl = tile + bf * JB * TS;
-    const int j = j0 + lane;
-    const bool jin = lane < JB && j <= n;
-    const int sj = jin ? S[j] : 0, bb = (jin && j < n) ? S[j + 1] : -1;
-    const int dmax = min(n - 1, j0 + JB - 2);
-#pragma unroll 4
-    for (int d = BF_TURN + 1 + (warp - w0); d <= dmax; d += nw) {
-      const int i = j - d;
-      if (jin && i >= 1) {
-        const int t = bf_ptype_bases(S[i], sj);
-        double v = 0.0;
-        if (t) v = __ldg(qb + tri_off(n, d) + i - 1) * bf_x_ext(T, t, (i > 1) ? S[i - 1] : -1, bb);
-        tl[lane * TS + i] = v;
-      }
-    }
-  };
-  // two columns per pass: lanes 0..15 the even column, 16..31 the odd one (JB = 16 columns per tile)
+  // two diagonals per pass (JB = 16 columns per tile: lanes 0..15 one diagonal, 16..31 the next); the table reads of eight passes
+  // are issued before any of them is used
   auto fill2 = [&](int j0, int bf, int w0, int nw) {
     double *tl = tile + bf * JB * TS;
-    const int col = lane & (JB - 1), half = lane / JB;            // JB = 16: two diagonals per pass
+    const int col = lane & (JB - 1), half = lane / JB;
     const int j = j0 + col;
     const bool jin = j <= n;
     const int sj = jin ? S[j] : 0, bb = (jin && j < n) ? S[j + 1] : -1;
     const int dmax = min(n - 1, j0 + JB - 2);
-#pragma unroll 4
-    for (int d = BF_TURN + 1 + 2 * (warp - w0) + half; d <= dmax; d += 2 * nw) {
-      const int i = j - d;
-      if (jin && i >= 1) {
-        const int t = bf_ptype_bases(S[i], sj);
-        double v = 0.0;
-        if (t) v = __ldg(qb + tri_off(n, d) + i - 1) * bf_x_ext(T, t, (i > 1) ? S[i - 1] : -1, bb);
-        tl[col * TS + i] = v;
+    for (int d0 = BF_TURN + 1 + 2 * (warp - w0) + half; d0 <= dmax; d0 += 16 * nw) {
+      double q[8];
+      int tt[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int d = d0 + 2 * k * nw, i = j - d;
+        tt[k] = (jin && d <= dmax && i >= 1) ? bf_ptype_bases(S[i], sj) : 0;
+        q[k] = tt[k] ? __ldg(qb + tri_off(n, d) + i - 1) : 0.0;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int d = d0 + 2 * k * nw, i = j - d;
+        if (jin && d <= dmax && i >= 1) tl[col * TS + i] = tt[k] ? q[k] * bf_x_ext(T, tt[k], (i > 1) ? S[i - 1] : -1, bb) : 0.0;
       }
     }
   };
-  (void)fill;
   fill2(1, 0, 0, NW);
   __syncthreads();
   int bf = 0;
