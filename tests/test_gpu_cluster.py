@@ -67,3 +67,41 @@ def test_outside_pass_on_cluster_tables(engine, monkeypatch):
     got = engine.score_batch(seqs, tg, want=want)
     assert np.allclose(ref["defect"], got["defect"], rtol=0, atol=1e-9)
     assert np.allclose(ref["pf"][:, 4], got["pf"][:, 4], rtol=1e-10, atol=0)
+
+
+def test_generic_kernels_on_single_strands_equal_the_fill_path(engine):
+    """the generic kernels (csrc/bf_kernels.cu: the two-strand path, and the fallback for lengths the fill path does not cover) on
+    plain single strands, forced by BF_FORCE_GENERIC=1 in a fresh interpreter (the switch is read at bf_init): same energies and
+    structures as the fill kernels of this process"""
+    import json
+    import os
+    import subprocess
+    import sys
+    seqs = ragged(5150, 12, 90)
+    ref = engine.score_batch(seqs, want=engine.WANT_MFE | engine.WANT_SS | engine.WANT_PF)
+    code = ("import json, sys; sys.path.insert(0, %r); from desirna_b200 import engine; engine.init(0); engine.params_builtin(1999); "
+            "o = engine.score_batch(%r, want=7); print(json.dumps({'mfe': o['mfe_dcal'].tolist(), 'ss': o['mfe_ss'], 'pf': o['pf'][:, 4].tolist()}))"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), seqs))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, BF_FORCE_GENERIC="1"), capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    got = json.loads(out.stdout.strip().split("\n")[-1])
+    assert got["mfe"] == ref["mfe_dcal"].tolist() and got["ss"] == list(ref["mfe_ss"])
+    assert np.allclose(got["pf"], ref["pf"][:, 4], rtol=1e-10, atol=0)
+
+
+@pytest.mark.parametrize("C", [4, 8, 16])
+def test_cluster_kernels_fold_the_eterna100_solutions_into_their_targets(engine, monkeypatch, C):
+    """the reference's own Eterna100-V1 results (eterna_benchmark/Eterna100V1_benchmark_results, tests/golden/E1.jsonl: sequences
+    ViennaRNA folds into their targets, 12..400 nt): forced through the cluster kernels at every cluster size, each still folds
+    into its target -- a pin to ViennaRNA-produced data, not to this repo's other kernels"""
+    from conftest import load_golden
+    rows = [r for r in load_golden("E1") if len(r["target"]) >= 60]
+    monkeypatch.setenv("BF_CL", "1")
+    monkeypatch.setenv("BF_CL_C", str(C))
+    for lo, hi in ((60, 130), (131, 260), (261, 400)):
+        part = [r for r in rows if lo <= len(r["target"]) <= hi]
+        out = engine.score_batch([r["sequence"] for r in part], [[r["target"]] for r in part],
+                                 want=engine.WANT_MFE | engine.WANT_SS | engine.WANT_PF | engine.WANT_EVAL)
+        for k, r in enumerate(part):
+            assert out["mfe_ss"][k] == r["target"], (r["file"], C)
+            assert out["eval_dcal"][k, 0] == out["mfe_dcal"][k] and out["pf"][k, 4] <= out["mfe_dcal"][k] / 100.0 + 1e-9
