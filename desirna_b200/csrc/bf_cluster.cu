@@ -39,7 +39,7 @@ constexpr int kEntW = 20;      // words per cell entry (layout of bf_fill3.cu; w
 constexpr int kPMax = 2;       // a chunk's split positions may be dealt to two warps
 constexpr int kNWcl = 16;      // warps per CTA (one CTA per SM)
 constexpr int kNoWrite = -2147483647 - 1;   // staging slot without a value
-constexpr int kNTcl = 6;       // of them tap warps; the others combine, split and clear
+constexpr int kNTcl = 8;       // of them tap warps; the others combine, split and clear
 
 __device__ __forceinline__ unsigned cl_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned cl_index() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
