@@ -62,7 +62,20 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
   const int W = wstride;  // row stride of the tables, >= n+2
 
   bf_stage(&T, &P->si);
-  for (int k = tid; k < BF_NCAND; k += blockDim.x) { cu1[k] = c_cand_u1[k]; cu2[k] = c_cand_u2[k]; }
+  // candidates of an interior loop, ordered by size: (u1, u2), kind (0: one of the nine shapes evaluated in full, 1 bulge, 2 1xn,
+  // 3 generic) and the size penalty of the decomposable kinds
+  __shared__ uint8_t ckind[BF_NCAND];
+  __shared__ int cpen[BF_NCAND];
+  __syncthreads();
+  for (int k = tid; k < BF_NCAND; k += blockDim.x) {
+    const int u1 = c_cand_u1[k], u2 = c_cand_u2[k], sz = u1 + u2;
+    cu1[k] = (uint8_t)u1; cu2[k] = (uint8_t)u2;
+    const bool special = sz <= 1 || (u1 == 1 && u2 == 1) || (sz == 3 && u1 >= 1 && u2 >= 1) || (u1 == 2 && u2 == 2) || (sz == 5 && (u1 == 2 || u1 == 3));
+    const int kind = special ? 0 : (u1 == 0 || u2 == 0) ? 1 : (u1 == 1 || u2 == 1) ? 2 : 3;
+    ckind[k] = (uint8_t)kind;
+    cpen[k] = kind == 1 ? T.bulge[sz] : kind == 2 ? T.interior[sz] + min(T.ninio_max, (sz - 2) * T.ninio_m)
+                        : kind == 3 ? T.interior[sz] + min(T.ninio_max, abs(u1 - u2) * T.ninio_m) : 0;
+  }
 
   // dynamic smem carve-up
   const int nmax = W - 2;
@@ -177,28 +190,21 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
           const int mmO = cMMO[i], mm1O = cMM1O[i], tauO = t > 2 ? T.TerminalAU : 0, mlc = cMLC[i];
           int e = BF_INF;
           const int smx = min(BF_MAXLOOP, d - 3), kmax = smx >= 0 ? (smx + 1) * (smx + 2) / 2 : 0;   // candidates are ordered by size
+          // the unpaired stretches of a regular loop may not contain the nick: p stays on i's strand, q on j's
+          const int pmax = (TWO && i < cp) ? cp - 1 : n, qmin = (TWO && j >= cp) ? cp : 0;
           for (int k = lane; k < kmax; k += 32) {
-            const int u1 = cu1[k], u2 = cu2[k], sz = u1 + u2;
-            const int p = i + 1 + u1, q = j - 1 - u2;
-            if (q <= p) continue;
-            if (TWO && (!bf_same<TWO>(X, i, p) || !bf_same<TWO>(X, q, j))) continue;
-            const bool special = sz <= 1 || (u1 == 1 && u2 == 1) || (sz == 3 && u1 >= 1 && u2 >= 1) || (u1 == 2 && u2 == 2) ||
-                                 (sz == 5 && (u1 == 2 || u1 == 3));
-            if (special) {
+            const int u1 = cu1[k], u2 = cu2[k], kind = ckind[k];
+            const int p = i + 1 + u1, q = j - 1 - u2;        // q > p: the candidates are cut off at size d - 3
+            if (p > pmax || q < qmin) continue;
+            if (kind == 0) {
               const int t2 = bf_ptype<TWO>(X, p, q);
               if (!t2) continue;
               const int cc = C_(p, q);
               if (cc >= BF_INF) continue;
               e = min(e, cc + bf_e_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]));
-            } else if (u1 == 0 || u2 == 0) {
-              const int cc = CB_(p, q);
-              if (cc < BF_INF) e = min(e, cc + T.bulge[sz] + tauO);
-            } else if (u1 == 1 || u2 == 1) {
-              const int cc = C1_(p, q);
-              if (cc < BF_INF) e = min(e, cc + T.interior[sz] + min(T.ninio_max, (sz - 2) * T.ninio_m) + mm1O);
             } else {
-              const int cc = CG_(p, q);
-              if (cc < BF_INF) e = min(e, cc + T.interior[sz] + min(T.ninio_max, abs(u1 - u2) * T.ninio_m) + mmO);
+              const int cc = (kind == 1 ? cB : kind == 2 ? c1 : cG)[p * W + q];
+              if (cc < BF_INF) e = min(e, cc + cpen[k] + (kind == 1 ? tauO : kind == 2 ? mm1O : mmO));
             }
           }
           if (mlc < BF_INF) {   // multiloop closed by (i,j)
@@ -471,7 +477,16 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = wstride;
   bf_stage(&T, &P->sd);
-  for (int k = tid; k < BF_NCAND; k += blockDim.x) { cu1[k] = c_cand_u1[k]; cu2[k] = c_cand_u2[k]; }
+  // candidates of an interior loop, ordered by size: kind as in bf_k_mfe; the weight of the decomposable kinds, scale included, is
+  // rebuilt for every sequence (cxw)
+  __shared__ uint8_t ckind[BF_NCAND];
+  __shared__ double cxw[BF_NCAND];
+  for (int k = tid; k < BF_NCAND; k += blockDim.x) {
+    const int u1 = c_cand_u1[k], u2 = c_cand_u2[k], sz = u1 + u2;
+    cu1[k] = (uint8_t)u1; cu2[k] = (uint8_t)u2;
+    const bool special = sz <= 1 || (u1 == 1 && u2 == 1) || (sz == 3 && u1 >= 1 && u2 >= 1) || (u1 == 2 && u2 == 2) || (sz == 5 && (u1 == 2 || u1 == 3));
+    ckind[k] = (uint8_t)(special ? 0 : (u1 == 0 || u2 == 0) ? 1 : (u1 == 1 || u2 == 1) ? 2 : 3);
+  }
 
   const int nmax = W - 2;
   double *scl = reinterpret_cast<double *>(dyn);  // scale^-k
@@ -529,6 +544,11 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
     }
     for (int k = tid; k <= n + 2; k += blockDim.x) { qA[k] = 0.0; qB[k] = 0.0; }
     __syncthreads();
+    for (int k = tid; k < BF_NCAND; k += blockDim.x) {   // weights of the decomposable candidates at this sequence's scale
+      const int u1 = cu1[k], u2 = cu2[k], sz = u1 + u2, kind = ckind[k];
+      const double w = kind == 1 ? T.x_bulge[sz] : kind == 2 ? T.x_interior[sz] * T.x_ninio[sz - 2] : kind == 3 ? T.x_interior[sz] * T.x_ninio[abs(u1 - u2)] : 0.0;
+      cxw[k] = w * exp(-s_lnscale * (sz + 2));
+    }
     if (TWO && cp <= n && tid == 0) { qA[cp] = 1.0; qB[cp - 1] = 1.0; }
     __syncthreads();
 
@@ -588,23 +608,17 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
           const double xmmO = cXMMO[i], xmm1O = cXMM1O[i], xtauO = t > 2 ? T.x_TerminalAU : 1.0, xmlc = cXMLC[i];
           double acc = 0.0;
           const int smx = min(BF_MAXLOOP, d - 3), kmax = smx >= 0 ? (smx + 1) * (smx + 2) / 2 : 0;   // candidates are ordered by size
+          const int pmax = (TWO && i < cp) ? cp - 1 : n, qmin = (TWO && j >= cp) ? cp : 0;
           for (int k = lane; k < kmax; k += 32) {
-            const int u1 = cu1[k], u2 = cu2[k], sz = u1 + u2;
-            const int p = i + 1 + u1, q = j - 1 - u2;
-            if (q <= p) continue;
-            if (TWO && (!bf_same<TWO>(X, i, p) || !bf_same<TWO>(X, q, j))) continue;
-            const bool special = sz <= 1 || (u1 == 1 && u2 == 1) || (sz == 3 && u1 >= 1 && u2 >= 1) || (u1 == 2 && u2 == 2) ||
-                                 (sz == 5 && (u1 == 2 || u1 == 3));
-            if (special) {
+            const int u1 = cu1[k], u2 = cu2[k], kind = ckind[k];
+            const int p = i + 1 + u1, q = j - 1 - u2;        // q > p: the candidates are cut off at size d - 3
+            if (p > pmax || q < qmin) continue;
+            if (kind == 0) {
               const int t2 = bf_ptype<TWO>(X, p, q);
               if (!t2) continue;
-              acc += QB_(p, q) * bf_x_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]) * scl[sz + 2];
-            } else if (u1 == 0 || u2 == 0) {
-              acc += QBB_(p, q) * (T.x_bulge[sz] * xtauO * scl[sz + 2]);
-            } else if (u1 == 1 || u2 == 1) {
-              acc += Q1_(p, q) * (T.x_interior[sz] * T.x_ninio[sz - 2] * xmm1O * scl[sz + 2]);
+              acc += QB_(p, q) * bf_x_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]) * scl[u1 + u2 + 2];
             } else {
-              acc += QG_(p, q) * (T.x_interior[sz] * T.x_ninio[abs(u1 - u2)] * xmmO * scl[sz + 2]);
+              acc += (kind == 1 ? qBB : kind == 2 ? q1 : qG)[p * W + q] * (cxw[k] * (kind == 1 ? xtauO : kind == 2 ? xmm1O : xmmO));
             }
           }
           if (xmlc != 0.0) {
