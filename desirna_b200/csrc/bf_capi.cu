@@ -187,7 +187,7 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
     BfBatchDev dbp = db;
     dbp.nopair = nullptr;  // hard constraints are added after fc.pf() in the reference (sequence_utils.py:1181)
     // a constrained MFE is not a bound on the unconstrained ensemble: only use it for scaling when unconstrained
-    const bool beside = scale_override && !want_out && !b->nopair && fill_pf;
+    const bool beside = scale_override && !want_out && !b->nopair;
     cudaStream_t sp = beside ? w.st2 : st;
     if (beside) CU(cudaStreamWaitEvent(sp, w.ev_fork, 0), "fork");
     const int *scale_src = beside ? scale_override : (b->nopair ? nullptr : mfe_for_scale);
@@ -232,7 +232,7 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
       size_t slot = bf_pf_slot_doubles(wstride) * sizeof(double);
       while (grid > g.sm_count && (size_t)grid * slot > ((size_t)64 << 30)) grid -= g.sm_count;
       CU(w.ws_pf.reserve((size_t)grid * slot), "cudaMalloc(pf workspace)");
-      CU(bf_launch_pf(g.dP, dbp, two, (double *)w.ws_pf.p, wstride, grid, w.d_counters + 1, scale_src, r->pf, st), "launch bf_k_pf");
+      CU(bf_launch_pf(g.dP, dbp, two, (double *)w.ws_pf.p, wstride, grid, w.d_counters + 1, scale_src, r->pf, sp), "launch bf_k_pf");
       g.launches++;
     }
     if (timing) cudaEventRecord(w.ev[3], sp);
@@ -608,7 +608,7 @@ int design_score(DesignLoop *h, bool init = false) {
   std::memset(&r, 0, sizeof r);
   r.mfe_dcal = h->D.o_mfe; r.mfe_ss = h->D.o_ss; r.pf = h->D.o_pf; r.eval_dcal = h->D.o_eval; r.defect = h->D.o_defect;
   // small batches: partition function beside the MFE fill, scaled by the parent sequence's MFE (kept per replica)
-  const bool beside = !init && !h->two && h->overlap && h->B * 2 <= g.sm_count * h->overlap_x2 && !(h->want & BF_WANT_DEFECT);
+  const bool beside = !init && h->overlap && h->B * 2 <= g.sm_count * (h->two ? 1 : h->overlap_x2) && !(h->want & BF_WANT_DEFECT);
   int rc = run_device(h->w, &b, &r, h->two, h->st, beside ? h->D.row_scale : nullptr, false);
   if (rc) return rc;
   if (h->C.subopt) {

@@ -24,6 +24,15 @@ namespace {
 __constant__ uint8_t c_cand_u1[BF_NCAND];
 __constant__ uint8_t c_cand_u2[BF_NCAND];
 
+// the nine interior-loop shapes that are not decomposed (stack, bulge 1, 1x1, 1x2, 2x1, 2x2, 2x3, 3x2): their index in the size-ordered
+// candidate list (size * (size + 1) / 2 + u1) and their (u1, u2)
+__device__ constexpr int kSpecK[9] = {0, 1, 2, 4, 7, 8, 12, 17, 18};
+__device__ constexpr int kSpecU1[9] = {0, 0, 1, 1, 1, 2, 2, 2, 3};
+__device__ constexpr int kSpecU2[9] = {0, 1, 0, 1, 2, 1, 2, 3, 2};
+constexpr int kPreArr = 15;   // sequence-only arrays per diagonal buffer (PRE variants)
+constexpr int kPreArrD = 13;  // partition function: arrays of doubles per diagonal buffer
+constexpr int kPreMax = 256;  // longest sequence (both strands) the PRE variants take
+
 struct __align__(8) BfSector { short i, j; int kind; };  // kind: 0 exterior(f5 up to j) 1 multiloop part 2 pair 3 fcA from i 4 fcB up to j
 
 __device__ __forceinline__ size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -50,31 +59,35 @@ __device__ __forceinline__ void load_sequence(const BfBatchDev &b, int s, uint8_
 // =====================================================================================================
 //                                               MFE
 // =====================================================================================================
-template <bool TWO, int NWG>
+// PRE (sequences up to kPreMax nt): two barriers per diagonal instead of four.  Everything of a cell that depends on the sequence only
+// is computed ONE DIAGONAL AHEAD, as items of the long middle stage (its parameter-table reads in L2 then overlap the other warps'
+// candidate work instead of sitting on the critical path), the nick-side recursions fcA / fcB are items of that stage too (what they
+// write is first read a diagonal later), and the items are dealt to the warps through a shared counter.
+template <bool TWO, int NWG, bool PRE>
 __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict__ P, BfBatchDev b, int *ws, size_t ws_slot_ints,
                                                        int wstride, int *work_counter, int *out_mfe, char *out_ss, int ss_stride,
                                                        unsigned tables_smem_off) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ BfSmallI T;
-  __shared__ uint8_t cu1[BF_NCAND], cu2[BF_NCAND];
   __shared__ int s_seq;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = wstride;  // row stride of the tables, >= n+2
 
   bf_stage(&T, &P->si);
-  // candidates of an interior loop, ordered by size: (u1, u2), kind (0: one of the nine shapes evaluated in full, 1 bulge, 2 1xn,
-  // 3 generic) and the size penalty of the decomposable kinds
-  __shared__ uint8_t ckind[BF_NCAND];
-  __shared__ int cpen[BF_NCAND];
+  // candidates of an interior loop, ordered by size, one packed entry each: x = u1 | u2 << 8 | table << 16 | (shape + 1) << 24 with
+  // table 3 / 4 / 5 = the variant of c a decomposable candidate reads (generic / 1xn / bulge: c + inner mismatch / terminalAU),
+  // 0 for the nine shapes that are evaluated in full (shape = their index in kSpecK); y = size penalty of a decomposable candidate
+  __shared__ int2 cand2[BF_NCAND];
   __syncthreads();
   for (int k = tid; k < BF_NCAND; k += blockDim.x) {
     const int u1 = c_cand_u1[k], u2 = c_cand_u2[k], sz = u1 + u2;
-    cu1[k] = (uint8_t)u1; cu2[k] = (uint8_t)u2;
     const bool special = sz <= 1 || (u1 == 1 && u2 == 1) || (sz == 3 && u1 >= 1 && u2 >= 1) || (u1 == 2 && u2 == 2) || (sz == 5 && (u1 == 2 || u1 == 3));
-    const int kind = special ? 0 : (u1 == 0 || u2 == 0) ? 1 : (u1 == 1 || u2 == 1) ? 2 : 3;
-    ckind[k] = (uint8_t)kind;
-    cpen[k] = kind == 1 ? T.bulge[sz] : kind == 2 ? T.interior[sz] + min(T.ninio_max, (sz - 2) * T.ninio_m)
-                        : kind == 3 ? T.interior[sz] + min(T.ninio_max, abs(u1 - u2) * T.ninio_m) : 0;
+    const int tsel = special ? 0 : (u1 == 0 || u2 == 0) ? 5 : (u1 == 1 || u2 == 1) ? 4 : 3;
+    int shape = 0;
+    for (int q = 0; q < 9; q++) if (kSpecK[q] == k) shape = q + 1;
+    const int pen = tsel == 5 ? T.bulge[sz] : tsel == 4 ? T.interior[sz] + min(T.ninio_max, (sz - 2) * T.ninio_m)
+                  : tsel == 3 ? T.interior[sz] + min(T.ninio_max, abs(u1 - u2) * T.ninio_m) : 0;
+    cand2[k] = make_int2(u1 | u2 << 8 | tsel << 16 | shape << 24, pen);
   }
 
   // dynamic smem carve-up
@@ -86,11 +99,15 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
   int *fcB = fcA + (nmax + 4);
   BfSector *stk = reinterpret_cast<BfSector *>(fcB + (nmax + 4));
   // per-cell arrays of the diagonal in work (index = i)
-  int *cT = reinterpret_cast<int *>(stk + (2 * nmax + 16));
-  int *cE0 = cT + (nmax + 4), *cMMO = cE0 + (nmax + 4), *cMM1O = cMMO + (nmax + 4), *cMLC = cMM1O + (nmax + 4);
-  int *cEC = cMLC + (nmax + 4), *cMS = cEC + (nmax + 4), *cLIST = cMS + (nmax + 4);
-  __shared__ int s_np;
-  if (tid == 0) s_np = 0;
+  const int NA = nmax + 4;
+  int *cbase = reinterpret_cast<int *>(stk + (2 * nmax + 16));
+  // !PRE: cT cE0 cMMO cMM1O cMLC cEC cMS cLIST.   PRE: cEC cMS, then two buffers (diagonal parity) of the kPreArr sequence-only arrays
+  // cT cE0 cMMO cMM1O cMLC cLIST cE9[9] (the nine interior-loop shapes that are evaluated in full, INF where the inner pair is impossible)
+  int *cT = cbase, *cE0 = cT + NA, *cMMO = cE0 + NA, *cMM1O = cMMO + NA, *cMLC = cMM1O + NA;
+  int *cEC = PRE ? cbase : cMLC + NA, *cMS = cEC + NA, *cLIST = cMS + NA;
+  int *pre0 = cbase + 2 * NA;
+  __shared__ int s_np, s_np2[2], s_next;
+  if (tid == 0) { s_np = 0; s_np2[0] = s_np2[1] = 0; s_next = 0; }
 
   // short sequences: the three tables live in shared memory behind the per-sequence arrays (offset passed by the host), else in HBM
   int *c = tables_smem_off ? reinterpret_cast<int *>(dyn + tables_smem_off) : ws + (size_t)blockIdx.x * ws_slot_ints;
@@ -104,6 +121,32 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
 #define C_(i, j) c[(i) * W + (j)]
 #define M_(i, j) fml[(i) * W + (j)]
 #define MT_(j, i) fmlT[(j) * W + (i)]
+
+  // the decomposable interior-loop candidates of cell (i,j), this lane's share: four candidates in flight per round (one packed
+  // entry, one table value each); the nick test is two bounds (p stays on i's strand, q on j's)
+  auto decomp = [&](int i, int j, int kmax, int pmax, int qmin, int mmO, int mm1O, int tauO) -> int {
+    int e = BF_INF;
+    const int WW = W * W;
+    for (int k0 = lane; k0 < kmax; k0 += 128) {
+      int2 cd[4];
+      int cc[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) cd[u] = cand2[min(k0 + 32 * u, BF_NCAND - 1)];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int u1 = cd[u].x & 255, u2 = (cd[u].x >> 8) & 255, ts = (cd[u].x >> 16) & 255;
+        const int p = i + 1 + u1, q = j - 1 - u2;        // q > p: the candidates are cut off at size d - 3
+        const bool ok = k0 + 32 * u < kmax && ts != 0 && p <= pmax && q >= qmin;
+        cc[u] = ok ? c[ts * WW + p * W + q] : BF_INF;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int ts = (cd[u].x >> 16) & 255;
+        if (cc[u] < BF_INF) e = min(e, cc[u] + cd[u].y + (ts == 5 ? tauO : ts == 4 ? mm1O : mmO));
+      }
+    }
+    return e;
+  };
 
   for (;;) {
     __syncthreads();
@@ -123,6 +166,154 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
     for (int k = tid; k <= n + 2; k += blockDim.x) { fcA[k] = 0; fcB[k] = 0; }
     __syncthreads();
 
+    if constexpr (PRE) {
+      // sequence-only terms of the cells [32 * chunk, 32 * chunk + 32) of diagonal dd into buffer bf (lanes = cells)
+      auto setup = [&](int dd, int chunk, int bf) {
+        int *q = pre0 + (size_t)bf * kPreArr * NA;
+        const int i = chunk * 32 + lane + 1, j = i + dd;
+        if (i > n - dd) return;
+        const int t = bf_ptype<TWO>(X, i, j);
+        q[i] = t;
+        if (!t) return;
+        const int si1 = S[i + 1], sj1 = S[j - 1];
+        const bool span = TWO && i < cp && j >= cp;
+        int e0;
+        if (span) { int a, bb; bf_nick_nb(X, i, j, &a, &bb); e0 = bf_e_ext(T, bf_rtype(t), a, bb); }   // + fcA[i+1] + fcB[j-1] when the cell is computed
+        else e0 = bf_e_hairpin(P, T, S, i, j, t);
+        q[NA + i] = e0; q[2 * NA + i] = T.mmI[t][si1][sj1]; q[3 * NA + i] = T.mm1nI[t][si1][sj1];
+        q[4 * NA + i] = (!TWO || (bf_same<TWO>(X, i, i + 1) && bf_same<TWO>(X, j - 1, j))) ? T.MLclosing + bf_e_mlstem(T, bf_rtype(t), sj1, si1) : BF_INF;
+        const int pmax = (TWO && i < cp) ? cp - 1 : n, qmin = (TWO && j >= cp) ? cp : 0;
+#pragma unroll
+        for (int sh = 0; sh < 9; sh++) {
+          const int u1 = kSpecU1[sh], u2 = kSpecU2[sh], p = i + 1 + u1, qq = j - 1 - u2;
+          int e9 = BF_INF;
+          if (qq > p && p <= pmax && qq >= qmin) {
+            const int t2 = bf_ptype<TWO>(X, p, qq);
+            if (t2) e9 = bf_e_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[qq + 1]);
+          }
+          q[(6 + sh) * NA + i] = e9;
+        }
+        q[5 * NA + atomicAdd(&s_np2[bf], 1)] = i;
+      };
+      for (int ch = warp; ch * 32 < n - d0; ch += NWG) setup(d0, ch, d0 & 1);
+      __syncthreads();
+      for (int d = d0; d <= n - 1; d++) {
+        const int bf = d & 1;
+        const int *q = pre0 + (size_t)bf * kPreArr * NA;
+        const int *qT = q, *qE0 = q + NA, *qMMO = q + 2 * NA, *qMM1O = q + 3 * NA, *qMLC = q + 4 * NA, *qLIST = q + 5 * NA, *qE9 = q + 6 * NA;
+        const int ncell = n - d, np = s_np2[bf];
+        const int nfc = (TWO && cp <= n) ? 2 : 0, nset = d + 1 <= n - 1 ? (n - d - 1 + 31) / 32 : 0;
+        const int total = nfc + nset + np + ncell;
+        for (;;) {
+          int it = 0;
+          if (lane == 0) it = atomicAdd(&s_next, 1);
+          it = __shfl_sync(BF_FULL, it, 0);
+          if (it >= total) break;
+          if (it < nfc) {
+            // exterior-style decompositions next to the nick: fcA[k] for segment k..cp-1, fcB[k] for cp..k.  Segment span is d-1, so
+            // every c it needs is final; the cells of this diagonal read fcA / fcB at indices written on earlier diagonals only.
+            if (it == 0) {
+              const int k = cp - d;
+              if (k >= 1) {
+                int e = BF_INF;
+                for (int qq = k + 1 + lane; qq <= cp - 1; qq += 32) {
+                  const int t = bf_ptype<TWO>(X, k, qq);
+                  if (t) {
+                    const int cc = C_(k, qq);
+                    if (cc < BF_INF) { int a, bb; bf_ext_nb<TWO>(X, k, qq, &a, &bb); e = min(e, cc + bf_e_ext(T, t, a, bb) + fcA[qq + 1]); }
+                  }
+                }
+                e = bf_warp_min(e);
+                if (lane == 0) fcA[k] = min(e, fcA[k + 1]);
+              }
+            } else {
+              const int k = cp + d - 1;
+              if (k <= n) {
+                int e = BF_INF;
+                for (int p = cp + lane; p < k; p += 32) {
+                  const int t = bf_ptype<TWO>(X, p, k);
+                  if (t) {
+                    const int cc = C_(p, k);
+                    if (cc < BF_INF) { int a, bb; bf_ext_nb<TWO>(X, p, k, &a, &bb); e = min(e, fcB[p - 1] + cc + bf_e_ext(T, t, a, bb)); }
+                  }
+                }
+                e = bf_warp_min(e);
+                if (lane == 0) fcB[k] = min(e, fcB[k - 1]);
+              }
+            }
+          } else if (it < nfc + nset) {
+            setup(d + 1, it - nfc, bf ^ 1);
+          } else if (it < nfc + nset + np) {
+            const int i = qLIST[it - nfc - nset], j = i + d, t = qT[i];
+            const int mmO = qMMO[i], mm1O = qMM1O[i], tauO = t > 2 ? T.TerminalAU : 0, mlc = qMLC[i];
+            const int smx = min(BF_MAXLOOP, d - 3), kmax = smx >= 0 ? (smx + 1) * (smx + 2) / 2 : 0;   // candidates are ordered by size
+            // the unpaired stretches of a regular loop may not contain the nick: p stays on i's strand, q on j's
+            const int pmax = (TWO && i < cp) ? cp - 1 : n, qmin = (TWO && j >= cp) ? cp : 0;
+            int e = decomp(i, j, kmax, pmax, qmin, mmO, mm1O, tauO);
+            if (lane < min(kmax, 21)) {   // the shapes evaluated in full sit among the first 21 candidates
+              const int x = cand2[lane].x, sh = x >> 24;
+              const int p = i + 1 + (x & 255), qq = j - 1 - ((x >> 8) & 255);
+              if (sh && p <= pmax && qq >= qmin) {
+                const int e9 = qE9[(sh - 1) * NA + i];
+                if (e9 < BF_INF) {
+                  const int cc = C_(p, qq);
+                  if (cc < BF_INF) e = min(e, cc + e9);
+                }
+              }
+            }
+            if (mlc < BF_INF) {   // multiloop closed by (i,j)
+              int dec = BF_INF;
+              const int *rowL = &M_(i + 1, 0);
+              const int *rowR = &MT_(j - 1, 0);
+              const int ulo = TWO ? i + 2 : i + 2 + BF_TURN + 1, uhi = TWO ? j - 1 : j - 2 - BF_TURN;
+              for (int u = ulo + lane; u <= uhi; u += 32) {
+                if (TWO && !bf_same<TWO>(X, u - 1, u)) continue;
+                dec = min(dec, rowL[u - 1] + rowR[u]);
+              }
+              if (dec < BF_INF) e = min(e, dec + mlc);
+            }
+            e = bf_warp_min(e);
+            if (lane == 0) {
+              int e0 = qE0[i];
+              if (TWO && i < cp && j >= cp) e0 += fcA[i + 1] + fcB[j - 1];
+              cEC[i] = min(min(e, e0), BF_INF);
+            }
+          } else {
+            const int i = it - nfc - nset - np + 1, j = i + d;
+            int m = BF_INF;
+            const int *rowL = &M_(i, 0);
+            const int *rowR = &MT_(j, 0);
+            const int ulo = TWO ? i + 1 : i + 1 + BF_TURN + 1, uhi = TWO ? j : j - 1 - BF_TURN;
+            for (int u = ulo + lane; u <= uhi; u += 32) {
+              if (TWO && !bf_same<TWO>(X, u - 1, u)) continue;
+              m = min(m, rowL[u - 1] + rowR[u]);
+            }
+            m = bf_warp_min(m);
+            if (lane == 0) cMS[i] = m;
+          }
+        }
+        __syncthreads();
+        for (int i = 1 + tid; i <= ncell; i += blockDim.x) {
+          const int j = i + d, t = qT[i];
+          const int e = t ? cEC[i] : BF_INF;
+          int m = cMS[i];
+          if (e < BF_INF && i > 1 && j < n && bf_same<TWO>(X, i - 1, i) && bf_same<TWO>(X, j, j + 1))
+            m = min(m, e + bf_e_mlstem(T, t, S[i - 1], S[j + 1]));
+          if (bf_same<TWO>(X, i, i + 1)) m = min(m, M_(i + 1, j) + T.MLbase);
+          if (bf_same<TWO>(X, j - 1, j)) m = min(m, M_(i, j - 1) + T.MLbase);
+          m = min(m, BF_INF);
+          C_(i, j) = e; M_(i, j) = m; MT_(j, i) = m;
+          if (e < BF_INF) {
+            const int tr = bf_rtype(t), a = S[j + 1], bb = S[i - 1];
+            CG_(i, j) = e + T.mmI[tr][a][bb]; C1_(i, j) = e + T.mm1nI[tr][a][bb]; CB_(i, j) = e + (t > 2 ? T.TerminalAU : 0);
+          } else {
+            CG_(i, j) = BF_INF; C1_(i, j) = BF_INF; CB_(i, j) = BF_INF;
+          }
+        }
+        if (tid == 0) { s_np2[bf] = 0; s_next = 0; }
+        __syncthreads();
+      }
+    } else {
     for (int d = d0; d <= n - 1; d++) {
       if (TWO && cp <= n) {
         // exterior-style decompositions next to the nick: fcA[k] for segment k..cp-1, fcB[k] for cp..k.
@@ -188,23 +379,17 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
           const int i = cLIST[it], j = i + d, t = cT[i];
           const int si1 = S[i + 1], sj1 = S[j - 1];
           const int mmO = cMMO[i], mm1O = cMM1O[i], tauO = t > 2 ? T.TerminalAU : 0, mlc = cMLC[i];
-          int e = BF_INF;
           const int smx = min(BF_MAXLOOP, d - 3), kmax = smx >= 0 ? (smx + 1) * (smx + 2) / 2 : 0;   // candidates are ordered by size
           // the unpaired stretches of a regular loop may not contain the nick: p stays on i's strand, q on j's
           const int pmax = (TWO && i < cp) ? cp - 1 : n, qmin = (TWO && j >= cp) ? cp : 0;
-          for (int k = lane; k < kmax; k += 32) {
-            const int u1 = cu1[k], u2 = cu2[k], kind = ckind[k];
-            const int p = i + 1 + u1, q = j - 1 - u2;        // q > p: the candidates are cut off at size d - 3
-            if (p > pmax || q < qmin) continue;
-            if (kind == 0) {
+          int e = decomp(i, j, kmax, pmax, qmin, mmO, mm1O, tauO);
+          if (lane < min(kmax, 21)) {   // the shapes evaluated in full sit among the first 21 candidates
+            const int x = cand2[lane].x, u1 = x & 255, u2 = (x >> 8) & 255;
+            const int p = i + 1 + u1, q = j - 1 - u2;
+            if ((x >> 24) && p <= pmax && q >= qmin) {
               const int t2 = bf_ptype<TWO>(X, p, q);
-              if (!t2) continue;
-              const int cc = C_(p, q);
-              if (cc >= BF_INF) continue;
-              e = min(e, cc + bf_e_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]));
-            } else {
-              const int cc = (kind == 1 ? cB : kind == 2 ? c1 : cG)[p * W + q];
-              if (cc < BF_INF) e = min(e, cc + cpen[k] + (kind == 1 ? tauO : kind == 2 ? mm1O : mmO));
+              const int cc = t2 ? C_(p, q) : BF_INF;
+              if (cc < BF_INF) e = min(e, cc + bf_e_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]));
             }
           }
           if (mlc < BF_INF) {   // multiloop closed by (i,j)
@@ -254,6 +439,8 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
       }
       if (tid == 0) s_np = 0;
       __syncthreads();
+    }
+
     }
 
     // ---- exterior loop f5 (warp 0), then backtrack (warp 0)
@@ -465,27 +652,28 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
 // =====================================================================================================
 //                                     partition function (inside)
 // =====================================================================================================
-template <bool TWO, int NWG>
+template <bool TWO, int NWG, bool PRE>
 __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__ P, BfBatchDev b, double *ws, size_t ws_slot_dbl,
                                                       int wstride, int *work_counter, const int *mfe_for_scale, double *out5,
                                                       unsigned tables_smem_off) {
   extern __shared__ __align__(16) unsigned char dyn[];
   __shared__ BfSmallD T;
-  __shared__ uint8_t cu1[BF_NCAND], cu2[BF_NCAND];
   __shared__ int s_seq;
   __shared__ double s_lnscale;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = wstride;
   bf_stage(&T, &P->sd);
-  // candidates of an interior loop, ordered by size: kind as in bf_k_mfe; the weight of the decomposable kinds, scale included, is
-  // rebuilt for every sequence (cxw)
-  __shared__ uint8_t ckind[BF_NCAND];
+  // candidates of an interior loop, ordered by size: packed as in bf_k_mfe (u1 | u2 << 8 | table << 16 | (shape + 1) << 24); the weight
+  // of the decomposable ones, scale included, is rebuilt for every sequence (cxw)
+  __shared__ int cand1[BF_NCAND];
   __shared__ double cxw[BF_NCAND];
   for (int k = tid; k < BF_NCAND; k += blockDim.x) {
     const int u1 = c_cand_u1[k], u2 = c_cand_u2[k], sz = u1 + u2;
-    cu1[k] = (uint8_t)u1; cu2[k] = (uint8_t)u2;
     const bool special = sz <= 1 || (u1 == 1 && u2 == 1) || (sz == 3 && u1 >= 1 && u2 >= 1) || (u1 == 2 && u2 == 2) || (sz == 5 && (u1 == 2 || u1 == 3));
-    ckind[k] = (uint8_t)(special ? 0 : (u1 == 0 || u2 == 0) ? 1 : (u1 == 1 || u2 == 1) ? 2 : 3);
+    const int tsel = special ? 0 : (u1 == 0 || u2 == 0) ? 5 : (u1 == 1 || u2 == 1) ? 4 : 3;
+    int shape = 0;
+    for (int q = 0; q < 9; q++) if (kSpecK[q] == k) shape = q + 1;
+    cand1[k] = u1 | u2 << 8 | tsel << 16 | shape << 24;
   }
 
   const int nmax = W - 2;
@@ -495,13 +683,19 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
   double *qA = q5 + (nmax + 4);
   double *qB = qA + (nmax + 4);
   // per-cell arrays of the diagonal in work (index = i)
-  double *cB0 = qB + (nmax + 4), *cXMMO = cB0 + (nmax + 4), *cXMM1O = cXMMO + (nmax + 4), *cXMLC = cXMM1O + (nmax + 4);
-  double *cQBr = cXMLC + (nmax + 4), *cQS = cQBr + (nmax + 4);
-  int *cT = reinterpret_cast<int *>(cQS + (nmax + 4)), *cLIST = cT + (nmax + 4);
-  uint8_t *S = reinterpret_cast<uint8_t *>(cLIST + (nmax + 4));
+  // !PRE: cB0 cXMMO cXMM1O cXMLC cQBr cQS | cT cLIST | S SP.   PRE (see bf_k_mfe): cQBr cQS, two buffers of kPreArrD arrays of doubles
+  // cB0 cXMMO cXMM1O cXMLC cXE9[9] | two buffers of cT cLIST | S SP
+  const int NA = nmax + 4;
+  double *dbase = qB + NA;
+  double *cB0 = dbase, *cXMMO = cB0 + NA, *cXMM1O = cXMMO + NA, *cXMLC = cXMM1O + NA;
+  double *cQBr = PRE ? dbase : cXMLC + NA, *cQS = cQBr + NA;
+  double *pre0 = dbase + 2 * NA;
+  int *ibase = reinterpret_cast<int *>(PRE ? pre0 + (size_t)2 * kPreArrD * NA : cQS + NA);
+  int *cT = ibase, *cLIST = cT + NA;
+  uint8_t *S = reinterpret_cast<uint8_t *>(ibase + (PRE ? 4 : 2) * NA);
   uint8_t *SP = S + align_up(nmax + 2, 16);
-  __shared__ int s_np;
-  if (tid == 0) s_np = 0;
+  __shared__ int s_np, s_np2[2], s_next;
+  if (tid == 0) { s_np = 0; s_np2[0] = s_np2[1] = 0; s_next = 0; }
 
   double *qb = tables_smem_off ? reinterpret_cast<double *>(dyn + tables_smem_off) : ws + (size_t)blockIdx.x * ws_slot_dbl;
   double *qm = qb + (size_t)W * W;
@@ -513,6 +707,31 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
 #define QB_(i, j) qb[(i) * W + (j)]
 #define QM_(i, j) qm[(i) * W + (j)]
 #define QM1T_(j, i) qm1T[(j) * W + (i)]
+
+  // the decomposable interior-loop candidates of cell (i,j), this lane's share, four in flight per round (see bf_k_mfe)
+  auto decomp = [&](int i, int j, int kmax, int pmax, int qmin, double xmmO, double xmm1O, double xtauO) -> double {
+    double acc = 0.0;
+    const int WW = W * W;
+    for (int k0 = lane; k0 < kmax; k0 += 128) {
+      int cd[4];
+      double cw[4], v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) { const int kk = min(k0 + 32 * u, BF_NCAND - 1); cd[u] = cand1[kk]; cw[u] = cxw[kk]; }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int u1 = cd[u] & 255, u2 = (cd[u] >> 8) & 255, ts = (cd[u] >> 16) & 255;
+        const int p = i + 1 + u1, q = j - 1 - u2;        // q > p: the candidates are cut off at size d - 3
+        const bool ok = k0 + 32 * u < kmax && ts != 0 && p <= pmax && q >= qmin;
+        v[u] = ok ? qb[ts * WW + p * W + q] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int ts = (cd[u] >> 16) & 255;
+        acc += v[u] * (cw[u] * (ts == 5 ? xtauO : ts == 4 ? xmm1O : xmmO));
+      }
+    }
+    return acc;
+  };
 
   for (;;) {
     __syncthreads();
@@ -545,13 +764,148 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
     for (int k = tid; k <= n + 2; k += blockDim.x) { qA[k] = 0.0; qB[k] = 0.0; }
     __syncthreads();
     for (int k = tid; k < BF_NCAND; k += blockDim.x) {   // weights of the decomposable candidates at this sequence's scale
-      const int u1 = cu1[k], u2 = cu2[k], sz = u1 + u2, kind = ckind[k];
-      const double w = kind == 1 ? T.x_bulge[sz] : kind == 2 ? T.x_interior[sz] * T.x_ninio[sz - 2] : kind == 3 ? T.x_interior[sz] * T.x_ninio[abs(u1 - u2)] : 0.0;
+      const int x = cand1[k], u1 = x & 255, u2 = (x >> 8) & 255, sz = u1 + u2, ts = (x >> 16) & 255;
+      const double w = ts == 5 ? T.x_bulge[sz] : ts == 4 ? T.x_interior[sz] * T.x_ninio[sz - 2] : ts == 3 ? T.x_interior[sz] * T.x_ninio[abs(u1 - u2)] : 0.0;
       cxw[k] = w * exp(-s_lnscale * (sz + 2));
     }
     if (TWO && cp <= n && tid == 0) { qA[cp] = 1.0; qB[cp - 1] = 1.0; }
     __syncthreads();
 
+    if constexpr (PRE) {
+      auto setup = [&](int dd, int chunk, int bf) {
+        double *q = pre0 + (size_t)bf * kPreArrD * NA;
+        int *qi = ibase + (size_t)bf * 2 * NA;
+        const int i = chunk * 32 + lane + 1, j = i + dd;
+        if (i > n - dd) return;
+        const int t = bf_ptype<TWO>(X, i, j);
+        qi[i] = t;
+        if (!t) return;
+        const int si1 = S[i + 1], sj1 = S[j - 1];
+        const bool span = TWO && i < cp && j >= cp;
+        double b0;
+        if (span) { int a, bb; bf_nick_nb(X, i, j, &a, &bb); b0 = bf_x_ext(T, bf_rtype(t), a, bb) * scl[2]; }   // x qA[i+1] x qB[j-1] when the cell is computed
+        else b0 = bf_x_hairpin(P, T, S, i, j, t) * scl[dd + 1];
+        q[i] = b0; q[NA + i] = T.x_mmI[t][si1][sj1]; q[2 * NA + i] = T.x_mm1nI[t][si1][sj1];
+        q[3 * NA + i] = (!TWO || (bf_same<TWO>(X, i, i + 1) && bf_same<TWO>(X, j - 1, j))) ? T.x_MLclosing * bf_x_mlstem(T, bf_rtype(t), sj1, si1) * scl[2] : 0.0;
+        const int pmax = (TWO && i < cp) ? cp - 1 : n, qmin = (TWO && j >= cp) ? cp : 0;
+#pragma unroll
+        for (int sh = 0; sh < 9; sh++) {
+          const int u1 = kSpecU1[sh], u2 = kSpecU2[sh], p = i + 1 + u1, qq = j - 1 - u2;
+          double x9 = 0.0;
+          if (qq > p && p <= pmax && qq >= qmin) {
+            const int t2 = bf_ptype<TWO>(X, p, qq);
+            if (t2) x9 = bf_x_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[qq + 1]) * scl[u1 + u2 + 2];
+          }
+          q[(4 + sh) * NA + i] = x9;
+        }
+        qi[NA + atomicAdd(&s_np2[bf], 1)] = i;
+      };
+      for (int ch = warp; ch * 32 < n - d0; ch += NWG) setup(d0, ch, d0 & 1);
+      __syncthreads();
+      for (int d = d0; d <= n - 1; d++) {
+        const int bf = d & 1;
+        const double *q = pre0 + (size_t)bf * kPreArrD * NA;
+        const double *qB0 = q, *qXMMO = q + NA, *qXMM1O = q + 2 * NA, *qXMLC = q + 3 * NA, *qXE9 = q + 4 * NA;
+        const int *qT = ibase + (size_t)bf * 2 * NA, *qLIST = qT + NA;
+        const int ncell = n - d, np = s_np2[bf];
+        const int nfc = (TWO && cp <= n) ? 2 : 0, nset = d + 1 <= n - 1 ? (n - d - 1 + 31) / 32 : 0;
+        const int total = nfc + nset + np + ncell;
+        for (;;) {
+          int it = 0;
+          if (lane == 0) it = atomicAdd(&s_next, 1);
+          it = __shfl_sync(BF_FULL, it, 0);
+          if (it >= total) break;
+          if (it < nfc) {
+            if (it == 0) {
+              const int k = cp - d;
+              if (k >= 1) {
+                double sum = 0.0;
+                for (int qq = k + 1 + lane; qq <= cp - 1; qq += 32) {
+                  const int t = bf_ptype<TWO>(X, k, qq);
+                  if (t) { int a, bb; bf_ext_nb<TWO>(X, k, qq, &a, &bb); sum += QB_(k, qq) * bf_x_ext(T, t, a, bb) * qA[qq + 1]; }
+                }
+                sum = bf_warp_sum(sum);
+                if (lane == 0) qA[k] = sum + qA[k + 1] * scl[1];
+              }
+            } else {
+              const int k = cp + d - 1;
+              if (k <= n) {
+                double sum = 0.0;
+                for (int p = cp + lane; p < k; p += 32) {
+                  const int t = bf_ptype<TWO>(X, p, k);
+                  if (t) { int a, bb; bf_ext_nb<TWO>(X, p, k, &a, &bb); sum += qB[p - 1] * QB_(p, k) * bf_x_ext(T, t, a, bb); }
+                }
+                sum = bf_warp_sum(sum);
+                if (lane == 0) qB[k] = sum + qB[k - 1] * scl[1];
+              }
+            }
+          } else if (it < nfc + nset) {
+            setup(d + 1, it - nfc, bf ^ 1);
+          } else if (it < nfc + nset + np) {
+            const int i = qLIST[it - nfc - nset], j = i + d, t = qT[i];
+            const double xmmO = qXMMO[i], xmm1O = qXMM1O[i], xtauO = t > 2 ? T.x_TerminalAU : 1.0, xmlc = qXMLC[i];
+            const int smx = min(BF_MAXLOOP, d - 3), kmax = smx >= 0 ? (smx + 1) * (smx + 2) / 2 : 0;   // candidates are ordered by size
+            const int pmax = (TWO && i < cp) ? cp - 1 : n, qmin = (TWO && j >= cp) ? cp : 0;
+            double acc = decomp(i, j, kmax, pmax, qmin, xmmO, xmm1O, xtauO);
+            if (lane < min(kmax, 21)) {   // the shapes evaluated in full sit among the first 21 candidates
+              const int x = cand1[lane], sh = x >> 24;
+              const int p = i + 1 + (x & 255), qq = j - 1 - ((x >> 8) & 255);
+              if (sh && p <= pmax && qq >= qmin) acc += QB_(p, qq) * qXE9[(sh - 1) * NA + i];
+            }
+            if (xmlc != 0.0) {
+              double dec = 0.0;
+              const double *rowL = &QM_(i + 1, 0);
+              const double *rowR = &QM1T_(j - 1, 0);
+              const int ulo = TWO ? i + 2 : i + 2 + BF_TURN + 1, uhi = TWO ? j - 1 : j - 2 - BF_TURN;
+              for (int u = ulo + lane; u <= uhi; u += 32) {
+                if (TWO && !bf_same<TWO>(X, u - 1, u)) continue;
+                dec += rowL[u - 1] * rowR[u];
+              }
+              acc += dec * xmlc;
+            }
+            acc = bf_warp_sum(acc);
+            if (lane == 0) {
+              double b0 = qB0[i];
+              if (TWO && i < cp && j >= cp) b0 *= qA[i + 1] * qB[j - 1];
+              cQBr[i] = acc + b0;
+            }
+          } else {
+            // qm[i][j] - qm1[i][j] = sum_u (bu[u-i] + qm[i][u-1]) * qm1[u][j]
+            const int i = it - nfc - nset - np + 1, j = i + d;
+            double sum = 0.0;
+            const double *rowL = &QM_(i, 0);
+            const double *rowR = &QM1T_(j, 0);
+            const int uhi = TWO ? j : j - BF_TURN - 1;
+            for (int u = i + 1 + lane; u <= uhi; u += 32) {
+              double left = 0.0;
+              if (!TWO || bf_same<TWO>(X, i, u)) left = bu[u - i];
+              if (!TWO || bf_same<TWO>(X, u - 1, u)) left += rowL[u - 1];
+              sum += left * rowR[u];
+            }
+            sum = bf_warp_sum(sum);
+            if (lane == 0) cQS[i] = sum;
+          }
+        }
+        __syncthreads();
+        for (int i = 1 + tid; i <= ncell; i += blockDim.x) {
+          const int j = i + d, t = qT[i];
+          const double qbij = t ? cQBr[i] : 0.0;
+          // qm1[i][j]: exactly one stem, starting at i, unpaired tail up to j
+          double qm1ij = 0.0;
+          if (bf_same<TWO>(X, j - 1, j)) qm1ij = QM1T_(j - 1, i) * bu[1];
+          if (t && i > 1 && j < n && bf_same<TWO>(X, i - 1, i) && bf_same<TWO>(X, j, j + 1)) qm1ij += qbij * bf_x_mlstem(T, t, S[i - 1], S[j + 1]);
+          QB_(i, j) = qbij; QM_(i, j) = cQS[i] + qm1ij; QM1T_(j, i) = qm1ij;
+          if (t) {
+            const int tr = bf_rtype(t), a = S[j + 1], bb = S[i - 1];
+            QG_(i, j) = qbij * T.x_mmI[tr][a][bb]; Q1_(i, j) = qbij * T.x_mm1nI[tr][a][bb]; QBB_(i, j) = qbij * (t > 2 ? T.x_TerminalAU : 1.0);
+          } else {
+            QG_(i, j) = 0.0; Q1_(i, j) = 0.0; QBB_(i, j) = 0.0;
+          }
+        }
+        if (tid == 0) { s_np2[bf] = 0; s_next = 0; }
+        __syncthreads();
+      }
+    } else {
     for (int d = d0; d <= n - 1; d++) {
       if (TWO && cp <= n) {
         if (warp == 0) {
@@ -606,19 +960,15 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
           const int i = cLIST[it], j = i + d, t = cT[i];
           const int si1 = S[i + 1], sj1 = S[j - 1];
           const double xmmO = cXMMO[i], xmm1O = cXMM1O[i], xtauO = t > 2 ? T.x_TerminalAU : 1.0, xmlc = cXMLC[i];
-          double acc = 0.0;
           const int smx = min(BF_MAXLOOP, d - 3), kmax = smx >= 0 ? (smx + 1) * (smx + 2) / 2 : 0;   // candidates are ordered by size
           const int pmax = (TWO && i < cp) ? cp - 1 : n, qmin = (TWO && j >= cp) ? cp : 0;
-          for (int k = lane; k < kmax; k += 32) {
-            const int u1 = cu1[k], u2 = cu2[k], kind = ckind[k];
-            const int p = i + 1 + u1, q = j - 1 - u2;        // q > p: the candidates are cut off at size d - 3
-            if (p > pmax || q < qmin) continue;
-            if (kind == 0) {
+          double acc = decomp(i, j, kmax, pmax, qmin, xmmO, xmm1O, xtauO);
+          if (lane < min(kmax, 21)) {   // the shapes evaluated in full sit among the first 21 candidates
+            const int x = cand1[lane], u1 = x & 255, u2 = (x >> 8) & 255;
+            const int p = i + 1 + u1, q = j - 1 - u2;
+            if ((x >> 24) && p <= pmax && q >= qmin) {
               const int t2 = bf_ptype<TWO>(X, p, q);
-              if (!t2) continue;
-              acc += QB_(p, q) * bf_x_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]) * scl[u1 + u2 + 2];
-            } else {
-              acc += (kind == 1 ? qBB : kind == 2 ? q1 : qG)[p * W + q] * (cxw[k] * (kind == 1 ? xtauO : kind == 2 ? xmm1O : xmmO));
+              if (t2) acc += QB_(p, q) * bf_x_intloop(P, T, u1, u2, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]) * scl[u1 + u2 + 2];
             }
           }
           if (xmlc != 0.0) {
@@ -669,6 +1019,8 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
       }
       if (tid == 0) s_np = 0;
       __syncthreads();
+    }
+
     }
 
     if (warp == 0) {
@@ -832,14 +1184,6 @@ cudaError_t bf_upload_constants() {
 size_t bf_mfe_slot_ints(int wstride) { return (size_t)6 * wstride * wstride; }      // c, fML, fML^T + the three inner-term variants of c
 size_t bf_pf_slot_doubles(int wstride) { return (size_t)6 * wstride * wstride; }   // qb, qm, qm1^T + the three variants of qb
 
-static size_t mfe_smem(int wstride) {
-  size_t nmax = wstride - 2;
-  return 2 * ((nmax + 2 + 15) / 16 * 16) + (3 + 8) * (nmax + 4) * sizeof(int) + (2 * nmax + 16) * sizeof(BfSector);
-}
-static size_t pf_smem(int wstride) {
-  size_t nmax = wstride - 2;
-  return (5 + 6) * (nmax + 4) * sizeof(double) + 2 * (nmax + 4) * sizeof(int) + 2 * ((nmax + 2 + 15) / 16 * 16);
-}
 // The generic kernels (two strands; any length the fill path does not cover) keep three W x W tables per CTA.  Short sequences --
 // the reference's two-strand examples are 17 & 18 nt -- fit in shared memory next to the per-sequence arrays, which takes the L2
 // round trip out of every table access (BF_GEN_SMEM=0: always HBM).  Capped so that at least two CTAs share an SM.
@@ -849,33 +1193,63 @@ static bool gen_wide(int B) {
   const char *v = getenv("BF_WIDE");
   return B > 0 && B <= sms && !(v && *v && atoi(v) == 0);
 }
+// the two-barrier variants: batches that leave SMs idle, i.e. latency matters (measured: 17 & 18 nt x 64 MFE 0.164 -> 0.150 ms, but
+// 50 & 50 nt x 4096 16.7 -> 25.5 ms); BF_GEN_PRE=0: the four-barrier ones everywhere
+static bool gen_pre(int wstride, bool wide) {
+  const char *v = getenv("BF_GEN_PRE");
+  return wide && wstride - 2 <= kPreMax && !(v && *v && atoi(v) == 0);
+}
+static size_t mfe_smem(int wstride, bool pre) {
+  size_t nmax = wstride - 2;
+  const size_t arrays = pre ? 3 + 2 + 2 * kPreArr : 3 + 8;
+  return 2 * ((nmax + 2 + 15) / 16 * 16) + arrays * (nmax + 4) * sizeof(int) + (2 * nmax + 16) * sizeof(BfSector);
+}
+static size_t pf_smem(int wstride, bool pre) {
+  size_t nmax = wstride - 2;
+  return (pre ? 5 + 2 + 2 * kPreArrD : 5 + 6) * (nmax + 4) * sizeof(double) + (pre ? 4 : 2) * (nmax + 4) * sizeof(int) + 2 * ((nmax + 2 + 15) / 16 * 16);
+}
 static size_t gen_tables_cap() {
   const char *v = getenv("BF_GEN_SMEM");
   if (v && *v && atoi(v) == 0) return 0;
   return (size_t)100 * 1024;
 }
-static unsigned mfe_tables_off(int wstride) {   // 0: tables in HBM
-  const size_t base = (mfe_smem(wstride) + 15) / 16 * 16;
+static unsigned mfe_tables_off(int wstride, bool pre) {   // 0: tables in HBM
+  const size_t base = (mfe_smem(wstride, pre) + 15) / 16 * 16;
   return base + bf_mfe_slot_ints(wstride) * sizeof(int) <= gen_tables_cap() ? (unsigned)base : 0u;
 }
-static unsigned pf_tables_off(int wstride) {
-  const size_t base = (pf_smem(wstride) + 15) / 16 * 16;
+static unsigned pf_tables_off(int wstride, bool pre) {
+  const size_t base = (pf_smem(wstride, pre) + 15) / 16 * 16;
   return base + bf_pf_slot_doubles(wstride) * sizeof(double) <= gen_tables_cap() ? (unsigned)base : 0u;
 }
-static size_t mfe_smem_total(int wstride) { const unsigned o = mfe_tables_off(wstride); return o ? o + bf_mfe_slot_ints(wstride) * sizeof(int) : mfe_smem(wstride); }
-static size_t pf_smem_total(int wstride) { const unsigned o = pf_tables_off(wstride); return o ? o + bf_pf_slot_doubles(wstride) * sizeof(double) : pf_smem(wstride); }
+static size_t mfe_smem_total(int wstride, bool pre) { const unsigned o = mfe_tables_off(wstride, pre); return o ? o + bf_mfe_slot_ints(wstride) * sizeof(int) : mfe_smem(wstride, pre); }
+static size_t pf_smem_total(int wstride, bool pre) { const unsigned o = pf_tables_off(wstride, pre); return o ? o + bf_pf_slot_doubles(wstride) * sizeof(double) : pf_smem(wstride, pre); }
+// the 48 KB a launch gets without opting in cover static + dynamic shared memory; the generic kernels hold 10-18 KB of static arrays
+static const size_t kOptIn = 16 * 1024;
 static size_t eval_smem(int stride) { return 2 * (stride + 4) * sizeof(short) + 2 * ((stride + 2 + 15) / 16 * 16); }
+
+using MfeKernel = void (*)(const BfParams *, BfBatchDev, int *, size_t, int, int *, int *, char *, int, unsigned);
+using PfKernel = void (*)(const BfParams *, BfBatchDev, double *, size_t, int, int *, const int *, double *, unsigned);
+template <bool PRE>
+static MfeKernel mfe_kernel_p(bool two, bool wide) {
+  return two ? (wide ? bf_k_mfe<true, 16, PRE> : bf_k_mfe<true, BF_WARPS, PRE>) : (wide ? bf_k_mfe<false, 16, PRE> : bf_k_mfe<false, BF_WARPS, PRE>);
+}
+template <bool PRE>
+static PfKernel pf_kernel_p(bool two, bool wide) {
+  return two ? (wide ? bf_k_pf<true, 16, PRE> : bf_k_pf<true, BF_WARPS, PRE>) : (wide ? bf_k_pf<false, 16, PRE> : bf_k_pf<false, BF_WARPS, PRE>);
+}
+static MfeKernel mfe_kernel(bool two, bool wide, bool pre) { return pre ? mfe_kernel_p<true>(two, wide) : mfe_kernel_p<false>(two, wide); }
+static PfKernel pf_kernel(bool two, bool wide, bool pre) { return pre ? pf_kernel_p<true>(two, wide) : pf_kernel_p<false>(two, wide); }
 
 cudaError_t bf_launch_mfe(const BfParams *dP, const BfBatchDev &b, bool two, int *ws, int wstride, int grid, int *work_counter,
                           int *out_mfe, char *out_ss, int ss_stride, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
-  size_t sm = mfe_smem_total(wstride);
   // a warp per cell: with few sequences (a CTA owns its SM) 16 warps per CTA halve the rounds per diagonal
-  const bool wide = gen_wide(b.B);
-  auto kern = two ? (wide ? bf_k_mfe<true, 16> : bf_k_mfe<true, BF_WARPS>) : (wide ? bf_k_mfe<false, 16> : bf_k_mfe<false, BF_WARPS>);
-  if (sm > 48 * 1024) { e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; }
-  kern<<<grid, (wide ? 16 : BF_WARPS) * 32, sm, st>>>(dP, b, ws, bf_mfe_slot_ints(wstride), wstride, work_counter, out_mfe, out_ss, ss_stride, mfe_tables_off(wstride));
+  const bool wide = gen_wide(b.B), pre = gen_pre(wstride, wide);
+  const size_t sm = mfe_smem_total(wstride, pre);
+  auto kern = mfe_kernel(two, wide, pre);
+  if (sm > kOptIn) { e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; }
+  kern<<<grid, (wide ? 16 : BF_WARPS) * 32, sm, st>>>(dP, b, ws, bf_mfe_slot_ints(wstride), wstride, work_counter, out_mfe, out_ss, ss_stride, mfe_tables_off(wstride, pre));
   return cudaGetLastError();
 }
 
@@ -883,11 +1257,11 @@ cudaError_t bf_launch_pf(const BfParams *dP, const BfBatchDev &b, bool two, doub
                          const int *mfe_for_scale, double *out5, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
-  size_t sm = pf_smem_total(wstride);
-  const bool wide = gen_wide(b.B);
-  auto kern = two ? (wide ? bf_k_pf<true, 16> : bf_k_pf<true, BF_WARPS>) : (wide ? bf_k_pf<false, 16> : bf_k_pf<false, BF_WARPS>);
-  if (sm > 48 * 1024) { e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; }
-  kern<<<grid, (wide ? 16 : BF_WARPS) * 32, sm, st>>>(dP, b, ws, bf_pf_slot_doubles(wstride), wstride, work_counter, mfe_for_scale, out5, pf_tables_off(wstride));
+  const bool wide = gen_wide(b.B), pre = gen_pre(wstride, wide);
+  const size_t sm = pf_smem_total(wstride, pre);
+  auto kern = pf_kernel(two, wide, pre);
+  if (sm > kOptIn) { e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; }
+  kern<<<grid, (wide ? 16 : BF_WARPS) * 32, sm, st>>>(dP, b, ws, bf_pf_slot_doubles(wstride), wstride, work_counter, mfe_for_scale, out5, pf_tables_off(wstride, pre));
   return cudaGetLastError();
 }
 
@@ -895,22 +1269,24 @@ cudaError_t bf_launch_eval(const BfParams *dP, const BfBatchDev &b, const char *
                            cudaStream_t st) {
   if (b.B * n_targets == 0) return cudaSuccess;
   size_t sm = eval_smem(b.stride);
-  if (sm > 48 * 1024) { cudaError_t e = cudaFuncSetAttribute(bf_k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; }
+  if (sm > kOptIn) { cudaError_t e = cudaFuncSetAttribute(bf_k_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; }
   bf_k_eval<<<b.B * n_targets, 128, sm, st>>>(dP, b, targets, n_targets, tstride, out_e);
   return cudaGetLastError();
 }
 
-int bf_occupancy_mfe(bool two, int wstride) {
+int bf_occupancy_mfe(bool two, int wstride) {   // of the 8-warp kernels: what sizes the grid of a large batch
   int nb = 0;
-  auto kern = two ? bf_k_mfe<true, BF_WARPS> : bf_k_mfe<false, BF_WARPS>;
-  if (mfe_smem_total(wstride) > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mfe_smem_total(wstride));
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, BF_THREADS, mfe_smem_total(wstride)) != cudaSuccess) return 1;
+  auto kern = mfe_kernel(two, false, false);
+  const size_t sm = mfe_smem_total(wstride, false);
+  if (sm > kOptIn) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, BF_THREADS, sm) != cudaSuccess) return 1;
   return nb < 1 ? 1 : nb;
 }
 int bf_occupancy_pf(bool two, int wstride) {
   int nb = 0;
-  auto kern = two ? bf_k_pf<true, BF_WARPS> : bf_k_pf<false, BF_WARPS>;
-  if (pf_smem_total(wstride) > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pf_smem_total(wstride));
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, BF_THREADS, pf_smem_total(wstride)) != cudaSuccess) return 1;
+  auto kern = pf_kernel(two, false, false);
+  const size_t sm = pf_smem_total(wstride, false);
+  if (sm > kOptIn) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, BF_THREADS, sm) != cudaSuccess) return 1;
   return nb < 1 ? 1 : nb;
 }

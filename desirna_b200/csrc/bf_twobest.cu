@@ -195,7 +195,7 @@ cudaError_t bf_launch_twobest(const BfParams *dP, const BfBatchDev &b, int2 *ws,
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
   const size_t sm = twobest_smem(wstride);
-  if (sm > 48 * 1024) { e = cudaFuncSetAttribute(bf_k_mfe2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; }
+  if (sm > 32 * 1024) { e = cudaFuncSetAttribute(bf_k_mfe2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); if (e != cudaSuccess) return e; }
   bf_k_mfe2<<<grid, kNW2 * 32, sm, st>>>(dP, b, ws, bf_twobest_slot(wstride), wstride, work_counter, out_e1, out_e2, only);
   return cudaGetLastError();
 }
