@@ -384,6 +384,32 @@ def run_ours(args):
                                "defect_in_0_1": bool(((d4 >= -1e-9) & (d4 <= 1.0 + 1e-9)).all().item())}
         del b4, d4
 
+    # ---- cofold sweep: the same generator, L/2 + L/2 strands -- fc.mfe_dimer() / fc.pf_dimer() on the two-strand kernels
+    cofold = None
+    if not args.no_sweep:
+        cofold = {}
+        for l in (36, 100):
+            _cc, bc = make(l, B)
+            cut = torch.full((B,), l // 2 + 1, dtype=torch.int32, device=dev)
+            def stepC():
+                eng.score_batch_device(bc["seq"], bc["lens"], WANT, cut=cut, targets=bc["targets"], mfe=bc["mfe"], ss=bc["ss"], pf=bc["pf"], ev=bc["ev"], stream=stream)
+            for _ in range(2):
+                stepC()
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(3):
+                stepC()
+            c1.record(); c1.synchronize()
+            tC = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tC, op=dist.ReduceOp.MAX)
+            pfc = bc["pf"]
+            cofold[f"{l // 2}&{l - l // 2}"] = {"value": world * B * 3 / (float(tC.item()) * 1e-3), "unit": "folds/s", "ms_per_step": float(tC.item()) / 3,
+                                                 "kernel_ms": eng.last_kernel_ms(),
+                                                 "fab_le_fa_plus_fb": bool((pfc[:, 3] <= pfc[:, 0] + pfc[:, 1] + 1e-9).all().item())}
+            del bc
+
     # ---- the path's caller: Monte-Carlo sub-steps of the device-resident replica-exchange design loop (N=1 only)
     design_blk = bench_design_loop() if world == 1 else None
 
@@ -485,7 +511,7 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": "folds/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "timer": "host clock around the synchronous C-ABI call"},
         "gpu_launches": int(launches),
         "roofline": roof, "cpu_baseline": cpu, "by_length": by, "kernel_ms_by_length": kern, "with_ensemble_defect": with_defect,
-        "design_loop": design_blk,
+        "cofold": cofold, "design_loop": design_blk,
         "checks": {"ed_equals_mfe_and_epf_le_mfe": checks, "e2e_matches_device_path": e2e_ok},
         "clocks": clocks,
     }

@@ -1308,12 +1308,14 @@ int bf_fill_pf_mode(int nmax) {
   if (nmax < 1 || nmax > 2000) return 0;
   return pf_cfg(nmax).pl + 1;
 }
-// third-generation kernels (bf_fill3.cu) take every batch they cover, except the small batches of the 16-warp variants
+// third-generation kernels (bf_fill3.cu) take every batch they cover; small batches (want_wide) get their 16-warp variants, and the
+// 16-warp round-1 kernels of this file only what those do not cover (BF_FILL3_SMALL=0: as before round 2's last session)
 // cluster-per-sequence kernels (bf_cluster.cu): small batches of long sequences (rule in bf_cluster.cu; BF_CL=0/1 overrides)
 static bool use_cl_mfe(int nmax, int B) { return B > 0 && bf_cl_mfe_use(nmax, B); }
-static bool use_fill3_mfe(int nmax, int B) { return !use_cl_mfe(nmax, B) && !want_wide(B) && bf_fill3_mfe_ok(nmax); }
+static bool small3(int B) { return want_wide(B) && env_int("BF_FILL3_SMALL", 1) != 0; }
+static bool use_fill3_mfe(int nmax, int B) { return !use_cl_mfe(nmax, B) && (!want_wide(B) || small3(B)) && bf_fill3_mfe_ok(nmax, small3(B)); }
 static bool use_cl_pf(int nmax, int B) { return B > 0 && bf_cl_pf_use(nmax, B); }
-static bool use_fill3_pf(int nmax, int B) { return !use_cl_pf(nmax, B) && !want_wide(B) && bf_fill3_pf_ok(nmax); }
+static bool use_fill3_pf(int nmax, int B) { return !use_cl_pf(nmax, B) && (!want_wide(B) || small3(B)) && bf_fill3_pf_ok(nmax, small3(B)); }
 
 size_t bf_mfe_ws_slot(int nmax, int B) {  // ints of per-CTA HBM workspace: [rings when they are not on chip][tile-major fML mirror when blocked]
   if (use_cl_mfe(nmax, B)) return bf_cl_mfe_ws_slot(nmax, B);
@@ -1418,7 +1420,7 @@ static cudaError_t mfe_fill_dispatch(const BfParams *dP, const BfBatchDev &b, in
 }
 cudaError_t bf_mfe_fill_grid(const BfBatchDev &b, int sms, int *grid) {
   if (use_cl_mfe(b.stride, b.B)) return bf_cl_mfe_grid(b, sms, grid);
-  if (use_fill3_mfe(b.stride, b.B)) return bf_fill3_mfe_grid(b, sms, grid);
+  if (use_fill3_mfe(b.stride, b.B)) return bf_fill3_mfe_grid(b, sms, grid, small3(b.B));
   return mfe_fill_dispatch(nullptr, b, nullptr, nullptr, nullptr, sms, grid, false, nullptr, nullptr);
 }
 // true: the fill kernel chosen for this batch also runs the exterior recursion and leaves f5 (B x (stride + 4) ints) for bf_k_trace
@@ -1427,7 +1429,7 @@ bool bf_mfe_fill_does_ext(int nmax, int B) { return !use_cl_mfe(nmax, B) && !use
 cudaError_t bf_launch_mfe_fill(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *work_counter,
                                cudaStream_t st, int *f5_out) {
   if (use_cl_mfe(b.stride, b.B)) return bf_launch_mfe_cl(dP, b, ctri, ftri, ws, sms, work_counter, st);
-  if (use_fill3_mfe(b.stride, b.B)) return bf_launch_mfe_fill3(dP, b, ctri, ftri, ws, sms, work_counter, st);
+  if (use_fill3_mfe(b.stride, b.B)) return bf_launch_mfe_fill3(dP, b, ctri, ftri, ws, sms, work_counter, st, small3(b.B));
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
   g_f5_out = f5_out;
@@ -1510,7 +1512,7 @@ static cudaError_t pf_fill_dispatch(const BfParams *dP, const BfBatchDev &b, dou
 // grid size the fill will use (the caller sizes the per-CTA workspace with it)
 cudaError_t bf_pf_fill_grid(const BfBatchDev &b, int sms, int *grid) {
   if (use_cl_pf(b.stride, b.B)) return bf_cl_pf_grid(b, sms, grid);
-  if (use_fill3_pf(b.stride, b.B)) return bf_fill3_pf_grid(b, sms, grid);
+  if (use_fill3_pf(b.stride, b.B)) return bf_fill3_pf_grid(b, sms, grid, small3(b.B));
   return pf_fill_dispatch(nullptr, b, nullptr, nullptr, nullptr, nullptr, nullptr, sms, grid, false, nullptr, nullptr);
 }
 
@@ -1520,7 +1522,7 @@ bool bf_pf_fill_does_ext(int nmax, int B) { return !use_cl_pf(nmax, B) && !use_f
 cudaError_t bf_launch_pf_fill(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *qmws, double *qmseq, const int *mfe_for_scale,
                               double *lnscale, int sms, int *work_counter, cudaStream_t st, double *out5) {
   if (use_cl_pf(b.stride, b.B)) return bf_launch_pf_cl(dP, b, qbtri, qmws, qmseq, mfe_for_scale, lnscale, sms, work_counter, st);
-  if (use_fill3_pf(b.stride, b.B)) return bf_launch_pf_fill3(dP, b, qbtri, qmws, qmseq, mfe_for_scale, lnscale, sms, work_counter, st);
+  if (use_fill3_pf(b.stride, b.B)) return bf_launch_pf_fill3(dP, b, qbtri, qmws, qmseq, mfe_for_scale, lnscale, sms, work_counter, st, small3(b.B));
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
   g_pf_out5 = out5;

@@ -830,13 +830,16 @@ int env_int(const char *name, int dflt) {
 }
 
 struct Mfe3Cfg { bool ok; int rs; bool fms; size_t smem; int nw, nwi; };
-Mfe3Cfg mfe3_cfg(int nmax) {
+// small: a batch that leaves SMs idle (a replica-exchange sub-step) -- one 16-warp CTA (12 tap + 4 auxiliary warps) per sequence with the
+// whole shared memory of its SM; measured against the 16-warp round-1 kernels at B = 64 (profiles/r02_small_batch_fill3.txt): 36 nt 0.089 ->
+// 0.076 ms, 100 nt 0.340 -> 0.257, 148 nt 0.678 -> 0.427, 200 nt 1.07 -> 0.66, as long as the fML table fits on chip (~230 nt)
+Mfe3Cfg mfe3_cfg(int nmax, bool small) {
   Mfe3Cfg c;
   c.ok = false;
   if (nmax < 1 || env_int("BF_FILL3", 1) == 0 || env_int("BF_FILL3_MFE", 1) == 0) return c;
   c.rs = pick_rs(nmax, 32);
-  c.nw = env_int("BF_FILL3_NW", 8);
-  c.nwi = env_int("BF_FILL3_NWI", c.nw == 8 ? 6 : c.nw / 2);
+  c.nw = env_int("BF_FILL3_NW", small ? 16 : 8);
+  c.nwi = env_int("BF_FILL3_NWI", c.nw == 8 ? 6 : c.nw * 3 / 4);
   const int NWA = c.nw - c.nwi;
   // The fML table has to be on chip: with two auxiliary warps per CTA the split cannot hide L2 latency (measured: L = 120 7.8 ms
   // per 4096 folds against 5.96 ms of the round-1 kernel, L = 200 33 against 16).  Three CTAs per SM up to ~105 nt, two up to
@@ -845,14 +848,14 @@ Mfe3Cfg mfe3_cfg(int nmax) {
   const int fm_env = env_int("BF_FILL3_FMS", -1);
   c.fms = fm_env >= 0 ? fm_env != 0 : true;
   c.smem = c.fms ? with : without;
-  const size_t cap = fm_env >= 0 ? kSmemBudget : (size_t)env_int("BF_FILL3_MFE_KB", 112) * 1024;
+  const size_t cap = (fm_env >= 0 || small) ? kSmemBudget : (size_t)env_int("BF_FILL3_MFE_KB", 112) * 1024;
   c.ok = c.smem <= cap && c.smem <= kSmemBudget && nmax <= env_int("BF_FILL3_MAXN", 2000);
   return c;
 }
 
 }  // namespace
 
-bool bf_fill3_mfe_ok(int nmax) { return mfe3_cfg(nmax).ok; }
+bool bf_fill3_mfe_ok(int nmax, bool small) { return mfe3_cfg(nmax, small).ok; }
 size_t bf_fill3_mfe_ws_slot(int nmax) { return 2 * ((tri_size(nmax) * kEntWords + 7) / 8 * 8); }   // ints per CTA: entries of every cell, two sequences
 
 template <int NW, int NWI, bool FMS>
@@ -885,8 +888,8 @@ static cudaError_t mfe3_launch(const BfParams *dP, const BfBatchDev &b, int *ctr
 }
 
 static cudaError_t mfe3_dispatch(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *work_counter,
-                                 cudaStream_t st, int *grid_out) {
-  const Mfe3Cfg c = mfe3_cfg(b.stride);
+                                 cudaStream_t st, int *grid_out, bool small) {
+  const Mfe3Cfg c = mfe3_cfg(b.stride, small);
   if (!c.ok) return cudaErrorInvalidValue;
 #define BF_GO(NW_, NWI_)                                                                                          \
   if (c.nw == NW_ && c.nwi == NWI_)                                                                                \
@@ -897,21 +900,21 @@ static cudaError_t mfe3_dispatch(const BfParams *dP, const BfBatchDev &b, int *c
   return cudaErrorInvalidValue;
 }
 
-cudaError_t bf_fill3_mfe_grid(const BfBatchDev &b, int sms, int *grid) {
-  return mfe3_dispatch(nullptr, b, nullptr, nullptr, nullptr, sms, nullptr, nullptr, grid);
+cudaError_t bf_fill3_mfe_grid(const BfBatchDev &b, int sms, int *grid, bool small) {
+  return mfe3_dispatch(nullptr, b, nullptr, nullptr, nullptr, sms, nullptr, nullptr, grid, small);
 }
 
 cudaError_t bf_launch_mfe_fill3(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *work_counter,
-                                cudaStream_t st) {
+                                cudaStream_t st, bool small) {
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
-  return mfe3_dispatch(dP, b, ctri, ftri, ws, sms, work_counter, st, nullptr);
+  return mfe3_dispatch(dP, b, ctri, ftri, ws, sms, work_counter, st, nullptr, small);
 }
 
 // ---------------------------------------------------------------------------------------------------- partition function, host side
 namespace {
 struct Pf3Cfg { bool ok; int rs; bool qms; size_t smem; int nw, nwi; };
-Pf3Cfg pf3_cfg(int nmax) {
+Pf3Cfg pf3_cfg(int nmax, bool small) {
   Pf3Cfg c;
   c.ok = false;
   if (nmax < 1 || env_int("BF_FILL3", 1) == 0 || env_int("BF_FILL3_PF", 1) == 0) return c;
@@ -922,7 +925,9 @@ Pf3Cfg pf3_cfg(int nmax) {
   const int nw_env = env_int("BF_FILL3_PF_NW", 0);
   // 16 warps with cells in pairs from 90 nt (L = 100: 4.90 ms per 4096 folds against 5.14 for two 8-warp CTAs); below, two or three
   // 8-warp CTAs per SM are ahead (L = 30 / 50 / 75: 0.60 / 1.26 / 2.79 ms against 0.88 / 1.71 / 3.13; scripts/sweep_pfnw.sh)
-  c.nw = nw_env ? nw_env : (nmax < 90 ? 8 : 116);
+  // small batches (see mfe3_cfg): 16 warps at every length (B = 64: 36 nt 0.071 -> 0.058 ms, 100 nt 0.336 -> 0.227, 148 nt 0.776 -> 0.550,
+  // 170 nt 1.00 -> 0.76; at 200 nt the round-1 kernel is ahead, 1.41 against 2.03)
+  c.nw = nw_env ? nw_env : small ? 16 : (nmax < 90 ? 8 : 116);
   const int nwr = c.nw % 100;   // (100 + warps: the paired variant)
   c.nwi = env_int("BF_FILL3_PF_NWI", nwr == 8 ? 6 : nwr == 16 ? 12 : nwr * 3 / 4);
   const int nwa = nwr - c.nwi;
@@ -932,12 +937,12 @@ Pf3Cfg pf3_cfg(int nmax) {
   if (c.qms && with > kSmemBudget) c.qms = false;
   c.smem = c.qms ? with : without;
   // measured against the round-1 kernel (profiles/r02_sweep_len.txt): ahead up to 150 nt, level beyond
-  c.ok = c.smem <= kSmemBudget && nmax <= env_int("BF_FILL3_PF_MAXN", 150);
+  c.ok = c.smem <= kSmemBudget && nmax <= (small ? env_int("BF_FILL3_PF_MAXN_SMALL", 180) : env_int("BF_FILL3_PF_MAXN", 150));
   return c;
 }
 }  // namespace
 
-bool bf_fill3_pf_ok(int nmax) { return pf3_cfg(nmax).ok; }
+bool bf_fill3_pf_ok(int nmax, bool small) { return pf3_cfg(nmax, small).ok; }
 size_t bf_fill3_pf_ws_slot(int nmax) {   // doubles per CTA: entries of every cell, qm and qm1
   const size_t tri_pad = (tri_size(nmax) + 7) / 8 * 8;
   return tri_pad * kEntD + 2 * tri_pad;
@@ -973,8 +978,8 @@ static cudaError_t pf3_launch(const BfParams *dP, const BfBatchDev &b, double *q
 }
 
 static cudaError_t pf3_dispatch(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale,
-                                double *lnscale, int sms, int *counter, cudaStream_t st, int *grid_out) {
-  const Pf3Cfg c = pf3_cfg(b.stride);
+                                double *lnscale, int sms, int *counter, cudaStream_t st, int *grid_out, bool small) {
+  const Pf3Cfg c = pf3_cfg(b.stride, small);
   if (!c.ok) return cudaErrorInvalidValue;
 #define BF_GO(NW_, NWI_)                                                                                                              \
   if (c.nw == NW_ && c.nwi == NWI_)                                                                                                    \
@@ -992,13 +997,13 @@ static cudaError_t pf3_dispatch(const BfParams *dP, const BfBatchDev &b, double 
   return cudaErrorInvalidValue;
 }
 
-cudaError_t bf_fill3_pf_grid(const BfBatchDev &b, int sms, int *grid) {
-  return pf3_dispatch(nullptr, b, nullptr, nullptr, nullptr, nullptr, nullptr, sms, nullptr, nullptr, grid);
+cudaError_t bf_fill3_pf_grid(const BfBatchDev &b, int sms, int *grid, bool small) {
+  return pf3_dispatch(nullptr, b, nullptr, nullptr, nullptr, nullptr, nullptr, sms, nullptr, nullptr, grid, small);
 }
 
 cudaError_t bf_launch_pf_fill3(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale,
-                               double *lnscale, int sms, int *work_counter, cudaStream_t st) {
+                               double *lnscale, int sms, int *work_counter, cudaStream_t st, bool small) {
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
-  return pf3_dispatch(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, work_counter, st, nullptr);
+  return pf3_dispatch(dP, b, qbtri, ws, qmseq, mfe_for_scale, lnscale, sms, work_counter, st, nullptr, small);
 }

@@ -167,25 +167,26 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
     __syncthreads();
 
     if constexpr (PRE) {
-      // sequence-only terms of the cells [32 * chunk, 32 * chunk + 32) of diagonal dd into buffer bf (lanes = cells)
+      // sequence-only terms of diagonal dd into buffer bf: ten tasks per cell (0: pair type, hairpin / nick term, closing-pair terms and
+      // the list of pairable cells; 1..9: the shapes evaluated in full), lanes = tasks [32 * chunk, 32 * chunk + 32)
       auto setup = [&](int dd, int chunk, int bf) {
         int *q = pre0 + (size_t)bf * kPreArr * NA;
-        const int i = chunk * 32 + lane + 1, j = i + dd;
+        const int g = chunk * 32 + lane, i = g / 10 + 1, task = g - (i - 1) * 10, j = i + dd;
         if (i > n - dd) return;
         const int t = bf_ptype<TWO>(X, i, j);
-        q[i] = t;
-        if (!t) return;
+        if (!t) { if (task == 0) q[i] = 0; return; }
         const int si1 = S[i + 1], sj1 = S[j - 1];
-        const bool span = TWO && i < cp && j >= cp;
-        int e0;
-        if (span) { int a, bb; bf_nick_nb(X, i, j, &a, &bb); e0 = bf_e_ext(T, bf_rtype(t), a, bb); }   // + fcA[i+1] + fcB[j-1] when the cell is computed
-        else e0 = bf_e_hairpin(P, T, S, i, j, t);
-        q[NA + i] = e0; q[2 * NA + i] = T.mmI[t][si1][sj1]; q[3 * NA + i] = T.mm1nI[t][si1][sj1];
-        q[4 * NA + i] = (!TWO || (bf_same<TWO>(X, i, i + 1) && bf_same<TWO>(X, j - 1, j))) ? T.MLclosing + bf_e_mlstem(T, bf_rtype(t), sj1, si1) : BF_INF;
-        const int pmax = (TWO && i < cp) ? cp - 1 : n, qmin = (TWO && j >= cp) ? cp : 0;
-#pragma unroll
-        for (int sh = 0; sh < 9; sh++) {
-          const int u1 = kSpecU1[sh], u2 = kSpecU2[sh], p = i + 1 + u1, qq = j - 1 - u2;
+        if (task == 0) {
+          q[i] = t;
+          int e0;
+          if (TWO && i < cp && j >= cp) { int a, bb; bf_nick_nb(X, i, j, &a, &bb); e0 = bf_e_ext(T, bf_rtype(t), a, bb); }   // + fcA[i+1] + fcB[j-1] when the cell is computed
+          else e0 = bf_e_hairpin(P, T, S, i, j, t);
+          q[NA + i] = e0; q[2 * NA + i] = T.mmI[t][si1][sj1]; q[3 * NA + i] = T.mm1nI[t][si1][sj1];
+          q[4 * NA + i] = (!TWO || (bf_same<TWO>(X, i, i + 1) && bf_same<TWO>(X, j - 1, j))) ? T.MLclosing + bf_e_mlstem(T, bf_rtype(t), sj1, si1) : BF_INF;
+          q[5 * NA + atomicAdd(&s_np2[bf], 1)] = i;
+        } else {
+          const int pmax = (TWO && i < cp) ? cp - 1 : n, qmin = (TWO && j >= cp) ? cp : 0;
+          const int sh = task - 1, u1 = kSpecU1[sh], u2 = kSpecU2[sh], p = i + 1 + u1, qq = j - 1 - u2;
           int e9 = BF_INF;
           if (qq > p && p <= pmax && qq >= qmin) {
             const int t2 = bf_ptype<TWO>(X, p, qq);
@@ -193,16 +194,15 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
           }
           q[(6 + sh) * NA + i] = e9;
         }
-        q[5 * NA + atomicAdd(&s_np2[bf], 1)] = i;
       };
-      for (int ch = warp; ch * 32 < n - d0; ch += NWG) setup(d0, ch, d0 & 1);
+      for (int ch = warp; ch * 32 < (n - d0) * 10; ch += NWG) setup(d0, ch, d0 & 1);
       __syncthreads();
       for (int d = d0; d <= n - 1; d++) {
         const int bf = d & 1;
         const int *q = pre0 + (size_t)bf * kPreArr * NA;
         const int *qT = q, *qE0 = q + NA, *qMMO = q + 2 * NA, *qMM1O = q + 3 * NA, *qMLC = q + 4 * NA, *qLIST = q + 5 * NA, *qE9 = q + 6 * NA;
         const int ncell = n - d, np = s_np2[bf];
-        const int nfc = (TWO && cp <= n) ? 2 : 0, nset = d + 1 <= n - 1 ? (n - d - 1 + 31) / 32 : 0;
+        const int nfc = (TWO && cp <= n) ? 2 : 0, nset = d + 1 <= n - 1 ? ((n - d - 1) * 10 + 31) / 32 : 0;
         const int total = nfc + nset + np + ncell;
         for (;;) {
           int it = 0;
@@ -772,25 +772,25 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
     __syncthreads();
 
     if constexpr (PRE) {
-      auto setup = [&](int dd, int chunk, int bf) {
+      auto setup = [&](int dd, int chunk, int bf) {   // ten tasks per cell, lanes = tasks (see bf_k_mfe)
         double *q = pre0 + (size_t)bf * kPreArrD * NA;
         int *qi = ibase + (size_t)bf * 2 * NA;
-        const int i = chunk * 32 + lane + 1, j = i + dd;
+        const int g = chunk * 32 + lane, i = g / 10 + 1, task = g - (i - 1) * 10, j = i + dd;
         if (i > n - dd) return;
         const int t = bf_ptype<TWO>(X, i, j);
-        qi[i] = t;
-        if (!t) return;
+        if (!t) { if (task == 0) qi[i] = 0; return; }
         const int si1 = S[i + 1], sj1 = S[j - 1];
-        const bool span = TWO && i < cp && j >= cp;
-        double b0;
-        if (span) { int a, bb; bf_nick_nb(X, i, j, &a, &bb); b0 = bf_x_ext(T, bf_rtype(t), a, bb) * scl[2]; }   // x qA[i+1] x qB[j-1] when the cell is computed
-        else b0 = bf_x_hairpin(P, T, S, i, j, t) * scl[dd + 1];
-        q[i] = b0; q[NA + i] = T.x_mmI[t][si1][sj1]; q[2 * NA + i] = T.x_mm1nI[t][si1][sj1];
-        q[3 * NA + i] = (!TWO || (bf_same<TWO>(X, i, i + 1) && bf_same<TWO>(X, j - 1, j))) ? T.x_MLclosing * bf_x_mlstem(T, bf_rtype(t), sj1, si1) * scl[2] : 0.0;
-        const int pmax = (TWO && i < cp) ? cp - 1 : n, qmin = (TWO && j >= cp) ? cp : 0;
-#pragma unroll
-        for (int sh = 0; sh < 9; sh++) {
-          const int u1 = kSpecU1[sh], u2 = kSpecU2[sh], p = i + 1 + u1, qq = j - 1 - u2;
+        if (task == 0) {
+          qi[i] = t;
+          double b0;
+          if (TWO && i < cp && j >= cp) { int a, bb; bf_nick_nb(X, i, j, &a, &bb); b0 = bf_x_ext(T, bf_rtype(t), a, bb) * scl[2]; }   // x qA[i+1] x qB[j-1] when the cell is computed
+          else b0 = bf_x_hairpin(P, T, S, i, j, t) * scl[dd + 1];
+          q[i] = b0; q[NA + i] = T.x_mmI[t][si1][sj1]; q[2 * NA + i] = T.x_mm1nI[t][si1][sj1];
+          q[3 * NA + i] = (!TWO || (bf_same<TWO>(X, i, i + 1) && bf_same<TWO>(X, j - 1, j))) ? T.x_MLclosing * bf_x_mlstem(T, bf_rtype(t), sj1, si1) * scl[2] : 0.0;
+          qi[NA + atomicAdd(&s_np2[bf], 1)] = i;
+        } else {
+          const int pmax = (TWO && i < cp) ? cp - 1 : n, qmin = (TWO && j >= cp) ? cp : 0;
+          const int sh = task - 1, u1 = kSpecU1[sh], u2 = kSpecU2[sh], p = i + 1 + u1, qq = j - 1 - u2;
           double x9 = 0.0;
           if (qq > p && p <= pmax && qq >= qmin) {
             const int t2 = bf_ptype<TWO>(X, p, qq);
@@ -798,9 +798,8 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
           }
           q[(4 + sh) * NA + i] = x9;
         }
-        qi[NA + atomicAdd(&s_np2[bf], 1)] = i;
       };
-      for (int ch = warp; ch * 32 < n - d0; ch += NWG) setup(d0, ch, d0 & 1);
+      for (int ch = warp; ch * 32 < (n - d0) * 10; ch += NWG) setup(d0, ch, d0 & 1);
       __syncthreads();
       for (int d = d0; d <= n - 1; d++) {
         const int bf = d & 1;
@@ -808,7 +807,7 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
         const double *qB0 = q, *qXMMO = q + NA, *qXMM1O = q + 2 * NA, *qXMLC = q + 3 * NA, *qXE9 = q + 4 * NA;
         const int *qT = ibase + (size_t)bf * 2 * NA, *qLIST = qT + NA;
         const int ncell = n - d, np = s_np2[bf];
-        const int nfc = (TWO && cp <= n) ? 2 : 0, nset = d + 1 <= n - 1 ? (n - d - 1 + 31) / 32 : 0;
+        const int nfc = (TWO && cp <= n) ? 2 : 0, nset = d + 1 <= n - 1 ? ((n - d - 1) * 10 + 31) / 32 : 0;
         const int total = nfc + nset + np + ncell;
         for (;;) {
           int it = 0;

@@ -45,17 +45,18 @@ cudaError_t bf_launch_pf_ext(const BfParams *dP, const BfBatchDev &b, const doub
                              cudaStream_t st);
 
 // ---- third-generation fill kernels (bf_fill3.cu): flat tap tables, rings always on chip
-bool bf_fill3_mfe_ok(int nmax);
+// small: the batch leaves SMs idle -- 16-warp CTAs with the whole shared memory of their SM (the caller decides, see bf_fill.cu)
+bool bf_fill3_mfe_ok(int nmax, bool small);
 size_t bf_fill3_mfe_ws_slot(int nmax);   // ints of per-CTA HBM workspace (per-cell constants of one sequence)
-cudaError_t bf_fill3_mfe_grid(const BfBatchDev &b, int sms, int *grid);
+cudaError_t bf_fill3_mfe_grid(const BfBatchDev &b, int sms, int *grid, bool small);
 cudaError_t bf_launch_mfe_fill3(const BfParams *dP, const BfBatchDev &b, int *ctri, int *ftri, int *ws, int sms, int *work_counter,
-                                cudaStream_t st);
+                                cudaStream_t st, bool small);
 
-bool bf_fill3_pf_ok(int nmax);
+bool bf_fill3_pf_ok(int nmax, bool small);
 size_t bf_fill3_pf_ws_slot(int nmax);    // doubles of per-CTA HBM workspace
-cudaError_t bf_fill3_pf_grid(const BfBatchDev &b, int sms, int *grid);
+cudaError_t bf_fill3_pf_grid(const BfBatchDev &b, int sms, int *grid, bool small);
 cudaError_t bf_launch_pf_fill3(const BfParams *dP, const BfBatchDev &b, double *qbtri, double *ws, double *qmseq, const int *mfe_for_scale,
-                               double *lnscale, int sms, int *work_counter, cudaStream_t st);
+                               double *lnscale, int sms, int *work_counter, cudaStream_t st, bool small);
 
 // ---- cluster-per-sequence fill kernels (bf_cluster.cu): tables partitioned over the shared memories of a thread-block cluster
 bool bf_cl_mfe_use(int nmax, int B);           // does the cluster kernel take this batch (default rule, BF_CL=0/1 override)

@@ -251,3 +251,36 @@ def test_fill3_outside_pass_uses_its_tables(engine, oracle, monkeypatch):
         pf, bpp = oracle.pf(seqs[k], bpp=True)
         assert np.abs(out["bpp"][k][:70, :70] - bpp).max() < 1e-9
         assert abs(out["defect"][k] - oracle.ensemble_defect(bpp, ss[k])) < 1e-9
+
+
+@pytest.mark.parametrize("L", [36, 100, 148, 200])
+def test_small_batch_fill3_variants(engine, oracle, monkeypatch, L):
+    """batches that leave SMs idle take the 16-warp third-generation kernels (one CTA per sequence with the whole shared memory of its
+    SM; MFE while the fML table fits on chip, partition function up to 180 nt); BF_FILL3_SMALL=0 puts the 16-warp round-1 kernels
+    back.  Same integers, ensemble energies to 1e-12, and the oracle on every fifth sequence; ragged lengths in one batch."""
+    seqs = rand_seqs(4242 + L, 40, L) + rand_seqs(4243 + L, 8, max(5, L // 3))
+    want = engine.WANT_MFE | engine.WANT_SS | engine.WANT_PF
+    monkeypatch.setenv("BF_CL", "0")
+    monkeypatch.setenv("BF_FILL3_SMALL", "1")
+    new = engine.score_batch(seqs, want=want)
+    monkeypatch.setenv("BF_FILL3_SMALL", "0")
+    old = engine.score_batch(seqs, want=want)
+    assert (new["mfe_dcal"] == old["mfe_dcal"]).all() and new["mfe_ss"] == old["mfe_ss"]
+    assert np.allclose(new["pf"][:, 4], old["pf"][:, 4], rtol=1e-12, atol=0)
+    for k in range(0, len(seqs), 5):
+        e, ss = oracle.mfe(seqs[k])
+        assert new["mfe_dcal"][k] == e and new["mfe_ss"][k] == ss, (L, k)
+        assert close(new["pf"][k, 4], oracle.pf(seqs[k])[4]), (L, k)
+
+
+@pytest.mark.parametrize("L", [70, 120])
+def test_small_batch_outside_pass_on_fill3_tables(engine, oracle, L):
+    """base-pair probabilities and ensemble defect of a small batch: the outside pass reads the qb / qm / qm1 tables the 16-warp
+    third-generation inside kernel leaves per sequence"""
+    seqs = rand_seqs(5151 + L, 12, L)
+    mfe, ss, epf, ed = oracle.fold_batch(seqs, nthreads=8)
+    out = engine.score_batch(seqs, [[s] for s in ss], want=engine.WANT_BPP | engine.WANT_DEFECT)
+    for k in range(0, 12, 3):
+        pf, bpp = oracle.pf(seqs[k], bpp=True)
+        assert np.abs(out["bpp"][k][:L, :L] - bpp).max() < 1e-9
+        assert abs(out["defect"][k] - oracle.ensemble_defect(bpp, ss[k])) < 1e-9
