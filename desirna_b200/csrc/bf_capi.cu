@@ -74,6 +74,11 @@ struct Engine {
   bool force_generic = false;                     // BF_FORCE_GENERIC=1: route single strands through the generic kernels too
   // staging for the host-buffer entry point
   DevBuf d_seq, d_len, d_cut, d_nopair, d_targets, d_mfe, d_ss, d_pf, d_eval, d_defect, d_bpp;
+  // small batches (a replica-exchange sub-step scored through the host-buffer call): inputs packed into one pinned block and one H2D
+  // copy, results into one device block and one D2H copy
+  DevBuf d_in, d_out, d_zero;
+  void *h_in = nullptr, *h_out = nullptr;
+  size_t h_in_cap = 0, h_out_cap = 0, zero_cap = 0;
   int64_t launches = 0;
   int last_stride = 0;
   std::string err;
@@ -249,6 +254,36 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
   return BF_OK;
 }
 
+// A small batch asked for both the MFE and the ensemble energy: the partition function does not wait for the MFE (which would set
+// its per-nucleotide scale) but runs beside it with ViennaRNA's default scale estimate (a zero in scale_override selects it; the
+// result depends on the scale through rounding only).  Both grids are one CTA per sequence, so they overlap while 2 B <= SM count;
+// up to 400 nt the default scale keeps every scaled quantity far inside the double range (|E| <= 0.9 kcal/mol/nt: < 1e201).
+int overlap_scale(const bf_batch_t *b, const int **ov) {
+  *ov = nullptr;
+  const char *v = getenv("BF_SCORE_OVERLAP");
+  if (v && v[0] == '0') return BF_OK;
+  if (!(b->want & (BF_WANT_MFE | BF_WANT_SS)) || !(b->want & BF_WANT_PF) || (b->want & (BF_WANT_BPP | BF_WANT_DEFECT)) || b->nopair) return BF_OK;
+  if (2 * b->B > g.sm_count || b->stride > 400) return BF_OK;
+  if (g.zero_cap < (size_t)b->B) {
+    const size_t n = std::max<size_t>(256, (size_t)b->B);
+    CU(g.d_zero.reserve(n * sizeof(int)), "cudaMalloc(zero scale)");
+    CU(cudaMemset(g.d_zero.p, 0, n * sizeof(int)), "clear zero scale");
+    g.zero_cap = n;
+  }
+  *ov = (const int *)g.d_zero.p;
+  return BF_OK;
+}
+
+cudaError_t reserve_pinned(void **p, size_t *cap, size_t n) {
+  if (n <= *cap) return cudaSuccess;
+  if (*p) cudaFreeHost(*p);
+  *p = nullptr; *cap = 0;
+  const size_t want = std::max<size_t>(n, 64 << 10);
+  cudaError_t e = cudaMallocHost(p, want);
+  if (e == cudaSuccess) *cap = want;
+  return e;
+}
+
 bool any_cut(const bf_batch_t *b, const int32_t *host_cut) {
   if (!host_cut) return false;
   for (int i = 0; i < b->B; i++) if (host_cut[i] > 0) return true;
@@ -287,7 +322,10 @@ int bf_init(int device) {
 int bf_shutdown(void) {
   if (!g.inited) return BF_OK;
   cudaStreamSynchronize(g.stream);
-  for (DevBuf *b : {&g.d_defect, &g.d_bpp, &g.d_seq, &g.d_len, &g.d_cut, &g.d_nopair, &g.d_targets, &g.d_mfe, &g.d_ss, &g.d_pf, &g.d_eval}) b->release();
+  for (DevBuf *b : {&g.d_defect, &g.d_bpp, &g.d_seq, &g.d_len, &g.d_cut, &g.d_nopair, &g.d_targets, &g.d_mfe, &g.d_ss, &g.d_pf, &g.d_eval, &g.d_in, &g.d_out, &g.d_zero}) b->release();
+  if (g.h_in) cudaFreeHost(g.h_in);
+  if (g.h_out) cudaFreeHost(g.h_out);
+  g.h_in = g.h_out = nullptr; g.h_in_cap = g.h_out_cap = g.zero_cap = 0;
   g.w.destroy();
   if (g.dP) cudaFree(g.dP);
   cudaStreamDestroy(g.stream);
@@ -359,7 +397,10 @@ int bf_score_batch_device(const bf_batch_t *b, bf_result_t *r, void *cuda_stream
   int rc = validate(b, r);
   if (rc) return rc;
   // the cut array lives on the device: the two-strand kernels handle cut == 0 rows as single strands
-  return run_device(g.w, b, r, b->cut != nullptr, (cudaStream_t)cuda_stream);
+  const int *ov = nullptr;
+  rc = overlap_scale(b, &ov);
+  if (rc) return rc;
+  return run_device(g.w, b, r, b->cut != nullptr, (cudaStream_t)cuda_stream, ov);
 }
 
 int bf_score_batch(const bf_batch_t *b, bf_result_t *r) {
@@ -378,6 +419,52 @@ int bf_score_batch(const bf_batch_t *b, bf_result_t *r) {
   bf_batch_t db = *b;
   bf_result_t dr;
   std::memset(&dr, 0, sizeof dr);
+  const int *ov = nullptr;
+  rc = overlap_scale(b, &ov);
+  if (rc) return rc;
+  const size_t T = (b->want & (BF_WANT_EVAL | BF_WANT_DEFECT)) ? (size_t)b->n_targets : 0;
+  auto up = [](size_t x) { return (x + 15) / 16 * 16; };
+  // ---- small batches: one pinned block in, one out
+  const size_t o_len = up(B * S), o_cut = o_len + up(B * sizeof(int)), o_np = o_cut + (two ? up(B * sizeof(int)) : 0),
+               o_tg = o_np + (b->nopair ? up(B * S) : 0), in_bytes = o_tg + up(B * T * S);
+  const size_t p_ss = up(B * sizeof(int)), p_pf = p_ss + up(B * (S + 1)), p_ev = p_pf + up(B * 5 * sizeof(double)),
+               p_df = p_ev + up(B * std::max<size_t>(T, 1) * sizeof(int)), out_bytes = p_df + up(B * sizeof(double));
+  const char *stage_env = getenv("BF_STAGE");
+  if (in_bytes <= ((size_t)256 << 10) && out_bytes <= ((size_t)256 << 10) && !(stage_env && stage_env[0] == '0')) {
+    CU(reserve_pinned(&g.h_in, &g.h_in_cap, in_bytes), "cudaMallocHost(inputs)");
+    CU(reserve_pinned(&g.h_out, &g.h_out_cap, out_bytes), "cudaMallocHost(results)");
+    CU(g.d_in.reserve(in_bytes), "cudaMalloc(inputs)");
+    CU(g.d_out.reserve(out_bytes), "cudaMalloc(results)");
+    char *hi = (char *)g.h_in, *di = (char *)g.d_in.p, *dou = (char *)g.d_out.p;
+    std::memcpy(hi, b->seq, B * S);
+    std::memcpy(hi + o_len, b->len, B * sizeof(int));
+    if (two) std::memcpy(hi + o_cut, b->cut, B * sizeof(int));
+    if (b->nopair) std::memcpy(hi + o_np, b->nopair, B * S);
+    if (T) std::memcpy(hi + o_tg, b->targets, B * T * S);
+    CU(cudaMemcpyAsync(di, hi, in_bytes, cudaMemcpyHostToDevice, st), "H2D inputs");
+    db.seq = di; db.len = (const int32_t *)(di + o_len);
+    db.cut = two ? (const int32_t *)(di + o_cut) : nullptr;
+    db.nopair = b->nopair ? (const uint8_t *)(di + o_np) : nullptr;
+    db.targets = T ? di + o_tg : nullptr;
+    if (b->want & (BF_WANT_MFE | BF_WANT_SS)) dr.mfe_dcal = (int32_t *)dou;
+    if (b->want & BF_WANT_SS) dr.mfe_ss = dou + p_ss;
+    if (b->want & (BF_WANT_PF | BF_WANT_BPP | BF_WANT_DEFECT)) dr.pf = (double *)(dou + p_pf);
+    if (b->want & BF_WANT_EVAL) dr.eval_dcal = (int32_t *)(dou + p_ev);
+    if (b->want & BF_WANT_DEFECT) dr.defect = (double *)(dou + p_df);
+    if (b->want & BF_WANT_BPP) { CU(g.d_bpp.reserve(B * S * S * sizeof(double)), "cudaMalloc(bpp)"); dr.bpp = (double *)g.d_bpp.p; }
+    rc = run_device(g.w, &db, &dr, two, st, ov);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(g.h_out, dou, out_bytes, cudaMemcpyDeviceToHost, st), "D2H results");
+    if (b->want & BF_WANT_BPP) CU(cudaMemcpyAsync(r->bpp, dr.bpp, B * S * S * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H bpp");
+    CU(cudaStreamSynchronize(st), "bf_score_batch");
+    const char *ho = (const char *)g.h_out;
+    if ((b->want & BF_WANT_MFE) && r->mfe_dcal) std::memcpy(r->mfe_dcal, ho, B * sizeof(int));
+    if (b->want & BF_WANT_SS) std::memcpy(r->mfe_ss, ho + p_ss, B * (S + 1));
+    if ((b->want & (BF_WANT_PF | BF_WANT_BPP | BF_WANT_DEFECT)) && r->pf) std::memcpy(r->pf, ho + p_pf, B * 5 * sizeof(double));
+    if (b->want & BF_WANT_EVAL) std::memcpy(r->eval_dcal, ho + p_ev, B * T * sizeof(int));
+    if (b->want & BF_WANT_DEFECT) std::memcpy(r->defect, ho + p_df, B * sizeof(double));
+    return BF_OK;
+  }
   CU(g.d_seq.reserve(B * S), "cudaMalloc(seq)");
   CU(g.d_len.reserve(B * sizeof(int)), "cudaMalloc(len)");
   CU(cudaMemcpyAsync(g.d_seq.p, b->seq, B * S, cudaMemcpyHostToDevice, st), "H2D seq");
@@ -406,7 +493,7 @@ int bf_score_batch(const bf_batch_t *b, bf_result_t *r) {
   if (b->want & (BF_WANT_MFE | BF_WANT_SS)) { CU(g.d_mfe.reserve(B * sizeof(int)), "cudaMalloc(mfe)"); dr.mfe_dcal = (int32_t *)g.d_mfe.p; }
   if (b->want & BF_WANT_SS) { CU(g.d_ss.reserve(B * (S + 1)), "cudaMalloc(ss)"); dr.mfe_ss = (char *)g.d_ss.p; }
   if (b->want & (BF_WANT_PF | BF_WANT_BPP | BF_WANT_DEFECT)) { CU(g.d_pf.reserve(B * 5 * sizeof(double)), "cudaMalloc(pf)"); dr.pf = (double *)g.d_pf.p; }
-  rc = run_device(g.w, &db, &dr, two, st);
+  rc = run_device(g.w, &db, &dr, two, st, ov);
   if (rc) return rc;
   if ((b->want & BF_WANT_MFE) && r->mfe_dcal) CU(cudaMemcpyAsync(r->mfe_dcal, dr.mfe_dcal, B * sizeof(int), cudaMemcpyDeviceToHost, st), "D2H mfe");
   if (b->want & BF_WANT_SS) CU(cudaMemcpyAsync(r->mfe_ss, dr.mfe_ss, B * (S + 1), cudaMemcpyDeviceToHost, st), "D2H ss");
