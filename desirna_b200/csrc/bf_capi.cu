@@ -185,6 +185,7 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
     w.ran[0] = timing;
     mfe_for_scale = out_mfe;
   }
+  bool eval_done = false;
   const bool want_out = (b->want & (BF_WANT_BPP | BF_WANT_DEFECT)) != 0;
   if (want_out && (two || !fill_pf))
     return fail(BF_ERR_UNAVAILABLE, "base-pair probabilities / ensemble defect: single-strand sequences within the fill path's length range only");
@@ -241,10 +242,18 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
       g.launches++;
     }
     if (timing) cudaEventRecord(w.ev[3], sp);
+    if (beside && (b->want & BF_WANT_EVAL)) {   // eval_structure reads the sequence and the targets only: behind the shorter chain
+      if (timing) cudaEventRecord(w.ev[4], sp);
+      CU(bf_launch_eval(g.dP, db, b->targets, b->n_targets, b->stride, r->eval_dcal, sp), "launch bf_k_eval");
+      if (timing) cudaEventRecord(w.ev[5], sp);
+      w.ran[2] = true;
+      g.launches++;
+      eval_done = true;
+    }
     if (beside) { CU(cudaEventRecord(w.ev_join, sp), "join"); CU(cudaStreamWaitEvent(st, w.ev_join, 0), "join"); }
     w.ran[1] = timing;
   }
-  if (b->want & BF_WANT_EVAL) {
+  if ((b->want & BF_WANT_EVAL) && !eval_done) {
     if (timing) cudaEventRecord(w.ev[4], st);
     CU(bf_launch_eval(g.dP, db, b->targets, b->n_targets, b->stride, r->eval_dcal, st), "launch bf_k_eval");
     if (timing) cudaEventRecord(w.ev[5], st);

@@ -595,8 +595,24 @@ __global__ void __launch_bounds__(WPB * 32) bf_k_trace(const BfParams *__restric
       __syncwarp();
       i = fu; to_pair = true;
     } else if (sec.kind == 1) {
-      while (j > i && M_(i, j) == M_(i, j - 1) + T.MLbase) j--;
-      while (i < j && M_(i, j) == M_(i + 1, j) + T.MLbase) i++;
+      // unpaired ends of the multiloop part: `while (M(i,j) == M(i,j-1) + MLbase) j--`, then the same from the left -- 32 positions
+      // per table round trip instead of one (the run of positions that satisfy the test, counted from the current end)
+      for (;;) {
+        const int jj = j - lane;
+        const bool ok = jj > i && M_(i, jj) == M_(i, jj - 1) + T.MLbase;
+        const unsigned mk = __ballot_sync(BF_FULL, ok);
+        if (mk == BF_FULL) { j -= 32; continue; }
+        j -= __ffs(~mk) - 1;
+        break;
+      }
+      for (;;) {
+        const int ii = i + lane;
+        const bool ok = ii < j && M_(ii, j) == M_(ii + 1, j) + T.MLbase;
+        const unsigned mk = __ballot_sync(BF_FULL, ok);
+        if (mk == BF_FULL) { i += 32; continue; }
+        i += __ffs(~mk) - 1;
+        break;
+      }
       const int mij = M_(i, j);
       const int t = ptype_sp(SP, i, j);
       const int cij = C_(i, j);
@@ -633,19 +649,39 @@ __global__ void __launch_bounds__(WPB * 32) bf_k_trace(const BfParams *__restric
       if (cij == bf_e_hairpin(P, T, S, i, j, t)) break;
       int fp = 0, fq = 0;
       const int pmax = min(j - 2, i + BF_MAXLOOP + 1);
-      for (int p = i + 1; p <= pmax && !fp; p++) {
-        const int minq = max(p + 1, j - i + p - BF_MAXLOOP - 2);
-        const int q = j - 1 - lane;
+      // inner pairs in the order p ascending, q descending (lanes = q).  The first row alone (a stacked pair or a bulge on the 3' side:
+      // most steps end here), the others four rows per round so that their table reads are in flight together -- a pair that closes a
+      // multiloop walks all 31 rows before the split is tried
+      {
+        const int p = i + 1, q = j - 1 - lane;
         bool ok = false;
-        if (q >= minq) {
+        if (p <= pmax && q >= max(p + 1, j - i + p - BF_MAXLOOP - 2)) {
           const int t2 = ptype_sp(SP, p, q);
           if (t2) {
             const int cc = C_(p, q);
-            ok = cc < BF_INF && cij == cc + bf_e_intloop(P, T, p - i - 1, j - q - 1, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]);
+            ok = cc < BF_INF && cij == cc + bf_e_intloop(P, T, 0, j - q - 1, t, bf_rtype(t2), si1, sj1, S[p - 1], S[q + 1]);
           }
         }
         const unsigned mk = __ballot_sync(BF_FULL, ok);
         if (mk) { fp = p; fq = j - 1 - (__ffs(mk) - 1); }
+      }
+      for (int p0 = i + 2; p0 <= pmax && !fp; p0 += 4) {
+        const int q = j - 1 - lane;
+        int cc[4], t2[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const int p = p0 + r;
+          const bool in = p <= pmax && q >= max(p + 1, j - i + p - BF_MAXLOOP - 2);
+          t2[r] = in ? ptype_sp(SP, p, q) : 0;
+          cc[r] = t2[r] ? C_(p, q) : BF_INF;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const int p = p0 + r;
+          const bool ok = cc[r] < BF_INF && cij == cc[r] + bf_e_intloop(P, T, p - i - 1, j - q - 1, t, bf_rtype(t2[r]), si1, sj1, S[p - 1], S[q + 1]);
+          const unsigned mk = __ballot_sync(BF_FULL, ok);
+          if (mk && !fp) { fp = p; fq = j - 1 - (__ffs(mk) - 1); }
+        }
       }
       if (fp) { i = fp; j = fq; continue; }
       int fu = 0;

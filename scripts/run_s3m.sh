@@ -1,0 +1,4 @@
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q -k "parity" > gpurun_out/s3m_pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/s3m_pytest_gpu.log
+(python scripts/design_substep.py; python scripts/lat2.py) 2>&1 | tee gpurun_out/s3m_small.log
+python bench.py --steps 5 --warmup 3 --no-sweep --no-cpu 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['e2e']['value'], d['kernel_ms_by_length'])"
