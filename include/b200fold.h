@@ -109,7 +109,10 @@ int bf_sm_count(void);
 /* Tuning / test hook.  Kernel variants are chosen per call by default rules that BF_* environment variables override; this sets
  * the variable BF_<KEY> from the host program (value < 0: remove it).  E.g. "cl" 0 / 1: never / always use the cluster-per-sequence
  * fill kernels where they cover the length, "cl_c" 4 | 8 | 16: their cluster size, "ext_wide" 0 / 1: exterior recursions by one warp /
- * one CTA per sequence, "wide" 0: no 16-warp variants for small batches. */
+ * one CTA per sequence, "wide" 0: no 16-warp variants for small batches, "fill3_small" 0: small batches on the 16-warp round-1 kernels
+ * instead of the 16-warp third-generation ones, "gen_pre" 0: two-strand kernels with four barriers per diagonal at every batch size,
+ * "score_overlap" 0: bf_score_batch[_device] never runs the partition function beside the MFE fill, "stage" 0: bf_score_batch copies
+ * every host array on its own instead of one pinned block each way for small batches. */
 int bf_set_option(const char *key, int value);
 /* Test hook: copy one engine-internal DP table of the most recent call to host memory.
  * which: 0 = c (int32), 1 = fML (int32), 2 = qb (double); layout: per sequence a packed, diagonal-major triangle of
