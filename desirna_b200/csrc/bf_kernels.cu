@@ -15,6 +15,7 @@
 #include "bf_kernels.h"
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "bf_device.cuh"
 
@@ -23,6 +24,12 @@ namespace {
 // (u1,u2) enumeration of interior-loop candidates, u1 major: consecutive lanes walk q downwards in one row of c
 __constant__ uint8_t c_cand_u1[BF_NCAND];
 __constant__ uint8_t c_cand_u2[BF_NCAND];
+// the 487 decomposable candidates as three lists, each ordered by loop size: generic [0, 375), 1xn [375, 429), bulge [429, 487);
+// c_list_cnt[t][s] = entries of list t with size <= s
+constexpr int kNDecomp = 487, kListStart[4] = {0, 375, 429, 487};
+__constant__ uint8_t c_list_u1[kNDecomp];
+__constant__ uint8_t c_list_u2[kNDecomp];
+__constant__ short c_list_cnt[3][32];
 
 // the nine interior-loop shapes that are not decomposed (stack, bulge 1, 1x1, 1x2, 2x1, 2x2, 2x3, 3x2): their index in the size-ordered
 // candidate list (size * (size + 1) / 2 + u1) and their (u1, u2)
@@ -74,20 +81,24 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
   const int W = wstride;  // row stride of the tables, >= n+2
 
   bf_stage(&T, &P->si);
-  // candidates of an interior loop, ordered by size, one packed entry each: x = u1 | u2 << 8 | table << 16 | (shape + 1) << 24 with
-  // table 3 / 4 / 5 = the variant of c a decomposable candidate reads (generic / 1xn / bulge: c + inner mismatch / terminalAU),
-  // 0 for the nine shapes that are evaluated in full (shape = their index in kSpecK); y = size penalty of a decomposable candidate
-  __shared__ int2 cand2[BF_NCAND];
+  // decomposable interior-loop candidates: three size-ordered lists (generic, 1xn, bulge: the variant of c they read and the term of
+  // the closing pair they add are constant within a list).  Entry: x = offset of the inner pair's table entry relative to cell
+  // (i,j)'s (table + (1 + u1) rows - (1 + u2) columns), y = size penalty (16 bits) | u1 << 16 | u2 << 24 (the nick test)
+  __shared__ int2 lst[kNDecomp];
+  __shared__ short lcnt[3][32];
+  __shared__ int spec21[32];   // the first 21 candidates by size: u1 | u2 << 8 | (shape + 1) << 24 for the nine shapes evaluated in full
   __syncthreads();
-  for (int k = tid; k < BF_NCAND; k += blockDim.x) {
-    const int u1 = c_cand_u1[k], u2 = c_cand_u2[k], sz = u1 + u2;
-    const bool special = sz <= 1 || (u1 == 1 && u2 == 1) || (sz == 3 && u1 >= 1 && u2 >= 1) || (u1 == 2 && u2 == 2) || (sz == 5 && (u1 == 2 || u1 == 3));
-    const int tsel = special ? 0 : (u1 == 0 || u2 == 0) ? 5 : (u1 == 1 || u2 == 1) ? 4 : 3;
+  for (int k = tid; k < kNDecomp; k += blockDim.x) {
+    const int u1 = c_list_u1[k], u2 = c_list_u2[k], sz = u1 + u2, t = k < 375 ? 0 : k < 429 ? 1 : 2;
+    const int pen = t == 2 ? T.bulge[sz] : t == 1 ? T.interior[sz] + min(T.ninio_max, (sz - 2) * T.ninio_m)
+                           : T.interior[sz] + min(T.ninio_max, abs(u1 - u2) * T.ninio_m);
+    lst[k] = make_int2((3 + t) * W * W + (1 + u1) * W - (1 + u2), (min(pen, 32767) & 0xffff) | u1 << 16 | u2 << 24);
+  }
+  for (int k = tid; k < 96; k += blockDim.x) lcnt[k >> 5][k & 31] = c_list_cnt[k >> 5][k & 31];
+  if (tid < 32) {
     int shape = 0;
-    for (int q = 0; q < 9; q++) if (kSpecK[q] == k) shape = q + 1;
-    const int pen = tsel == 5 ? T.bulge[sz] : tsel == 4 ? T.interior[sz] + min(T.ninio_max, (sz - 2) * T.ninio_m)
-                  : tsel == 3 ? T.interior[sz] + min(T.ninio_max, abs(u1 - u2) * T.ninio_m) : 0;
-    cand2[k] = make_int2(u1 | u2 << 8 | tsel << 16 | shape << 24, pen);
+    for (int q = 0; q < 9; q++) if (kSpecK[q] == tid) shape = q + 1;
+    spec21[tid] = tid < 21 ? (c_cand_u1[tid] | c_cand_u2[tid] << 8 | shape << 24) : 0;
   }
 
   // dynamic smem carve-up
@@ -122,29 +133,35 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
 #define M_(i, j) fml[(i) * W + (j)]
 #define MT_(j, i) fmlT[(j) * W + (i)]
 
-  // the decomposable interior-loop candidates of cell (i,j), this lane's share: four candidates in flight per round (one packed
-  // entry, one table value each); the nick test is two bounds (p stays on i's strand, q on j's)
-  auto decomp = [&](int i, int j, int kmax, int pmax, int qmin, int mmO, int mm1O, int tauO) -> int {
+  // the decomposable interior-loop candidates of cell (i,j) up to loop size smx, this lane's share: per candidate one list entry, one
+  // table value, add + min; four (generic) / two in flight per round.  A cell that spans the nick tests u1 <= a, u2 <= bq (p stays
+  // on i's strand, q on j's); for every other cell the test is vacuous
+  auto decomp = [&](int i, int j, int smx, bool span, int a, int bq, int mmO, int mm1O, int tauO) -> int {
     int e = BF_INF;
-    const int WW = W * W;
-    for (int k0 = lane; k0 < kmax; k0 += 128) {
-      int2 cd[4];
-      int cc[4];
+    if (smx < 0) return e;
+    const int *cij = c + i * W + j;
+    auto run = [&](auto uc, auto tc, int outer) {
+      constexpr int U = decltype(uc)::value, t = decltype(tc)::value, first = kListStart[t], last = kListStart[t + 1] - 1;
+      const int cnt = lcnt[t][smx];
+      for (int k0 = first + lane; k0 < first + cnt; k0 += 32 * U) {
+        int2 cd[U];
+        int cc[U];
 #pragma unroll
-      for (int u = 0; u < 4; u++) cd[u] = cand2[min(k0 + 32 * u, BF_NCAND - 1)];
+        for (int u = 0; u < U; u++) cd[u] = lst[min(k0 + 32 * u, last)];
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int u1 = cd[u].x & 255, u2 = (cd[u].x >> 8) & 255, ts = (cd[u].x >> 16) & 255;
-        const int p = i + 1 + u1, q = j - 1 - u2;        // q > p: the candidates are cut off at size d - 3
-        const bool ok = k0 + 32 * u < kmax && ts != 0 && p <= pmax && q >= qmin;
-        cc[u] = ok ? c[ts * WW + p * W + q] : BF_INF;
+        for (int u = 0; u < U; u++) {
+          bool ok = k0 + 32 * u < first + cnt;
+          if (TWO && span) ok = ok && ((cd[u].y >> 16) & 255) <= a && ((cd[u].y >> 24) & 255) <= bq;
+          cc[u] = ok ? cij[cd[u].x] : BF_INF;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+          if (cc[u] < BF_INF) e = min(e, cc[u] + (int)(short)(cd[u].y & 0xffff) + outer);
       }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int ts = (cd[u].x >> 16) & 255;
-        if (cc[u] < BF_INF) e = min(e, cc[u] + cd[u].y + (ts == 5 ? tauO : ts == 4 ? mm1O : mmO));
-      }
-    }
+    };
+    run(std::integral_constant<int, 4>(), std::integral_constant<int, 0>(), mmO);
+    run(std::integral_constant<int, 2>(), std::integral_constant<int, 1>(), mm1O);
+    run(std::integral_constant<int, 2>(), std::integral_constant<int, 2>(), tauO);
     return e;
   };
 
@@ -249,9 +266,9 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
             const int smx = min(BF_MAXLOOP, d - 3), kmax = smx >= 0 ? (smx + 1) * (smx + 2) / 2 : 0;   // candidates are ordered by size
             // the unpaired stretches of a regular loop may not contain the nick: p stays on i's strand, q on j's
             const int pmax = (TWO && i < cp) ? cp - 1 : n, qmin = (TWO && j >= cp) ? cp : 0;
-            int e = decomp(i, j, kmax, pmax, qmin, mmO, mm1O, tauO);
+            int e = decomp(i, j, smx, TWO && i < cp && j >= cp, pmax - i - 1, j - 1 - qmin, mmO, mm1O, tauO);
             if (lane < min(kmax, 21)) {   // the shapes evaluated in full sit among the first 21 candidates
-              const int x = cand2[lane].x, sh = x >> 24;
+              const int x = spec21[lane], sh = x >> 24;
               const int p = i + 1 + (x & 255), qq = j - 1 - ((x >> 8) & 255);
               if (sh && p <= pmax && qq >= qmin) {
                 const int e9 = qE9[(sh - 1) * NA + i];
@@ -382,9 +399,9 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_mfe(const BfParams *__restrict_
           const int smx = min(BF_MAXLOOP, d - 3), kmax = smx >= 0 ? (smx + 1) * (smx + 2) / 2 : 0;   // candidates are ordered by size
           // the unpaired stretches of a regular loop may not contain the nick: p stays on i's strand, q on j's
           const int pmax = (TWO && i < cp) ? cp - 1 : n, qmin = (TWO && j >= cp) ? cp : 0;
-          int e = decomp(i, j, kmax, pmax, qmin, mmO, mm1O, tauO);
+          int e = decomp(i, j, smx, TWO && i < cp && j >= cp, pmax - i - 1, j - 1 - qmin, mmO, mm1O, tauO);
           if (lane < min(kmax, 21)) {   // the shapes evaluated in full sit among the first 21 candidates
-            const int x = cand2[lane].x, u1 = x & 255, u2 = (x >> 8) & 255;
+            const int x = spec21[lane], u1 = x & 255, u2 = (x >> 8) & 255;
             const int p = i + 1 + u1, q = j - 1 - u2;
             if ((x >> 24) && p <= pmax && q >= qmin) {
               const int t2 = bf_ptype<TWO>(X, p, q);
@@ -663,17 +680,21 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int W = wstride;
   bf_stage(&T, &P->sd);
-  // candidates of an interior loop, ordered by size: packed as in bf_k_mfe (u1 | u2 << 8 | table << 16 | (shape + 1) << 24); the weight
-  // of the decomposable ones, scale included, is rebuilt for every sequence (cxw)
-  __shared__ int cand1[BF_NCAND];
-  __shared__ double cxw[BF_NCAND];
-  for (int k = tid; k < BF_NCAND; k += blockDim.x) {
-    const int u1 = c_cand_u1[k], u2 = c_cand_u2[k], sz = u1 + u2;
-    const bool special = sz <= 1 || (u1 == 1 && u2 == 1) || (sz == 3 && u1 >= 1 && u2 >= 1) || (u1 == 2 && u2 == 2) || (sz == 5 && (u1 == 2 || u1 == 3));
-    const int tsel = special ? 0 : (u1 == 0 || u2 == 0) ? 5 : (u1 == 1 || u2 == 1) ? 4 : 3;
+  // decomposable interior-loop candidates in three size-ordered lists as in bf_k_mfe: x = table-entry offset relative to the cell's,
+  // y = u1 << 16 | u2 << 24; the weight of an entry, scale included, is rebuilt for every sequence (lw)
+  __shared__ int2 lst[kNDecomp];
+  __shared__ double lw[kNDecomp];
+  __shared__ short lcnt[3][32];
+  __shared__ int spec21[32];
+  for (int k = tid; k < kNDecomp; k += blockDim.x) {
+    const int u1 = c_list_u1[k], u2 = c_list_u2[k], t = k < 375 ? 0 : k < 429 ? 1 : 2;
+    lst[k] = make_int2((3 + t) * W * W + (1 + u1) * W - (1 + u2), u1 << 16 | u2 << 24);
+  }
+  for (int k = tid; k < 96; k += blockDim.x) lcnt[k >> 5][k & 31] = c_list_cnt[k >> 5][k & 31];
+  if (tid < 32) {
     int shape = 0;
-    for (int q = 0; q < 9; q++) if (kSpecK[q] == k) shape = q + 1;
-    cand1[k] = u1 | u2 << 8 | tsel << 16 | shape << 24;
+    for (int q = 0; q < 9; q++) if (kSpecK[q] == tid) shape = q + 1;
+    spec21[tid] = tid < 21 ? (c_cand_u1[tid] | c_cand_u2[tid] << 8 | shape << 24) : 0;
   }
 
   const int nmax = W - 2;
@@ -708,28 +729,35 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
 #define QM_(i, j) qm[(i) * W + (j)]
 #define QM1T_(j, i) qm1T[(j) * W + (i)]
 
-  // the decomposable interior-loop candidates of cell (i,j), this lane's share, four in flight per round (see bf_k_mfe)
-  auto decomp = [&](int i, int j, int kmax, int pmax, int qmin, double xmmO, double xmm1O, double xtauO) -> double {
+  // the decomposable interior-loop candidates of cell (i,j) up to loop size smx, this lane's share (see bf_k_mfe); the closing pair's
+  // factor multiplies the sum of a list once
+  auto decomp = [&](int i, int j, int smx, bool span, int a, int bq, double xmmO, double xmm1O, double xtauO) -> double {
     double acc = 0.0;
-    const int WW = W * W;
-    for (int k0 = lane; k0 < kmax; k0 += 128) {
-      int cd[4];
-      double cw[4], v[4];
+    if (smx < 0) return acc;
+    const double *qij = qb + i * W + j;
+    auto run = [&](auto uc, auto tc, double outer) {
+      constexpr int U = decltype(uc)::value, t = decltype(tc)::value, first = kListStart[t], last = kListStart[t + 1] - 1;
+      const int cnt = lcnt[t][smx];
+      double part = 0.0;
+      for (int k0 = first + lane; k0 < first + cnt; k0 += 32 * U) {
+        int2 cd[U];
+        double cw[U], v[U];
 #pragma unroll
-      for (int u = 0; u < 4; u++) { const int kk = min(k0 + 32 * u, BF_NCAND - 1); cd[u] = cand1[kk]; cw[u] = cxw[kk]; }
+        for (int u = 0; u < U; u++) { const int kk = min(k0 + 32 * u, last); cd[u] = lst[kk]; cw[u] = lw[kk]; }
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int u1 = cd[u] & 255, u2 = (cd[u] >> 8) & 255, ts = (cd[u] >> 16) & 255;
-        const int p = i + 1 + u1, q = j - 1 - u2;        // q > p: the candidates are cut off at size d - 3
-        const bool ok = k0 + 32 * u < kmax && ts != 0 && p <= pmax && q >= qmin;
-        v[u] = ok ? qb[ts * WW + p * W + q] : 0.0;
+        for (int u = 0; u < U; u++) {
+          bool ok = k0 + 32 * u < first + cnt;
+          if (TWO && span) ok = ok && ((cd[u].y >> 16) & 255) <= a && ((cd[u].y >> 24) & 255) <= bq;
+          v[u] = ok ? qij[cd[u].x] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) part = fma(v[u], cw[u], part);
       }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int ts = (cd[u] >> 16) & 255;
-        acc += v[u] * (cw[u] * (ts == 5 ? xtauO : ts == 4 ? xmm1O : xmmO));
-      }
-    }
+      acc = fma(part, outer, acc);
+    };
+    run(std::integral_constant<int, 4>(), std::integral_constant<int, 0>(), xmmO);
+    run(std::integral_constant<int, 2>(), std::integral_constant<int, 1>(), xmm1O);
+    run(std::integral_constant<int, 2>(), std::integral_constant<int, 2>(), xtauO);
     return acc;
   };
 
@@ -763,10 +791,10 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
     }
     for (int k = tid; k <= n + 2; k += blockDim.x) { qA[k] = 0.0; qB[k] = 0.0; }
     __syncthreads();
-    for (int k = tid; k < BF_NCAND; k += blockDim.x) {   // weights of the decomposable candidates at this sequence's scale
-      const int x = cand1[k], u1 = x & 255, u2 = (x >> 8) & 255, sz = u1 + u2, ts = (x >> 16) & 255;
-      const double w = ts == 5 ? T.x_bulge[sz] : ts == 4 ? T.x_interior[sz] * T.x_ninio[sz - 2] : ts == 3 ? T.x_interior[sz] * T.x_ninio[abs(u1 - u2)] : 0.0;
-      cxw[k] = w * exp(-s_lnscale * (sz + 2));
+    for (int k = tid; k < kNDecomp; k += blockDim.x) {   // weights of the decomposable candidates at this sequence's scale
+      const int u1 = (lst[k].y >> 16) & 255, u2 = (lst[k].y >> 24) & 255, sz = u1 + u2;
+      const double w = k >= 429 ? T.x_bulge[sz] : k >= 375 ? T.x_interior[sz] * T.x_ninio[sz - 2] : T.x_interior[sz] * T.x_ninio[abs(u1 - u2)];
+      lw[k] = w * exp(-s_lnscale * (sz + 2));
     }
     if (TWO && cp <= n && tid == 0) { qA[cp] = 1.0; qB[cp - 1] = 1.0; }
     __syncthreads();
@@ -845,9 +873,9 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
             const double xmmO = qXMMO[i], xmm1O = qXMM1O[i], xtauO = t > 2 ? T.x_TerminalAU : 1.0, xmlc = qXMLC[i];
             const int smx = min(BF_MAXLOOP, d - 3), kmax = smx >= 0 ? (smx + 1) * (smx + 2) / 2 : 0;   // candidates are ordered by size
             const int pmax = (TWO && i < cp) ? cp - 1 : n, qmin = (TWO && j >= cp) ? cp : 0;
-            double acc = decomp(i, j, kmax, pmax, qmin, xmmO, xmm1O, xtauO);
+            double acc = decomp(i, j, smx, TWO && i < cp && j >= cp, pmax - i - 1, j - 1 - qmin, xmmO, xmm1O, xtauO);
             if (lane < min(kmax, 21)) {   // the shapes evaluated in full sit among the first 21 candidates
-              const int x = cand1[lane], sh = x >> 24;
+              const int x = spec21[lane], sh = x >> 24;
               const int p = i + 1 + (x & 255), qq = j - 1 - ((x >> 8) & 255);
               if (sh && p <= pmax && qq >= qmin) acc += QB_(p, qq) * qXE9[(sh - 1) * NA + i];
             }
@@ -961,9 +989,9 @@ __global__ void __launch_bounds__(NWG * 32) bf_k_pf(const BfParams *__restrict__
           const double xmmO = cXMMO[i], xmm1O = cXMM1O[i], xtauO = t > 2 ? T.x_TerminalAU : 1.0, xmlc = cXMLC[i];
           const int smx = min(BF_MAXLOOP, d - 3), kmax = smx >= 0 ? (smx + 1) * (smx + 2) / 2 : 0;   // candidates are ordered by size
           const int pmax = (TWO && i < cp) ? cp - 1 : n, qmin = (TWO && j >= cp) ? cp : 0;
-          double acc = decomp(i, j, kmax, pmax, qmin, xmmO, xmm1O, xtauO);
+          double acc = decomp(i, j, smx, TWO && i < cp && j >= cp, pmax - i - 1, j - 1 - qmin, xmmO, xmm1O, xtauO);
           if (lane < min(kmax, 21)) {   // the shapes evaluated in full sit among the first 21 candidates
-            const int x = cand1[lane], u1 = x & 255, u2 = (x >> 8) & 255;
+            const int x = spec21[lane], u1 = x & 255, u2 = (x >> 8) & 255;
             const int p = i + 1 + u1, q = j - 1 - u2;
             if ((x >> 24) && p <= pmax && q >= qmin) {
               const int t2 = bf_ptype<TWO>(X, p, q);
@@ -1176,6 +1204,28 @@ cudaError_t bf_upload_constants() {
   cudaError_t e = cudaMemcpyToSymbol(c_cand_u1, u1, sizeof u1);
   if (e != cudaSuccess) return e;
   e = cudaMemcpyToSymbol(c_cand_u2, u2, sizeof u2);
+  if (e != cudaSuccess) return e;
+  // the decomposable candidates by kind, each list ordered by size (kinds as in the kernels: the nine special shapes are left out)
+  uint8_t l1[kNDecomp], l2[kNDecomp];
+  short cnt[3][32];
+  int pos[3] = {kListStart[0], kListStart[1], kListStart[2]};
+  for (int sz = 0; sz <= BF_MAXLOOP; sz++) {
+    for (int a = 0; a <= sz; a++) {
+      const int b = sz - a;
+      const bool special = sz <= 1 || (a == 1 && b == 1) || (sz == 3 && a >= 1 && b >= 1) || (a == 2 && b == 2) || (sz == 5 && (a == 2 || a == 3));
+      if (special) continue;
+      const int t = (a == 0 || b == 0) ? 2 : (a == 1 || b == 1) ? 1 : 0;
+      if (pos[t] >= kListStart[t + 1]) return cudaErrorInvalidValue;
+      l1[pos[t]] = (uint8_t)a; l2[pos[t]] = (uint8_t)b; pos[t]++;
+    }
+    for (int t = 0; t < 3; t++) cnt[t][sz] = (short)(pos[t] - kListStart[t]);
+  }
+  for (int t = 0; t < 3; t++) { if (pos[t] != kListStart[t + 1]) return cudaErrorInvalidValue; cnt[t][31] = cnt[t][30]; }
+  e = cudaMemcpyToSymbol(c_list_u1, l1, sizeof l1);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyToSymbol(c_list_u2, l2, sizeof l2);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyToSymbol(c_list_cnt, cnt, sizeof cnt);
   if (e == cudaSuccess) g_cand_uploaded = true;
   return e;
 }
