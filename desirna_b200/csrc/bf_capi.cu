@@ -272,7 +272,7 @@ int overlap_scale(const bf_batch_t *b, const int **ov) {
   const char *v = getenv("BF_SCORE_OVERLAP");
   if (v && v[0] == '0') return BF_OK;
   if (!(b->want & (BF_WANT_MFE | BF_WANT_SS)) || !(b->want & BF_WANT_PF) || (b->want & (BF_WANT_BPP | BF_WANT_DEFECT)) || b->nopair) return BF_OK;
-  if (2 * b->B > g.sm_count || b->stride > 400) return BF_OK;
+  if ((2 * b->B > g.sm_count && !(v && v[0] == '2')) || b->stride > 400) return BF_OK;   // 2: any batch size (experiments)
   if (g.zero_cap < (size_t)b->B) {
     const size_t n = std::max<size_t>(256, (size_t)b->B);
     CU(g.d_zero.reserve(n * sizeof(int)), "cudaMalloc(zero scale)");

@@ -29,6 +29,7 @@
 //    All of it only reads diagonals <= d-2, so a phase still ends with a single barrier.
 #include "bf_kernels.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -877,7 +878,9 @@ static cudaError_t mfe3_launch(const BfParams *dP, const BfBatchDev &b, int *ctr
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorInvalidConfiguration;
   }
-  const int grid = b.B < sms * occ ? b.B : sms * occ;
+  const int cap = env_int("BF_FILL3_MFE_CTAS", 0), per_sm = cap > 0 && cap < occ ? cap : occ;   // fewer CTAs per SM: room for the other fill beside it
+  if (env_int("BF_CFG_PRINT", 0)) fprintf(stderr, "mfe_fill3<%d,%d,%d> stride %d smem %zu occ %d per_sm %d\n", NW, NWI, (int)FMS, b.stride, c.smem, occ, per_sm);
+  const int grid = b.B < sms * per_sm ? b.B : sms * per_sm;
   if (grid_out) { *grid_out = grid; return cudaSuccess; }
   const uint32_t *taps = nullptr;
   e = taps_device(c.rs, 32, &taps);
@@ -967,7 +970,9 @@ static cudaError_t pf3_launch(const BfParams *dP, const BfBatchDev &b, double *q
     if (e != cudaSuccess) return e;
     if (occ < 1) return cudaErrorInvalidConfiguration;
   }
-  const int grid = b.B < sms * occ ? b.B : sms * occ;
+  const int cap = env_int("BF_FILL3_PF_CTAS", 0), per_sm = cap > 0 && cap < occ ? cap : occ;
+  if (env_int("BF_CFG_PRINT", 0)) fprintf(stderr, "pf_fill3<%d,%d,%d,%d> stride %d smem %zu occ %d per_sm %d\n", NW, NWI, (int)QMSM, (int)PAIR, b.stride, c.smem, occ, per_sm);
+  const int grid = b.B < sms * per_sm ? b.B : sms * per_sm;
   if (grid_out) { *grid_out = grid; return cudaSuccess; }
   const uint32_t *taps = nullptr;
   e = taps_device(c.rs, 16, &taps);
