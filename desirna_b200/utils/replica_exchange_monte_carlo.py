@@ -200,6 +200,30 @@ def _all_gather_records(local_objs, counts, stride, device):
 
 
 # ------------------------------------------------------------------------------------------ the fan-out
+class _ReplicaStreams:
+    """One random.Random per replica, seeded with the replica index like the reference's workers (:227-228).  use(r) binds the
+    module-level functions of `random` (bound methods of its hidden instance) to replica r's generator, restore() puts the
+    parent's back; code that calls random.choice / random.random / ... -- DesiRNA's own move generator included -- then draws from
+    that replica's stream."""
+    _NAMES = [n for n in random.__all__ if callable(getattr(random._inst, n, None))]
+
+    def __init__(self, replicas):
+        self._saved = [(n, getattr(random, n)) for n in self._NAMES]
+        self._bound = {}
+        for r in replicas:
+            g = random.Random()
+            g.seed(r)
+            self._bound[r] = [(n, getattr(g, n)) for n in self._NAMES]
+
+    def use(self, r):
+        for n, f in self._bound[r]:
+            setattr(random, n, f)
+
+    def restore(self):
+        for n, f in self._saved:
+            setattr(random, n, f)
+
+
 def mutate_sequence_re(lst_seq_obj, nt_list, stats_obj, sim_options, input_file, mutate=None, device=None):
     """One global step of the reference's fan-out (:233-271): every replica makes `sim_options.RE_attempt`
     Metropolis sub-steps.  Returns (new list of ScoreSeq in replica order, stats_obj) on every rank.
@@ -213,35 +237,35 @@ def mutate_sequence_re(lst_seq_obj, nt_list, stats_obj, sim_options, input_file,
     R = len(lst_seq_obj)
     mine = [r for r in range(R) if r % world == rank]
     cur = {r: lst_seq_obj[r] for r in mine}
-    # every worker of the reference starts each global step from random.seed(replica index)  (:227-228, :250)
-    parent_state = random.getstate()
-    states = {}
-    for r in mine:
-        random.seed(r)
-        states[r] = random.getstate()
+    # every worker of the reference starts each global step from random.seed(replica index)  (:227-228, :250): one generator per
+    # replica, switched in under the module-level names the move generator and mc_delta call (random.choice, random.random, ...) --
+    # the same draws as random.seed(r) followed by getstate / setstate around every use, without copying the 625-word state
+    streams = _ReplicaStreams(mine)
     acc = better = rej = 0
-    for _ in range(sim_options.RE_attempt):
-        mutants = []
-        for r in mine:
-            random.setstate(states[r])
-            mutants.append(_propose(mutate, cur[r], nt_list, sim_options, input_file))
-            states[r] = random.getstate()
-        scored = es.score_sequences(mutants, input_file, sim_options)
-        for r, new in zip(mine, scored):
-            old = cur[r]
-            # what mutate_sequence copies from the parent record (sequence_utils.py:1133-1134)
-            new.get_replica_num(old.replica_num)
-            new.get_temp_shelf(old.temp_shelf)
-            random.setstate(states[r])
-            ok, was_better = mc_delta(old.scoring_function, new.scoring_function, old.temp_shelf, sim_options)
-            states[r] = random.getstate()
-            if ok:
-                cur[r] = new
-                acc += 1
-                better += int(was_better)
-            else:
-                rej += 1
-    random.setstate(parent_state)  # the parent stream drives replica_exchange only
+    try:
+        for _ in range(sim_options.RE_attempt):
+            mutants = []
+            for r in mine:
+                streams.use(r)
+                mutants.append(_propose(mutate, cur[r], nt_list, sim_options, input_file))
+            streams.restore()
+            scored = es.score_sequences(mutants, input_file, sim_options)
+            for r, new in zip(mine, scored):
+                old = cur[r]
+                # what mutate_sequence copies from the parent record (sequence_utils.py:1133-1134)
+                new.get_replica_num(old.replica_num)
+                new.get_temp_shelf(old.temp_shelf)
+                streams.use(r)
+                ok, was_better = mc_delta(old.scoring_function, new.scoring_function, old.temp_shelf, sim_options)
+                if ok:
+                    cur[r] = new
+                    acc += 1
+                    better += int(was_better)
+                else:
+                    rej += 1
+            streams.restore()
+    finally:
+        streams.restore()   # the parent stream, untouched by the replicas, drives replica_exchange only
 
     if dist:
         import torch

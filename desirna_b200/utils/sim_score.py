@@ -7,15 +7,18 @@ pair map.  Values and rounding are the reference's: MCC with eps 1e-5 (:126-127)
 precision with +0.001 in the denominator (:137,:147), each rounded to 3 decimals.
 """
 import bisect
+import functools
 import math
 
 OPEN_BRACKETS = {"(": "0", "[": "1", "<": "2", "{": "3", "A": "4", "B": "5", "C": "6", "D": "7", "E": "8"}
 CLOSE_BRACKETS = {")": "0", "]": "1", ">": "2", "}": "3", "a": "4", "b": "5", "c": "6", "d": "7", "e": "8"}
 
 
+@functools.lru_cache(maxsize=8192)
 def pairing_positions(s1):
     """dot-bracket string -> {position: partner or -1}; characters that are neither bracket nor
-    '.'/'-' get no entry, as in the reference (sim_score.py:41-48)."""
+    '.'/'-' get no entry, as in the reference (sim_score.py:41-48).  Memoised (the target recurs in every call, MFE structures
+    recur across mutants); the returned dict is shared, callers only read it."""
     pairs = {}
     stacks = {}
     closes = {}
