@@ -29,12 +29,13 @@ def metropolis_score(temp, dE, sim_options):
     return math.exp((-sim_options.L / temp) * dE)
 
 
-def mc_delta(deltaF_o, deltaF_m, T_replica, sim_options):
-    """accept if not worse, else with probability exp(-L/T * dS); returns (accept, accepted_because_better)"""
+def mc_delta(deltaF_o, deltaF_m, T_replica, sim_options, rng=None):
+    """accept if not worse, else with probability exp(-L/T * dS); returns (accept, accepted_because_better).
+    rng: the generator the uniform number is drawn from (default: the module-level stream, as in the reference)"""
     if deltaF_m <= deltaF_o:
         return True, True
     p = metropolis_score(T_replica, deltaF_m - deltaF_o, sim_options)
-    return p > random.random(), False
+    return p > (rng.random() if rng is not None else random.random()), False
 
 
 def replica_exchange_attempt(T0, T1, dE0, dE1, sim_options):
@@ -210,9 +211,11 @@ class _ReplicaStreams:
     def __init__(self, replicas):
         self._saved = [(n, getattr(random, n)) for n in self._NAMES]
         self._bound = {}
+        self.gen = {}
         for r in replicas:
             g = random.Random()
             g.seed(r)
+            self.gen[r] = g
             self._bound[r] = [(n, getattr(g, n)) for n in self._NAMES]
 
     def use(self, r):
@@ -255,15 +258,13 @@ def mutate_sequence_re(lst_seq_obj, nt_list, stats_obj, sim_options, input_file,
                 # what mutate_sequence copies from the parent record (sequence_utils.py:1133-1134)
                 new.get_replica_num(old.replica_num)
                 new.get_temp_shelf(old.temp_shelf)
-                streams.use(r)
-                ok, was_better = mc_delta(old.scoring_function, new.scoring_function, old.temp_shelf, sim_options)
+                ok, was_better = mc_delta(old.scoring_function, new.scoring_function, old.temp_shelf, sim_options, rng=streams.gen[r])
                 if ok:
                     cur[r] = new
                     acc += 1
                     better += int(was_better)
                 else:
                     rej += 1
-            streams.restore()
     finally:
         streams.restore()   # the parent stream, untouched by the replicas, drives replica_exchange only
 

@@ -44,6 +44,24 @@ def pairing_positions(s1):
     return dict(sorted(pairs.items()))
 
 
+@functools.lru_cache(maxsize=8192)
+def _confusion(ref_ss, query_ss):
+    """(tp, fp, fn, tn) per POSITION as the reference counts them (sim_score.py:104-119); memoised on the two strings"""
+    tp = fp = tn = fn = 0
+    r, q = pairing_positions(ref_ss), pairing_positions(query_ss)
+    for i in range(len(r)):
+        if r[i] == q[i]:
+            if r[i] != -1:
+                tp += 1
+            else:
+                tn += 1
+        elif r[i] == -1:
+            fp += 1
+        else:
+            fn += 1
+    return (tp, fp, fn, tn)
+
+
 class SimScore:
     def __init__(self, ref_ss, query_ss):
         self.ref_ss = ref_ss
@@ -54,19 +72,7 @@ class SimScore:
         self.bp_dict_q = pairing_positions(self.query_ss)
 
     def cofusion_matrix(self):
-        tp = fp = tn = fn = 0
-        r, q = self.bp_dict_r, self.bp_dict_q
-        for i in range(len(r)):
-            if r[i] == q[i]:
-                if r[i] != -1:
-                    tp += 1
-                else:
-                    tn += 1
-            elif r[i] == -1:
-                fp += 1
-            else:
-                fn += 1
-        self.conf_mat = (tp, fp, fn, tn)
+        self.conf_mat = _confusion(self.ref_ss, self.query_ss)
 
     def mcc(self):
         tp, fp, fn, tn = self.conf_mat
