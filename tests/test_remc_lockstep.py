@@ -191,3 +191,37 @@ def test_lockstep_with_the_mirrored_move_generator():
                 assert (o.sequence[a], o.sequence[b]) in {("A", "U"), ("U", "A"), ("G", "C"), ("C", "G"), ("G", "U"), ("U", "G")}
     finally:
         oracle_backend.install(old)
+
+
+def test_replica_streams_draw_like_seed_getstate_setstate():
+    """the per-replica generators of the lock-step loop (random.Random seeded with the replica index, bound under the module-level
+    names) give the draws of the reference's scheme: random.seed(r) in each worker, its state carried from use to use
+    (utils/replica_exchange_monte_carlo.py:227-228, :250); the parent stream is left where it was"""
+    from desirna_b200.utils import replica_exchange_monte_carlo as remc
+    random.seed(99)
+    parent_before = random.getstate()
+    # reference scheme: one module-level stream, state saved / restored around every use
+    states = {}
+    for r in (0, 3, 5):
+        random.seed(r)
+        states[r] = random.getstate()
+    want = []
+    for rnd in range(4):
+        for r in (0, 3, 5):
+            random.setstate(states[r])
+            want.append((random.choice("ACGU"), random.random(), random.choices([1, 2, 3], weights=[0.2, 0.3, 0.5])[0], random.randint(0, 99)))
+            states[r] = random.getstate()
+    random.setstate(parent_before)
+    streams = remc._ReplicaStreams([0, 3, 5])
+    got = []
+    try:
+        for rnd in range(4):
+            for r in (0, 3, 5):
+                streams.use(r)
+                got.append((random.choice("ACGU"), random.random(), random.choices([1, 2, 3], weights=[0.2, 0.3, 0.5])[0], random.randint(0, 99)))
+            streams.restore()
+    finally:
+        streams.restore()
+    assert got == want
+    assert random.getstate() == parent_before
+    assert random.random.__self__ is random._inst
