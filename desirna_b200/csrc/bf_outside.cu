@@ -259,9 +259,10 @@ constexpr int kORing = 32;
 
 struct Out2Plan {
   int rs, rr;
-  size_t o_wg, o_wb, o_w1, o_scl, o_q5, o_q3, o_prow, o_ppair, o_ap, o_bqm, o_bqm1, o_g, o_pi, o_p1, o_p2, o_og, o_toff, o_pt, o_stk, o_list, o_S, total;
+  size_t o_wg, o_wb, o_w1, o_scl, o_q5, o_q3, o_prow, o_ppair, o_ap, o_bqm, o_bqm1, o_g, o_pi, o_p1, o_p2, o_og, o_h, o_toff, o_pt, o_stk, o_list, o_S, total;
 };
-__host__ __device__ inline Out2Plan out2_plan(int nmax, int nw, bool rgs) {
+// hsm: the H triangle this pass writes and the qm / qm1 triangles of the inside pass on chip too (short sequences, one CTA per SM)
+__host__ __device__ inline Out2Plan out2_plan(int nmax, int nw, bool rgs, bool hsm = false) {
   Out2Plan p;
   p.rs = (nmax + 8 + 3) / 4 * 4;
   p.rr = p.rs + 32;
@@ -282,6 +283,7 @@ __host__ __device__ inline Out2Plan out2_plan(int nmax, int nw, bool rgs) {
   p.o_p1 = o; o += (size_t)2 * nw * p.rs * sizeof(double);
   p.o_p2 = o; o += (size_t)2 * nw * p.rs * sizeof(double);
   p.o_og = o; o += rgs ? (size_t)kORing * p.rr * sizeof(double) : 0;
+  p.o_h = o; o += hsm ? (size_t)3 * ((tri_size(nmax) + 7) / 8 * 8) * sizeof(double) : 0;
   p.o_toff = o; o += (size_t)p.rs * sizeof(int);
   p.o_pt = o; o += (size_t)p.rs * sizeof(short);
   p.o_stk = o; o += (size_t)p.rs * sizeof(short);
@@ -300,7 +302,7 @@ __host__ __device__ inline size_t out2_ws_doubles(int nmax, bool rgs) {
   for (int idx_ = (warp), flip_ = 0, s = (smax) - idx_; s >= 0;                                  \
        idx_ += flip_ ? 2 * (warp) + 1 : 2 * ((NW) - 1 - (warp)) + 1, flip_ ^= 1, s = (smax) - idx_)
 
-template <int NW, bool RGS>
+template <int NW, bool RGS, bool HSM>
 __global__ void __launch_bounds__(NW * 32) bf_k_pf_out2(const BfParams *__restrict__ P, BfBatchDev b, const double *qbtri, const double *qmseq,
                                                         size_t tri_slot, double *ws, size_t ws_slot, const double *lnscale, const char *targets,
                                                         int n_targets, int tstride, double *out_defect, double *out_bpp, int *work_counter) {
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_out2(const BfParams *__restri
   __shared__ double s_red[NW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nmax = b.stride;
-  const Out2Plan pl = out2_plan(nmax, NW, RGS);
+  const Out2Plan pl = out2_plan(nmax, NW, RGS, HSM);
   const int RS = pl.rs, RR = pl.rr;
   const BfSmallD &T = P->sd;
   double *wg = reinterpret_cast<double *>(dyn + pl.o_wg);
@@ -333,8 +335,10 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_out2(const BfParams *__restri
   unsigned short *LST = reinterpret_cast<unsigned short *>(dyn + pl.o_list);
   uint8_t *S = dyn + pl.o_S;
   double *wsp = ws + (size_t)blockIdx.x * ws_slot;
-  double *H = wsp;
-  double *rings = wsp + (tri_size(nmax) + 7) / 8 * 8;
+  const size_t tri_pad = (tri_size(nmax) + 7) / 8 * 8;
+  double *HQ = reinterpret_cast<double *>(dyn + pl.o_h);   // HSM: H, qm, qm1 of the sequence in work
+  double *H = HSM ? HQ : wsp;
+  double *rings = wsp + tri_pad;
   double *OG = RGS ? reinterpret_cast<double *>(dyn + pl.o_og) : rings + 2 * kORing * RR;
   double *O1 = rings, *OB = rings + kORing * RR;
   // ring entry of position p (1-based index along the diagonal) of diagonal x: row (x & 31), offset 32 + p
@@ -366,7 +370,12 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_out2(const BfParams *__restri
       w1[tid] = (tid >= 4 && tid <= 30) ? T.x_interior[tid] * T.x_ninio[tid - 2] * scl[tid + 2] : 0.0;
     }
     const double *qb = qbtri + (size_t)sq * tri_slot;
-    const double *QM = qmseq + (size_t)sq * 2 * tri_slot, *QM1 = QM + tri_slot;
+    const double *QMg = qmseq + (size_t)sq * 2 * tri_slot;
+    const double *QM = HSM ? HQ + tri_pad : QMg, *QM1 = HSM ? HQ + 2 * tri_pad : QMg + tri_slot;
+    if (HSM) {   // visible after the barrier that precedes the diagonal loop
+      const int nt = (int)tri_size(n);
+      for (int k = tid; k < nt; k += blockDim.x) { HQ[tri_pad + k] = QMg[k]; HQ[2 * tri_pad + k] = QMg[tri_slot + k]; }
+    }
     const double bu1 = exp(log(T.x_MLbase) - lns), sc1 = scl[1];
     const double xtau = T.x_TerminalAU, inv_tau = 1.0 / xtau;
     const double xclose = T.x_MLclosing * scl[2];
@@ -581,17 +590,24 @@ __global__ void __launch_bounds__(NW * 32) bf_k_pf_out2(const BfParams *__restri
 #include <cstdlib>
 namespace {
 constexpr size_t kOutSmemBudget = 232448 - 1024 - 256;
-int out_version(int nmax, bool *rgs) {
+int out_version(int nmax, bool *rgs, bool *hsm = nullptr, int B = 0, int sms = 148) {
   const char *v = getenv("BF_OUT_V");
+  if (hsm) *hsm = false;
   if (v && v[0] == '1') return 1;
+  // H / qm / qm1 of the sequence on chip as well: measured against reading them through L2 (profiles/r02_outside_hsm.txt) -- ahead
+  // while two CTAs still share an SM (<= ~60 nt: 3-5 %) and for batches that leave SMs idle (B = 64: 0.96 -> 0.82 ms at 100 nt);
+  // behind for big batches once it costs the second CTA (4096 x 100 nt: 16.2 against 11.3 ms).  BF_OUT_HSM=0 / 1: never / whenever it fits.
+  const char *h = getenv("BF_OUT_HSM");
+  const bool want = h && *h ? h[0] != '0' : (out2_plan(nmax, 8, true, true).total <= 113 * 1024 || (B > 0 && B <= sms));
+  if (hsm && want && out2_plan(nmax, 8, true, true).total <= kOutSmemBudget) { *rgs = true; *hsm = true; return 2; }
   if (out2_plan(nmax, 8, true).total <= 113 * 1024) { *rgs = true; return 2; }
   if (out2_plan(nmax, 8, false).total <= kOutSmemBudget) { *rgs = false; return 2; }
   return 1;
 }
-template <bool RGS>
+template <bool RGS, bool HSM>
 cudaError_t out2_setup(const BfBatchDev &b, int sms, int *grid, size_t *smem) {
-  auto kern = bf_k_pf_out2<8, RGS>;
-  const size_t sm = out2_plan(b.stride, 8, RGS).total;
+  auto kern = bf_k_pf_out2<8, RGS, HSM>;
+  const size_t sm = out2_plan(b.stride, 8, RGS, HSM).total;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sm > 1024 ? sm : 1024));
   if (e != cudaSuccess) return e;
   int occ = 0;
@@ -611,8 +627,9 @@ size_t bf_out_ws_slot(int nmax) {
 }
 
 cudaError_t bf_out_grid(const BfBatchDev &b, int sms, int *grid) {
-  bool rgs = false;
-  if (out_version(b.stride, &rgs) == 2) return rgs ? out2_setup<true>(b, sms, grid, nullptr) : out2_setup<false>(b, sms, grid, nullptr);
+  bool rgs = false, hsm = false;
+  if (out_version(b.stride, &rgs, &hsm, b.B, sms) == 2)
+    return hsm ? out2_setup<true, true>(b, sms, grid, nullptr) : rgs ? out2_setup<true, false>(b, sms, grid, nullptr) : out2_setup<false, false>(b, sms, grid, nullptr);
   auto kern = bf_k_pf_out<8>;
   const size_t sm = out_plan(b.stride).total;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sm > 1024 ? sm : 1024));
@@ -630,15 +647,20 @@ cudaError_t bf_launch_pf_out(const BfParams *dP, const BfBatchDev &b, const doub
                              int grid, int *work_counter, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
-  bool rgs = false;
-  if (out_version(b.stride, &rgs) == 2) {
-    const size_t sm = out2_plan(b.stride, 8, rgs).total, tslot = (tri_size(b.stride) + 7) / 8 * 8, wslot = bf_out_ws_slot(b.stride);
-    if (rgs)
-      bf_k_pf_out2<8, true><<<grid, 256, sm, st>>>(dP, b, qbtri, qmseq, tslot, ws, wslot, lnscale, targets, n_targets, tstride, out_defect,
-                                                   out_bpp, work_counter);
+  bool rgs = false, hsm = false;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (out_version(b.stride, &rgs, &hsm, b.B, sms) == 2) {
+    const size_t sm = out2_plan(b.stride, 8, rgs, hsm).total, tslot = (tri_size(b.stride) + 7) / 8 * 8, wslot = bf_out_ws_slot(b.stride);
+    if (hsm)
+      bf_k_pf_out2<8, true, true><<<grid, 256, sm, st>>>(dP, b, qbtri, qmseq, tslot, ws, wslot, lnscale, targets, n_targets, tstride, out_defect,
+                                                         out_bpp, work_counter);
+    else if (rgs)
+      bf_k_pf_out2<8, true, false><<<grid, 256, sm, st>>>(dP, b, qbtri, qmseq, tslot, ws, wslot, lnscale, targets, n_targets, tstride, out_defect,
+                                                          out_bpp, work_counter);
     else
-      bf_k_pf_out2<8, false><<<grid, 256, sm, st>>>(dP, b, qbtri, qmseq, tslot, ws, wslot, lnscale, targets, n_targets, tstride, out_defect,
-                                                    out_bpp, work_counter);
+      bf_k_pf_out2<8, false, false><<<grid, 256, sm, st>>>(dP, b, qbtri, qmseq, tslot, ws, wslot, lnscale, targets, n_targets, tstride, out_defect,
+                                                           out_bpp, work_counter);
     return cudaGetLastError();
   }
   const size_t sm = out_plan(b.stride).total;
