@@ -42,14 +42,16 @@ struct Workspace {
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // begin/end of mfe, pf, eval in the last call
   bool ran[3] = {false, false, false};
   // the partition function of a small batch can run beside the MFE fill on SMs of its own (run_device: scale_override)
-  cudaStream_t st2 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t st2 = nullptr, st3 = nullptr;   // st3: eval_structure of a small batch (it reads the sequence and the targets only)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
   cudaError_t create() {
     cudaError_t e = cudaMalloc(&d_counters, 8 * sizeof(int));
     for (int k = 0; k < 6 && e == cudaSuccess; k++) e = cudaEventCreate(&ev[k]);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st3, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev_join3, cudaEventDisableTiming);
     return e;
   }
   void destroy() {
@@ -59,8 +61,10 @@ struct Workspace {
     for (int k = 0; k < 6; k++) { if (ev[k]) cudaEventDestroy(ev[k]); ev[k] = nullptr; }
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
+    if (ev_join3) cudaEventDestroy(ev_join3);
     if (st2) cudaStreamDestroy(st2);
-    ev_fork = ev_join = nullptr; st2 = nullptr;
+    if (st3) cudaStreamDestroy(st3);
+    ev_fork = ev_join = ev_join3 = nullptr; st2 = st3 = nullptr;
   }
 };
 
@@ -138,6 +142,18 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
   if (scale_override) CU(cudaEventRecord(w.ev_fork, st), "fork");   // what the second stream has to wait for: the work before this call
   const int *mfe_for_scale = nullptr;
   w.ran[0] = w.ran[1] = w.ran[2] = false;
+  bool eval_done = false;
+  if (scale_override && (b->want & BF_WANT_EVAL) && (b->want & BF_WANT_PF) && !(b->want & (BF_WANT_BPP | BF_WANT_DEFECT)) && !b->nopair) {
+    // side-by-side fills: eval_structure on a stream of its own from the start (the SMs the two fills leave free take it)
+    CU(cudaStreamWaitEvent(w.st3, w.ev_fork, 0), "fork eval");
+    if (timing) cudaEventRecord(w.ev[4], w.st3);
+    CU(bf_launch_eval(g.dP, db, b->targets, b->n_targets, b->stride, r->eval_dcal, w.st3), "launch bf_k_eval");
+    if (timing) cudaEventRecord(w.ev[5], w.st3);
+    CU(cudaEventRecord(w.ev_join3, w.st3), "join eval");
+    w.ran[2] = true;
+    g.launches++;
+    eval_done = true;
+  }
   const bool fill_mfe = !two && !g.force_generic && bf_fill_mfe_mode(b->stride) != 0;
   const bool fill_pf = !two && !g.force_generic && bf_fill_pf_mode(b->stride) != 0;
   if (b->want & (BF_WANT_MFE | BF_WANT_SS)) {
@@ -185,7 +201,6 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
     w.ran[0] = timing;
     mfe_for_scale = out_mfe;
   }
-  bool eval_done = false;
   const bool want_out = (b->want & (BF_WANT_BPP | BF_WANT_DEFECT)) != 0;
   if (want_out && (two || !fill_pf))
     return fail(BF_ERR_UNAVAILABLE, "base-pair probabilities / ensemble defect: single-strand sequences within the fill path's length range only");
@@ -242,17 +257,10 @@ int run_device(Workspace &w, const bf_batch_t *b, const bf_result_t *r, bool two
       g.launches++;
     }
     if (timing) cudaEventRecord(w.ev[3], sp);
-    if (beside && (b->want & BF_WANT_EVAL)) {   // eval_structure reads the sequence and the targets only: behind the shorter chain
-      if (timing) cudaEventRecord(w.ev[4], sp);
-      CU(bf_launch_eval(g.dP, db, b->targets, b->n_targets, b->stride, r->eval_dcal, sp), "launch bf_k_eval");
-      if (timing) cudaEventRecord(w.ev[5], sp);
-      w.ran[2] = true;
-      g.launches++;
-      eval_done = true;
-    }
     if (beside) { CU(cudaEventRecord(w.ev_join, sp), "join"); CU(cudaStreamWaitEvent(st, w.ev_join, 0), "join"); }
     w.ran[1] = timing;
   }
+  if (eval_done) CU(cudaStreamWaitEvent(st, w.ev_join3, 0), "join eval");
   if ((b->want & BF_WANT_EVAL) && !eval_done) {
     if (timing) cudaEventRecord(w.ev[4], st);
     CU(bf_launch_eval(g.dP, db, b->targets, b->n_targets, b->stride, r->eval_dcal, st), "launch bf_k_eval");

@@ -644,6 +644,29 @@ __global__ void __launch_bounds__(WPB * 32) bf_k_trace(const BfParams *__restric
     if (!to_pair) continue;
     for (;;) {
       if (lane == 0) { ss[i - 1] = '('; ss[j - 1] = ')'; }
+      {
+        // a helix in one table round trip: lane k asks whether pair (i+k, j-k) -- a pair of the structure if all lanes before it say
+        // yes -- continues with the stacked pair (i+k+1, j-k-1).  That is the walk's own first choice for a pair that is not an
+        // optimal hairpin closing (hairpin test first, then inner pairs by p ascending, q descending: the stack comes first)
+        const int ik = i + lane, jk = j - lane;
+        bool stacked = false;
+        if (jk - ik > 2) {
+          const int tk = ptype_sp(SP, ik, jk), t2 = ptype_sp(SP, ik + 1, jk - 1);
+          if (tk && t2) {
+            const int ck = C_(ik, jk), cc = C_(ik + 1, jk - 1);
+            stacked = ck < BF_INF && cc < BF_INF && ck == cc + bf_e_intloop(P, T, 0, 0, tk, bf_rtype(t2), S[ik + 1], S[jk - 1], S[ik], S[jk]) &&
+                      ck != bf_e_hairpin(P, T, S, ik, jk, tk);
+          }
+        }
+        const unsigned mk = __ballot_sync(BF_FULL, stacked);
+        const int run = mk == BF_FULL ? 32 : __ffs(~mk) - 1;
+        if (run > 0) {
+          if (lane < run) { ss[ik - 1] = '('; ss[jk - 1] = ')'; }
+          __syncwarp();
+          i += run; j -= run;
+          continue;
+        }
+      }
       const int t = ptype_sp(SP, i, j), cij = C_(i, j);
       const int si1 = S[i + 1], sj1 = S[j - 1];
       if (cij == bf_e_hairpin(P, T, S, i, j, t)) break;
