@@ -929,7 +929,7 @@ Pf3Cfg pf3_cfg(int nmax, bool small) {
   // 16 warps with cells in pairs from 90 nt (L = 100: 4.90 ms per 4096 folds against 5.14 for two 8-warp CTAs); below, two or three
   // 8-warp CTAs per SM are ahead (L = 30 / 50 / 75: 0.60 / 1.26 / 2.79 ms against 0.88 / 1.71 / 3.13; scripts/sweep_pfnw.sh)
   // small batches (see mfe3_cfg): 16 warps at every length (B = 64: 36 nt 0.071 -> 0.058 ms, 100 nt 0.336 -> 0.227, 148 nt 0.776 -> 0.550,
-  // 170 nt 1.00 -> 0.76; at 200 nt the round-1 kernel is ahead, 1.41 against 2.03)
+  // 170 nt 1.00 -> 0.69, 176 nt 1.10 -> 0.72; the plan stops fitting the shared memory at ~178 nt, longer sequences stay on the round-1 kernel)
   // (beyond ~110 nt, qm / qm1 off chip, the split wants more auxiliary warps: paired cells with 10 tap + 6 auxiliary warps, B = 64 x 140 nt 0.51 -> 0.46 ms)
   c.nw = nw_env ? nw_env : small ? (nmax > 110 ? 116 : 16) : (nmax < 90 ? 8 : 116);
   const int nwr = c.nw % 100;   // (100 + warps: the paired variant)
@@ -941,7 +941,7 @@ Pf3Cfg pf3_cfg(int nmax, bool small) {
   if (c.qms && with > kSmemBudget) c.qms = false;
   c.smem = c.qms ? with : without;
   // measured against the round-1 kernel (profiles/r02_sweep_len.txt): ahead up to 150 nt, level beyond
-  c.ok = c.smem <= kSmemBudget && nmax <= (small ? env_int("BF_FILL3_PF_MAXN_SMALL", 172) : env_int("BF_FILL3_PF_MAXN", 150));
+  c.ok = c.smem <= kSmemBudget && nmax <= (small ? env_int("BF_FILL3_PF_MAXN_SMALL", 230) : env_int("BF_FILL3_PF_MAXN", 150));
   return c;
 }
 }  // namespace

@@ -253,10 +253,10 @@ def test_fill3_outside_pass_uses_its_tables(engine, oracle, monkeypatch):
         assert abs(out["defect"][k] - oracle.ensemble_defect(bpp, ss[k])) < 1e-9
 
 
-@pytest.mark.parametrize("L", [36, 100, 148, 200])
+@pytest.mark.parametrize("L", [36, 100, 148, 176, 200])
 def test_small_batch_fill3_variants(engine, oracle, monkeypatch, L):
     """batches that leave SMs idle take the 16-warp third-generation kernels (one CTA per sequence with the whole shared memory of its
-    SM; MFE while the fML table fits on chip, partition function up to 172 nt); BF_FILL3_SMALL=0 puts the 16-warp round-1 kernels
+    SM; MFE while the fML table fits on chip, partition function up to ~178 nt); BF_FILL3_SMALL=0 puts the 16-warp round-1 kernels
     back.  Same integers, ensemble energies to 1e-12, and the oracle on every fifth sequence; ragged lengths in one batch."""
     seqs = rand_seqs(4242 + L, 40, L) + rand_seqs(4243 + L, 8, max(5, L // 3))
     want = engine.WANT_MFE | engine.WANT_SS | engine.WANT_PF
