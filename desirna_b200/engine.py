@@ -225,9 +225,9 @@ def pack(seqs, stride=None):
     lens = np.array([len(s) for s in clean], np.int32)
     if stride is None:
         stride = max(1, int(lens.max()) if B else 1)
-    buf = np.zeros((B, stride), np.uint8)
-    for k, s in enumerate(clean):
-        buf[k, :len(s)] = np.frombuffer(s.encode("ascii"), np.uint8)
+    # one join + one frombuffer instead of a numpy assignment per row (rows padded with NUL to the stride)
+    flat = "".join(s if len(s) == stride else s.ljust(stride, "\0") for s in clean).encode("ascii")
+    buf = np.frombuffer(flat, np.uint8).reshape(B, stride).copy() if B else np.zeros((0, stride), np.uint8)
     return buf, lens, cuts
 
 
@@ -235,13 +235,16 @@ def pack_targets(targets, stride):
     """targets: list (per sequence) of list of dot-bracket strings ('&' dropped) -> uint8[B,T,stride]"""
     B = len(targets)
     T = len(targets[0]) if B else 0
-    buf = np.full((B, T, stride), ord("."), np.uint8)
-    for k, row in enumerate(targets):
+    rows = []
+    for row in targets:
         assert len(row) == T, "every sequence needs the same number of targets"
-        for t, db in enumerate(row):
-            db = db.replace("&", "")
-            buf[k, t, :len(db)] = np.frombuffer(db.encode("ascii"), np.uint8)
-    return buf
+        for db in row:
+            if "&" in db:
+                db = db.replace("&", "")
+            rows.append(db if len(db) == stride else db.ljust(stride, "."))
+    if not rows:
+        return np.full((B, T, stride), ord("."), np.uint8)
+    return np.frombuffer("".join(rows).encode("ascii"), np.uint8).reshape(B, T, stride).copy()
 
 
 def score_batch(seqs, targets=None, nopair=None, want=WANT_MFE | WANT_SS | WANT_PF):
@@ -295,6 +298,7 @@ def score_batch(seqs, targets=None, nopair=None, want=WANT_MFE | WANT_SS | WANT_
     b.want = want
     _check(lib().bf_score_batch(C.byref(b), C.byref(r)))
     if want & WANT_SS:
-        out["mfe_ss"] = [bytes(ss[k, :lens[k]]).decode("ascii") for k in range(B)]
+        raw, w = ss.tobytes().decode("ascii"), stride + 1
+        out["mfe_ss"] = [raw[k * w:k * w + int(lens[k])] for k in range(B)]
     out["len"], out["cut"] = lens, cuts
     return out
